@@ -1,0 +1,119 @@
+"""Synthetic initial conditions for the benchmark / parity workloads
+(BASELINE.md section 4).
+
+Counter-based (Philox) streams keyed by (seed, chunk) so that any rank can
+regenerate exactly its own contiguous slice [lo, hi) of the global particle
+set without generating the rest: chunk k always holds global particles
+[k*CHUNK, (k+1)*CHUNK).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+CHUNK = 1 << 20
+
+
+def _chunks(lo: int, hi: int):
+    k = lo // CHUNK
+    while k * CHUNK < hi:
+        a, b = max(lo, k * CHUNK), min(hi, (k + 1) * CHUNK)
+        yield k, a - k * CHUNK, b - k * CHUNK
+        k += 1
+
+
+def _rng(seed: int, chunk: int) -> np.random.Generator:
+    return np.random.Generator(np.random.Philox(key=[seed, chunk]))
+
+
+def _isotropic(rng, n):
+    cost = rng.uniform(-1.0, 1.0, n)
+    phi = rng.uniform(0.0, 2.0 * math.pi, n)
+    sint = np.sqrt(1.0 - cost * cost)
+    return np.stack([sint * np.cos(phi), sint * np.sin(phi), cost], axis=1)
+
+
+def _assemble(gen_chunk, lo, hi, total_mass, ntot):
+    pos = np.empty((hi - lo, 3))
+    vel = np.empty((hi - lo, 3))
+    o = 0
+    for k, a, b in _chunks(lo, hi):
+        p, v = gen_chunk(k)
+        pos[o:o + b - a] = p[a:b]
+        vel[o:o + b - a] = v[a:b]
+        o += b - a
+    mass = np.full(hi - lo, total_mass / ntot)
+    return pos, vel, mass
+
+
+def hernquist_halo(ntot: int, lo: int = 0, hi: int | None = None, seed: int = 42,
+                   a: float = 1.0, mass: float = 1.0, rmax: float = 50.0):
+    """Hernquist sphere: r = a sqrt(u)/(1-sqrt(u)), u ~ U(0, u_max) (truncated at
+    rmax), isotropic directions; isotropic Gaussian velocities with the
+    Jeans dispersion of the untruncated model (only used by level assignment)."""
+    hi = ntot if hi is None else hi
+    umax = (rmax / (rmax + a)) ** 2
+
+    def gen(k):
+        rng = _rng(seed, k)
+        s = np.sqrt(rng.uniform(0.0, umax, CHUNK))
+        r = a * s / (1.0 - s)
+        pos = r[:, None] * _isotropic(rng, CHUNK)
+        x = r / a
+        # Hernquist (1990) eq. 10 radial dispersion
+        sig2 = (mass / (12.0 * a)) * (12.0 * x * (1 + x) ** 3 * np.log1p(1.0 / x)
+                                      - x / (1 + x) * (25 + 52 * x + 42 * x * x + 12 * x ** 3))
+        sig = np.sqrt(np.maximum(sig2, 1e-12))
+        vel = rng.standard_normal((CHUNK, 3)) * sig[:, None]
+        return pos, vel
+
+    return _assemble(gen, lo, hi, mass, ntot)
+
+
+def nfw_halo(ntot: int, lo: int = 0, hi: int | None = None, seed: int = 43,
+             rs: float = 1.0, c: float = 10.0, mass: float = 1.0):
+    """NFW sphere truncated at c*rs: inverse CDF of m(x)=ln(1+x)-x/(1+x) by
+    bisection; velocities Gaussian with sigma^2 ~ |Phi|/3 (level assignment only)."""
+    hi = ntot if hi is None else hi
+    mu = lambda x: np.log1p(x) - x / (1.0 + x)
+    mc = mu(c)
+
+    def gen(k):
+        rng = _rng(seed, k)
+        u = rng.uniform(0.0, 1.0, CHUNK) * mc
+        a_, b_ = np.zeros(CHUNK), np.full(CHUNK, float(c))
+        for _ in range(60):
+            mid = 0.5 * (a_ + b_)
+            less = mu(mid) < u
+            a_ = np.where(less, mid, a_)
+            b_ = np.where(less, b_, mid)
+        r = rs * 0.5 * (a_ + b_)
+        pos = r[:, None] * _isotropic(rng, CHUNK)
+        phi = mass / mc * np.log1p(r / rs) / np.maximum(r, 1e-12)
+        vel = rng.standard_normal((CHUNK, 3)) * np.sqrt(phi / 3.0)[:, None]
+        return pos, vel
+
+    return _assemble(gen, lo, hi, mass, ntot)
+
+
+def exponential_disk(ntot: int, lo: int = 0, hi: int | None = None, seed: int = 44,
+                     a: float = 0.01, h: float = 0.001, mass: float = 0.05,
+                     vcirc: float = 1.0):
+    """Exponential disk: R = -a ln(u1 u2) (Gamma(2)), z = h atanh(2u-1) (sech^2),
+    phi uniform; flat rotation curve + small dispersion."""
+    hi = ntot if hi is None else hi
+
+    def gen(k):
+        rng = _rng(seed, k)
+        u1 = rng.uniform(1e-300, 1.0, CHUNK)
+        u2 = rng.uniform(1e-300, 1.0, CHUNK)
+        R = -a * np.log(u1 * u2)
+        z = h * np.arctanh(np.clip(2.0 * rng.uniform(0.0, 1.0, CHUNK) - 1.0, -1 + 1e-15, 1 - 1e-15))
+        phi = rng.uniform(0.0, 2.0 * math.pi, CHUNK)
+        pos = np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1)
+        vel = np.stack([-vcirc * np.sin(phi), vcirc * np.cos(phi), np.zeros(CHUNK)], axis=1)
+        vel += 0.05 * vcirc * rng.standard_normal((CHUNK, 3))
+        return pos, vel
+
+    return _assemble(gen, lo, hi, mass, ntot)

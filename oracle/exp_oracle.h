@@ -1,0 +1,149 @@
+/*
+ * exp_oracle.h -- C interface of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the reference
+ * (EXP-code/EXP v7.9.3) basis-function-expansion force loop, written from
+ * the reference sources' behaviour, each function citing the file:line it
+ * follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it; the product (exp_b200/, libexpb200.so)
+ * never does.
+ *
+ * PARITY UNPINNED: the reference ships no golden vectors for this path
+ *  and cannot be built here (needs Eigen3, MPI, HDF5,
+ * gfortran).  Exception: oracle/_ref/libexpref_basis.so compiles the
+ * reference's own src/Basis.cc (Legendre / trig recursions) against shim
+ * headers and is used to pin orc_legendre_R / orc_dlegendre_R /
+ * orc_sinecosine_R bit-for-bit (tests/test_oracle_ref.py).
+ *
+ * All arrays are plain row-major C arrays.  Coefficient layout is the
+ * reference's: row index = l*l + {0 (m=0), 2m-1 (cos), 2m (sin)}, nmax
+ * doubles per row  (src/SphericalBasis.cc:513-590).
+ */
+#ifndef EXP_ORACLE_H
+#define EXP_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- a1-a4: recursions (src/Basis.cc:14-111, src/SphericalBasis.cc:330-335) */
+void   orc_legendre_R (int lmax, double x, double *p);              /* p[l*(lmax+1)+m] */
+void   orc_dlegendre_R(int lmax, double x, double *p, double *dp);
+void   orc_sinecosine_R(int mmax, double phi, double *c, double *s);
+double orc_factorial  (int l, int m);
+
+/* ---- a5-a7: SLGridSph radial table (exputil/SLGridMP2.cc:711-765,872-989,1355-1382) */
+typedef struct {
+  int lmax, nmax, numr, cmap;
+  double rmin, rmax, rmap;
+  const double *ev;   /* [(lmax+1)][nmax]            */
+  const double *ef;   /* [(lmax+1)][nmax][numr]      */
+  const double *p0;   /* [numr]                      */
+  const double *d0;   /* [numr] (may be NULL)        */
+  /* derived by orc_slgrid_init */
+  double xmin, xmax, dxi;
+} orc_slgrid;
+
+void   orc_slgrid_init (orc_slgrid *g);
+double orc_r_to_xi     (const orc_slgrid *g, double r);
+double orc_xi_to_r     (const orc_slgrid *g, double xi);
+double orc_d_xi_to_r   (const orc_slgrid *g, double xi);
+void   orc_slgrid_get_pot  (const orc_slgrid *g, double r, double *mat); /* [(lmax+1)][nmax] */
+void   orc_slgrid_get_force(const orc_slgrid *g, double r, double *mat);
+void   orc_slgrid_get_dens (const orc_slgrid *g, double r, double *mat);
+
+/* ---- a8-a11: SphericalBasis / Sphere */
+typedef struct {
+  double scale;            /* SphericalBasis::scale  (src/SphericalBasis.cc:97-100) */
+  double rmin, rmax;       /* expansion radii after Sphere ctor (src/Sphere.cc:65-66) */
+  int NO_L0, NO_L1, EVEN_L, EVEN_M, M0_only;
+} orc_sph_params;
+
+/* Particle set: structure of plain arrays, n particles.  `center` is
+ * com0+center, i.e. what Pos(.., Local|Centered) subtracts
+ * (src/Component.H:747-757); rtrunc is Component::rtrunc (freeze test,
+ * src/Component.cc:4194-4202). */
+typedef struct {
+  long n;
+  double *pos;     /* [n][3] */
+  double *vel;     /* [n][3] */
+  double *acc;     /* [n][3] */
+  double *pot;     /* [n]    */
+  double *potext;  /* [n]    */
+  double *mass;    /* [n]    */
+  double *scale;   /* [n]   Particle::scale (may be NULL => -1) */
+  unsigned *level; /* [n]    */
+  float  *dtreq;   /* [n]    */
+  double center[3];
+  double rtrunc;
+} orc_particles;
+
+/* determine_coefficients_thread + thread sum (src/SphericalBasis.cc:429-599,855-858).
+ * list/nlist = levlist[mlevel]; the slice of thread id is
+ * [nlist*id/nthreads, nlist*(id+1)/nthreads).  coef: [(lmax+1)^2][nmax], overwritten.
+ * Returns number of particles used (sum of use[id]). */
+long orc_sph_coefficients(const orc_slgrid *g, const orc_sph_params *P,
+                          const orc_particles *S, const int *list, long nlist,
+                          double adb, int nthreads, double *coef);
+
+/* Same with the pcavar covariance (src/SphericalBasis.cc:501-509,525-545,563-581):
+ * whch = indx % sampT;  massT[sampT], countT[sampT],
+ * coefT[sampT][(L+1)(L+2)/2][nmax][2 (re,im)],
+ * coefM[sampT][(L+1)(L+2)/2][nmax][nmax] (real part; the imaginary part is
+ * identically zero in the reference).  All accumulated into (caller zeroes). */
+long orc_sph_coefficients_cov(const orc_slgrid *g, const orc_sph_params *P,
+                              const orc_particles *S, const int *list, long nlist,
+                              double adb, int sampT, double *coef, double *muse,
+                              double *massT, unsigned *countT,
+                              double *coefT, double *coefM);
+
+/* determine_acceleration_and_potential_thread (src/SphericalBasis.cc:1476-1660)
+ * for the particles in list (the caller concatenates levlist[lev>=mlevel]).
+ * Adds into acc and pot. */
+void orc_sph_accel(const orc_slgrid *g, const orc_sph_params *P,
+                   const orc_particles *S, const int *list, long nlist,
+                   const double *coef, int nthreads);
+
+/* multistep_update for one particle (src/SphericalBasis.cc:1156-1228):
+ * differ[(multistep+1)][(lmax+1)^2][nmax], from/to levels. */
+void orc_sph_multistep_update(const orc_slgrid *g, const orc_sph_params *P,
+                              const orc_particles *S, int indx, double adb,
+                              int from, int to, double *differ);
+
+/* compute_multistep_coefficients (src/SphericalBasis.cc:1231-1333):
+ * coefL/coefN [(multistep+1)][ncoef]; out[ncoef]. */
+void orc_multistep_interp(int multistep, int mdrft, const int *mfirst,
+                          const int *dstepL, const int *dstepN, /* [(multistep+1)][Mstep] */
+                          long ncoef, const double *coefL, const double *coefN,
+                          double *out);
+
+/* ---- a21: leapfrog (src/incpos.cc:15-70, src/incvel.cc:15-89) */
+void orc_incr_position(orc_particles *S, const int *list, long nlist, double dt, int dim);
+void orc_incr_velocity(orc_particles *S, const int *list, long nlist, double dt, int dim);
+
+/* ---- a22-a23: multistep (src/multistep.cc:52-236,630-679) */
+typedef struct {
+  double dtime;
+  double dynfracS, dynfracD, dynfracV, dynfracA, dynfracP;
+  int multistep, shiftlevl;
+  int mfirst_mdrft;        /* mfirst[mdrft] */
+  int noswitch, reset_dtreq, apply;
+  int dim;
+} orc_level_params;
+
+/* Returns number of level switches.  newlevel[i] for i in list is written
+ * (and S->level updated, S->dtreq updated).  which[i] = index of the
+ * controlling criterion (dseq.begin()->second).  offlo/offhi counters. */
+long orc_adjust_levels(orc_particles *S, const int *list, long nlist,
+                       const orc_level_params *P, int *which,
+                       long *offlo, long *offhi);
+
+/* initialize_multistep tables: mintvl[multistep+1], mfirst[Mstep+1],
+ * dstepL/dstepN[(multistep+1)][Mstep]. */
+void orc_multistep_tables(int multistep, int *mintvl, int *mfirst,
+                          int *dstepL, int *dstepN);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
