@@ -1,0 +1,136 @@
+"""ctypes loader for libexpb200.so (the C ABI declared in include/expb200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing or a call
+fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libexpb200.so")
+CSRC = os.path.join(_HERE, "csrc")
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_up = C.POINTER(C.c_uint)
+c_fp = C.POINTER(C.c_float)
+c_u64p = C.POINTER(C.c_uint64)
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class Expb200Error(RuntimeError):
+    pass
+
+
+class SphereConfig(C.Structure):
+    _fields_ = [("lmax", C.c_int), ("nmax", C.c_int), ("numr", C.c_int), ("cmap", C.c_int),
+                ("rmin_grid", C.c_double), ("rmax_grid", C.c_double), ("rmap", C.c_double),
+                ("scale", C.c_double), ("rmin", C.c_double), ("rmax", C.c_double),
+                ("NO_L0", C.c_int), ("NO_L1", C.c_int), ("EVEN_L", C.c_int), ("EVEN_M", C.c_int),
+                ("M0_only", C.c_int), ("multistep", C.c_int)]
+
+
+class LevelParams(C.Structure):
+    _fields_ = [("dtime", C.c_double), ("dynfracS", C.c_double), ("dynfracD", C.c_double),
+                ("dynfracV", C.c_double), ("dynfracA", C.c_double), ("dynfracP", C.c_double),
+                ("multistep", C.c_int), ("shiftlevl", C.c_int), ("mfirst_mdrft", C.c_int),
+                ("minlev", C.c_int), ("noswitch", C.c_int), ("reset_dtreq", C.c_int),
+                ("apply", C.c_int), ("dim", C.c_int)]
+
+
+class LevelStats(C.Structure):
+    _fields_ = [("examined", C.c_uint64), ("switched", C.c_uint64), ("offlo", C.c_uint64),
+                ("offhi", C.c_uint64), ("mindt", C.c_double), ("maxdt", C.c_double)]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into exp_b200/lib/libexpb200.so."""
+    srcs = sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(_HERE, "..", "include", "expb200.h"))
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps)):
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs + ["-ldl"]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise Expb200Error("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+# symbol -> (restype, argtypes); every symbol include/expb200.h declares
+_H = C.c_void_p
+SIGNATURES = {
+    "expb200_last_error": (C.c_char_p, []),
+    "expb200_version": (C.c_int, []),
+    "expb200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "expb200_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_size_t)]),
+    "expb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "expb200_host_free": (C.c_int, [C.c_void_p]),
+    "expb200_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "expb200_host_unregister": (C.c_int, [C.c_void_p]),
+    "expb200_component_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_H)]),
+    "expb200_component_destroy": (C.c_int, [_H]),
+    "expb200_component_upload": (C.c_int, [_H, C.c_size_t, c_dp, c_dp, c_dp, c_up, c_fp, c_dp]),
+    "expb200_component_upload_range": (C.c_int, [_H, C.c_size_t, C.c_size_t, c_dp, c_dp, c_dp]),
+    "expb200_component_set_count": (C.c_int, [_H, C.c_size_t]),
+    "expb200_component_sync": (C.c_int, [_H]),
+    "expb200_component_download": (C.c_int, [_H, c_dp, c_dp, c_dp, c_dp, c_up, c_fp]),
+    "expb200_component_download_range": (C.c_int, [_H, C.c_size_t, C.c_size_t, c_dp, c_dp, c_dp, c_dp]),
+    "expb200_component_count": (C.c_size_t, [_H]),
+    "expb200_component_set_center": (C.c_int, [_H, c_dp, C.c_double]),
+    "expb200_component_zero_pot_acc": (C.c_int, [_H, C.c_int]),
+    "expb200_component_set_levels": (C.c_int, [_H, c_up]),
+    "expb200_component_set_acc_pot": (C.c_int, [_H, c_dp, c_dp]),
+    "expb200_component_level_counts": (C.c_int, [_H, C.c_int, c_u64p]),
+    "expb200_incr_position": (C.c_int, [_H, C.c_double, C.c_int]),
+    "expb200_incr_velocity": (C.c_int, [_H, C.c_double, C.c_int]),
+    "expb200_adjust_multistep_level": (C.c_int, [_H, C.POINTER(LevelParams), C.POINTER(LevelStats)]),
+    "expb200_sphere_create": (C.c_int, [C.c_int, C.POINTER(SphereConfig), c_dp, c_dp, c_dp,
+                                        C.POINTER(_H)]),
+    "expb200_sphere_destroy": (C.c_int, [_H]),
+    "expb200_sphere_determine_coefficients": (C.c_int, [_H, _H, C.c_int, C.c_double, c_dp, c_u64p]),
+    "expb200_sphere_coef_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_void_p)]),
+    "expb200_sphere_set_coefficients": (C.c_int, [_H, c_dp]),
+    "expb200_sphere_determine_acceleration": (C.c_int, [_H, _H, C.c_int]),
+    "expb200_sphere_step": (C.c_int, [_H, _H, C.c_double, C.c_double, C.c_void_p]),
+    "expb200_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "expb200_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "expb200_comm_destroy": (C.c_int, [C.c_void_p]),
+    "expb200_allreduce_sum": (C.c_int, [C.c_void_p, c_dp, C.c_size_t, C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise Expb200Error(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().expb200_last_error()
+        raise Expb200Error(f"expb200 error {rc}: {msg.decode() if msg else '?'}")

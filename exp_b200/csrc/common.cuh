@@ -1,0 +1,127 @@
+// common.cuh -- shared host/device utilities of libexpb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/expb200.h"
+
+namespace expb200 {
+
+constexpr int kSMsB200 = 148;          // B200: 148 SMs on two dies
+constexpr int kMaxL    = 12;           // template instantiations cover lmax <= kMaxL
+constexpr int kWarp    = 32;
+
+// src/expand.H:130 -- added to every radius by the reference
+#define EXPB200_DSMALL 1.0e-16
+// src/Basis.cc:7 -- clamp for the Legendre derivative
+#define EXPB200_MINEPS (3.0 * 2.220446049250313e-16)
+
+// ---- error plumbing: no exceptions across the C ABI ------------------------
+void set_error(const char *fmt, ...);
+int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CU_TRY(expr)                                                           \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) return ::expb200::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define CU_LAUNCH_CHECK() CU_TRY(cudaGetLastError())
+
+#define REQUIRE(cond, ...)                                                     \
+  do {                                                                         \
+    if (!(cond)) { ::expb200::set_error(__VA_ARGS__); return EXPB200_EINVAL; } \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Grid size for a grid-stride kernel: enough CTAs to fill the 148 SMs a few
+// times over, never more than the work needs.
+inline unsigned grid_for(size_t n, int threads, int ctas_per_sm = 8)
+{
+  size_t need = (n + threads - 1) / threads;
+  size_t cap = (size_t)kSMsB200 * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+// ---- 32-byte particle records ---------------------------------------------
+// One particle attribute group = one 32-byte sector: {x,y,z,m}, {vx,vy,vz,potext},
+// {ax,ay,az,pot}.  A gather through the sort permutation then costs exactly one
+// sector per group and a streaming pass is a fully coalesced 2x LDG.128.
+struct __align__(32) rec4 { double x, y, z, w; };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ rec4 ld_rec(const rec4 *p)
+{
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  double2 a = __ldg(q), b = __ldg(q + 1);
+  return rec4{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ rec4 ld_rec_rw(const rec4 *p)   // plain load (data is written by this kernel family)
+{
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  double2 a = q[0], b = q[1];
+  return rec4{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void st_rec(rec4 *p, const rec4 &v)
+{
+  double2 *q = reinterpret_cast<double2 *>(p);
+  q[0] = make_double2(v.x, v.y);
+  q[1] = make_double2(v.z, v.w);
+}
+#endif
+
+} // namespace expb200
+
+// ---- the device-resident particle store ------------------------------------
+struct expb200_component_s {
+  int device = 0;
+  size_t cap = 0, n = 0;
+  cudaStream_t stream = nullptr;        // compute stream
+  cudaStream_t copy_stream = nullptr;   // H2D/D2H pipelining
+  cudaEvent_t  copy_done = nullptr;
+
+  expb200::rec4 *posm = nullptr;        // {x,y,z,mass}
+  expb200::rec4 *vel = nullptr;         // {vx,vy,vz,potext}
+  expb200::rec4 *accp = nullptr;        // {ax,ay,az,pot}
+  unsigned *level = nullptr;
+  float *dtreq = nullptr;
+  float *scale = nullptr;
+
+  double center[3] = {0, 0, 0};
+  double rtrunc = 1.0e20;
+
+  // staging for (un)packing host AoS arrays
+  double *stage = nullptr;              // 7*chunk doubles
+  size_t stage_chunk = 0;
+
+  // sort state: perm[cur] = particle slots ordered by key, keys[cur] sorted keys
+  uint32_t *keys[2] = {nullptr, nullptr};
+  uint32_t *perm[2] = {nullptr, nullptr};
+  uint32_t *hist = nullptr;             // radix histograms
+  size_t hist_cap = 0;
+  uint32_t *seg = nullptr;              // seg[k] = first sorted position with key >= k
+  size_t seg_cap = 0;
+  int cur = 0;
+  int sort_kind = 0;                    // 0 none, 1 level only, 2 (level, radial cell) of sort_owner
+  const void *sort_owner = nullptr;
+  uint32_t keys_per_level = 1;
+  uint64_t pos_ver = 1, lev_ver = 1, sort_pos_ver = 0, sort_lev_ver = 0;
+
+  // multistep statistics scratch
+  unsigned long long *stats = nullptr;  // device, 8 words
+};

@@ -1,0 +1,674 @@
+// component.cu -- device-resident particle store, leapfrog and multistep level
+// assignment.  Replaces the reference's Component CUDA seams
+// (src/cudaComponent.cu), incr_position_cuda / incr_velocity_cuda
+// (src/cudaIncpos.cu, src/cudaIncvel.cu) and cuda_compute_levels
+// (src/cudaMultistep.cu); the arithmetic follows the CPU path
+// (src/incpos.cc:63-66, src/incvel.cc:68-69, src/multistep.cc:52-236).
+#include "common.cuh"
+#include "sort.cuh"
+
+#include <cmath>
+#include <mutex>
+
+namespace expb200 {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+  set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  return e == cudaErrorMemoryAllocation ? EXPB200_ENOMEM : EXPB200_ECUDA;
+}
+
+namespace {
+
+constexpr size_t kStageChunk = 1u << 20;   // particles per staging chunk
+constexpr int kStageDoubles = 10;          // pos3 vel3 acc3 pot1 (download) / pos3 vel3 mass1 (upload)
+
+// ---------------------------------------------------------------------------
+// pack / unpack between host AoS field arrays and the 32-byte device records
+// ---------------------------------------------------------------------------
+__global__ void pack_kernel(rec4 *__restrict__ posm, rec4 *__restrict__ vel, rec4 *__restrict__ accp,
+                            const double *__restrict__ pos, const double *__restrict__ v,
+                            const double *__restrict__ mass, const double *__restrict__ potext,
+                            size_t first, size_t count, int reset_acc)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t s = first + i;
+    st_rec(&posm[s], rec4{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]});
+    double pe = potext ? potext[i] : 0.0;
+    if (v) st_rec(&vel[s], rec4{v[3 * i], v[3 * i + 1], v[3 * i + 2], pe});
+    else   st_rec(&vel[s], rec4{0.0, 0.0, 0.0, pe});
+    if (reset_acc) st_rec(&accp[s], rec4{0.0, 0.0, 0.0, 0.0});
+  }
+}
+
+__global__ void unpack_kernel(const rec4 *__restrict__ posm, const rec4 *__restrict__ vel,
+                              const rec4 *__restrict__ accp, double *__restrict__ pos,
+                              double *__restrict__ v, double *__restrict__ acc,
+                              double *__restrict__ pot, size_t first, size_t count)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t s = first + i;
+    if (pos) { rec4 p = ld_rec_rw(&posm[s]); pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z; }
+    if (v)   { rec4 q = ld_rec_rw(&vel[s]);  v[3 * i] = q.x;   v[3 * i + 1] = q.y;   v[3 * i + 2] = q.z; }
+    if (acc || pot) {
+      rec4 a = ld_rec_rw(&accp[s]);
+      if (acc) { acc[3 * i] = a.x; acc[3 * i + 1] = a.y; acc[3 * i + 2] = a.z; }
+      if (pot) pot[i] = a.w;
+    }
+  }
+}
+
+__global__ void fill_u32_kernel(unsigned *a, size_t n, unsigned v)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) a[i] = v;
+}
+__global__ void fill_f32_kernel(float *a, size_t n, float v)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) a[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// a21: leapfrog.  pos += vel*dt (src/incpos.cc:63-66), vel += acc*dt
+// (src/incvel.cc:68-69) over levlist[mlevel] (mlevel>=0) or every particle.
+// Natural order, one 32-byte record in and out per particle: HBM-bound.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+drift_kernel(rec4 *__restrict__ posm, const rec4 *__restrict__ vel,
+             const unsigned *__restrict__ level, size_t n, double dt, int mlevel, int dim)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (mlevel >= 0 && level[i] != (unsigned)mlevel) continue;
+    rec4 p = ld_rec_rw(&posm[i]);
+    rec4 v = ld_rec_rw(&vel[i]);
+    p.x += v.x * dt;
+    if (dim > 1) p.y += v.y * dt;
+    if (dim > 2) p.z += v.z * dt;
+    st_rec(&posm[i], p);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kick_kernel(rec4 *__restrict__ vel, const rec4 *__restrict__ accp,
+            const unsigned *__restrict__ level, size_t n, double dt, int mlevel, int dim)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (mlevel >= 0 && level[i] != (unsigned)mlevel) continue;
+    rec4 v = ld_rec_rw(&vel[i]);
+    rec4 a = ld_rec_rw(&accp[i]);
+    v.x += a.x * dt;
+    if (dim > 1) v.y += a.y * dt;
+    if (dim > 2) v.z += a.z * dt;
+    st_rec(&vel[i], v);
+  }
+}
+
+// ~ zeroPotAccKernel (src/cudaComponent.cu:729-748)
+__global__ void __launch_bounds__(256)
+zero_kernel(rec4 *__restrict__ accp, const unsigned *__restrict__ level, size_t n, int minlev)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (minlev > 0 && level[i] < (unsigned)minlev) continue;
+    st_rec(&accp[i], rec4{0.0, 0.0, 0.0, 0.0});
+  }
+}
+
+// ---------------------------------------------------------------------------
+// a22: adjust_multistep_level_thread (src/multistep.cc:52-236).
+// Bit-exact with the CPU path: every operation is an explicit IEEE round-to-
+// nearest intrinsic (no FMA contraction), dtreq rounds through float, and
+// floor(log(dtime/dtreq)/log(2)) is evaluated as the exact binary exponent,
+// except when the ratio is exactly 2^k, where the host libm's own answer
+// (pow2lev[k], computed with log() on the host at call time) is used.
+// ---------------------------------------------------------------------------
+struct LevelArgs {
+  double dtime, fS, fD, fV, fA, fP;
+  int multistep, shiftlevl, mfirst, minlev, noswitch, reset_dtreq, apply, dim;
+  int pow2lev[64];
+};
+
+__global__ void __launch_bounds__(256)
+levels_kernel(const rec4 *__restrict__ vel, const rec4 *__restrict__ accp,
+              const float *__restrict__ scale, unsigned *__restrict__ level,
+              float *__restrict__ dtreq, size_t n, LevelArgs A,
+              unsigned long long *__restrict__ stats)
+{
+  const double eps = 1.0e-10;
+  unsigned long long examined = 0, switched = 0, offlo = 0, offhi = 0;
+  double mindt = 1.0e300, maxdt = 0.0;
+
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    unsigned plev = level[i];
+    if ((int)plev < A.minlev) continue;
+
+    rec4 v = ld_rec_rw(&vel[i]);
+    rec4 a = ld_rec_rw(&accp[i]);
+
+    double dtr = __dmul_rn(v.x, a.x), vtot = __dmul_rn(v.x, v.x), atot = __dmul_rn(a.x, a.x);
+    if (A.dim > 1) {
+      dtr = __dadd_rn(dtr, __dmul_rn(v.y, a.y));
+      vtot = __dadd_rn(vtot, __dmul_rn(v.y, v.y));
+      atot = __dadd_rn(atot, __dmul_rn(a.y, a.y));
+    }
+    if (A.dim > 2) {
+      dtr = __dadd_rn(dtr, __dmul_rn(v.z, a.z));
+      vtot = __dadd_rn(vtot, __dmul_rn(v.z, v.z));
+      atot = __dadd_rn(atot, __dmul_rn(a.z, a.z));
+    }
+    double ptot = fabs(__dadd_rn(a.w, v.w));          // |pot + potext|
+
+    double dsr = (double)scale[i];
+    double dts;
+    if (dsr > 0) dts = __ddiv_rn(__dmul_rn(A.fS, dsr), fabs(__dadd_rn(__dsqrt_rn(vtot), eps)));
+    else         dts = __ddiv_rn(1.0, eps);
+
+    double dtd = __ddiv_rn(__dmul_rn(A.fD, 1.0), __dsqrt_rn(__dadd_rn(vtot, eps)));
+    double dtv = __dmul_rn(A.fV, __dsqrt_rn(__ddiv_rn(vtot, __dadd_rn(atot, eps))));
+    double dta = __ddiv_rn(__dmul_rn(A.fA, ptot), __dadd_rn(fabs(dtr), eps));
+    double dtA = __dmul_rn(A.fP, __dsqrt_rn(__ddiv_rn(ptot, __dadd_rn(atot, eps))));
+
+    double best = dtd;
+    if (dtv < best) best = dtv;
+    if (dts < best) best = dts;
+    if (dta > 0.0 && dta < best) best = dta;
+    if (dtA > 0.0 && dtA < best) best = dtA;
+    double dt = best > eps ? best : eps;              // std::max(eps, best)
+
+    float dq;
+    if (A.noswitch) {
+      dq = dtreq[i];
+      if (A.reset_dtreq) dq = __double2float_rn(1.7976931348623157e308);
+      if (dt < (double)dq) dq = __double2float_rn(dt);
+    } else {
+      dq = __double2float_rn(dt);
+    }
+    dtreq[i] = dq;
+
+    if (A.apply) {
+      unsigned nlev = plev;
+      double dqd = (double)dq;
+      if (dqd > A.dtime) {
+        nlev = 0;
+        offhi++;
+        maxdt = fmax(maxdt, dqd);
+      } else {
+        double x = __ddiv_rn(A.dtime, dqd);           // >= 1
+        long long bits = __double_as_longlong(x);
+        int e = (int)((bits >> 52) & 0x7ff) - 1023;
+        bool pow2 = (bits & 0x000fffffffffffffLL) == 0;
+        if (e > 62) e = 62;                           // inf / absurd ratios: clamp, multistep wins below
+        if (e < 0) e = 0;
+        nlev = (unsigned)(pow2 ? A.pow2lev[e] : e);
+      }
+      if (A.shiftlevl) {
+        if (nlev > plev) {
+          if (nlev - plev > (unsigned)A.shiftlevl) nlev = plev + A.shiftlevl;
+        } else if (plev > nlev) {
+          if (plev - nlev > (unsigned)A.shiftlevl) nlev = plev - A.shiftlevl;
+        }
+      }
+      if (nlev > (unsigned)A.multistep) {
+        nlev = A.multistep;
+        offlo++;
+        mindt = fmin(mindt, dqd);
+      }
+      if ((int)nlev < A.mfirst) nlev = A.mfirst;
+      if (nlev != plev) {
+        level[i] = nlev;
+        switched++;
+      }
+      examined++;
+    }
+  }
+
+  // CTA reduction of the counters, then one integer atomic per CTA
+  __shared__ unsigned long long sh[4][8];
+  __shared__ double shd[2][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    examined += __shfl_down_sync(0xffffffffu, examined, o);
+    switched += __shfl_down_sync(0xffffffffu, switched, o);
+    offlo += __shfl_down_sync(0xffffffffu, offlo, o);
+    offhi += __shfl_down_sync(0xffffffffu, offhi, o);
+    mindt = fmin(mindt, __shfl_down_sync(0xffffffffu, mindt, o));
+    maxdt = fmax(maxdt, __shfl_down_sync(0xffffffffu, maxdt, o));
+  }
+  if (lane == 0) { sh[0][w] = examined; sh[1][w] = switched; sh[2][w] = offlo; sh[3][w] = offhi;
+                   shd[0][w] = mindt; shd[1][w] = maxdt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long e = 0, s = 0, lo = 0, hi = 0;
+    double mn = 1.0e300, mx = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) {
+      e += sh[0][k]; s += sh[1][k]; lo += sh[2][k]; hi += sh[3][k];
+      mn = fmin(mn, shd[0][k]); mx = fmax(mx, shd[1][k]);
+    }
+    if (e)  atomicAdd(&stats[0], e);
+    if (s)  atomicAdd(&stats[1], s);
+    if (lo) atomicAdd(&stats[2], lo);
+    if (hi) atomicAdd(&stats[3], hi);
+    // positive doubles order like their bit patterns
+    atomicMin(&stats[4], (unsigned long long)__double_as_longlong(mn));
+    atomicMax(&stats[5], (unsigned long long)__double_as_longlong(mx));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+level_count_kernel(const unsigned *__restrict__ level, size_t n, int nlev,
+                   unsigned long long *__restrict__ counts)
+{
+  __shared__ unsigned int h[64];
+  if (threadIdx.x < 64) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    unsigned l = level[i];
+    atomicAdd(&h[l < (unsigned)nlev ? l : nlev - 1], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nlev && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+} // namespace
+} // namespace expb200
+
+using namespace expb200;
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *expb200_last_error(void) { return g_err.c_str(); }
+
+int expb200_version(void) { return 100; }
+
+int expb200_device_count(int *count)
+{
+  REQUIRE(count, "count is NULL");
+  CU_TRY(cudaGetDeviceCount(count));
+  return EXPB200_OK;
+}
+
+int expb200_device_info(int device, char *name, int name_len, int *sm_count, size_t *hbm_bytes)
+{
+  cudaDeviceProp p;
+  CU_TRY(cudaGetDeviceProperties(&p, device));
+  if (name && name_len > 0) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+  return EXPB200_OK;
+}
+
+int expb200_host_alloc(void **ptr, size_t bytes)
+{
+  REQUIRE(ptr, "ptr is NULL");
+  CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return EXPB200_OK;
+}
+
+int expb200_host_free(void *ptr)
+{
+  CU_TRY(cudaFreeHost(ptr));
+  return EXPB200_OK;
+}
+
+int expb200_host_register(void *ptr, size_t bytes)
+{
+  CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return EXPB200_OK;
+}
+
+int expb200_host_unregister(void *ptr)
+{
+  CU_TRY(cudaHostUnregister(ptr));
+  return EXPB200_OK;
+}
+
+int expb200_component_create(int device, size_t capacity, expb200_component *out)
+{
+  REQUIRE(out, "out is NULL");
+  REQUIRE(capacity > 0 && capacity < 0xfffffff0ull, "capacity %zu out of range", capacity);
+  int ndev = 0;
+  CU_TRY(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, "device %d not present (%d visible)", device, ndev);
+  DeviceGuard g(device);
+  auto *c = new expb200_component_s;
+  c->device = device;
+  c->cap = capacity;
+  CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+  CU_TRY(cudaMalloc(&c->posm, capacity * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->vel, capacity * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->accp, capacity * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->level, capacity * sizeof(unsigned)));
+  CU_TRY(cudaMalloc(&c->dtreq, capacity * sizeof(float)));
+  CU_TRY(cudaMalloc(&c->scale, capacity * sizeof(float)));
+  for (int k = 0; k < 2; k++) {
+    CU_TRY(cudaMalloc(&c->keys[k], capacity * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->perm[k], capacity * sizeof(uint32_t)));
+  }
+  c->hist_cap = sort_hist_words(capacity);
+  CU_TRY(cudaMalloc(&c->hist, c->hist_cap * sizeof(uint32_t)));
+  c->stage_chunk = capacity < kStageChunk ? capacity : kStageChunk;
+  CU_TRY(cudaMalloc(&c->stage, 2 * c->stage_chunk * kStageDoubles * sizeof(double)));
+  CU_TRY(cudaMalloc(&c->stats, 8 * sizeof(unsigned long long)));
+  CU_TRY(cudaMemsetAsync(c->accp, 0, capacity * sizeof(rec4), c->stream));
+  CU_TRY(cudaMemsetAsync(c->level, 0, capacity * sizeof(unsigned), c->stream));
+  CU_TRY(cudaMemsetAsync(c->dtreq, 0, capacity * sizeof(float), c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return EXPB200_OK;
+}
+
+int expb200_component_destroy(expb200_component c)
+{
+  if (!c) return EXPB200_OK;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
+  cudaFree(c->posm); cudaFree(c->vel); cudaFree(c->accp);
+  cudaFree(c->level); cudaFree(c->dtreq); cudaFree(c->scale);
+  for (int k = 0; k < 2; k++) { cudaFree(c->keys[k]); cudaFree(c->perm[k]); }
+  cudaFree(c->hist); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats);
+  cudaEventDestroy(c->copy_done);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return EXPB200_OK;
+}
+
+size_t expb200_component_count(expb200_component c) { return c ? c->n : 0; }
+
+int expb200_component_set_count(expb200_component c, size_t n)
+{
+  REQUIRE(c, "component is NULL");
+  REQUIRE(n <= c->cap, "n=%zu exceeds capacity %zu", n, c->cap);
+  c->n = n;
+  c->pos_ver++; c->lev_ver++;
+  return EXPB200_OK;
+}
+
+// Upload [first, first+count): H2D on the copy stream into one of two staging
+// buffers, pack on the compute stream; the two alternate so that the copy of
+// chunk k+1 overlaps the pack of chunk k.
+int expb200_component_upload_range(expb200_component c, size_t first, size_t count,
+                                   const double *pos, const double *vel, const double *mass)
+{
+  REQUIRE(c && pos && mass, "NULL argument");
+  REQUIRE(first + count <= c->cap, "range [%zu,%zu) exceeds capacity %zu", first, first + count, c->cap);
+  DeviceGuard g(c->device);
+  const size_t ch = c->stage_chunk;
+  int b = 0;
+  for (size_t off = 0; off < count; off += ch, b ^= 1) {
+    size_t m = count - off < ch ? count - off : ch;
+    double *s = c->stage + (size_t)b * ch * kStageDoubles;
+    double *spos = s, *svel = s + 3 * ch, *smass = s + 6 * ch;
+    // the pack kernel that last read this staging buffer must be done
+    CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0));
+    CU_TRY(cudaMemcpyAsync(spos, pos + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    if (vel) CU_TRY(cudaMemcpyAsync(svel, vel + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    CU_TRY(cudaMemcpyAsync(smass, mass + off, m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    cudaEvent_t ev;
+    CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(ev, c->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(c->stream, ev, 0));
+    CU_TRY(cudaEventDestroy(ev));
+    pack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp, spos,
+                                                         vel ? svel : nullptr, smass, nullptr,
+                                                         first + off, m, 0);
+    CU_LAUNCH_CHECK();
+    CU_TRY(cudaEventRecord(c->copy_done, c->stream));
+  }
+  c->pos_ver++;
+  return EXPB200_OK;
+}
+
+int expb200_component_upload(expb200_component c, size_t n, const double *pos, const double *vel,
+                             const double *mass, const unsigned *level, const float *scale,
+                             const double *potext)
+{
+  REQUIRE(c && pos && mass, "NULL argument");
+  REQUIRE(n <= c->cap, "n=%zu exceeds capacity %zu", n, c->cap);
+  DeviceGuard g(c->device);
+  c->n = n;
+  if (n == 0) { c->pos_ver++; c->lev_ver++; return EXPB200_OK; }
+  int rc = expb200_component_upload_range(c, 0, n, pos, vel, mass);
+  if (rc) return rc;
+  CU_TRY(cudaMemsetAsync(c->accp, 0, n * sizeof(rec4), c->stream));
+  if (level) CU_TRY(cudaMemcpyAsync(c->level, level, n * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  else fill_u32_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->level, n, 0u);
+  if (scale) CU_TRY(cudaMemcpyAsync(c->scale, scale, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  else fill_f32_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->scale, n, -1.0f);
+  CU_TRY(cudaMemsetAsync(c->dtreq, 0, n * sizeof(float), c->stream));
+  if (potext) {
+    // potext rides in vel.w: re-pack chunk-wise with it
+    const size_t ch = c->stage_chunk;
+    for (size_t off = 0; off < n; off += ch) {
+      size_t m = n - off < ch ? n - off : ch;
+      double *s = c->stage;
+      CU_TRY(cudaStreamSynchronize(c->stream));
+      CU_TRY(cudaMemcpy(s, pos + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice));
+      if (vel) CU_TRY(cudaMemcpy(s + 3 * ch, vel + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice));
+      CU_TRY(cudaMemcpy(s + 6 * ch, mass + off, m * sizeof(double), cudaMemcpyHostToDevice));
+      CU_TRY(cudaMemcpy(s + 7 * ch, potext + off, m * sizeof(double), cudaMemcpyHostToDevice));
+      pack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp, s,
+                                                           vel ? s + 3 * ch : nullptr, s + 6 * ch,
+                                                           s + 7 * ch, off, m, 0);
+      CU_LAUNCH_CHECK();
+    }
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->pos_ver++; c->lev_ver++;
+  return EXPB200_OK;
+}
+
+int expb200_component_sync(expb200_component c)
+{
+  REQUIRE(c, "component is NULL");
+  DeviceGuard g(c->device);
+  CU_TRY(cudaStreamSynchronize(c->copy_stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return EXPB200_OK;
+}
+
+int expb200_component_download_range(expb200_component c, size_t first, size_t count,
+                                     double *pos, double *vel, double *acc, double *pot)
+{
+  REQUIRE(c, "component is NULL");
+  REQUIRE(first + count <= c->n, "range [%zu,%zu) exceeds count %zu", first, first + count, c->n);
+  DeviceGuard g(c->device);
+  const size_t ch = c->stage_chunk;
+  int b = 0;
+  cudaEvent_t unpacked[2], copied[2];
+  for (int k = 0; k < 2; k++) {
+    CU_TRY(cudaEventCreateWithFlags(&unpacked[k], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+  }
+  // order after any upload staging still in flight
+  CU_TRY(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+  size_t round = 0;
+  for (size_t off = 0; off < count; off += ch, b ^= 1, round++) {
+    size_t m = count - off < ch ? count - off : ch;
+    double *s = c->stage + (size_t)b * ch * kStageDoubles;
+    double *spos = s, *svel = s + 3 * ch, *sacc = s + 6 * ch, *spot = s + 9 * ch;
+    if (round >= 2) CU_TRY(cudaStreamWaitEvent(c->stream, copied[b], 0));
+    unpack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp,
+                                                           pos ? spos : nullptr, vel ? svel : nullptr,
+                                                           acc ? sacc : nullptr, pot ? spot : nullptr,
+                                                           first + off, m);
+    CU_LAUNCH_CHECK();
+    CU_TRY(cudaEventRecord(unpacked[b], c->stream));
+    CU_TRY(cudaStreamWaitEvent(c->copy_stream, unpacked[b], 0));
+    if (pos) CU_TRY(cudaMemcpyAsync(pos + 3 * off, spos, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (vel) CU_TRY(cudaMemcpyAsync(vel + 3 * off, svel, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (acc) CU_TRY(cudaMemcpyAsync(acc + 3 * off, sacc, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (pot) CU_TRY(cudaMemcpyAsync(pot + off, spot, m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    CU_TRY(cudaEventRecord(copied[b], c->copy_stream));
+  }
+  CU_TRY(cudaStreamSynchronize(c->copy_stream));
+  // later uploads must not overwrite staging before these copies finished (they have)
+  CU_TRY(cudaEventRecord(c->copy_done, c->stream));
+  for (int k = 0; k < 2; k++) { cudaEventDestroy(unpacked[k]); cudaEventDestroy(copied[k]); }
+  return EXPB200_OK;
+}
+
+int expb200_component_download(expb200_component c, double *pos, double *vel, double *acc,
+                               double *pot, unsigned *level, float *dtreq)
+{
+  REQUIRE(c, "component is NULL");
+  DeviceGuard g(c->device);
+  if (c->n == 0) return EXPB200_OK;
+  if (pos || vel || acc || pot) {
+    int rc = expb200_component_download_range(c, 0, c->n, pos, vel, acc, pot);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  if (level) CU_TRY(cudaMemcpy(level, c->level, c->n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  if (dtreq) CU_TRY(cudaMemcpy(dtreq, c->dtreq, c->n * sizeof(float), cudaMemcpyDeviceToHost));
+  return EXPB200_OK;
+}
+
+int expb200_component_set_center(expb200_component c, const double center[3], double rtrunc)
+{
+  REQUIRE(c && center, "NULL argument");
+  for (int k = 0; k < 3; k++) c->center[k] = center[k];
+  c->rtrunc = rtrunc;
+  c->pos_ver++;              // radial cells depend on the centre
+  return EXPB200_OK;
+}
+
+int expb200_component_zero_pot_acc(expb200_component c, int minlev)
+{
+  REQUIRE(c, "component is NULL");
+  if (c->n == 0) return EXPB200_OK;
+  DeviceGuard g(c->device);
+  zero_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->accp, c->level, c->n, minlev);
+  CU_LAUNCH_CHECK();
+  return EXPB200_OK;
+}
+
+int expb200_incr_position(expb200_component c, double dt, int mlevel)
+{
+  REQUIRE(c, "component is NULL");
+  if (c->n == 0) return EXPB200_OK;
+  DeviceGuard g(c->device);
+  drift_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->level, c->n, dt, mlevel, 3);
+  CU_LAUNCH_CHECK();
+  c->pos_ver++;
+  return EXPB200_OK;
+}
+
+int expb200_incr_velocity(expb200_component c, double dt, int mlevel)
+{
+  REQUIRE(c, "component is NULL");
+  if (c->n == 0) return EXPB200_OK;
+  DeviceGuard g(c->device);
+  kick_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->vel, c->accp, c->level, c->n, dt, mlevel, 3);
+  CU_LAUNCH_CHECK();
+  return EXPB200_OK;
+}
+
+int expb200_adjust_multistep_level(expb200_component c, const expb200_level_params *p,
+                                   expb200_level_stats *stats)
+{
+  REQUIRE(c && p, "NULL argument");
+  REQUIRE(p->multistep >= 0 && p->multistep < 32, "multistep=%d out of range", p->multistep);
+  DeviceGuard g(c->device);
+  LevelArgs A;
+  A.dtime = p->dtime; A.fS = p->dynfracS; A.fD = p->dynfracD; A.fV = p->dynfracV;
+  A.fA = p->dynfracA; A.fP = p->dynfracP;
+  A.multistep = p->multistep; A.shiftlevl = p->shiftlevl; A.mfirst = p->mfirst_mdrft;
+  A.minlev = p->minlev; A.noswitch = p->noswitch; A.reset_dtreq = p->reset_dtreq;
+  A.apply = p->apply; A.dim = p->dim > 0 ? p->dim : 3;
+  // The host libm's answer for exact powers of two (what the CPU path computes)
+  for (int k = 0; k < 64; k++) {
+    volatile double x = std::ldexp(1.0, k);
+    A.pow2lev[k] = (int)std::floor(std::log(x) / std::log(2.0));
+  }
+  unsigned long long init[8] = {0, 0, 0, 0, 0x7fefffffffffffffULL, 0, 0, 0};
+  CU_TRY(cudaMemcpyAsync(c->stats, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  if (c->n) {
+    levels_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->vel, c->accp, c->scale, c->level,
+                                                              c->dtreq, c->n, A, c->stats);
+    CU_LAUNCH_CHECK();
+  }
+  unsigned long long out[8];
+  CU_TRY(cudaMemcpyAsync(out, c->stats, sizeof out, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  if (out[1]) c->lev_ver++;
+  if (stats) {
+    stats->examined = out[0]; stats->switched = out[1]; stats->offlo = out[2]; stats->offhi = out[3];
+    double mn, mx;
+    memcpy(&mn, &out[4], 8); memcpy(&mx, &out[5], 8);
+    stats->mindt = mn; stats->maxdt = mx;
+  }
+  return EXPB200_OK;
+}
+
+int expb200_component_set_levels(expb200_component c, const unsigned *level)
+{
+  REQUIRE(c && level, "NULL argument");
+  DeviceGuard g(c->device);
+  CU_TRY(cudaMemcpyAsync(c->level, level, c->n * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->lev_ver++;
+  return EXPB200_OK;
+}
+
+int expb200_component_set_acc_pot(expb200_component c, const double *acc, const double *pot)
+{
+  // test / restart hook: install acc[n][3], pot[n] (e.g. to drive level assignment)
+  REQUIRE(c && acc && pot, "NULL argument");
+  DeviceGuard g(c->device);
+  std::string tmp;
+  tmp.resize(c->n * sizeof(rec4));
+  rec4 *h = reinterpret_cast<rec4 *>(&tmp[0]);
+  for (size_t i = 0; i < c->n; i++) h[i] = rec4{acc[3 * i], acc[3 * i + 1], acc[3 * i + 2], pot[i]};
+  CU_TRY(cudaMemcpyAsync(c->accp, h, c->n * sizeof(rec4), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return EXPB200_OK;
+}
+
+int expb200_component_level_counts(expb200_component c, int multistep, uint64_t *counts)
+{
+  REQUIRE(c && counts, "NULL argument");
+  REQUIRE(multistep >= 0 && multistep < 63, "multistep out of range");
+  DeviceGuard g(c->device);
+  unsigned long long *d = nullptr;
+  CU_TRY(cudaMalloc(&d, 64 * sizeof(unsigned long long)));
+  CU_TRY(cudaMemsetAsync(d, 0, 64 * sizeof(unsigned long long), c->stream));
+  if (c->n) level_count_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->level, c->n, multistep + 1, d);
+  unsigned long long h[64];
+  CU_TRY(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  for (int k = 0; k <= multistep; k++) counts[k] = h[k];
+  return EXPB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,633 @@
+// sphere.cu -- the sphereSL force (SphericalBasis + SLGridSph) on B200.
+//
+// Replaces SphericalBasis::determine_coefficients_cuda / determine_acceleration_cuda /
+// DtoH_coefs / HtoD_coefs and SLGridSph::initialize_cuda (src/SphericalBasis.H:186-270,
+// src/cudaSphericalBasis.cu, exputil/cudaSLGridMP2.cu).  Not a port of those kernels:
+// see sph_math.cuh for the factorised evaluation this file implements.
+//
+// Per coefficient call (levlist[mlevel]):
+//   key      : radial cell (and level) of every particle            [HBM stream]
+//   sort     : stable radix sort -> permutation + cell offsets      [HBM stream]
+//   deposit  : per particle Y_lm(theta,phi) * node weights, reduced per radial cell
+//              in sorted order by one warp per chunk (fixed order => deterministic)
+//   combine  : per-cell partials -> node sums G[row][i]              [tiny]
+//   contract : coef[row][n] = sum_i E[l][n][i] G[row][i]             [tiny]
+// Per force call:
+//   field    : H[i][slot] = sum_n E[l][n][i] coef[row][n]            [tiny]
+//   force    : per particle 3-node stencil on H, Legendre + derivative, acc/pot
+#include "common.cuh"
+#include "sort.cuh"
+#include "sph_math.cuh"
+#include "sph_host.h"
+#include "nccl_shim.h"
+
+#include <cmath>
+#include <vector>
+
+namespace expb200 {
+
+__constant__ double c_K[(kMaxL + 1) * (kMaxL + 1)];   // factorial(l,m), src/SphericalBasis.cc:330-335
+__constant__ double c_inv[2 * kMaxL + 4];             // 1/k
+
+namespace {
+
+constexpr int kDepositWarps = 4;
+constexpr int kForceThreads = 128;
+
+template <int L> struct DepositShape {
+  static constexpr int NROW = (L + 1) * (L + 1);
+  static constexpr int STRIDE = (NROW + 2) | 1;         // odd: conflict-free 64-bit lanes
+  static constexpr int RPL = (NROW + 31) / 32;          // rows per lane in the reduce phase
+  static constexpr size_t WARP_DOUBLES = 32 * STRIDE + 16;   // + 32 ints of cell ids
+};
+
+// ---------------------------------------------------------------------------
+// key: (level, radial cell) per particle
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sph_key_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+               size_t n, int use_levels, int maxlev, uint32_t *__restrict__ keys)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    rec4 pm = ld_rec(&posm[i]);
+    uint32_t cell = sph_cell_of(g, pm);
+    uint32_t lev = 0;
+    if (use_levels) {
+      lev = level[i];
+      if (lev > (uint32_t)maxlev) lev = maxlev;
+    }
+    keys[i] = lev * (uint32_t)g.numr + cell;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// deposit: one warp per chunk of CH sorted particles.
+// phase 1 (lane = particle): Y rows -> shared tile; phase 2 (lane = row): walk the 32
+// particles in order, accumulate w1*Y and w2*Y, flush when the radial cell changes.
+// A flush goes to partial slot (chunk + cell), which is unique because both chunk and
+// cell are non-decreasing along the sorted order.
+// ---------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(kDepositWarps * 32)
+sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ posm,
+                   const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg,
+                   int keybase, int CH, double adb,
+                   double *__restrict__ PA, double *__restrict__ PB)
+{
+  using S = DepositShape<L>;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double *tile = smem + (size_t)w * S::WARP_DOUBLES;
+  int *cells = reinterpret_cast<int *>(tile + 32 * S::STRIDE);
+
+  const uint32_t lo = seg[keybase], hi = seg[keybase + g.numr - 1];
+  const size_t chunk = (size_t)blockIdx.x * kDepositWarps + w;
+  const size_t beg = (size_t)lo + chunk * (size_t)CH;
+  if (beg >= hi) return;
+  const size_t end = beg + CH < hi ? beg + CH : hi;
+
+  double accA[S::RPL], accB[S::RPL];
+#pragma unroll
+  for (int q = 0; q < S::RPL; q++) accA[q] = accB[q] = 0.0;
+  int cur = -1;
+
+  auto flush = [&](int c) {
+    size_t slot = (chunk + (size_t)c) * S::NROW;
+#pragma unroll
+    for (int q = 0; q < S::RPL; q++) {
+      int r = lane + 32 * q;
+      if (r < S::NROW) {
+        PA[slot + r] = accA[q];
+        PB[slot + r] = accB[q];
+      }
+      accA[q] = accB[q] = 0.0;
+    }
+  };
+
+  double *my = tile + lane * S::STRIDE;
+  for (size_t k0 = beg; k0 < end; k0 += 32) {
+    const size_t k = k0 + lane;
+    int cell = -1;
+    double w1 = 0.0, w2 = 0.0;
+    bool used = false;
+    if (k < end) {
+      rec4 pm = ld_rec(&posm[perm[k]]);
+      used = sph_deposit_particle<L>(g, c_K, c_inv, p0, pm, adb, cell, w1, w2,
+                                     [&](int row, double v) { my[row] = v; });
+    }
+    if (!used) {
+      cell = -1;
+      w1 = w2 = 0.0;
+      for (int r = 0; r < S::NROW; r++) my[r] = 0.0;
+    }
+    my[S::NROW] = w1;
+    my[S::NROW + 1] = w2;
+    cells[lane] = cell;
+    __syncwarp();
+
+    const int cnt = end - k0 < 32 ? (int)(end - k0) : 32;
+    for (int jj = 0; jj < cnt; jj++) {
+      const int c = cells[jj];                 // warp-uniform
+      if (c < 0) continue;
+      if (c != cur) {
+        if (cur >= 0) flush(cur);
+        cur = c;
+      }
+      const double *row = tile + jj * S::STRIDE;
+      const double a = row[S::NROW], b = row[S::NROW + 1];
+#pragma unroll
+      for (int q = 0; q < S::RPL; q++) {
+        int r = lane + 32 * q;
+        double v = r < S::NROW ? row[r] : 0.0;
+        accA[q] += a * v;
+        accB[q] += b * v;
+      }
+    }
+    __syncwarp();
+  }
+  if (cur >= 0) flush(cur);
+}
+
+// ---------------------------------------------------------------------------
+// combine: G[row][i] = sum over the chunks holding cell i of PA + same for cell i-1 of PB,
+// chunks visited in increasing order (fixed order).
+// ---------------------------------------------------------------------------
+__global__ void sph_combine_kernel(SphGeom g, const uint32_t *__restrict__ seg, int keybase, int CH,
+                                   const double *__restrict__ PA, const double *__restrict__ PB,
+                                   double *__restrict__ G)
+{
+  const int i = blockIdx.x;
+  const int nrow = g.nrow;
+  const uint32_t lo = seg[keybase];
+  for (int row = threadIdx.x; row < nrow; row += blockDim.x) {
+    double sum = 0.0;
+    if (i <= g.numr - 2) {
+      uint32_t s0 = seg[keybase + i], s1 = seg[keybase + i + 1];
+      if (s1 > s0) {
+        size_t j0 = (s0 - lo) / CH, j1 = (s1 - 1 - lo) / CH;
+        for (size_t j = j0; j <= j1; j++) sum += PA[(j + i) * nrow + row];
+      }
+    }
+    if (i >= 1) {
+      const int c = i - 1;
+      uint32_t s0 = seg[keybase + c], s1 = seg[keybase + c + 1];
+      if (s1 > s0) {
+        size_t j0 = (s0 - lo) / CH, j1 = (s1 - 1 - lo) / CH;
+        double sb = 0.0;
+        for (size_t j = j0; j <= j1; j++) sb += PB[(j + c) * nrow + row];
+        sum += sb;
+      }
+    }
+    G[(size_t)row * g.numr + i] = sum;
+  }
+}
+
+// Fixed-order CTA sum of one double per thread (256 threads).
+__device__ __forceinline__ double block_sum_256(double v, double *sh)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += sh[k];
+  }
+  return t;   // valid in thread 0
+}
+
+// contract: coef[row][n] = sum_i E[l][n][i] * G[row][i]; one CTA per row.
+__global__ void __launch_bounds__(256)
+sph_contract_kernel(SphGeom g, const double *__restrict__ Ep, const double *__restrict__ G,
+                    const int *__restrict__ row_l, const int *__restrict__ row_m, int M0_only,
+                    double *__restrict__ coef)
+{
+  __shared__ double sh[8];
+  const int row = blockIdx.x;
+  const int l = row_l[row];
+  const bool dead = M0_only && row_m[row] != 0;     // src/SphericalBasis.cc:549
+  const double *Gr = G + (size_t)row * g.numr;
+  for (int n = 0; n < g.nmax; n++) {
+    const double *E = Ep + ((size_t)l * g.nmax + n) * g.numr;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < g.numr; i += 256) s += E[i] * Gr[i];
+    double t = block_sum_256(s, sh);
+    if (threadIdx.x == 0) coef[(size_t)row * g.nmax + n] = dead ? 0.0 : t;
+  }
+}
+
+// field: H[i][slot] = (sum_n E[l][n][i] coef[rowc][n], sum_n E[l][n][i] coef[rows][n]).
+// slot_rowc/slot_rows encode which coefficient rows the reference's force loop reads for
+// this (l,m), including its NO_L0/NO_L1/EVEN_L/EVEN_M/M0_only behaviour; -1 = no term.
+__global__ void __launch_bounds__(128)
+sph_field_kernel(SphGeom g, const double *__restrict__ Ep, const double *__restrict__ coef,
+                 const int *__restrict__ slot_l, const int *__restrict__ slot_rowc,
+                 const int *__restrict__ slot_rows, double2 *__restrict__ H)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = blockIdx.y;
+  if (i >= g.numr) return;
+  const int l = slot_l[slot], rc = slot_rowc[slot], rs = slot_rows[slot];
+  double c = 0.0, s = 0.0;
+  if (rc >= 0) {
+    const double *E = Ep + (size_t)l * g.nmax * g.numr + i;
+    const double *cc = coef + (size_t)rc * g.nmax;
+    const double *cs = rs >= 0 ? coef + (size_t)rs * g.nmax : nullptr;
+    for (int n = 0; n < g.nmax; n++) {
+      double e = E[(size_t)n * g.numr];
+      c += e * cc[n];
+      if (cs) s += e * cs[n];
+    }
+  }
+  H[(size_t)i * g.nslot + slot] = make_double2(c, s);
+}
+
+// force: one thread per particle, sorted order (neighbouring lanes share table rows).
+template <int L>
+__global__ void __launch_bounds__(kForceThreads)
+sph_force_kernel(SphGeom g, const double *__restrict__ p0, const double2 *__restrict__ H,
+                 const rec4 *__restrict__ posm, rec4 *__restrict__ accp,
+                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg,
+                 int keybase, size_t n)
+{
+  const size_t lo = seg ? seg[keybase] : 0;
+  const size_t k = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const size_t i = perm ? perm[k] : k;
+  rec4 pm = ld_rec(&posm[i]);
+  double ax = 0.0, ay = 0.0, az = 0.0, pot = 0.0;
+  if (!sph_force_particle<L>(g, c_K, c_inv, p0, H, pm, ax, ay, az, pot)) return;
+  rec4 a = ld_rec_rw(&accp[i]);
+  a.x += ax; a.y += ay; a.z += az; a.w += pot;
+  st_rec(&accp[i], a);
+}
+
+template <int L> struct Launch {
+  static int deposit(cudaStream_t st, unsigned nblocks, const SphGeom &g, const double *p0,
+                     const rec4 *posm, const uint32_t *perm, const uint32_t *seg, int keybase,
+                     int CH, double adb, double *PA, double *PB)
+  {
+    size_t sm = kDepositWarps * DepositShape<L>::WARP_DOUBLES * sizeof(double);
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 63]) {
+      CU_TRY(cudaFuncSetAttribute(sph_deposit_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      attr[dev & 63] = true;
+    }
+    sph_deposit_kernel<L><<<nblocks, kDepositWarps * 32, sm, st>>>(g, p0, posm, perm, seg, keybase,
+                                                                    CH, adb, PA, PB);
+    CU_LAUNCH_CHECK();
+    return EXPB200_OK;
+  }
+  static int force(cudaStream_t st, const SphGeom &g, const double *p0, const double2 *H,
+                   const rec4 *posm, rec4 *accp, const uint32_t *perm, const uint32_t *seg,
+                   int keybase, size_t n)
+  {
+    sph_force_kernel<L><<<div_up(n, kForceThreads), kForceThreads, 0, st>>>(g, p0, H, posm, accp,
+                                                                           perm, seg, keybase, n);
+    CU_LAUNCH_CHECK();
+    return EXPB200_OK;
+  }
+};
+
+#define DISPATCH_L(lmax, CALL)                                                \
+  switch (lmax) {                                                             \
+    case 0: return Launch<0>::CALL;   case 1: return Launch<1>::CALL;         \
+    case 2: return Launch<2>::CALL;   case 3: return Launch<3>::CALL;         \
+    case 4: return Launch<4>::CALL;   case 5: return Launch<5>::CALL;         \
+    case 6: return Launch<6>::CALL;   case 7: return Launch<7>::CALL;         \
+    case 8: return Launch<8>::CALL;   case 9: return Launch<9>::CALL;         \
+    case 10: return Launch<10>::CALL; case 11: return Launch<11>::CALL;       \
+    case 12: return Launch<12>::CALL;                                         \
+    default: set_error("lmax=%d not instantiated (max %d)", lmax, kMaxL); return EXPB200_EINVAL; \
+  }
+
+int launch_deposit(int lmax, cudaStream_t st, unsigned nblocks, const SphGeom &g, const double *p0,
+                   const rec4 *posm, const uint32_t *perm, const uint32_t *seg, int keybase, int CH,
+                   double adb, double *PA, double *PB)
+{
+  DISPATCH_L(lmax, deposit(st, nblocks, g, p0, posm, perm, seg, keybase, CH, adb, PA, PB))
+}
+
+int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double *p0, const double2 *H,
+                 const rec4 *posm, rec4 *accp, const uint32_t *perm, const uint32_t *seg,
+                 int keybase, size_t n)
+{
+  DISPATCH_L(lmax, force(st, g, p0, H, posm, accp, perm, seg, keybase, n))
+}
+
+} // namespace
+} // namespace expb200
+
+using namespace expb200;
+
+struct expb200_sphere_s {
+  int device = 0;
+  expb200_sphere_config cfg;
+  SphGeom geom;              // centre fields filled per call from the component
+  int nlev = 1;
+  size_t ncoef = 0;
+
+  double *Ep = nullptr;      // [l][n][i] = ef / sqrt(ev)
+  double *p0 = nullptr;      // [numr]
+  double *coef = nullptr;    // device expcoef0: last accumulated vector
+  double *coef_use = nullptr;// coefficients installed for the force
+  double2 *H = nullptr;      // field table [numr][nslot]
+  double *G = nullptr;       // node sums [nrow][numr]
+  double *PA = nullptr, *PB = nullptr;
+  size_t part_slots = 0;
+  int *row_l = nullptr, *row_m = nullptr;
+  int *slot_l = nullptr, *slot_rowc = nullptr, *slot_rows = nullptr;
+  bool field_valid = false;
+  bool have_accum = false;
+  uint32_t *used_dev = nullptr;
+  cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+int deposit_chunk(size_t n)
+{
+  // one warp per chunk; enough chunks to fill 148 SMs x 32 warps, at most 1024 particles each
+  size_t q = n / ((size_t)kSMsB200 * 32 * 32);
+  if (q < 1) q = 1;
+  if (q > 32) q = 32;
+  return (int)q * 32;
+}
+
+SphGeom geom_for(const expb200_sphere_s *s, const expb200_component_s *c)
+{
+  SphGeom g = s->geom;
+  g.cx = c->center[0]; g.cy = c->center[1]; g.cz = c->center[2];
+  g.rtrunc2 = c->rtrunc * c->rtrunc;
+  return g;
+}
+
+// (level, radial cell) sort of component c for sphere s, reused while neither positions
+// nor levels changed.
+int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
+{
+  if (c->sort_kind == 2 && c->sort_owner == s && c->sort_pos_ver == c->pos_ver &&
+      c->sort_lev_ver == c->lev_ver)
+    return EXPB200_OK;
+  const uint32_t nkeys = (uint32_t)s->nlev * (uint32_t)s->cfg.numr;
+  if (c->seg_cap < (size_t)nkeys + 2) {
+    if (c->seg) cudaFree(c->seg);
+    c->seg = nullptr;
+    CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
+    c->seg_cap = (size_t)nkeys + 2;
+  }
+  SphGeom g = geom_for(s, c);
+  if (c->n) {
+    sph_key_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(g, c->posm, c->level, c->n,
+                                                               s->nlev > 1, s->nlev - 1, c->keys[0]);
+    CU_LAUNCH_CHECK();
+    int cur = 0;
+    int rc = radix_sort_pairs(c->stream, c->keys, c->perm, c->hist, c->n, nkeys, &cur);
+    if (rc) return rc;
+    c->cur = cur;
+  }
+  int rc = segment_offsets(c->stream, c->keys[c->cur], c->n, c->seg, nkeys);
+  if (rc) return rc;
+  c->sort_kind = 2;
+  c->sort_owner = s;
+  c->keys_per_level = s->cfg.numr;
+  c->sort_pos_ver = c->pos_ver;
+  c->sort_lev_ver = c->lev_ver;
+  return EXPB200_OK;
+}
+
+int ensure_partials(expb200_sphere_s *s, size_t n, int CH)
+{
+  size_t slots = (n + CH - 1) / CH + (size_t)s->cfg.numr + 1;
+  if (slots <= s->part_slots) return EXPB200_OK;
+  if (s->PA) cudaFree(s->PA);
+  if (s->PB) cudaFree(s->PB);
+  s->PA = s->PB = nullptr;
+  s->part_slots = 0;
+  CU_TRY(cudaMalloc(&s->PA, slots * s->geom.nrow * sizeof(double)));
+  CU_TRY(cudaMalloc(&s->PB, slots * s->geom.nrow * sizeof(double)));
+  s->part_slots = slots;
+  return EXPB200_OK;
+}
+
+int build_field(expb200_sphere_s *s, cudaStream_t st)
+{
+  const SphGeom &g = s->geom;
+  dim3 grid(div_up(g.numr, 128), g.nslot);
+  sph_field_kernel<<<grid, 128, 0, st>>>(g, s->Ep, s->coef_use, s->slot_l, s->slot_rowc,
+                                         s->slot_rows, s->H);
+  CU_LAUNCH_CHECK();
+  s->field_valid = true;
+  return EXPB200_OK;
+}
+
+int accumulate(expb200_sphere_s *s, expb200_component_s *c, int mlevel, double adb)
+{
+  int rc = ensure_sorted(s, c);
+  if (rc) return rc;
+  const int CH = deposit_chunk(c->n);
+  rc = ensure_partials(s, c->n, CH);
+  if (rc) return rc;
+  SphGeom g = geom_for(s, c);
+  const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
+  if (c->n) {
+    unsigned nchunks = div_up(c->n, CH);
+    rc = launch_deposit(s->cfg.lmax, c->stream, div_up(nchunks, kDepositWarps), g, s->p0, c->posm,
+                        c->perm[c->cur], c->seg, keybase, CH, adb, s->PA, s->PB);
+    if (rc) return rc;
+  }
+  sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, s->PA, s->PB, s->G);
+  sph_contract_kernel<<<g.nrow, 256, 0, c->stream>>>(g, s->Ep, s->G, s->row_l, s->row_m,
+                                                     s->cfg.M0_only, s->coef);
+  CU_LAUNCH_CHECK();
+  s->have_accum = true;
+  s->last_stream = c->stream;
+  return EXPB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int expb200_sphere_create(int device, const expb200_sphere_config *cfg, const double *ev,
+                          const double *ef, const double *p0, expb200_sphere *out)
+{
+  REQUIRE(cfg && ev && ef && p0 && out, "NULL argument");
+  REQUIRE(cfg->lmax >= 0 && cfg->lmax <= kMaxL, "lmax=%d outside [0,%d]", cfg->lmax, kMaxL);
+  REQUIRE(cfg->nmax >= 1 && cfg->nmax <= 1024, "nmax=%d out of range", cfg->nmax);
+  REQUIRE(cfg->numr >= 4, "numr=%d too small", cfg->numr);
+  REQUIRE(cfg->cmap >= 0 && cfg->cmap <= 2, "cmap=%d unknown", cfg->cmap);
+  REQUIRE(cfg->multistep >= 0 && cfg->multistep < 30, "multistep=%d out of range", cfg->multistep);
+  REQUIRE(cfg->scale > 0.0, "scale must be positive");
+  int ndev = 0;
+  CU_TRY(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, "device %d not present (%d visible)", device, ndev);
+  DeviceGuard gd(device);
+
+  auto *s = new expb200_sphere_s;
+  s->device = device;
+  s->cfg = *cfg;
+  s->nlev = cfg->multistep + 1;
+  const int L = cfg->lmax, N = cfg->nmax, R = cfg->numr;
+  s->geom = make_sph_geom(*cfg);
+  SphGeom &g = s->geom;
+  s->ncoef = (size_t)g.nrow * N;
+
+  // constants for this device
+  {
+    std::vector<double> K, inv;
+    make_sph_constants(K, inv);
+    CU_TRY(cudaMemcpyToSymbol(c_K, K.data(), K.size() * sizeof(double)));
+    CU_TRY(cudaMemcpyToSymbol(c_inv, inv.data(), inv.size() * sizeof(double)));
+  }
+
+  // tables: fold 1/sqrt(ev) into ef
+  {
+    std::vector<double> E((size_t)(L + 1) * N * R);
+    for (int l = 0; l <= L; l++)
+      for (int n = 0; n < N; n++) {
+        double q = std::sqrt(ev[l * N + n]);
+        const double *src = ef + ((size_t)l * N + n) * R;
+        double *dst = E.data() + ((size_t)l * N + n) * R;
+        for (int i = 0; i < R; i++) dst[i] = src[i] / q;
+      }
+    CU_TRY(cudaMalloc(&s->Ep, E.size() * sizeof(double)));
+    CU_TRY(cudaMemcpy(s->Ep, E.data(), E.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMalloc(&s->p0, R * sizeof(double)));
+    CU_TRY(cudaMemcpy(s->p0, p0, R * sizeof(double), cudaMemcpyHostToDevice));
+  }
+
+  // row -> (l,m) and the force loop's slot -> coefficient rows map (sph_host.h)
+  {
+    SphMaps M = make_sph_maps(*cfg);
+    auto up = [&](int **d, const std::vector<int> &h) -> int {
+      CU_TRY(cudaMalloc(d, h.size() * sizeof(int)));
+      CU_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+      return 0;
+    };
+    int rc;
+    if ((rc = up(&s->row_l, M.row_l)) || (rc = up(&s->row_m, M.row_m)) || (rc = up(&s->slot_l, M.slot_l)) ||
+        (rc = up(&s->slot_rowc, M.rowc)) || (rc = up(&s->slot_rows, M.rows)))
+      return rc;
+  }
+
+  CU_TRY(cudaMalloc(&s->coef, s->ncoef * sizeof(double)));
+  CU_TRY(cudaMalloc(&s->coef_use, s->ncoef * sizeof(double)));
+  CU_TRY(cudaMemset(s->coef, 0, s->ncoef * sizeof(double)));
+  CU_TRY(cudaMemset(s->coef_use, 0, s->ncoef * sizeof(double)));
+  CU_TRY(cudaMalloc(&s->H, (size_t)R * g.nslot * sizeof(double2)));
+  CU_TRY(cudaMalloc(&s->G, (size_t)g.nrow * R * sizeof(double)));
+  CU_TRY(cudaMalloc(&s->used_dev, 2 * sizeof(uint32_t)));
+  *out = s;
+  return EXPB200_OK;
+}
+
+int expb200_sphere_destroy(expb200_sphere s)
+{
+  if (!s) return EXPB200_OK;
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  cudaFree(s->Ep); cudaFree(s->p0); cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->H);
+  cudaFree(s->G); cudaFree(s->PA); cudaFree(s->PB); cudaFree(s->row_l); cudaFree(s->row_m);
+  cudaFree(s->slot_l); cudaFree(s->slot_rowc); cudaFree(s->slot_rows); cudaFree(s->used_dev);
+  delete s;
+  return EXPB200_OK;
+}
+
+int expb200_sphere_determine_coefficients(expb200_sphere s, expb200_component c, int mlevel,
+                                          double adb, double *coef_host, uint64_t *used)
+{
+  REQUIRE(s && c, "NULL argument");
+  REQUIRE(s->device == c->device, "sphere on device %d, component on device %d", s->device, c->device);
+  REQUIRE(mlevel >= 0 && mlevel < s->nlev, "mlevel=%d outside [0,%d]", mlevel, s->nlev - 1);
+  DeviceGuard g(s->device);
+  int rc = accumulate(s, c, mlevel, adb);
+  if (rc) return rc;
+  if (coef_host)
+    CU_TRY(cudaMemcpyAsync(coef_host, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (used) {
+    const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
+    uint32_t lohi[2];
+    CU_TRY(cudaMemcpyAsync(&lohi[0], c->seg + keybase, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(&lohi[1], c->seg + keybase + s->cfg.numr - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *used = lohi[1] - lohi[0];
+  } else if (coef_host) {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  return EXPB200_OK;
+}
+
+int expb200_sphere_coef_device(expb200_sphere s, double **dptr, void **stream)
+{
+  REQUIRE(s && dptr, "NULL argument");
+  *dptr = s->coef;
+  if (stream) *stream = s->last_stream;
+  return EXPB200_OK;
+}
+
+int expb200_sphere_set_coefficients(expb200_sphere s, const double *coef_host)
+{
+  REQUIRE(s, "sphere is NULL");
+  DeviceGuard g(s->device);
+  cudaStream_t st = s->last_stream;
+  if (coef_host) {
+    if (st) CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaMemcpy(s->coef_use, coef_host, s->ncoef * sizeof(double), cudaMemcpyHostToDevice));
+  } else {
+    REQUIRE(s->have_accum, "no coefficients accumulated on the device yet");
+    CU_TRY(cudaMemcpyAsync(s->coef_use, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  s->field_valid = false;
+  return EXPB200_OK;
+}
+
+int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c, int mlevel)
+{
+  REQUIRE(s && c, "NULL argument");
+  REQUIRE(s->device == c->device, "sphere on device %d, component on device %d", s->device, c->device);
+  REQUIRE(mlevel >= 0 && mlevel < s->nlev, "mlevel=%d outside [0,%d]", mlevel, s->nlev - 1);
+  DeviceGuard g(s->device);
+  if (c->n == 0) return EXPB200_OK;
+  int rc = ensure_sorted(s, c);
+  if (rc) return rc;
+  if (s->last_stream && s->last_stream != c->stream) CU_TRY(cudaStreamSynchronize(s->last_stream));
+  if (!s->field_valid) {
+    rc = build_field(s, c->stream);
+    if (rc) return rc;
+  }
+  s->last_stream = c->stream;
+  SphGeom gm = geom_for(s, c);
+  const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
+  return launch_force(s->cfg.lmax, c->stream, gm, s->p0, s->H, c->posm, c->accp, c->perm[c->cur],
+                      c->seg, keybase, c->n);
+}
+
+int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb, void *nccl_comm)
+{
+  REQUIRE(s && c, "NULL argument");
+  REQUIRE(s->nlev == 1, "expb200_sphere_step is the single-level driver (multistep=0)");
+  DeviceGuard g(s->device);
+  int rc;
+  // do_step, multistep == 0 branch (src/step.cc:272-322)
+  if ((rc = expb200_incr_velocity(c, 0.5 * dt, -1))) return rc;
+  if ((rc = expb200_incr_position(c, dt, -1))) return rc;
+  if ((rc = accumulate(s, c, 0, adb))) return rc;
+  if (nccl_comm) {
+    if ((rc = nccl_allreduce_sum_f64(nccl_comm, s->coef, s->ncoef, c->stream))) return rc;
+  }
+  CU_TRY(cudaMemcpyAsync(s->coef_use, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  s->field_valid = false;
+  if ((rc = expb200_component_zero_pot_acc(c, 0))) return rc;
+  if ((rc = expb200_sphere_determine_acceleration(s, c, 0))) return rc;
+  if ((rc = expb200_incr_velocity(c, 0.5 * dt, -1))) return rc;
+  return EXPB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,89 @@
+"""Host-side mirror of the reference's ``Sphere`` / ``SphericalBasis`` force
+(force id ``sphereSL``) over the C ABI.  Method names and argument meaning follow
+``PotAccel`` (reference src/PotAccel.H:173-288): ``determine_coefficients``,
+``get_acceleration_and_potential``, ``set_multistep_level``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_dp, check
+from .component import Component
+
+
+class Sphere:
+    def __init__(self, table, *, scale=1.0, rmin=None, rmax=None, NO_L0=False, NO_L1=False,
+                 EVEN_L=False, EVEN_M=False, M0_only=False, multistep=0, device=0):
+        """``table``: an object with the SLGridSph fields lmax, nmax, numr, cmap, rmin, rmax,
+        rmap, ev, ef, p0 (exp_b200.slgrid.SLGridSphTable or EXP's own arrays).  rmin/rmax
+        default to the table's, as the Sphere constructor does (src/Sphere.cc:65-66)."""
+        self.lmax, self.nmax = table.lmax, table.nmax
+        self.device = device
+        self.multistep = multistep
+        self.mlevel = 0
+        cfg = _lib.SphereConfig(table.lmax, table.nmax, table.numr, table.cmap, table.rmin,
+                                table.rmax, table.rmap, scale,
+                                table.rmin if rmin is None else rmin,
+                                table.rmax if rmax is None else rmax,
+                                int(NO_L0), int(NO_L1), int(EVEN_L), int(EVEN_M), int(M0_only),
+                                multistep)
+        ev = np.ascontiguousarray(table.ev, dtype=np.float64)
+        ef = np.ascontiguousarray(table.ef, dtype=np.float64)
+        p0 = np.ascontiguousarray(table.p0, dtype=np.float64)
+        self._h = C.c_void_p()
+        check(_lib.lib().expb200_sphere_create(device, C.byref(cfg), ev.ctypes.data_as(c_dp),
+                                               ef.ctypes.data_as(c_dp), p0.ctypes.data_as(c_dp),
+                                               C.byref(self._h)))
+        self.nrow = (self.lmax + 1) ** 2
+        self.expcoef = np.zeros((self.nrow, self.nmax))
+        self.used = 0
+
+    def close(self):
+        if self._h:
+            _lib.lib().expb200_sphere_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_multistep_level(self, n: int):
+        self.mlevel = int(n)
+
+    def determine_coefficients(self, c: Component, adb: float = 1.0, to_host: bool = True):
+        """Accumulate levlist[mlevel] of ``c``; returns expcoef0 (rows x nmax)."""
+        used = C.c_uint64(0)
+        coef = np.empty((self.nrow, self.nmax)) if to_host else None
+        check(_lib.lib().expb200_sphere_determine_coefficients(
+            self._h, c._h, self.mlevel, float(adb),
+            coef.ctypes.data_as(c_dp) if to_host else None, C.byref(used)))
+        self.used = used.value
+        return coef
+
+    def set_coefficients(self, coef=None):
+        """HtoD_coefs: install the coefficients the force evaluation uses (None: the
+        vector accumulated on the device)."""
+        if coef is None:
+            check(_lib.lib().expb200_sphere_set_coefficients(self._h, None))
+        else:
+            a = np.ascontiguousarray(coef, dtype=np.float64)
+            assert a.size == self.nrow * self.nmax
+            self.expcoef = a.reshape(self.nrow, self.nmax).copy()
+            check(_lib.lib().expb200_sphere_set_coefficients(self._h, a.ctypes.data_as(c_dp)))
+
+    def get_acceleration_and_potential(self, c: Component):
+        """Adds acc/pot to particles of ``c`` with level >= mlevel."""
+        check(_lib.lib().expb200_sphere_determine_acceleration(self._h, c._h, self.mlevel))
+
+    def step(self, c: Component, dt: float, adb: float = 1.0, comm=None):
+        check(_lib.lib().expb200_sphere_step(self._h, c._h, float(dt), float(adb), comm))
+
+    def coef_device(self):
+        p = c_dp()
+        st = C.c_void_p()
+        check(_lib.lib().expb200_sphere_coef_device(self._h, C.byref(p), C.byref(st)))
+        return p, st

@@ -1,0 +1,209 @@
+/*
+ * expb200.h -- C ABI of the B200-native basis-function-expansion force loop.
+ *
+ * This is the drop-in boundary.  The reference has no C
+ * ABI for primary forces; its GPU seams are C++ members compiled under
+ * HAVE_LIBCUDA.  Every entry point below names the reference seam it replaces,
+ * so that a maintainer can forward that member to the call (INTEGRATION.md
+ * shows the stubs).  Plain pointers and sizes only; no exceptions cross the
+ * boundary: every function returns 0 on success or a negative EXPB200_E* code,
+ * and expb200_last_error() returns the message for the calling thread.
+ *
+ * Threading: one host thread per GPU (the reference calls these seams from the
+ * rank's main thread, src/Component.H:1041-1079).  Handles are not re-entrant.
+ *
+ * Units / layout conventions
+ *   - host particle arrays are the reference's AoS fields flattened:
+ *     pos[n][3], vel[n][3], acc[n][3], mass[n], pot[n], potext[n],
+ *     level[n] (unsigned), dtreq[n] (float), scale[n] (float)
+ *     (include/Particle.H:31-67).  Slot i on the host is slot i on return:
+ *     particle order is never changed across the ABI.
+ *   - spherical coefficients: rows l*l + {0, 2m-1 (cos), 2m (sin)}, nmax
+ *     doubles per row, exactly expcoef[row][n] (src/SphericalBasis.cc:513-590).
+ */
+#ifndef EXPB200_H
+#define EXPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXPB200_OK          0
+#define EXPB200_EINVAL     -1   /* bad argument                              */
+#define EXPB200_ECUDA      -2   /* CUDA runtime error (message has details)  */
+#define EXPB200_ENOMEM     -3
+#define EXPB200_ESTATE     -4   /* call made in the wrong state              */
+#define EXPB200_ENCCL      -5
+
+typedef struct expb200_component_s *expb200_component;
+typedef struct expb200_sphere_s    *expb200_sphere;
+
+const char *expb200_last_error(void);
+/* Library/ABI version, number of visible devices, name + SM count of a device. */
+int  expb200_version(void);
+int  expb200_device_count(int *count);
+int  expb200_device_info(int device, char *name, int name_len, int *sm_count, size_t *hbm_bytes);
+
+/* Pinned host memory for asynchronous transfers (cudaHostAlloc / cudaHostRegister). */
+int  expb200_host_alloc(void **ptr, size_t bytes);
+int  expb200_host_free(void *ptr);
+int  expb200_host_register(void *ptr, size_t bytes);
+int  expb200_host_unregister(void *ptr);
+
+/* ------------------------------------------------------------------------
+ * Component: the device-resident particle store.
+ * Replaces Component::ParticlesToCuda / CudaToParticles / HostToDev / DevToHost
+ * (src/Component.H:1082-1139, src/cudaComponent.cu).
+ * ---------------------------------------------------------------------- */
+int expb200_component_create(int device, size_t capacity, expb200_component *out);
+int expb200_component_destroy(expb200_component c);
+
+/* Upload n particles (n <= capacity).  vel, level, scale, potext may be NULL
+ * (zeros / level 0 / scale -1).  ~ Component::ParticlesToCuda. */
+int expb200_component_upload(expb200_component c, size_t n,
+                             const double *pos, const double *vel, const double *mass,
+                             const unsigned *level, const float *scale, const double *potext);
+/* Chunked upload/download for pipelined host<->device traffic: particles
+ * [first, first+count) from host arrays that start at particle `first`.
+ * Asynchronous on the component's copy stream when the host memory is pinned;
+ * expb200_component_sync() waits for everything issued so far. */
+int expb200_component_upload_range(expb200_component c, size_t first, size_t count,
+                                   const double *pos, const double *vel, const double *mass);
+int expb200_component_set_count(expb200_component c, size_t n);
+int expb200_component_sync(expb200_component c);
+
+/* Download; any pointer may be NULL.  ~ Component::CudaToParticles. */
+int expb200_component_download(expb200_component c,
+                               double *pos, double *vel, double *acc, double *pot,
+                               unsigned *level, float *dtreq);
+int expb200_component_download_range(expb200_component c, size_t first, size_t count,
+                                     double *pos, double *vel, double *acc, double *pot);
+size_t expb200_component_count(expb200_component c);
+
+/* Install levels (Particle::level) / acc+pot (restart, tests). */
+int expb200_component_set_levels(expb200_component c, const unsigned *level);
+int expb200_component_set_acc_pot(expb200_component c, const double *acc, const double *pot);
+
+/* center = com0 + center, what Pos(..., Local|Centered) subtracts
+ * (src/Component.H:747-757); rtrunc for Component::freeze
+ * (src/Component.cc:4194-4202). */
+int expb200_component_set_center(expb200_component c, const double center[3], double rtrunc);
+
+/* Zero acc/pot(/potext) of particles with level >= minlev.
+ * ~ Component::ZeroPotAccel (src/cudaComponent.cu:729-797). */
+int expb200_component_zero_pot_acc(expb200_component c, int minlev);
+
+/* Leapfrog.  mlevel < 0: all particles; else levlist[mlevel].
+ * ~ incr_position_cuda / incr_velocity_cuda (src/cudaIncpos.cu, src/cudaIncvel.cu),
+ * arithmetic of src/incpos.cc:63-66, src/incvel.cc:68-69. */
+int expb200_incr_position(expb200_component c, double dt, int mlevel);
+int expb200_incr_velocity(expb200_component c, double dt, int mlevel);
+
+/* Multistep level assignment.  ~ cuda_compute_levels (src/cudaMultistep.cu),
+ * arithmetic of adjust_multistep_level_thread (src/multistep.cc:52-236),
+ * bit-exact with the CPU path (dtreq rounds through float). */
+typedef struct {
+  double dtime;
+  double dynfracS, dynfracD, dynfracV, dynfracA, dynfracP;
+  int multistep;       /* highest level                                  */
+  int shiftlevl;       /* max level shift per call (0 = unlimited)       */
+  int mfirst_mdrft;    /* mfirst[mdrft]: lowest level that may be set    */
+  int minlev;          /* examine particles with level >= minlev         */
+  int noswitch;        /* Component::NoSwitch()                          */
+  int reset_dtreq;     /* (DTreset && mstep==0) || firstCall             */
+  int apply;           /* assign levels on this call                     */
+  int dim;             /* Component::dim                                 */
+} expb200_level_params;
+
+typedef struct {
+  uint64_t examined;   /* numtt */
+  uint64_t switched;   /* numsw */
+  uint64_t offlo;      /* wanted a level above multistep                 */
+  uint64_t offhi;      /* wanted a step larger than dtime                */
+  double   mindt, maxdt;
+} expb200_level_stats;
+
+int expb200_adjust_multistep_level(expb200_component c, const expb200_level_params *p,
+                                   expb200_level_stats *stats);
+/* Populations per level: counts[multistep+1].  ~ CudaGetLevelRange
+ * (src/cudaComponent.cu:490-526). */
+int expb200_component_level_counts(expb200_component c, int multistep, uint64_t *counts);
+
+/* ------------------------------------------------------------------------
+ * Sphere (force id "sphereSL"): SphericalBasis + SLGridSph tables.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int lmax, nmax, numr, cmap;      /* SLGridSph (include/SLGridMP2.H:28-240)      */
+  double rmin_grid, rmax_grid;     /* radial table range                          */
+  double rmap;                     /* coordinate-map scale (rmapping)             */
+  double scale;                    /* SphericalBasis::scale                       */
+  double rmin, rmax;               /* expansion radii (src/Sphere.cc:65-66)       */
+  int NO_L0, NO_L1, EVEN_L, EVEN_M, M0_only;   /* src/SphericalBasis.cc:114-119   */
+  int multistep;                   /* number of levels - 1 (0 = single level)     */
+} expb200_sphere_config;
+
+/* Tables as SLGridSph holds them: ev[(lmax+1)][nmax], ef[(lmax+1)][nmax][numr],
+ * p0[numr].  ~ SLGridSph::initialize_cuda (exputil/cudaSLGridMP2.cu:52-140) +
+ * SphericalBasis::initialize_cuda. */
+int expb200_sphere_create(int device, const expb200_sphere_config *cfg,
+                          const double *ev, const double *ef, const double *p0,
+                          expb200_sphere *out);
+int expb200_sphere_destroy(expb200_sphere s);
+
+/* ~ SphericalBasis::determine_coefficients_cuda(compute) + DtoH_coefs
+ * (src/SphericalBasis.cc:832-843).  Accumulates levlist[mlevel] (all particles
+ * when the sphere was created with multistep == 0) into the device copy of
+ * expcoef0; if coef_host != NULL the (lmax+1)^2*nmax doubles are copied back.
+ * used (may be NULL) receives the number of particles inside [rmin,rmax].
+ * adb = Component::Adiabatic(). */
+int expb200_sphere_determine_coefficients(expb200_sphere s, expb200_component c, int mlevel,
+                                          double adb, double *coef_host, uint64_t *used);
+
+/* Device pointer of the last accumulated coefficient vector ((lmax+1)^2*nmax
+ * doubles), e.g. to all-reduce it in place with NCCL on `stream`. */
+int expb200_sphere_coef_device(expb200_sphere s, double **dptr, void **stream);
+
+/* ~ SphericalBasis::HtoD_coefs(expcoef) (src/SphericalBasis.cc:1707): install
+ * the coefficients used by the next force evaluation.  coef_host == NULL means
+ * "use the vector accumulated on the device by determine_coefficients". */
+int expb200_sphere_set_coefficients(expb200_sphere s, const double *coef_host);
+
+/* ~ SphericalBasis::determine_acceleration_cuda (src/SphericalBasis.cc:1715):
+ * adds this basis' acceleration and potential to particles of c with
+ * level >= mlevel.  c may be a different component (use_external). */
+int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c, int mlevel);
+
+/* Covariance (pcavar) accumulation, src/SphericalBasis.cc:501-509,525-545,563-581.
+ * Outputs are device-accumulated and copied to the host arrays:
+ *   massT[sampT], countT[sampT],
+ *   coefT[sampT][(L+1)(L+2)/2][nmax][2], coefM[sampT][(L+1)(L+2)/2][nmax][nmax]. */
+int expb200_sphere_determine_coefficients_cov(expb200_sphere s, expb200_component c, int mlevel,
+                                              double adb, int sampT, double *coef_host,
+                                              double *muse, double *massT, unsigned *countT,
+                                              double *coefT, double *coefM);
+
+/* One fused single-level KDK step for a self-gravitating component, the
+ * sequence of do_step (src/step.cc:272-322) with results identical to the
+ * separate calls: kick(dt/2) drift(dt) coefficients force kick(dt/2).
+ * If comm != NULL it is an ncclComm_t and the coefficient vector is summed
+ * across ranks (the reference's MPI_Allreduce, src/SphericalBasis.cc:864-903). */
+int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb,
+                        void *nccl_comm);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU: one process (MPI rank) per GPU; NCCL is loaded with dlopen.
+ * Replaces the host MPI_Allreduce of the coefficient vector
+ * (src/SphericalBasis.cc:864-903) by one in-place device all-reduce.
+ * ---------------------------------------------------------------------- */
+int expb200_comm_unique_id(char id[128]);                       /* ncclGetUniqueId (rank 0) */
+int expb200_comm_create(int device, int nranks, int rank, const char id[128], void **comm);
+int expb200_comm_destroy(void *comm);
+int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXPB200_H */
