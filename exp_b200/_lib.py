@@ -95,6 +95,8 @@ SIGNATURES = {
     "expb200_component_zero_pot_acc": (C.c_int, [_H, C.c_int]),
     "expb200_component_set_levels": (C.c_int, [_H, c_up]),
     "expb200_component_set_acc_pot": (C.c_int, [_H, c_dp, c_dp]),
+    "expb200_component_event_record": (C.c_int, [_H, C.c_int]),
+    "expb200_component_event_elapsed": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_component_level_counts": (C.c_int, [_H, C.c_int, c_u64p]),
     "expb200_incr_position": (C.c_int, [_H, C.c_double, C.c_int]),
     "expb200_incr_velocity": (C.c_int, [_H, C.c_double, C.c_int]),
@@ -107,6 +109,12 @@ SIGNATURES = {
     "expb200_sphere_set_coefficients": (C.c_int, [_H, c_dp]),
     "expb200_sphere_determine_acceleration": (C.c_int, [_H, _H, C.c_int]),
     "expb200_sphere_step": (C.c_int, [_H, _H, C.c_double, C.c_double, C.c_void_p]),
+    "expb200_profile_enable": (C.c_int, [C.c_int]),
+    "expb200_profile_reset": (C.c_int, []),
+    "expb200_profile_kernels": (C.c_int, []),
+    "expb200_profile_name": (C.c_char_p, [C.c_int]),
+    "expb200_profile_read": (C.c_int, [C.POINTER(C.c_ulonglong), c_dp, C.POINTER(C.c_ulonglong)]),
+    "expb200_fp64_peak": (C.c_int, [C.c_int, c_dp, c_dp]),
     "expb200_comm_unique_id": (C.c_int, [C.c_char_p]),
     "expb200_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "expb200_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -134,3 +142,14 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = lib().expb200_last_error()
         raise Expb200Error(f"expb200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def profile_read():
+    """{kernel: (launches, ms, timed_regions)} since the last reset."""
+    L = lib()
+    k = L.expb200_profile_kernels()
+    la = (C.c_ulonglong * k)()
+    ms = (C.c_double * k)()
+    tm = (C.c_ulonglong * k)()
+    check(L.expb200_profile_read(la, ms, tm))
+    return {L.expb200_profile_name(i).decode(): (int(la[i]), float(ms[i]), int(tm[i])) for i in range(k)}

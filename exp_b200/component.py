@@ -121,6 +121,14 @@ class Component:
         return dict(examined=S.examined, switched=S.switched, offlo=S.offlo, offhi=S.offhi,
                     mindt=S.mindt, maxdt=S.maxdt)
 
+    def event_record(self, slot):
+        check(_lib.lib().expb200_component_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double(0.0)
+        check(_lib.lib().expb200_component_event_elapsed(self._h, a, b, C.byref(ms)))
+        return ms.value
+
     def level_counts(self, multistep):
         out = np.zeros(multistep + 1, dtype=np.uint64)
         check(_lib.lib().expb200_component_level_counts(self._h, multistep,

@@ -6,6 +6,7 @@
 // (src/incpos.cc:63-66, src/incvel.cc:68-69, src/multistep.cc:52-236).
 #include "common.cuh"
 #include "sort.cuh"
+#include "profile.cuh"
 
 #include <cmath>
 #include <mutex>
@@ -438,6 +439,7 @@ int expb200_component_upload_range(expb200_component c, size_t first, size_t cou
     CU_TRY(cudaEventRecord(ev, c->copy_stream));
     CU_TRY(cudaStreamWaitEvent(c->stream, ev, 0));
     CU_TRY(cudaEventDestroy(ev));
+    ProfRegion pr(K_PACK, c->stream);
     pack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp, spos,
                                                          vel ? svel : nullptr, smass, nullptr,
                                                          first + off, m, 0);
@@ -517,6 +519,7 @@ int expb200_component_download_range(expb200_component c, size_t first, size_t c
     double *s = c->stage + (size_t)b * ch * kStageDoubles;
     double *spos = s, *svel = s + 3 * ch, *sacc = s + 6 * ch, *spot = s + 9 * ch;
     if (round >= 2) CU_TRY(cudaStreamWaitEvent(c->stream, copied[b], 0));
+    ProfRegion pr(K_PACK, c->stream);
     unpack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp,
                                                            pos ? spos : nullptr, vel ? svel : nullptr,
                                                            acc ? sacc : nullptr, pot ? spot : nullptr,
@@ -567,6 +570,7 @@ int expb200_component_zero_pot_acc(expb200_component c, int minlev)
   REQUIRE(c, "component is NULL");
   if (c->n == 0) return EXPB200_OK;
   DeviceGuard g(c->device);
+  ProfRegion pr(K_ZERO, c->stream);
   zero_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->accp, c->level, c->n, minlev);
   CU_LAUNCH_CHECK();
   return EXPB200_OK;
@@ -577,6 +581,7 @@ int expb200_incr_position(expb200_component c, double dt, int mlevel)
   REQUIRE(c, "component is NULL");
   if (c->n == 0) return EXPB200_OK;
   DeviceGuard g(c->device);
+  ProfRegion pr(K_DRIFT, c->stream);
   drift_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->level, c->n, dt, mlevel, 3);
   CU_LAUNCH_CHECK();
   c->pos_ver++;
@@ -588,6 +593,7 @@ int expb200_incr_velocity(expb200_component c, double dt, int mlevel)
   REQUIRE(c, "component is NULL");
   if (c->n == 0) return EXPB200_OK;
   DeviceGuard g(c->device);
+  ProfRegion pr(K_KICK, c->stream);
   kick_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->vel, c->accp, c->level, c->n, dt, mlevel, 3);
   CU_LAUNCH_CHECK();
   return EXPB200_OK;
@@ -613,6 +619,7 @@ int expb200_adjust_multistep_level(expb200_component c, const expb200_level_para
   unsigned long long init[8] = {0, 0, 0, 0, 0x7fefffffffffffffULL, 0, 0, 0};
   CU_TRY(cudaMemcpyAsync(c->stats, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
   if (c->n) {
+    ProfRegion pr(K_LEVELS, c->stream);
     levels_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->vel, c->accp, c->scale, c->level,
                                                               c->dtreq, c->n, A, c->stats);
     CU_LAUNCH_CHECK();
@@ -651,6 +658,39 @@ int expb200_component_set_acc_pot(expb200_component c, const double *acc, const 
   for (size_t i = 0; i < c->n; i++) h[i] = rec4{acc[3 * i], acc[3 * i + 1], acc[3 * i + 2], pot[i]};
   CU_TRY(cudaMemcpyAsync(c->accp, h, c->n * sizeof(rec4), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
+  return EXPB200_OK;
+}
+
+// Device-side timing of a region that may span both streams of the component:
+// slot in [0,8).  record joins the copy stream into the compute stream, records there
+// and makes the copy stream wait for it, so everything issued before/after on either
+// stream falls on the right side of the event.
+static cudaEvent_t g_tev[8] = {};
+
+int expb200_component_event_record(expb200_component c, int slot)
+{
+  REQUIRE(c && slot >= 0 && slot < 8, "bad argument");
+  DeviceGuard g(c->device);
+  if (!g_tev[slot]) CU_TRY(cudaEventCreate(&g_tev[slot]));
+  cudaEvent_t j;
+  CU_TRY(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(j, c->copy_stream));
+  CU_TRY(cudaStreamWaitEvent(c->stream, j, 0));
+  CU_TRY(cudaEventDestroy(j));
+  CU_TRY(cudaEventRecord(g_tev[slot], c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->copy_stream, g_tev[slot], 0));
+  return EXPB200_OK;
+}
+
+int expb200_component_event_elapsed(expb200_component c, int slot_a, int slot_b, double *ms)
+{
+  REQUIRE(c && ms && slot_a >= 0 && slot_a < 8 && slot_b >= 0 && slot_b < 8, "bad argument");
+  REQUIRE(g_tev[slot_a] && g_tev[slot_b], "event slot never recorded");
+  DeviceGuard g(c->device);
+  CU_TRY(cudaEventSynchronize(g_tev[slot_b]));
+  float f = 0.f;
+  CU_TRY(cudaEventElapsedTime(&f, g_tev[slot_a], g_tev[slot_b]));
+  *ms = f;
   return EXPB200_OK;
 }
 

@@ -20,6 +20,7 @@
 #include "sph_math.cuh"
 #include "sph_host.h"
 #include "nccl_shim.h"
+#include "profile.cuh"
 
 #include <cmath>
 #include <vector>
@@ -384,15 +385,22 @@ int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
   }
   SphGeom g = geom_for(s, c);
   if (c->n) {
+    { ProfRegion pr(K_KEY, c->stream);
     sph_key_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(g, c->posm, c->level, c->n,
                                                                s->nlev > 1, s->nlev - 1, c->keys[0]);
+    }
     CU_LAUNCH_CHECK();
     int cur = 0;
+    int npass = 0;
+    { int nbits = 1; while ((1ull << nbits) < nkeys) nbits++; npass = (nbits + 7) / 8; }
+    ProfRegion pr(K_SORT, c->stream, 3 * npass);
     int rc = radix_sort_pairs(c->stream, c->keys, c->perm, c->hist, c->n, nkeys, &cur);
     if (rc) return rc;
     c->cur = cur;
   }
-  int rc = segment_offsets(c->stream, c->keys[c->cur], c->n, c->seg, nkeys);
+  int rc;
+  { ProfRegion pr(K_SEG, c->stream);
+    rc = segment_offsets(c->stream, c->keys[c->cur], c->n, c->seg, nkeys); }
   if (rc) return rc;
   c->sort_kind = 2;
   c->sort_owner = s;
@@ -420,6 +428,7 @@ int build_field(expb200_sphere_s *s, cudaStream_t st)
 {
   const SphGeom &g = s->geom;
   dim3 grid(div_up(g.numr, 128), g.nslot);
+  ProfRegion pr(K_FIELD, st);
   sph_field_kernel<<<grid, 128, 0, st>>>(g, s->Ep, s->coef_use, s->slot_l, s->slot_rowc,
                                          s->slot_rows, s->H);
   CU_LAUNCH_CHECK();
@@ -438,13 +447,16 @@ int accumulate(expb200_sphere_s *s, expb200_component_s *c, int mlevel, double a
   const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
   if (c->n) {
     unsigned nchunks = div_up(c->n, CH);
+    ProfRegion pr(K_DEPOSIT, c->stream);
     rc = launch_deposit(s->cfg.lmax, c->stream, div_up(nchunks, kDepositWarps), g, s->p0, c->posm,
                         c->perm[c->cur], c->seg, keybase, CH, adb, s->PA, s->PB);
     if (rc) return rc;
   }
-  sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, s->PA, s->PB, s->G);
-  sph_contract_kernel<<<g.nrow, 256, 0, c->stream>>>(g, s->Ep, s->G, s->row_l, s->row_m,
-                                                     s->cfg.M0_only, s->coef);
+  { ProfRegion pr(K_COMBINE, c->stream);
+    sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, s->PA, s->PB, s->G); }
+  { ProfRegion pr(K_CONTRACT, c->stream);
+    sph_contract_kernel<<<g.nrow, 256, 0, c->stream>>>(g, s->Ep, s->G, s->row_l, s->row_m,
+                                                       s->cfg.M0_only, s->coef); }
   CU_LAUNCH_CHECK();
   s->have_accum = true;
   s->last_stream = c->stream;
@@ -605,6 +617,7 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   s->last_stream = c->stream;
   SphGeom gm = geom_for(s, c);
   const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
+  ProfRegion pr(K_FORCE, c->stream);
   return launch_force(s->cfg.lmax, c->stream, gm, s->p0, s->H, c->posm, c->accp, c->perm[c->cur],
                       c->seg, keybase, c->n);
 }
@@ -620,6 +633,7 @@ int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double
   if ((rc = expb200_incr_position(c, dt, -1))) return rc;
   if ((rc = accumulate(s, c, 0, adb))) return rc;
   if (nccl_comm) {
+    ProfRegion pr(K_ALLREDUCE, c->stream, 0);
     if ((rc = nccl_allreduce_sum_f64(nccl_comm, s->coef, s->ncoef, c->stream))) return rc;
   }
   CU_TRY(cudaMemcpyAsync(s->coef_use, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));

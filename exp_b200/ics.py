@@ -37,12 +37,25 @@ def _isotropic(rng, n):
 def _assemble(gen_chunk, lo, hi, total_mass, ntot):
     pos = np.empty((hi - lo, 3))
     vel = np.empty((hi - lo, 3))
-    o = 0
+    jobs, o = [], 0
     for k, a, b in _chunks(lo, hi):
+        jobs.append((k, a, b, o))
+        o += b - a
+
+    def run(job):
+        k, a, b, o = job
         p, v = gen_chunk(k)
         pos[o:o + b - a] = p[a:b]
         vel[o:o + b - a] = v[a:b]
-        o += b - a
+
+    if len(jobs) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1, 16)) as ex:
+            list(ex.map(run, jobs))
+    else:
+        for j in jobs:
+            run(j)
     mass = np.full(hi - lo, total_mass / ntot)
     return pos, vel, mass
 
@@ -74,21 +87,20 @@ def hernquist_halo(ntot: int, lo: int = 0, hi: int | None = None, seed: int = 42
 def nfw_halo(ntot: int, lo: int = 0, hi: int | None = None, seed: int = 43,
              rs: float = 1.0, c: float = 10.0, mass: float = 1.0):
     """NFW sphere truncated at c*rs: inverse CDF of m(x)=ln(1+x)-x/(1+x) by
-    bisection; velocities Gaussian with sigma^2 ~ |Phi|/3 (level assignment only)."""
+    table lookup + Newton; velocities Gaussian with sigma^2 ~ |Phi|/3 (level assignment only)."""
     hi = ntot if hi is None else hi
     mu = lambda x: np.log1p(x) - x / (1.0 + x)
     mc = mu(c)
+    tab_x = np.concatenate([[0.0], np.geomspace(1e-6, c, 8192)])
+    tab_m = mu(tab_x)
 
     def gen(k):
         rng = _rng(seed, k)
         u = rng.uniform(0.0, 1.0, CHUNK) * mc
-        a_, b_ = np.zeros(CHUNK), np.full(CHUNK, float(c))
-        for _ in range(60):
-            mid = 0.5 * (a_ + b_)
-            less = mu(mid) < u
-            a_ = np.where(less, mid, a_)
-            b_ = np.where(less, b_, mid)
-        r = rs * 0.5 * (a_ + b_)
+        x = np.interp(u, tab_m, tab_x)              # table guess, then Newton on m(x) = u
+        for _ in range(4):
+            x = np.clip(x - (mu(x) - u) * (1.0 + x) ** 2 / np.maximum(x, 1e-300), 1e-12, c)
+        r = rs * x
         pos = r[:, None] * _isotropic(rng, CHUNK)
         phi = mass / mc * np.log1p(r / rs) / np.maximum(r, 1e-12)
         vel = rng.standard_normal((CHUNK, 3)) * np.sqrt(phi / 3.0)[:, None]

@@ -83,6 +83,10 @@ int expb200_component_download_range(expb200_component c, size_t first, size_t c
                                      double *pos, double *vel, double *acc, double *pot);
 size_t expb200_component_count(expb200_component c);
 
+/* Device-side timing across both streams of a component (slot in [0,8)). */
+int expb200_component_event_record(expb200_component c, int slot);
+int expb200_component_event_elapsed(expb200_component c, int slot_a, int slot_b, double *ms);
+
 /* Install levels (Particle::level) / acc+pot (restart, tests). */
 int expb200_component_set_levels(expb200_component c, const unsigned *level);
 int expb200_component_set_acc_pot(expb200_component c, const double *acc, const double *pot);
@@ -202,6 +206,19 @@ int expb200_comm_unique_id(char id[128]);                       /* ncclGetUnique
 int expb200_comm_create(int device, int nranks, int rank, const char id[128], void **comm);
 int expb200_comm_destroy(void *comm);
 int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Instrumentation (what bench.py reads): launch counters are always on; event
+ * timing of each kernel family on its launching stream only while enabled.
+ * ~ the reference's per-phase timers (src/step.cc:347-374, `timers: true`).
+ * ---------------------------------------------------------------------- */
+int expb200_profile_enable(int on);
+int expb200_profile_reset(void);
+int expb200_profile_kernels(void);                 /* number of kernel families */
+const char *expb200_profile_name(int id);
+int expb200_profile_read(unsigned long long *launches, double *ms, unsigned long long *timed);
+/* Dependency-free DFMA microbenchmark: the FP64 roofline denominator. */
+int expb200_fp64_peak(int device, double *tflops, double *sm_mhz_hint);
 
 #ifdef __cplusplus
 }
