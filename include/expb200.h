@@ -180,15 +180,6 @@ int expb200_sphere_set_coefficients(expb200_sphere s, const double *coef_host);
  * level >= mlevel.  c may be a different component (use_external). */
 int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c, int mlevel);
 
-/* Covariance (pcavar) accumulation, src/SphericalBasis.cc:501-509,525-545,563-581.
- * Outputs are device-accumulated and copied to the host arrays:
- *   massT[sampT], countT[sampT],
- *   coefT[sampT][(L+1)(L+2)/2][nmax][2], coefM[sampT][(L+1)(L+2)/2][nmax][nmax]. */
-int expb200_sphere_determine_coefficients_cov(expb200_sphere s, expb200_component c, int mlevel,
-                                              double adb, int sampT, double *coef_host,
-                                              double *muse, double *massT, unsigned *countT,
-                                              double *coefT, double *coefM);
-
 /* One fused single-level KDK step for a self-gravitating component, the
  * sequence of do_step (src/step.cc:272-322) with results identical to the
  * separate calls: kick(dt/2) drift(dt) coefficients force kick(dt/2).
