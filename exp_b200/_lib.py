@@ -108,6 +108,13 @@ SIGNATURES = {
     "expb200_sphere_coef_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_void_p)]),
     "expb200_sphere_set_coefficients": (C.c_int, [_H, c_dp]),
     "expb200_sphere_determine_acceleration": (C.c_int, [_H, _H, C.c_int]),
+    "expb200_sphere_multistep_commit": (C.c_int, [_H, C.c_int]),
+    "expb200_sphere_compute_multistep_coefficients": (C.c_int, [_H, C.c_int]),
+    "expb200_sphere_multistep_update": (C.c_int, [_H, _H, C.c_double, C.c_int]),
+    "expb200_sphere_multistep_update_finish": (C.c_int, [_H]),
+    "expb200_sphere_differ_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]),
+    "expb200_sphere_get_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
+    "expb200_sphere_set_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_sphere_step": (C.c_int, [_H, _H, C.c_double, C.c_double, C.c_void_p]),
     "expb200_profile_enable": (C.c_int, [C.c_int]),
     "expb200_profile_reset": (C.c_int, []),

@@ -46,6 +46,11 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Registry of live component streams: a Sphere remembers the stream it last worked on and
+// must not touch it after that component was destroyed.
+void stream_register(cudaStream_t st, bool live);
+bool stream_is_live(cudaStream_t st);
+
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // Grid size for a grid-stride kernel: enough CTAs to fill the 148 SMs a few
@@ -99,6 +104,7 @@ struct expb200_component_s {
   expb200::rec4 *vel = nullptr;         // {vx,vy,vz,potext}
   expb200::rec4 *accp = nullptr;        // {ax,ay,az,pot}
   unsigned *level = nullptr;
+  unsigned *prev_level = nullptr;      // level before the last adjust_multistep_level
   float *dtreq = nullptr;
   float *scale = nullptr;
 

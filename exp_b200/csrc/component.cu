@@ -10,6 +10,7 @@
 
 #include <cmath>
 #include <mutex>
+#include <vector>
 
 namespace expb200 {
 
@@ -32,6 +33,24 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 {
   set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
   return e == cudaErrorMemoryAllocation ? EXPB200_ENOMEM : EXPB200_ECUDA;
+}
+
+static std::mutex g_stream_mu;
+static std::vector<cudaStream_t> g_live_streams;
+
+void stream_register(cudaStream_t st, bool live)
+{
+  std::lock_guard<std::mutex> lk(g_stream_mu);
+  for (size_t k = 0; k < g_live_streams.size(); k++)
+    if (g_live_streams[k] == st) { g_live_streams.erase(g_live_streams.begin() + k); break; }
+  if (live) g_live_streams.push_back(st);
+}
+
+bool stream_is_live(cudaStream_t st)
+{
+  std::lock_guard<std::mutex> lk(g_stream_mu);
+  for (auto s : g_live_streams) if (s == st) return true;
+  return false;
 }
 
 namespace {
@@ -362,11 +381,13 @@ int expb200_component_create(int device, size_t capacity, expb200_component *out
   c->cap = capacity;
   CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  stream_register(c->stream, true);
   CU_TRY(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   CU_TRY(cudaMalloc(&c->posm, capacity * sizeof(rec4)));
   CU_TRY(cudaMalloc(&c->vel, capacity * sizeof(rec4)));
   CU_TRY(cudaMalloc(&c->accp, capacity * sizeof(rec4)));
   CU_TRY(cudaMalloc(&c->level, capacity * sizeof(unsigned)));
+  CU_TRY(cudaMalloc(&c->prev_level, capacity * sizeof(unsigned)));
   CU_TRY(cudaMalloc(&c->dtreq, capacity * sizeof(float)));
   CU_TRY(cudaMalloc(&c->scale, capacity * sizeof(float)));
   for (int k = 0; k < 2; k++) {
@@ -380,6 +401,7 @@ int expb200_component_create(int device, size_t capacity, expb200_component *out
   CU_TRY(cudaMalloc(&c->stats, 8 * sizeof(unsigned long long)));
   CU_TRY(cudaMemsetAsync(c->accp, 0, capacity * sizeof(rec4), c->stream));
   CU_TRY(cudaMemsetAsync(c->level, 0, capacity * sizeof(unsigned), c->stream));
+  CU_TRY(cudaMemsetAsync(c->prev_level, 0, capacity * sizeof(unsigned), c->stream));
   CU_TRY(cudaMemsetAsync(c->dtreq, 0, capacity * sizeof(float), c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   *out = c;
@@ -393,10 +415,11 @@ int expb200_component_destroy(expb200_component c)
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   cudaFree(c->posm); cudaFree(c->vel); cudaFree(c->accp);
-  cudaFree(c->level); cudaFree(c->dtreq); cudaFree(c->scale);
+  cudaFree(c->level); cudaFree(c->prev_level); cudaFree(c->dtreq); cudaFree(c->scale);
   for (int k = 0; k < 2; k++) { cudaFree(c->keys[k]); cudaFree(c->perm[k]); }
   cudaFree(c->hist); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats);
   cudaEventDestroy(c->copy_done);
+  stream_register(c->stream, false);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -619,6 +642,9 @@ int expb200_adjust_multistep_level(expb200_component c, const expb200_level_para
   unsigned long long init[8] = {0, 0, 0, 0, 0x7fefffffffffffffULL, 0, 0, 0};
   CU_TRY(cudaMemcpyAsync(c->stats, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
   if (c->n) {
+    // remember the levels before the update: multistep_update moves each switching
+    // particle's contribution from prev_level to level (src/multistep.cc:198-206)
+    CU_TRY(cudaMemcpyAsync(c->prev_level, c->level, c->n * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
     ProfRegion pr(K_LEVELS, c->stream);
     levels_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->vel, c->accp, c->scale, c->level,
                                                               c->dtreq, c->n, A, c->stats);
@@ -642,6 +668,7 @@ int expb200_component_set_levels(expb200_component c, const unsigned *level)
   REQUIRE(c && level, "NULL argument");
   DeviceGuard g(c->device);
   CU_TRY(cudaMemcpyAsync(c->level, level, c->n * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(c->prev_level, c->level, c->n * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   c->lev_ver++;
   return EXPB200_OK;

@@ -99,13 +99,20 @@ HD SphStencil sph_stencil(const SphGeom &g, double rs, double &xi_out)
 // Radial-cell key of a particle for the coefficient pass: its potential cell when it
 // contributes (not frozen, rmin <= r <= rmax: src/SphericalBasis.cc:489,
 // src/Component.cc:4194-4202), else the dead cell numr-1.
-HD uint32_t sph_cell_of(const SphGeom &g, const rec4 &pm)
+// mode 0: coefficient accumulation (rmin <= r <= rmax, src/SphericalBasis.cc:489);
+// mode 1: multistep_update (r < rmax only, src/SphericalBasis.cc:1177).
+HD bool sph_in_range(const SphGeom &g, double r, int mode)
+{
+  return mode == 0 ? (r >= g.rmin && r <= g.rmax) : (r < g.rmax);
+}
+
+HD uint32_t sph_cell_of(const SphGeom &g, const rec4 &pm, int mode = 0)
 {
   double x = pm.x - g.cx, y = pm.y - g.cy, z = pm.z - g.cz;
   double r2 = x * x + y * y + z * z;
   if (r2 > g.rtrunc2) return (uint32_t)(g.numr - 1);
   double r = sqrt(r2) + EXPB200_DSMALL;
-  if (!(r >= g.rmin && r <= g.rmax)) return (uint32_t)(g.numr - 1);
+  if (!sph_in_range(g, r, mode)) return (uint32_t)(g.numr - 1);
   double xi;
   SphStencil s = sph_stencil(g, r / g.scale, xi);
   return (uint32_t)s.cell;
@@ -165,13 +172,13 @@ HD void sph_azimuth(double x, double y, double &c1, double &s1, double &R2)
 template <int L, class Store>
 HD bool sph_deposit_particle(const SphGeom &g, const double *K, const double *inv,
                              const double *p0, const rec4 &pm, double adb,
-                             int &cell, double &w1, double &w2, Store &&store)
+                             int &cell, double &w1, double &w2, Store &&store, int mode = 0)
 {
   double x = pm.x - g.cx, y = pm.y - g.cy, z = pm.z - g.cz;
   double r2 = x * x + y * y + z * z;
   if (r2 > g.rtrunc2) return false;
   double r = sqrt(r2) + EXPB200_DSMALL;
-  if (!(r >= g.rmin && r <= g.rmax)) return false;
+  if (!sph_in_range(g, r, mode)) return false;
 
   double costh = z / r;
   double c1, s1, R2;

@@ -62,6 +62,47 @@ sph_key_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restr
   }
 }
 
+// keys for multistep_update: particles whose level changed get (side level, cell with the
+// update's own range test), everything else the sentinel key nlev*numr.
+__global__ void __launch_bounds__(256)
+sph_switch_key_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                      const unsigned *__restrict__ prev, size_t n, int use_prev, int nlev,
+                      uint32_t *__restrict__ keys)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    unsigned a = prev[i], b = level[i];
+    uint32_t key = (uint32_t)nlev * (uint32_t)g.numr;
+    if (a != b) {
+      uint32_t lev = use_prev ? a : b;
+      if (lev >= (uint32_t)nlev) lev = nlev - 1;
+      key = lev * (uint32_t)g.numr + sph_cell_of(g, ld_rec(&posm[i]), 1);
+    }
+    keys[i] = key;
+  }
+}
+
+// dst[k] += sign * src[k]
+__global__ void axpy_kernel(double *__restrict__ dst, const double *__restrict__ src, double sign, size_t n)
+{
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k < n) dst[k] += sign * src[k];
+}
+
+// compute_multistep_coefficients (src/SphericalBasis.cc:1252-1333):
+// out = sum_{M<mfirst} (a_M L[M] + b_M N[M]) + sum_{M>=mfirst} N[M], levels in order.
+struct InterpArgs { int nlev, mfirst; double a[32], b[32]; };
+__global__ void multistep_interp_kernel(const double *__restrict__ cL, const double *__restrict__ cN,
+                                        InterpArgs A, size_t ncoef, double *__restrict__ out)
+{
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k >= ncoef) return;
+  double s = 0.0;
+  for (int M = 0; M < A.mfirst; M++) s += A.a[M] * cL[M * ncoef + k] + A.b[M] * cN[M * ncoef + k];
+  for (int M = A.mfirst; M < A.nlev; M++) s += cN[M * ncoef + k];
+  out[k] = s;
+}
+
 // ---------------------------------------------------------------------------
 // deposit: one warp per chunk of CH sorted particles.
 // phase 1 (lane = particle): Y rows -> shared tile; phase 2 (lane = row): walk the 32
@@ -73,7 +114,7 @@ template <int L>
 __global__ void __launch_bounds__(kDepositWarps * 32)
 sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ posm,
                    const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg,
-                   int keybase, int CH, double adb,
+                   int keybase, int CH, double adb, int mode,
                    double *__restrict__ PA, double *__restrict__ PB)
 {
   using S = DepositShape<L>;
@@ -115,7 +156,7 @@ sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restr
     if (k < end) {
       rec4 pm = ld_rec(&posm[perm[k]]);
       used = sph_deposit_particle<L>(g, c_K, c_inv, p0, pm, adb, cell, w1, w2,
-                                     [&](int row, double v) { my[row] = v; });
+                                     [&](int row, double v) { my[row] = v; }, mode);
     }
     if (!used) {
       cell = -1;
@@ -270,7 +311,7 @@ sph_force_kernel(SphGeom g, const double *__restrict__ p0, const double2 *__rest
 template <int L> struct Launch {
   static int deposit(cudaStream_t st, unsigned nblocks, const SphGeom &g, const double *p0,
                      const rec4 *posm, const uint32_t *perm, const uint32_t *seg, int keybase,
-                     int CH, double adb, double *PA, double *PB)
+                     int CH, double adb, int mode, double *PA, double *PB)
   {
     size_t sm = kDepositWarps * DepositShape<L>::WARP_DOUBLES * sizeof(double);
     static bool attr[64] = {};
@@ -281,7 +322,7 @@ template <int L> struct Launch {
       attr[dev & 63] = true;
     }
     sph_deposit_kernel<L><<<nblocks, kDepositWarps * 32, sm, st>>>(g, p0, posm, perm, seg, keybase,
-                                                                    CH, adb, PA, PB);
+                                                                    CH, adb, mode, PA, PB);
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
@@ -310,9 +351,9 @@ template <int L> struct Launch {
 
 int launch_deposit(int lmax, cudaStream_t st, unsigned nblocks, const SphGeom &g, const double *p0,
                    const rec4 *posm, const uint32_t *perm, const uint32_t *seg, int keybase, int CH,
-                   double adb, double *PA, double *PB)
+                   double adb, int mode, double *PA, double *PB)
 {
-  DISPATCH_L(lmax, deposit(st, nblocks, g, p0, posm, perm, seg, keybase, CH, adb, PA, PB))
+  DISPATCH_L(lmax, deposit(st, nblocks, g, p0, posm, perm, seg, keybase, CH, adb, mode, PA, PB))
 }
 
 int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double *p0, const double2 *H,
@@ -348,6 +389,16 @@ struct expb200_sphere_s {
   bool have_accum = false;
   uint32_t *used_dev = nullptr;
   cudaStream_t last_stream = nullptr;
+  cudaStream_t own_stream = nullptr;   // used when no live component stream is known
+  // the stream this sphere's table operations are ordered on
+  cudaStream_t work_stream()
+  {
+    if (last_stream && expb200::stream_is_live(last_stream)) return last_stream;
+    last_stream = nullptr;
+    return own_stream;
+  }
+  // multistep: expcoefN / expcoefL per level and the level-switch differences
+  double *coefN = nullptr, *coefL = nullptr, *differ = nullptr, *tmp = nullptr;   // [nlev][ncoef]
 };
 
 namespace {
@@ -438,6 +489,7 @@ int build_field(expb200_sphere_s *s, cudaStream_t st)
 
 int accumulate(expb200_sphere_s *s, expb200_component_s *c, int mlevel, double adb)
 {
+  { cudaStream_t ws = s->work_stream(); if (ws != c->stream) CU_TRY(cudaStreamSynchronize(ws)); }
   int rc = ensure_sorted(s, c);
   if (rc) return rc;
   const int CH = deposit_chunk(c->n);
@@ -449,7 +501,7 @@ int accumulate(expb200_sphere_s *s, expb200_component_s *c, int mlevel, double a
     unsigned nchunks = div_up(c->n, CH);
     ProfRegion pr(K_DEPOSIT, c->stream);
     rc = launch_deposit(s->cfg.lmax, c->stream, div_up(nchunks, kDepositWarps), g, s->p0, c->posm,
-                        c->perm[c->cur], c->seg, keybase, CH, adb, s->PA, s->PB);
+                        c->perm[c->cur], c->seg, keybase, CH, adb, 0, s->PA, s->PB);
     if (rc) return rc;
   }
   { ProfRegion pr(K_COMBINE, c->stream);
@@ -536,6 +588,17 @@ int expb200_sphere_create(int device, const expb200_sphere_config *cfg, const do
   CU_TRY(cudaMalloc(&s->H, (size_t)R * g.nslot * sizeof(double2)));
   CU_TRY(cudaMalloc(&s->G, (size_t)g.nrow * R * sizeof(double)));
   CU_TRY(cudaMalloc(&s->used_dev, 2 * sizeof(uint32_t)));
+  CU_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  {
+    size_t bytes = (size_t)s->nlev * s->ncoef * sizeof(double);
+    CU_TRY(cudaMalloc(&s->coefN, bytes));
+    CU_TRY(cudaMalloc(&s->coefL, bytes));
+    CU_TRY(cudaMalloc(&s->differ, bytes));
+    CU_TRY(cudaMalloc(&s->tmp, s->ncoef * sizeof(double)));
+    CU_TRY(cudaMemset(s->coefN, 0, bytes));
+    CU_TRY(cudaMemset(s->coefL, 0, bytes));
+    CU_TRY(cudaMemset(s->differ, 0, bytes));
+  }
   *out = s;
   return EXPB200_OK;
 }
@@ -548,6 +611,8 @@ int expb200_sphere_destroy(expb200_sphere s)
   cudaFree(s->Ep); cudaFree(s->p0); cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->H);
   cudaFree(s->G); cudaFree(s->PA); cudaFree(s->PB); cudaFree(s->row_l); cudaFree(s->row_m);
   cudaFree(s->slot_l); cudaFree(s->slot_rowc); cudaFree(s->slot_rows); cudaFree(s->used_dev);
+  cudaFree(s->coefN); cudaFree(s->coefL); cudaFree(s->differ); cudaFree(s->tmp);
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
   return EXPB200_OK;
 }
@@ -580,7 +645,7 @@ int expb200_sphere_coef_device(expb200_sphere s, double **dptr, void **stream)
 {
   REQUIRE(s && dptr, "NULL argument");
   *dptr = s->coef;
-  if (stream) *stream = s->last_stream;
+  if (stream) *stream = s->work_stream();
   return EXPB200_OK;
 }
 
@@ -588,9 +653,9 @@ int expb200_sphere_set_coefficients(expb200_sphere s, const double *coef_host)
 {
   REQUIRE(s, "sphere is NULL");
   DeviceGuard g(s->device);
-  cudaStream_t st = s->last_stream;
+  cudaStream_t st = s->work_stream();
   if (coef_host) {
-    if (st) CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaMemcpy(s->coef_use, coef_host, s->ncoef * sizeof(double), cudaMemcpyHostToDevice));
   } else {
     REQUIRE(s->have_accum, "no coefficients accumulated on the device yet");
@@ -609,7 +674,7 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   if (c->n == 0) return EXPB200_OK;
   int rc = ensure_sorted(s, c);
   if (rc) return rc;
-  if (s->last_stream && s->last_stream != c->stream) CU_TRY(cudaStreamSynchronize(s->last_stream));
+  { cudaStream_t ws = s->work_stream(); if (ws != c->stream) CU_TRY(cudaStreamSynchronize(ws)); }
   if (!s->field_valid) {
     rc = build_field(s, c->stream);
     if (rc) return rc;
@@ -620,6 +685,147 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   ProfRegion pr(K_FORCE, c->stream);
   return launch_force(s->cfg.lmax, c->stream, gm, s->p0, s->H, c->posm, c->accp, c->perm[c->cur],
                       c->seg, keybase, c->n);
+}
+
+// ---- multistep coefficient tables -------------------------------------------------
+// ~ the bookkeeping of determine_coefficients_particles (src/SphericalBasis.cc:785-788,
+// 864-903): swap expcoefL[mlevel] <-> expcoefN[mlevel], then expcoefN[mlevel] = the
+// (all-reduced) vector just accumulated.
+int expb200_sphere_multistep_commit(expb200_sphere s, int mlevel)
+{
+  REQUIRE(s, "sphere is NULL");
+  REQUIRE(mlevel >= 0 && mlevel < s->nlev, "mlevel=%d outside [0,%d]", mlevel, s->nlev - 1);
+  REQUIRE(s->have_accum, "no coefficients accumulated yet");
+  DeviceGuard g(s->device);
+  cudaStream_t st = s->work_stream();
+  double *N = s->coefN + (size_t)mlevel * s->ncoef, *L = s->coefL + (size_t)mlevel * s->ncoef;
+  CU_TRY(cudaMemcpyAsync(L, N, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CU_TRY(cudaMemcpyAsync(N, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return EXPB200_OK;
+}
+
+// ~ SphericalBasis::compute_multistep_coefficients (src/SphericalBasis.cc:1231-1333) with
+// the interpolation tables of initialize_multistep (src/multistep.cc:656-671); installs
+// the result as the coefficients used by the next force evaluation.
+int expb200_sphere_compute_multistep_coefficients(expb200_sphere s, int mdrft)
+{
+  REQUIRE(s, "sphere is NULL");
+  const int multistep = s->nlev - 1, Mstep = 1 << multistep;
+  REQUIRE(mdrft >= 0 && mdrft <= Mstep, "mdrft=%d outside [0,%d]", mdrft, Mstep);
+  DeviceGuard g(s->device);
+  InterpArgs A;
+  A.nlev = s->nlev;
+  // mfirst[mdrft]: lowest active level (src/multistep.cc:646-654)
+  A.mfirst = 0;
+  for (int lev = 0; lev <= multistep; lev++)
+    if (mdrft == 0 || mdrft % (1 << (multistep - lev)) == 0) { A.mfirst = lev; break; }
+  for (int M = 0; M < A.mfirst; M++) {
+    int d = 1 << (multistep - M);                 // dstep for level M
+    int dL = (mdrft / d) * d, dN = dL + d;        // dstepL[M][mdrft], dstepN[M][mdrft]
+    double b = (double)(mdrft - dL) / (double)(dN - dL);
+    A.a[M] = 1.0 - b;
+    A.b[M] = b;
+  }
+  cudaStream_t st = s->work_stream();
+  multistep_interp_kernel<<<div_up(s->ncoef, 256), 256, 0, st>>>(s->coefL, s->coefN, A, s->ncoef, s->coef_use);
+  CU_LAUNCH_CHECK();
+  s->field_valid = false;
+  return EXPB200_OK;
+}
+
+// Host access to the per-level tables (which = 0: expcoefN, 1: expcoefL, 2: differ).
+int expb200_sphere_get_level_coefficients(expb200_sphere s, int which, int mlevel, double *host)
+{
+  REQUIRE(s && host && which >= 0 && which <= 2 && mlevel >= 0 && mlevel < s->nlev, "bad argument");
+  DeviceGuard g(s->device);
+  CU_TRY(cudaStreamSynchronize(s->work_stream()));
+  const double *src = (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * s->ncoef;
+  CU_TRY(cudaMemcpy(host, src, s->ncoef * sizeof(double), cudaMemcpyDeviceToHost));
+  return EXPB200_OK;
+}
+
+int expb200_sphere_set_level_coefficients(expb200_sphere s, int which, int mlevel, const double *host)
+{
+  REQUIRE(s && host && which >= 0 && which <= 1 && mlevel >= 0 && mlevel < s->nlev, "bad argument");
+  DeviceGuard g(s->device);
+  CU_TRY(cudaStreamSynchronize(s->work_stream()));
+  double *dst = (which == 0 ? s->coefN : s->coefL) + (size_t)mlevel * s->ncoef;
+  CU_TRY(cudaMemcpy(dst, host, s->ncoef * sizeof(double), cudaMemcpyHostToDevice));
+  return EXPB200_OK;
+}
+
+// ~ multistep_update_begin / multistep_update (per switching particle) /
+// multistep_update_finish (src/SphericalBasis.cc:1013-1228): for every particle whose
+// level changed in the last expb200_adjust_multistep_level, subtract its basis
+// contribution from differ[old level] and add it to differ[new level]; with
+// finish != 0 also expcoefN[M] += differ[M] (single rank; with several ranks all-reduce
+// differ first, then call expb200_sphere_multistep_update_finish).
+int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, double adb, int finish)
+{
+  REQUIRE(s && c, "NULL argument");
+  REQUIRE(s->device == c->device, "device mismatch");
+  DeviceGuard g(s->device);
+  cudaStream_t st = c->stream;
+  { cudaStream_t ws = s->work_stream(); if (ws != st) CU_TRY(cudaStreamSynchronize(ws)); }
+  s->last_stream = st;
+  const size_t all = (size_t)s->nlev * s->ncoef;
+  CU_TRY(cudaMemsetAsync(s->differ, 0, all * sizeof(double), st));
+  if (c->n && s->nlev > 1) {
+    SphGeom gm = geom_for(s, c);
+    const uint32_t nkeys = (uint32_t)s->nlev * (uint32_t)s->cfg.numr + 1;
+    if (c->seg_cap < (size_t)nkeys + 2) {
+      if (c->seg) cudaFree(c->seg);
+      c->seg = nullptr;
+      CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
+      c->seg_cap = (size_t)nkeys + 2;
+    }
+    const int CH = deposit_chunk(c->n);
+    int rc = ensure_partials(s, c->n, CH);
+    if (rc) return rc;
+    for (int side = 0; side < 2; side++) {          // 0: "to" (+), 1: "from" (-)
+      sph_switch_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(gm, c->posm, c->level, c->prev_level,
+                                                                 c->n, side, s->nlev, c->keys[0]);
+      CU_LAUNCH_CHECK();
+      int cur = 0;
+      if ((rc = radix_sort_pairs(st, c->keys, c->perm, c->hist, c->n, nkeys, &cur))) return rc;
+      c->cur = cur;
+      if ((rc = segment_offsets(st, c->keys[cur], c->n, c->seg, nkeys))) return rc;
+      for (int M = 0; M < s->nlev; M++) {
+        const int keybase = M * s->cfg.numr;
+        unsigned nchunks = div_up(c->n, CH);
+        rc = launch_deposit(s->cfg.lmax, st, div_up(nchunks, kDepositWarps), gm, s->p0, c->posm,
+                            c->perm[cur], c->seg, keybase, CH, adb, 1, s->PA, s->PB);
+        if (rc) return rc;
+        sph_combine_kernel<<<gm.numr, 64, 0, st>>>(gm, c->seg, keybase, CH, s->PA, s->PB, s->G);
+        sph_contract_kernel<<<gm.nrow, 256, 0, st>>>(gm, s->Ep, s->G, s->row_l, s->row_m, 0, s->tmp);
+        axpy_kernel<<<div_up(s->ncoef, 256), 256, 0, st>>>(s->differ + (size_t)M * s->ncoef, s->tmp,
+                                                          side == 0 ? 1.0 : -1.0, s->ncoef);
+        CU_LAUNCH_CHECK();
+      }
+    }
+    c->sort_kind = 0;          // the component's regular sort was overwritten
+  }
+  if (finish) return expb200_sphere_multistep_update_finish(s);
+  return EXPB200_OK;
+}
+
+int expb200_sphere_differ_device(expb200_sphere s, double **dptr, size_t *count, void **stream)
+{
+  REQUIRE(s && dptr, "NULL argument");
+  *dptr = s->differ;
+  if (count) *count = (size_t)s->nlev * s->ncoef;
+  if (stream) *stream = s->work_stream();
+  return EXPB200_OK;
+}
+
+int expb200_sphere_multistep_update_finish(expb200_sphere s)
+{
+  REQUIRE(s, "sphere is NULL");
+  DeviceGuard g(s->device);
+  const size_t all = (size_t)s->nlev * s->ncoef;
+  axpy_kernel<<<div_up(all, 256), 256, 0, s->work_stream()>>>(s->coefN, s->differ, 1.0, all);
+  CU_LAUNCH_CHECK();
+  return EXPB200_OK;
 }
 
 int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb, void *nccl_comm)

@@ -87,3 +87,34 @@ class Sphere:
         st = C.c_void_p()
         check(_lib.lib().expb200_sphere_coef_device(self._h, C.byref(p), C.byref(st)))
         return p, st
+
+    # ---- multistep tables (device resident) ---------------------------------
+    def multistep_commit(self, mlevel=None):
+        check(_lib.lib().expb200_sphere_multistep_commit(self._h, self.mlevel if mlevel is None else mlevel))
+
+    def compute_multistep_coefficients(self, mdrft: int):
+        check(_lib.lib().expb200_sphere_compute_multistep_coefficients(self._h, int(mdrft)))
+
+    def multistep_update(self, c: Component, adb: float = 1.0, finish: bool = True):
+        check(_lib.lib().expb200_sphere_multistep_update(self._h, c._h, float(adb), int(finish)))
+
+    def multistep_update_finish(self):
+        check(_lib.lib().expb200_sphere_multistep_update_finish(self._h))
+
+    def differ_device(self):
+        p = c_dp()
+        n = C.c_size_t(0)
+        st = C.c_void_p()
+        check(_lib.lib().expb200_sphere_differ_device(self._h, C.byref(p), C.byref(n), C.byref(st)))
+        return p, n.value, st
+
+    def level_coefficients(self, which: str, mlevel: int):
+        out = np.empty((self.nrow, self.nmax))
+        w = {"N": 0, "L": 1, "differ": 2}[which]
+        check(_lib.lib().expb200_sphere_get_level_coefficients(self._h, w, mlevel, out.ctypes.data_as(c_dp)))
+        return out
+
+    def set_level_coefficients(self, which: str, mlevel: int, coef):
+        a = np.ascontiguousarray(coef, dtype=np.float64)
+        w = {"N": 0, "L": 1}[which]
+        check(_lib.lib().expb200_sphere_set_level_coefficients(self._h, w, mlevel, a.ctypes.data_as(c_dp)))

@@ -180,6 +180,24 @@ int expb200_sphere_set_coefficients(expb200_sphere s, const double *coef_host);
  * level >= mlevel.  c may be a different component (use_external). */
 int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c, int mlevel);
 
+/* Multistep coefficient tables (expcoefN / expcoefL per level) kept on the device.
+ *  commit : swap L<->N for mlevel and store the vector just accumulated as expcoefN[mlevel]
+ *           (src/SphericalBasis.cc:785-788, 864-903)
+ *  compute_multistep_coefficients(mdrft): interpolate inactive levels, sum active ones and
+ *           install the result for the next force evaluation (src/SphericalBasis.cc:1231-1333)
+ *  multistep_update: move the contribution of every particle whose level changed in the last
+ *           expb200_adjust_multistep_level from its old to its new level table
+ *           (src/SphericalBasis.cc:1013-1228); finish=0 leaves the differences in the device
+ *           buffer (expb200_sphere_differ_device) for an all-reduce before _finish. */
+int expb200_sphere_multistep_commit(expb200_sphere s, int mlevel);
+int expb200_sphere_compute_multistep_coefficients(expb200_sphere s, int mdrft);
+int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, double adb, int finish);
+int expb200_sphere_multistep_update_finish(expb200_sphere s);
+int expb200_sphere_differ_device(expb200_sphere s, double **dptr, size_t *count, void **stream);
+/* which = 0: expcoefN, 1: expcoefL, 2: differ */
+int expb200_sphere_get_level_coefficients(expb200_sphere s, int which, int mlevel, double *host);
+int expb200_sphere_set_level_coefficients(expb200_sphere s, int which, int mlevel, const double *host);
+
 /* One fused single-level KDK step for a self-gravitating component, the
  * sequence of do_step (src/step.cc:272-322) with results identical to the
  * separate calls: kick(dt/2) drift(dt) coefficients force kick(dt/2).
