@@ -35,6 +35,15 @@ class SphereConfig(C.Structure):
                 ("M0_only", C.c_int), ("multistep", C.c_int)]
 
 
+class CylinderConfig(C.Structure):
+    _fields_ = [("mmax", C.c_int), ("norder", C.c_int), ("numx", C.c_int), ("numy", C.c_int),
+                ("cmapr", C.c_int), ("cmapz", C.c_int), ("ascale", C.c_double),
+                ("hscale", C.c_double), ("rmin", C.c_double), ("rmax", C.c_double),
+                ("rcylmax", C.c_double), ("acyl", C.c_double), ("EVEN_M", C.c_int),
+                ("MMIN", C.c_int), ("MLIM", C.c_int), ("NMIN", C.c_int), ("NLIM", C.c_int),
+                ("multistep", C.c_int)]
+
+
 class LevelParams(C.Structure):
     _fields_ = [("dtime", C.c_double), ("dynfracS", C.c_double), ("dynfracD", C.c_double),
                 ("dynfracV", C.c_double), ("dynfracA", C.c_double), ("dynfracP", C.c_double),
@@ -116,6 +125,18 @@ SIGNATURES = {
     "expb200_sphere_get_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_sphere_set_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_sphere_step": (C.c_int, [_H, _H, C.c_double, C.c_double, C.c_void_p]),
+    "expb200_cylinder_create": (C.c_int, [C.c_int, C.POINTER(CylinderConfig), c_dp, c_dp, c_dp, c_dp,
+                                          c_dp, c_dp, C.POINTER(_H)]),
+    "expb200_cylinder_destroy": (C.c_int, [_H]),
+    "expb200_cylinder_set_orientation": (C.c_int, [_H, c_dp, c_dp]),
+    "expb200_cylinder_determine_coefficients": (C.c_int, [_H, _H, C.c_int, C.c_double, c_dp, c_dp,
+                                                          c_u64p, c_dp]),
+    "expb200_cylinder_coef_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_size_t),
+                                               C.POINTER(C.c_void_p)]),
+    "expb200_cylinder_set_coefficients": (C.c_int, [_H, c_dp, c_dp, C.c_double]),
+    "expb200_cylinder_determine_acceleration": (C.c_int, [_H, _H, C.c_int]),
+    "expb200_cylinder_multistep_commit": (C.c_int, [_H, C.c_int]),
+    "expb200_cylinder_compute_multistep_coefficients": (C.c_int, [_H, C.c_int, C.c_double]),
     "expb200_profile_enable": (C.c_int, [C.c_int]),
     "expb200_profile_reset": (C.c_int, []),
     "expb200_profile_kernels": (C.c_int, []),

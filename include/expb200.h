@@ -40,6 +40,7 @@ extern "C" {
 
 typedef struct expb200_component_s *expb200_component;
 typedef struct expb200_sphere_s    *expb200_sphere;
+typedef struct expb200_cylinder_s  *expb200_cylinder;
 
 const char *expb200_last_error(void);
 /* Library/ABI version, number of visible devices, name + SM count of a device. */
@@ -205,6 +206,49 @@ int expb200_sphere_set_level_coefficients(expb200_sphere s, int which, int mleve
  * across ranks (the reference's MPI_Allreduce, src/SphericalBasis.cc:864-903). */
 int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb,
                         void *nccl_comm);
+
+/* ------------------------------------------------------------------------
+ * Cylinder (force id "cylinder"): Cylinder + EmpCylSL tables.
+ * Tables are the six EmpCylSL grids potC/potS/rforceC/rforceS/zforceC/zforceS
+ * (exputil/EmpCylSL.cc:2123-2187), each laid out [(mmax+1)][norder][(numx+1)][(numy+1)]
+ * (ix major, iy minor; the m=0 slabs of the S grids are unused).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int mmax, norder, numx, numy, cmapr, cmapz;  /* MMAX, NORDER, NUMX, NUMY, CMAPR, CMAPZ           */
+  double ascale, hscale;                        /* ASCALE, HSCALE                                   */
+  double rmin, rmax;                            /* EmpCylSL::RMIN, RMAX (units of ascale)           */
+  double rcylmax, acyl;                         /* Cylinder gate Rmax2 = (rcylmax*acyl)^2           */
+  int EVEN_M, MMIN, MLIM, NMIN, NLIM;           /* include/EmpCylSL.H:59-60                         */
+  int multistep;
+} expb200_cylinder_config;
+
+/* ~ EmpCylSL::initialize_cuda (src/cudaEmpCylSL.cu:56-150) + Cylinder::initialize_cuda */
+int expb200_cylinder_create(int device, const expb200_cylinder_config *cfg,
+                            const double *potC, const double *potS, const double *rforceC,
+                            const double *rforceS, const double *zforceC, const double *zforceS,
+                            expb200_cylinder *out);
+int expb200_cylinder_destroy(expb200_cylinder s);
+/* orient->transformBody() / transformOrig() (row-major 3x3); NULL, NULL = none
+ * (src/Cylinder.cc:846-847, 1352-1353, 1418-1419) */
+int expb200_cylinder_set_orientation(expb200_cylinder s, const double *body, const double *orig);
+/* ~ Cylinder::determine_coefficients_cuda + DtoH_coefs (src/Cylinder.cc:1057-1069,
+ * src/cudaCylinder.cu:1871-1924): accumulates levlist[mlevel]; cos/sin [(mmax+1)][norder]
+ * as EmpCylSL::set_coef takes them; used = use[] count, mass = cylmass0 sum. */
+int expb200_cylinder_determine_coefficients(expb200_cylinder s, expb200_component c, int mlevel,
+                                            double adb, double *cos_host, double *sin_host,
+                                            uint64_t *used, double *mass);
+/* device vector [cos | sin | mass] of the last accumulation (count doubles), for one
+ * in-place all-reduce (replaces exputil/EmpCylSL.cc:4192-4214 + src/Cylinder.cc:1093-1095) */
+int expb200_cylinder_coef_device(expb200_cylinder s, double **dptr, size_t *count, void **stream);
+/* ~ Cylinder::HtoD_coefs: install accum_cos/accum_sin and cylmass for the force; NULL,NULL =
+ * use the device vector (cylmass < 0 keeps the accumulated mass). */
+int expb200_cylinder_set_coefficients(expb200_cylinder s, const double *cos_host,
+                                      const double *sin_host, double cylmass);
+/* ~ Cylinder::determine_acceleration_cuda (src/Cylinder.cc:1481-1497) */
+int expb200_cylinder_determine_acceleration(expb200_cylinder s, expb200_component c, int mlevel);
+/* multistep tables cosL/cosN (exputil/EmpCylSL.cc:2004-2014, src/CylEXP.cc:192-282) */
+int expb200_cylinder_multistep_commit(expb200_cylinder s, int mlevel);
+int expb200_cylinder_compute_multistep_coefficients(expb200_cylinder s, int mdrft, double cylmass);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU: one process (MPI rank) per GPU; NCCL is loaded with dlopen.

@@ -143,6 +143,50 @@ long orc_adjust_levels(orc_particles *S, const int *list, long nlist,
 void orc_multistep_tables(int multistep, int *mintvl, int *mfirst,
                           int *dstepL, int *dstepN);
 
+/* ---- a14-a19: cylinder (EmpCylSL tables + Cylinder force)
+ * Tables are six arrays [(MMAX+1)][NORDER][(NUMX+1)][(NUMY+1)] (ix major, iy minor); the
+ * m=0 slabs of the S arrays are unused.  exputil/EmpCylSL.cc:2123-2187 (setup_table). */
+typedef struct {
+  int MMAX, NORDER, NUMX, NUMY, CMAPR, CMAPZ;
+  double ASCALE, HSCALE, RMIN, RMAX;       /* EmpCylSL statics; Rtable = RMAX/sqrt(2)        */
+  int EVEN_M, MMIN, MLIM, NMIN, NLIM;      /* include/EmpCylSL.H:59-60 (MLIM/NLIM may be huge) */
+  const double *potC, *potS, *rforceC, *rforceS, *zforceC, *zforceS;
+  /* derived by orc_cyl_init */
+  double Rtable, XMIN, XMAX, dX, YMIN, YMAX, dY;
+} orc_cylgrid;
+
+typedef struct {
+  double rcylmax, acyl;        /* src/Cylinder.cc:752: Rmax2 = (rcylmax*acyl)^2              */
+  const double *body;          /* orient->transformBody() 3x3 row-major, or NULL            */
+  const double *orig;          /* orient->transformOrig() 3x3 row-major, or NULL            */
+} orc_cyl_params;
+
+void orc_cyl_init(orc_cylgrid *g);
+double orc_cyl_r_to_xi(const orc_cylgrid *g, double r);    /* exputil/EmpCylSL.cc:6446-6463 */
+double orc_cyl_z_to_y(const orc_cylgrid *g, double z);     /* exputil/EmpCylSL.cc:7109-7117 */
+/* EmpCylSL::get_pot (exputil/EmpCylSL.cc:5557-5632): Vc, Vs [(MMAX+1)][NORDER] */
+void orc_cyl_get_pot(const orc_cylgrid *g, double r, double z, double *Vc, double *Vs);
+/* Cylinder::determine_coefficients_thread (src/Cylinder.cc:823-890) + EmpCylSL::accumulate
+ * (exputil/EmpCylSL.cc:4049-4146) + thread sum of make_coefficients (:4151-4346).
+ * cosN, sinN: [(MMAX+1)][NORDER], overwritten; *cylmass = sum of used masses. */
+long orc_cyl_coefficients(const orc_cylgrid *g, const orc_cyl_params *P, const orc_particles *S,
+                          const int *list, long nlist, double adb, int nthreads,
+                          double *cosN, double *sinN, double *cylmass);
+/* covariance variant (covar): VC[sampT][(MMAX+1)][NORDER][2], MV[sampT][(MMAX+1)][NORDER][NORDER][2],
+ * massT[sampT], numbT[sampT]; accumulated into (caller zeroes). */
+long orc_cyl_coefficients_cov(const orc_cylgrid *g, const orc_cyl_params *P, const orc_particles *S,
+                              const int *list, long nlist, double adb, int sampT,
+                              double *cosN, double *sinN, double *cylmass,
+                              double *massT, unsigned *numbT, double *VC, double *MV);
+/* EmpCylSL::accumulated_eval (exputil/EmpCylSL.cc:5256-5410) */
+void orc_cyl_accumulated_eval(const orc_cylgrid *g, const double *accum_cos, const double *accum_sin,
+                              double r, double z, double phi,
+                              double *p0, double *p, double *fr, double *fz, double *fp);
+/* Cylinder::determine_acceleration_and_potential_thread (src/Cylinder.cc:1266-1446) */
+void orc_cyl_accel(const orc_cylgrid *g, const orc_cyl_params *P, const orc_particles *S,
+                   const int *list, long nlist, const double *accum_cos, const double *accum_sin,
+                   double cylmass, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,21 @@ class LevelParams(C.Structure):
                 ("dim", C.c_int)]
 
 
+class CylGrid(C.Structure):
+    _fields_ = [("MMAX", C.c_int), ("NORDER", C.c_int), ("NUMX", C.c_int), ("NUMY", C.c_int),
+                ("CMAPR", C.c_int), ("CMAPZ", C.c_int), ("ASCALE", C.c_double), ("HSCALE", C.c_double),
+                ("RMIN", C.c_double), ("RMAX", C.c_double), ("EVEN_M", C.c_int), ("MMIN", C.c_int),
+                ("MLIM", C.c_int), ("NMIN", C.c_int), ("NLIM", C.c_int),
+                ("potC", c_dp), ("potS", c_dp), ("rforceC", c_dp), ("rforceS", c_dp),
+                ("zforceC", c_dp), ("zforceS", c_dp),
+                ("Rtable", C.c_double), ("XMIN", C.c_double), ("XMAX", C.c_double), ("dX", C.c_double),
+                ("YMIN", C.c_double), ("YMAX", C.c_double), ("dY", C.c_double)]
+
+
+class CylParams(C.Structure):
+    _fields_ = [("rcylmax", C.c_double), ("acyl", C.c_double), ("body", c_dp), ("orig", c_dp)]
+
+
 def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
@@ -97,6 +112,17 @@ def lib() -> C.CDLL:
         L.orc_adjust_levels.argtypes = [C.POINTER(Particles), c_ip, C.c_long,
                                         C.POINTER(LevelParams), c_ip, c_lp, c_lp]
         L.orc_multistep_tables.argtypes = [C.c_int, c_ip, c_ip, c_ip, c_ip]
+        L.orc_cyl_init.argtypes = [C.POINTER(CylGrid)]
+        L.orc_cyl_get_pot.argtypes = [C.POINTER(CylGrid), C.c_double, C.c_double, c_dp, c_dp]
+        L.orc_cyl_coefficients.restype = C.c_long
+        L.orc_cyl_coefficients.argtypes = [C.POINTER(CylGrid), C.POINTER(CylParams), C.POINTER(Particles),
+                                           c_ip, C.c_long, C.c_double, C.c_int, c_dp, c_dp, c_dp]
+        L.orc_cyl_coefficients_cov.restype = C.c_long
+        L.orc_cyl_coefficients_cov.argtypes = [C.POINTER(CylGrid), C.POINTER(CylParams), C.POINTER(Particles),
+                                               c_ip, C.c_long, C.c_double, C.c_int, c_dp, c_dp, c_dp,
+                                               c_dp, c_up, c_dp, c_dp]
+        L.orc_cyl_accel.argtypes = [C.POINTER(CylGrid), C.POINTER(CylParams), C.POINTER(Particles),
+                                    c_ip, C.c_long, c_dp, c_dp, C.c_double, C.c_int]
         _LIB = L
     return _LIB
 
@@ -285,3 +311,55 @@ def adjust_levels(S: ParticleSet, P: LevelParams, lst=None):
                                   S.n if l is None else len(l), C.byref(P),
                                   which.ctypes.data_as(c_ip), C.byref(offlo), C.byref(offhi))
     return nsw, which, offlo.value, offhi.value
+
+
+# ---- cylinder --------------------------------------------------------------------
+class CylGridPy:
+    def __init__(self, tab, EVEN_M=False, MMIN=0, MLIM=2 ** 30, NMIN=0, NLIM=2 ** 30):
+        self.arr = [_f64(getattr(tab, k)) for k in ("potC", "potS", "rforceC", "rforceS", "zforceC", "zforceS")]
+        self.c = CylGrid(tab.mmax, tab.norder, tab.numx, tab.numy, tab.cmapr, tab.cmapz, tab.ascale,
+                         tab.hscale, tab.rmin, tab.rmax, int(EVEN_M), MMIN, MLIM, NMIN, NLIM,
+                         *[_dp(a) for a in self.arr], 0, 0, 0, 0, 0, 0, 0)
+        lib().orc_cyl_init(C.byref(self.c))
+        self.mmax, self.norder = tab.mmax, tab.norder
+
+
+def cyl_params(rcylmax=20.0, acyl=0.01, body=None, orig=None):
+    keep = [None if body is None else _f64(body), None if orig is None else _f64(orig)]
+    p = CylParams(rcylmax, acyl, _dp(keep[0]), _dp(keep[1]))
+    p._keep = keep
+    return p
+
+
+def cyl_coefficients(g: CylGridPy, P, S: ParticleSet, lst=None, adb=1.0, nthreads=1):
+    lst = _list(S, lst)
+    shape = (g.mmax + 1, g.norder)
+    cs, sn = np.zeros(shape), np.zeros(shape)
+    mass = np.zeros(1)
+    sc = S.c()
+    used = lib().orc_cyl_coefficients(C.byref(g.c), C.byref(P), C.byref(sc), lst.ctypes.data_as(c_ip),
+                                      len(lst), adb, nthreads, _dp(cs), _dp(sn), _dp(mass))
+    return cs, sn, used, mass[0]
+
+
+def cyl_coefficients_cov(g: CylGridPy, P, S: ParticleSet, sampT, lst=None, adb=1.0):
+    lst = _list(S, lst)
+    M1, N = g.mmax + 1, g.norder
+    cs, sn = np.zeros((M1, N)), np.zeros((M1, N))
+    mass = np.zeros(1)
+    massT, numbT = np.zeros(sampT), np.zeros(sampT, dtype=np.uint32)
+    VC, MV = np.zeros((sampT, M1, N, 2)), np.zeros((sampT, M1, N, N, 2))
+    sc = S.c()
+    used = lib().orc_cyl_coefficients_cov(C.byref(g.c), C.byref(P), C.byref(sc), lst.ctypes.data_as(c_ip),
+                                          len(lst), adb, sampT, _dp(cs), _dp(sn), _dp(mass), _dp(massT),
+                                          numbT.ctypes.data_as(c_up), _dp(VC), _dp(MV))
+    return dict(cos=cs, sin=sn, used=used, mass=mass[0], massT=massT, numbT=numbT,
+                VC=VC[..., 0] + 1j * VC[..., 1], MV=MV[..., 0] + 1j * MV[..., 1])
+
+
+def cyl_accel(g: CylGridPy, P, S: ParticleSet, cos, sin, cylmass, lst=None, nthreads=1):
+    lst = _list(S, lst)
+    cos, sin = _f64(cos), _f64(sin)
+    sc = S.c()
+    lib().orc_cyl_accel(C.byref(g.c), C.byref(P), C.byref(sc), lst.ctypes.data_as(c_ip), len(lst),
+                        _dp(cos), _dp(sin), float(cylmass), nthreads)
