@@ -2,8 +2,7 @@
 ``adjust_multistep_level`` ordering (src/step.cc:67-323, src/begin.cc:86-127,
 src/multistep.cc:344-560) for one self-gravitating sphereSL component whose particles,
 coefficient tables and level bookkeeping all stay on the GPU.  The reference's engine keeps
-this logic as it is; this module exists so that the path can be driven (and tested against
-the oracle) without EXP itself."""
+this logic as it is; this module exists so that the path can be driven (and tested) without EXP itself."""
 from __future__ import annotations
 
 import ctypes as C
