@@ -62,20 +62,42 @@ def sources():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into exp_b200/lib/libexpb200.so."""
+    """Compile every CUDA source for sm_100a into exp_b200/lib/libexpb200.so: one object
+    per .cu (in parallel, only when stale), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = sources()
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(_HERE, "..", "include", "expb200.h"))
-    if (not force and os.path.exists(LIB_PATH)
-            and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps)):
-        return LIB_PATH
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs + ["-ldl"]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise Expb200Error("nvcc failed:\n" + r.stdout + r.stderr)
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(_HERE, "..", "include", "expb200.h"))
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
+    objdir = os.path.join(_HERE, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_time)):
+            return obj, None
+        cmd = ["nvcc"] + flags + ["-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, (r.stdout + r.stderr if r.returncode != 0 else None)
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(compile_one, srcs))
+    errs = [e for _, e in results if e]
+    if errs:
+        raise Expb200Error("nvcc failed:\n" + "\n".join(errs))
+    objs = [o for o, _ in results]
+    if (force or not os.path.exists(LIB_PATH)
+            or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs)):
+        cmd = ["nvcc", "-shared", "-o", LIB_PATH] + objs + ["-ldl"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise Expb200Error("link failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 

@@ -92,6 +92,14 @@ __device__ __forceinline__ void st_rec(rec4 *p, const rec4 &v)
 
 } // namespace expb200
 
+struct expb200_component_s;
+namespace expb200 {
+// Physically re-orders the particle store into the order of the component's current sort
+// (perm[cur]); afterwards the permutation is the identity and psort == posm.
+int component_reorder(expb200_component_s *c);
+constexpr int kReorderEvery = 64;      // sorts between physical re-orderings
+}
+
 // ---- the device-resident particle store ------------------------------------
 struct expb200_component_s {
   int device = 0;
@@ -103,6 +111,18 @@ struct expb200_component_s {
   expb200::rec4 *posm = nullptr;        // {x,y,z,mass}
   expb200::rec4 *vel = nullptr;         // {vx,vy,vz,potext}
   expb200::rec4 *accp = nullptr;        // {ax,ay,az,pot}
+  expb200::rec4 *posm_sorted = nullptr; // posm in the order of the current sort (scratch copy)
+  expb200::rec4 *spare = nullptr;       // scratch for re-ordering vel/accp
+  // Storage order.  Particles are stored in "epoch order": the radial-cell order of the
+  // last physical re-ordering (component_reorder), so that the per-step binning and every
+  // access through the sort permutation is nearly sequential.  Host slot i lives at
+  // storage index where[i]; slot_of is the inverse.  identity_order: storage == host order.
+  uint32_t *slot_of = nullptr, *where = nullptr;
+  bool identity_order = true;
+  bool never_reordered = true;
+  int sorts_since_reorder = 0;
+  const expb200::rec4 *psort = nullptr; // positions in sorted order: posm_sorted, or posm itself
+                                        // right after a re-ordering
   unsigned *level = nullptr;
   unsigned *prev_level = nullptr;      // level before the last adjust_multistep_level
   float *dtreq = nullptr;
@@ -119,6 +139,7 @@ struct expb200_component_s {
   uint32_t *keys[2] = {nullptr, nullptr};
   uint32_t *perm[2] = {nullptr, nullptr};
   uint32_t *hist = nullptr;             // radix histograms
+  uint32_t *rank = nullptr;             // sorted position of every item (sort scratch)
   size_t hist_cap = 0;
   uint32_t *seg = nullptr;              // seg[k] = first sorted position with key >= k
   size_t seg_cap = 0;

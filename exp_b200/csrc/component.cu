@@ -64,11 +64,11 @@ constexpr int kStageDoubles = 10;          // pos3 vel3 acc3 pot1 (download) / p
 __global__ void pack_kernel(rec4 *__restrict__ posm, rec4 *__restrict__ vel, rec4 *__restrict__ accp,
                             const double *__restrict__ pos, const double *__restrict__ v,
                             const double *__restrict__ mass, const double *__restrict__ potext,
-                            size_t first, size_t count, int reset_acc)
+                            size_t first, size_t count, int reset_acc, const uint32_t *__restrict__ where)
 {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
        i += (size_t)gridDim.x * blockDim.x) {
-    size_t s = first + i;
+    size_t s = where ? where[first + i] : first + i;
     st_rec(&posm[s], rec4{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]});
     double pe = potext ? potext[i] : 0.0;
     if (v) st_rec(&vel[s], rec4{v[3 * i], v[3 * i + 1], v[3 * i + 2], pe});
@@ -80,11 +80,12 @@ __global__ void pack_kernel(rec4 *__restrict__ posm, rec4 *__restrict__ vel, rec
 __global__ void unpack_kernel(const rec4 *__restrict__ posm, const rec4 *__restrict__ vel,
                               const rec4 *__restrict__ accp, double *__restrict__ pos,
                               double *__restrict__ v, double *__restrict__ acc,
-                              double *__restrict__ pot, size_t first, size_t count)
+                              double *__restrict__ pot, size_t first, size_t count,
+                              const uint32_t *__restrict__ where)
 {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
        i += (size_t)gridDim.x * blockDim.x) {
-    size_t s = first + i;
+    size_t s = where ? where[first + i] : first + i;
     if (pos) { rec4 p = ld_rec_rw(&posm[s]); pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z; }
     if (v)   { rec4 q = ld_rec_rw(&vel[s]);  v[3 * i] = q.x;   v[3 * i + 1] = q.y;   v[3 * i + 2] = q.z; }
     if (acc || pot) {
@@ -93,6 +94,45 @@ __global__ void unpack_kernel(const rec4 *__restrict__ posm, const rec4 *__restr
       if (pot) pot[i] = a.w;
     }
   }
+}
+
+// ---- storage re-ordering helpers ---------------------------------------------------
+__global__ void gather_rec_kernel(rec4 *__restrict__ dst, const rec4 *__restrict__ src,
+                                  const uint32_t *__restrict__ perm, size_t n)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    st_rec(&dst[k], ld_rec(&src[perm[k]]));
+}
+__global__ void scatter_rec_kernel(rec4 *__restrict__ dst, const rec4 *__restrict__ src,
+                                   const uint32_t *__restrict__ where, size_t n)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st_rec(&dst[where[i]], ld_rec(&src[i]));
+}
+// dst[k] = src[idx ? idx[k] : k]
+__global__ void gather_u32_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src,
+                                  const uint32_t *__restrict__ idx, size_t n)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    dst[k] = src[idx ? idx[k] : k];
+}
+// dst[idx[i]] = src[i]
+__global__ void scatter_u32_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src,
+                                   const uint32_t *__restrict__ idx, size_t n)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[idx[i]] = src[i];
+}
+// where[slot_of[k]] = k; slot_of == NULL means the identity
+__global__ void invert_kernel(uint32_t *__restrict__ where, const uint32_t *__restrict__ slot_of, size_t n)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    where[slot_of[k]] = (uint32_t)k;
+}
+__global__ void iota_kernel(uint32_t *__restrict__ a, size_t n)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    a[k] = (uint32_t)k;
 }
 
 __global__ void fill_u32_kernel(unsigned *a, size_t n, unsigned v)
@@ -120,9 +160,9 @@ drift_kernel(rec4 *__restrict__ posm, const rec4 *__restrict__ vel,
     if (mlevel >= 0 && level[i] != (unsigned)mlevel) continue;
     rec4 p = ld_rec_rw(&posm[i]);
     rec4 v = ld_rec_rw(&vel[i]);
-    p.x += v.x * dt;
-    if (dim > 1) p.y += v.y * dt;
-    if (dim > 2) p.z += v.z * dt;
+    p.x = fma(v.x, dt, p.x);
+    if (dim > 1) p.y = fma(v.y, dt, p.y);
+    if (dim > 2) p.z = fma(v.z, dt, p.z);
     st_rec(&posm[i], p);
   }
 }
@@ -136,9 +176,9 @@ kick_kernel(rec4 *__restrict__ vel, const rec4 *__restrict__ accp,
     if (mlevel >= 0 && level[i] != (unsigned)mlevel) continue;
     rec4 v = ld_rec_rw(&vel[i]);
     rec4 a = ld_rec_rw(&accp[i]);
-    v.x += a.x * dt;
-    if (dim > 1) v.y += a.y * dt;
-    if (dim > 2) v.z += a.z * dt;
+    v.x = fma(a.x, dt, v.x);
+    if (dim > 1) v.y = fma(a.y, dt, v.y);
+    if (dim > 2) v.z = fma(a.z, dt, v.z);
     st_rec(&vel[i], v);
   }
 }
@@ -313,6 +353,47 @@ level_count_kernel(const unsigned *__restrict__ level, size_t n, int nlev,
 }
 
 } // namespace
+
+// Applies the current sort permutation to the particle store (see common.cuh).  The
+// 4-byte arrays go through the sort's rank scratch, whose buffer they then swap with.
+int component_reorder(expb200_component_s *c)
+{
+  const size_t n = c->n;
+  if (n == 0) return EXPB200_OK;
+  cudaStream_t st = c->stream;
+  const uint32_t *perm = c->perm[c->cur];
+  const unsigned grid = grid_for(n, 256);
+  ProfRegion pr(K_REORDER, st, 10);
+  // positions: the sorted copy becomes the store
+  { rec4 *t = c->posm; c->posm = c->posm_sorted; c->posm_sorted = t; }
+  gather_rec_kernel<<<grid, 256, 0, st>>>(c->spare, c->vel, perm, n);
+  { rec4 *t = c->vel; c->vel = c->spare; c->spare = t; }
+  gather_rec_kernel<<<grid, 256, 0, st>>>(c->spare, c->accp, perm, n);
+  { rec4 *t = c->accp; c->accp = c->spare; c->spare = t; }
+  auto move_u32 = [&](uint32_t **arr) {
+    gather_u32_kernel<<<grid, 256, 0, st>>>(c->rank, *arr, perm, n);
+    uint32_t *t = *arr; *arr = c->rank; c->rank = t;
+  };
+  move_u32(reinterpret_cast<uint32_t **>(&c->level));
+  move_u32(reinterpret_cast<uint32_t **>(&c->prev_level));
+  move_u32(reinterpret_cast<uint32_t **>(&c->dtreq));
+  move_u32(reinterpret_cast<uint32_t **>(&c->scale));
+  if (c->identity_order) {
+    // slot_of_new[k] = perm[k]
+    CU_TRY(cudaMemcpyAsync(c->slot_of, perm, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  } else {
+    move_u32(&c->slot_of);
+  }
+  invert_kernel<<<grid, 256, 0, st>>>(c->where, c->slot_of, n);
+  iota_kernel<<<grid, 256, 0, st>>>(c->perm[c->cur], n);
+  CU_LAUNCH_CHECK();
+  c->identity_order = false;
+  c->never_reordered = false;
+  c->sorts_since_reorder = 0;
+  c->psort = c->posm;
+  return EXPB200_OK;
+}
+
 } // namespace expb200
 
 using namespace expb200;
@@ -386,6 +467,11 @@ int expb200_component_create(int device, size_t capacity, expb200_component *out
   CU_TRY(cudaMalloc(&c->posm, capacity * sizeof(rec4)));
   CU_TRY(cudaMalloc(&c->vel, capacity * sizeof(rec4)));
   CU_TRY(cudaMalloc(&c->accp, capacity * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->posm_sorted, capacity * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->spare, capacity * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->slot_of, capacity * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&c->where, capacity * sizeof(uint32_t)));
+  c->psort = c->posm_sorted;
   CU_TRY(cudaMalloc(&c->level, capacity * sizeof(unsigned)));
   CU_TRY(cudaMalloc(&c->prev_level, capacity * sizeof(unsigned)));
   CU_TRY(cudaMalloc(&c->dtreq, capacity * sizeof(float)));
@@ -394,6 +480,7 @@ int expb200_component_create(int device, size_t capacity, expb200_component *out
     CU_TRY(cudaMalloc(&c->keys[k], capacity * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->perm[k], capacity * sizeof(uint32_t)));
   }
+  CU_TRY(cudaMalloc(&c->rank, capacity * sizeof(uint32_t)));
   c->hist_cap = sort_hist_words(capacity);
   CU_TRY(cudaMalloc(&c->hist, c->hist_cap * sizeof(uint32_t)));
   c->stage_chunk = capacity < kStageChunk ? capacity : kStageChunk;
@@ -414,10 +501,11 @@ int expb200_component_destroy(expb200_component c)
   DeviceGuard g(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
-  cudaFree(c->posm); cudaFree(c->vel); cudaFree(c->accp);
+  cudaFree(c->posm); cudaFree(c->vel); cudaFree(c->accp); cudaFree(c->posm_sorted);
+  cudaFree(c->spare); cudaFree(c->slot_of); cudaFree(c->where);
   cudaFree(c->level); cudaFree(c->prev_level); cudaFree(c->dtreq); cudaFree(c->scale);
   for (int k = 0; k < 2; k++) { cudaFree(c->keys[k]); cudaFree(c->perm[k]); }
-  cudaFree(c->hist); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats);
+  cudaFree(c->hist); cudaFree(c->rank); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats);
   cudaEventDestroy(c->copy_done);
   stream_register(c->stream, false);
   cudaStreamDestroy(c->stream);
@@ -432,6 +520,12 @@ int expb200_component_set_count(expb200_component c, size_t n)
 {
   REQUIRE(c, "component is NULL");
   REQUIRE(n <= c->cap, "n=%zu exceeds capacity %zu", n, c->cap);
+  if (n != c->n) {            // a different particle set: storage order = host order again
+    c->identity_order = true;
+    c->never_reordered = true;
+    c->sorts_since_reorder = 0;
+    c->sort_kind = 0;
+  }
   c->n = n;
   c->pos_ver++; c->lev_ver++;
   return EXPB200_OK;
@@ -465,7 +559,8 @@ int expb200_component_upload_range(expb200_component c, size_t first, size_t cou
     ProfRegion pr(K_PACK, c->stream);
     pack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp, spos,
                                                          vel ? svel : nullptr, smass, nullptr,
-                                                         first + off, m, 0);
+                                                         first + off, m, 0,
+                                                         c->identity_order ? nullptr : c->where);
     CU_LAUNCH_CHECK();
     CU_TRY(cudaEventRecord(c->copy_done, c->stream));
   }
@@ -481,6 +576,11 @@ int expb200_component_upload(expb200_component c, size_t n, const double *pos, c
   REQUIRE(n <= c->cap, "n=%zu exceeds capacity %zu", n, c->cap);
   DeviceGuard g(c->device);
   c->n = n;
+  // a full upload defines a new particle set: storage order = host order again
+  c->identity_order = true;
+  c->never_reordered = true;
+  c->sorts_since_reorder = 0;
+  c->sort_kind = 0;
   if (n == 0) { c->pos_ver++; c->lev_ver++; return EXPB200_OK; }
   int rc = expb200_component_upload_range(c, 0, n, pos, vel, mass);
   if (rc) return rc;
@@ -503,7 +603,7 @@ int expb200_component_upload(expb200_component c, size_t n, const double *pos, c
       CU_TRY(cudaMemcpy(s + 7 * ch, potext + off, m * sizeof(double), cudaMemcpyHostToDevice));
       pack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp, s,
                                                            vel ? s + 3 * ch : nullptr, s + 6 * ch,
-                                                           s + 7 * ch, off, m, 0);
+                                                           s + 7 * ch, off, m, 0, nullptr);
       CU_LAUNCH_CHECK();
     }
   }
@@ -546,7 +646,8 @@ int expb200_component_download_range(expb200_component c, size_t first, size_t c
     unpack_kernel<<<grid_for(m, 256), 256, 0, c->stream>>>(c->posm, c->vel, c->accp,
                                                            pos ? spos : nullptr, vel ? svel : nullptr,
                                                            acc ? sacc : nullptr, pot ? spot : nullptr,
-                                                           first + off, m);
+                                                           first + off, m,
+                                                           c->identity_order ? nullptr : c->where);
     CU_LAUNCH_CHECK();
     CU_TRY(cudaEventRecord(unpacked[b], c->stream));
     CU_TRY(cudaStreamWaitEvent(c->copy_stream, unpacked[b], 0));
@@ -573,9 +674,18 @@ int expb200_component_download(expb200_component c, double *pos, double *vel, do
     int rc = expb200_component_download_range(c, 0, c->n, pos, vel, acc, pot);
     if (rc) return rc;
   }
+  const uint32_t *map = c->identity_order ? nullptr : c->where;
+  if (level) {
+    gather_u32_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->rank, c->level, map, c->n);
+    CU_TRY(cudaMemcpyAsync(level, c->rank, c->n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  if (dtreq) {
+    gather_u32_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(
+        c->rank, reinterpret_cast<const uint32_t *>(c->dtreq), map, c->n);
+    CU_TRY(cudaMemcpyAsync(dtreq, c->rank, c->n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
   CU_TRY(cudaStreamSynchronize(c->stream));
-  if (level) CU_TRY(cudaMemcpy(level, c->level, c->n * sizeof(unsigned), cudaMemcpyDeviceToHost));
-  if (dtreq) CU_TRY(cudaMemcpy(dtreq, c->dtreq, c->n * sizeof(float), cudaMemcpyDeviceToHost));
   return EXPB200_OK;
 }
 
@@ -667,7 +777,12 @@ int expb200_component_set_levels(expb200_component c, const unsigned *level)
 {
   REQUIRE(c && level, "NULL argument");
   DeviceGuard g(c->device);
-  CU_TRY(cudaMemcpyAsync(c->level, level, c->n * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  if (c->identity_order) {
+    CU_TRY(cudaMemcpyAsync(c->level, level, c->n * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CU_TRY(cudaMemcpyAsync(c->rank, level, c->n * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    scatter_u32_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->level, c->rank, c->where, c->n);
+  }
   CU_TRY(cudaMemcpyAsync(c->prev_level, c->level, c->n * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   c->lev_ver++;
@@ -683,7 +798,12 @@ int expb200_component_set_acc_pot(expb200_component c, const double *acc, const 
   tmp.resize(c->n * sizeof(rec4));
   rec4 *h = reinterpret_cast<rec4 *>(&tmp[0]);
   for (size_t i = 0; i < c->n; i++) h[i] = rec4{acc[3 * i], acc[3 * i + 1], acc[3 * i + 2], pot[i]};
-  CU_TRY(cudaMemcpyAsync(c->accp, h, c->n * sizeof(rec4), cudaMemcpyHostToDevice, c->stream));
+  if (c->identity_order) {
+    CU_TRY(cudaMemcpyAsync(c->accp, h, c->n * sizeof(rec4), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CU_TRY(cudaMemcpyAsync(c->spare, h, c->n * sizeof(rec4), cudaMemcpyHostToDevice, c->stream));
+    scatter_rec_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->accp, c->spare, c->where, c->n);
+  }
   CU_TRY(cudaStreamSynchronize(c->stream));
   return EXPB200_OK;
 }

@@ -323,11 +323,9 @@ int ensure_sorted(expb200_cylinder_s *s, expb200_component_s *c, int mlevel, dou
   }
   if (valid) return EXPB200_OK;      // keys recomputed into the spare buffer only for the mass
   if (c->n) {
-    int npass = 0;
-    { int nbits = 1; while ((1ull << nbits) < nkeys) nbits++; npass = (nbits + 7) / 8; }
-    ProfRegion pr(K_SORT, c->stream, 3 * npass);
+    ProfRegion pr(K_SORT, c->stream, radix_sort_launches(c->n, nkeys, false));
     int cur = 0;
-    int rc = radix_sort_pairs(c->stream, c->keys, c->perm, c->hist, c->n, nkeys, &cur);
+    int rc = radix_sort_pairs(c->stream, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur);
     if (rc) return rc;
     c->cur = cur;
   }

@@ -16,7 +16,7 @@ std::vector<Pair> g_free;
 
 const char *kNames[K_COUNT] = {"key", "sort", "segments", "deposit", "combine", "contract",
                                "field", "force", "kick", "drift", "zero", "levels", "allreduce",
-                               "pack", "covariance", "cyl_deposit", "cyl_force", "cyl_field", "other"};
+                               "pack", "covariance", "cyl_deposit", "cyl_force", "cyl_field", "kick_drift_key", "reorder", "other"};
 
 void resolve()
 {

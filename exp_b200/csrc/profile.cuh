@@ -8,7 +8,7 @@ namespace expb200 {
 enum KernelId {
   K_KEY = 0, K_SORT, K_SEG, K_DEPOSIT, K_COMBINE, K_CONTRACT, K_FIELD, K_FORCE,
   K_KICK, K_DRIFT, K_ZERO, K_LEVELS, K_ALLREDUCE, K_PACK, K_COV, K_CYL_DEPOSIT,
-  K_CYL_FORCE, K_CYL_FIELD, K_OTHER, K_COUNT
+  K_CYL_FORCE, K_CYL_FIELD, K_KDK, K_REORDER, K_OTHER, K_COUNT
 };
 
 // Counts `launches` kernel launches for id; when timing is enabled, brackets the

@@ -7,6 +7,15 @@
 // Stability matters: the summation order of the coefficient reduction is the
 // sorted order, so a stable sort of keys computed from the particle state makes
 // every result a deterministic function of that state.
+//
+// Shape of one pass (digits up to 11 bits, so the (level, radial cell) keys of a
+// single-level sphere are ONE pass):
+//   hist    : per-CTA digit histogram of its 8192-key tile          [n*4 B read]
+//   scan1/2 : two-level exclusive scan over hist[cta][digit]        [tiny, parallel]
+//   rank    : each warp ranks its 512 consecutive keys with match_any (stable) against
+//             per-warp digit counters in shared memory               [n*(4 R + 4 W) B]
+//   apply   : key, slot and -- in the last pass -- the particle's 32-byte position
+//             record go to their sorted position                    [n*(40 R + 40 W) B]
 #include "sort.cuh"
 
 namespace expb200 {
@@ -15,47 +24,96 @@ namespace {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItemsPerWarp = 512;                       // 16 rounds of 32
+constexpr int kItemsPerLane = 32;
+constexpr int kItemsPerWarp = 32 * kItemsPerLane;        // 512
 constexpr int kSortTile = kSortWarps * kItemsPerWarp;    // 4096 keys per CTA
-constexpr int kMaxRadix = 256;
+constexpr int kMaxDigitBits = 11;
+constexpr int kMaxRadix = 1 << kMaxDigitBits;
+constexpr int kScanGroups = 32;
 
 __device__ __forceinline__ uint32_t digit_of(uint32_t key, int shift, uint32_t mask)
 {
   return (key >> shift) & mask;
 }
 
-// Per-CTA digit histogram, written digit-major so that one exclusive scan over
-// hist[digit][cta] yields every CTA's output base for every digit.
+// Per-CTA digit histogram, hist[cta][digit].
 __global__ void __launch_bounds__(kSortThreads)
 sort_hist_kernel(const uint32_t *__restrict__ keys, size_t n, int shift, uint32_t mask,
-                 uint32_t *__restrict__ hist, unsigned nctas)
+                 uint32_t *__restrict__ hist)
 {
   __shared__ uint32_t h[kMaxRadix];
-  for (int d = threadIdx.x; d < kMaxRadix; d += kSortThreads) h[d] = 0;
+  const uint32_t R = mask + 1;
+  for (uint32_t d = threadIdx.x; d < R; d += kSortThreads) h[d] = 0;
   __syncthreads();
-  size_t base = (size_t)blockIdx.x * kSortTile;
-#pragma unroll 4
+  const size_t base = (size_t)blockIdx.x * kSortTile;
+#pragma unroll 8
   for (int it = 0; it < kSortTile / kSortThreads; it++) {
     size_t i = base + (size_t)it * kSortThreads + threadIdx.x;
     if (i < n) atomicAdd(&h[digit_of(keys[i], shift, mask)], 1u);   // integer: order-independent
   }
   __syncthreads();
-  for (uint32_t d = threadIdx.x; d <= mask; d += kSortThreads)
-    hist[(size_t)d * nctas + blockIdx.x] = h[d];
+  uint32_t *out = hist + (size_t)blockIdx.x * R;
+  for (uint32_t d = threadIdx.x; d < R; d += kSortThreads) out[d] = h[d];
 }
 
-// Exclusive scan of `total` counters by one CTA of 1024 threads: each thread owns
-// a contiguous slice (serial sum, block scan of the slice sums, serial rewrite).
+// Level 1: within each group of `gs` consecutive CTAs, exclusive prefix over the CTAs for
+// every digit (in place) and the group's total per digit.
+__global__ void __launch_bounds__(256)
+sort_scan1_kernel(uint32_t *__restrict__ hist, uint32_t *__restrict__ gtot, uint32_t R,
+                  unsigned nctas, unsigned gs)
+{
+  const uint32_t d = blockIdx.x * 256 + threadIdx.x;
+  if (d >= R) return;
+  const unsigned g = blockIdx.y;
+  unsigned c0 = g * gs, c1 = c0 + gs < nctas ? c0 + gs : nctas;
+  uint32_t run = 0;
+  for (unsigned c = c0; c < c1; c += 8) {          // loads batched: they do not depend on the stores
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = c + k < c1 ? hist[(size_t)(c + k) * R + d] : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (c + k < c1) hist[(size_t)(c + k) * R + d] = run;
+      run += v[k];
+    }
+  }
+  gtot[(size_t)g * R + d] = run;
+}
+
+// Level 2a: exclusive prefix over the groups for every digit (in place) and the digit totals.
+__global__ void __launch_bounds__(256)
+sort_scan2a_kernel(uint32_t *__restrict__ gtot, uint32_t *__restrict__ dtot, uint32_t R)
+{
+  const uint32_t d = blockIdx.x * 256 + threadIdx.x;
+  if (d >= R) return;
+  uint32_t v[kScanGroups];
+#pragma unroll
+  for (int g = 0; g < kScanGroups; g++) v[g] = gtot[(size_t)g * R + d];
+  uint32_t run = 0;
+#pragma unroll
+  for (int g = 0; g < kScanGroups; g++) {
+    gtot[(size_t)g * R + d] = run;
+    run += v[g];
+  }
+  dtot[d] = run;
+}
+
+// Level 2b (one CTA): exclusive scan of the digit totals across digits -> dbase[d], the
+// first output position of digit d.  With seg != NULL (single-pass sort: digit == key)
+// also seg[k] = first position of key k.
 __global__ void __launch_bounds__(1024)
-sort_scan_kernel(uint32_t *__restrict__ a, size_t total)
+sort_scan2b_kernel(const uint32_t *__restrict__ dtot, uint32_t *__restrict__ dbase, uint32_t R,
+                   uint32_t *__restrict__ seg, uint32_t nkeys, uint32_t n)
 {
   __shared__ uint32_t warp_sums[32];
   const int t = threadIdx.x;
-  size_t per = (total + 1023) / 1024;
-  size_t lo = (size_t)t * per, hi = lo + per < total ? lo + per : total;
-  uint32_t s = 0;
-  for (size_t i = lo; i < hi; i++) s += a[i];
-  // block exclusive scan of s
+  const uint32_t dpt = (R + 1023) / 1024;             // digits per thread (contiguous)
+  uint32_t tot[2] = {0, 0};
+  for (uint32_t j = 0; j < dpt; j++) {
+    uint32_t d = t * dpt + j;
+    if (d < R) tot[j] = dtot[d];
+  }
+  const uint32_t s = tot[0] + tot[1];
   uint32_t v = s;
   const int lane = t & 31, w = t >> 5;
 #pragma unroll
@@ -75,70 +133,101 @@ sort_scan_kernel(uint32_t *__restrict__ a, size_t total)
     warp_sums[lane] = x;
   }
   __syncthreads();
-  uint32_t run = v - s + (w ? warp_sums[w - 1] : 0u);
-  for (size_t i = lo; i < hi; i++) {
-    uint32_t c = a[i];
-    a[i] = run;
-    run += c;
+  uint32_t base = v - s + (w ? warp_sums[w - 1] : 0u);
+  for (uint32_t j = 0; j < dpt; j++) {
+    uint32_t d = t * dpt + j;
+    if (d >= R) break;
+    dbase[d] = base;
+    if (seg && d < nkeys) seg[d] = base;
+    base += tot[j];
   }
+  if (seg && t == 0) seg[nkeys] = n;
 }
 
-// Stable scatter.  Each warp owns 512 consecutive keys of the CTA tile and walks
-// them in order, 32 at a time; __match_any_sync groups equal digits, the lowest
-// lane of a group is its leader.
-__global__ void __launch_bounds__(kSortThreads)
-sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ perm_in,
-                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ perm_out,
-                    size_t n, int shift, uint32_t mask,
-                    const uint32_t *__restrict__ offs, unsigned nctas)
+// Stable ranking.  Each warp owns 512 consecutive keys of the CTA tile (kept in registers)
+// and walks them in order, 32 at a time; __match_any_sync groups equal digits, the lowest
+// lane of a group is its leader and advances the digit's counter with one shared-memory
+// atomic whose old value is the group's base.  Output: rank[i] = sorted position of item i
+// (a coalesced write); the data movement is sort_apply_kernel's.
+__global__ void __launch_bounds__(kSortThreads, 3)
+sort_rank_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ rank, size_t n,
+                 int shift, uint32_t mask, const uint32_t *__restrict__ hist,
+                 const uint32_t *__restrict__ gtot, const uint32_t *__restrict__ dbase, unsigned gs)
 {
-  __shared__ uint32_t wcount[kSortWarps][kMaxRadix];
+  extern __shared__ __align__(16) uint32_t wcount_all[];             // [kSortWarps][R]
+  const uint32_t R = mask + 1;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
+  uint32_t *wcount = wcount_all + (size_t)w * R;
 
-  for (int d = lane; d < kMaxRadix; d += 32) wcount[w][d] = 0;
+  for (uint32_t d = lane; d < R; d += 32) wcount[d] = 0;
   __syncwarp();
 
-  const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)w * kItemsPerWarp;
+  // 32-bit indexing (capacity < 2^32): one base per array, compile-time offsets per item
+  const uint32_t wbase = blockIdx.x * (uint32_t)kSortTile + (uint32_t)w * kItemsPerWarp + lane;
+  const uint32_t nn = (uint32_t)n;
+  const uint32_t nleft = wbase < nn ? nn - wbase : 0u;      // item `it` is valid iff it*32 < nleft
+  const uint32_t *kin = keys_in + wbase;
 
-  // pass A: per-warp digit counts
-  for (int it = 0; it < kItemsPerWarp / 32; it++) {
-    size_t i = wbase + it * 32 + lane;
-    uint32_t d = i < n ? digit_of(keys_in[i], shift, mask) : 0xffffffffu;
-    uint32_t grp = __match_any_sync(0xffffffffu, d);
-    if (i < n && (grp & lt) == 0) wcount[w][d] += __popc(grp);
-    __syncwarp();
+  // pass A: load the warp's keys, per-warp digit counts (fire-and-forget atomics)
+  uint32_t dig[kItemsPerLane];
+#pragma unroll
+  for (int it = 0; it < kItemsPerLane; it++)
+    dig[it] = (uint32_t)(it * 32) < nleft ? digit_of(kin[it * 32], shift, mask) : 0xffffffffu;
+#pragma unroll
+  for (int it = 0; it < kItemsPerLane; it++) {
+    uint32_t grp = __match_any_sync(0xffffffffu, dig[it]);
+    if (dig[it] != 0xffffffffu && (grp & lt) == 0) atomicAdd(&wcount[dig[it]], (uint32_t)__popc(grp));
   }
   __syncthreads();
 
   // pass B: turn counts into output bases, warps in order within the CTA
-  for (uint32_t d = threadIdx.x; d <= mask; d += kSortThreads) {
-    uint32_t run = offs[(size_t)d * nctas + blockIdx.x];
+  {
+    const uint32_t *hrow = hist + (size_t)blockIdx.x * R;
+    const uint32_t *grow = gtot + (size_t)(blockIdx.x / gs) * R;
+    for (uint32_t d = threadIdx.x; d < R; d += kSortThreads) {
+      uint32_t c[kSortWarps];
 #pragma unroll
-    for (int ww = 0; ww < kSortWarps; ww++) {
-      uint32_t c = wcount[ww][d];
-      wcount[ww][d] = run;
-      run += c;
+      for (int ww = 0; ww < kSortWarps; ww++) c[ww] = wcount_all[(size_t)ww * R + d];
+      uint32_t run = hrow[d] + grow[d] + dbase[d];
+#pragma unroll
+      for (int ww = 0; ww < kSortWarps; ww++) {
+        wcount_all[(size_t)ww * R + d] = run;
+        run += c[ww];
+      }
     }
   }
   __syncthreads();
 
-  // pass C: ranks within the group give the position; the leader advances the base
-  for (int it = 0; it < kItemsPerWarp / 32; it++) {
-    size_t i = wbase + it * 32 + lane;
-    bool ok = i < n;
-    uint32_t key = ok ? keys_in[i] : 0u;
-    uint32_t d = ok ? digit_of(key, shift, mask) : 0xffffffffu;
-    uint32_t grp = __match_any_sync(0xffffffffu, d);
-    uint32_t pos = 0;
-    if (ok) pos = wcount[w][d] + __popc(grp & lt);
-    __syncwarp();
-    if (ok && (grp & lt) == 0) wcount[w][d] += __popc(grp);
-    __syncwarp();
-    if (ok) {
-      keys_out[pos] = key;
-      perm_out[pos] = perm_in ? perm_in[i] : (uint32_t)i;
-    }
+  // pass C: the leader takes the group's base with an atomic and broadcasts it; the rank
+  // within the group gives the position
+  uint32_t *rout = rank + wbase;
+#pragma unroll
+  for (int it = 0; it < kItemsPerLane; it++) {
+    const bool ok = dig[it] != 0xffffffffu;
+    uint32_t grp = __match_any_sync(0xffffffffu, dig[it]);
+    uint32_t base = 0;
+    if (ok && (grp & lt) == 0) base = atomicAdd(&wcount[dig[it]], (uint32_t)__popc(grp));
+    __syncwarp();                   // orders this iteration's atomics before the next one's
+    base = __shfl_sync(0xffffffffu, base, __ffs(grp) - 1);
+    if (ok) rout[it * 32] = base + __popc(grp & lt);
+  }
+}
+
+// Data movement of one pass: every item goes to its sorted position.
+template <bool PAYLOAD>
+__global__ void __launch_bounds__(256)
+sort_apply_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ perm_in,
+                  const uint32_t *__restrict__ rank, uint32_t *__restrict__ keys_out,
+                  uint32_t *__restrict__ perm_out, uint32_t n, const rec4 *__restrict__ psrc,
+                  rec4 *__restrict__ pdst)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t pos = rank[i];
+    const uint32_t slot = perm_in ? perm_in[i] : i;
+    keys_out[pos] = keys_in[i];
+    perm_out[pos] = slot;
+    if (PAYLOAD) st_rec(&pdst[pos], ld_rec(&psrc[slot]));
   }
 }
 
@@ -156,35 +245,77 @@ __global__ void seg_offsets_kernel(const uint32_t *__restrict__ sorted, size_t n
   seg[k] = (uint32_t)lo;
 }
 
+struct Plan { int npass, bits; unsigned nctas, gs; };
+
+Plan plan_for(size_t n, uint32_t nkeys)
+{
+  int nbits = 1;
+  while ((1ull << nbits) < nkeys) nbits++;
+  Plan p;
+  p.npass = (nbits + kMaxDigitBits - 1) / kMaxDigitBits;
+  p.bits = (nbits + p.npass - 1) / p.npass;
+  p.nctas = div_up(n ? n : 1, kSortTile);
+  p.gs = (p.nctas + kScanGroups - 1) / kScanGroups;
+  return p;
+}
+
 } // namespace
 
 size_t sort_hist_words(size_t n)
 {
-  return (size_t)kMaxRadix * div_up(n ? n : 1, kSortTile);
+  // hist[cta][digit] + gtot[group][digit] + dtot[digit] + dbase[digit]
+  return (size_t)kMaxRadix * ((size_t)div_up(n ? n : 1, kSortTile) + kScanGroups + 2);
+}
+
+int radix_sort_launches(size_t n, uint32_t nkeys, bool want_seg)
+{
+  Plan p = plan_for(n, nkeys);
+  return 6 * p.npass + ((want_seg && p.npass > 1) ? 1 : 0);
 }
 
 int radix_sort_pairs(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], uint32_t *hist,
-                     size_t n, uint32_t nkeys, int *out_cur)
+                     uint32_t *rank, size_t n, uint32_t nkeys, int *out_cur, uint32_t *seg,
+                     SortPayload payload)
 {
   // keys[0] holds the unsorted keys; values start as the identity.
-  int nbits = 1;
-  while ((1ull << nbits) < nkeys) nbits++;
-  int npass = (nbits + 7) / 8;
-  int bits = (nbits + npass - 1) / npass;
-  unsigned nctas = div_up(n ? n : 1, kSortTile);
+  const Plan p = plan_for(n, nkeys);
+  const uint32_t R = 1u << p.bits, mask = R - 1u;
+  uint32_t *gtot = hist + (size_t)p.nctas * R;
+  uint32_t *dtot = gtot + (size_t)kScanGroups * R;
+  uint32_t *dbase = dtot + R;
+  const size_t smem = (size_t)kSortWarps * R * sizeof(uint32_t);
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    CU_TRY(cudaFuncSetAttribute(sort_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSortWarps * kMaxRadix * sizeof(uint32_t))));
+    attr_done[dev & 63] = true;
+  }
   int cur = 0;
-  for (int p = 0; p < npass; p++) {
-    int shift = p * bits;
-    uint32_t mask = (1u << bits) - 1u;
-    sort_hist_kernel<<<nctas, kSortThreads, 0, st>>>(keys[cur], n, shift, mask, hist, nctas);
-    sort_scan_kernel<<<1, 1024, 0, st>>>(hist, (size_t)(mask + 1) * nctas);
-    sort_scatter_kernel<<<nctas, kSortThreads, 0, st>>>(keys[cur], p == 0 ? nullptr : perm[cur],
-                                                        keys[cur ^ 1], perm[cur ^ 1], n, shift,
-                                                        mask, hist, nctas);
+  for (int q = 0; q < p.npass; q++) {
+    const int shift = q * p.bits;
+    const bool last = q == p.npass - 1;
+    sort_hist_kernel<<<p.nctas, kSortThreads, 0, st>>>(keys[cur], n, shift, mask, hist);
+    sort_scan1_kernel<<<dim3(div_up(R, 256), kScanGroups), 256, 0, st>>>(hist, gtot, R, p.nctas, p.gs);
+    sort_scan2a_kernel<<<div_up(R, 256), 256, 0, st>>>(gtot, dtot, R);
+    sort_scan2b_kernel<<<1, 1024, 0, st>>>(dtot, dbase, R, (seg && p.npass == 1) ? seg : nullptr, nkeys,
+                                           (uint32_t)n);
+    sort_rank_kernel<<<p.nctas, kSortThreads, smem, st>>>(keys[cur], rank, n, shift, mask, hist, gtot,
+                                                          dbase, p.gs);
+    const uint32_t *pin = q == 0 ? nullptr : perm[cur];
+    if (last && payload.src)
+      sort_apply_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(keys[cur], pin, rank, keys[cur ^ 1],
+                                                                perm[cur ^ 1], (uint32_t)n, payload.src,
+                                                                payload.dst);
+    else
+      sort_apply_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(keys[cur], pin, rank, keys[cur ^ 1],
+                                                                 perm[cur ^ 1], (uint32_t)n, nullptr, nullptr);
     cur ^= 1;
   }
   CU_LAUNCH_CHECK();
   *out_cur = cur;
+  if (seg && p.npass > 1) return segment_offsets(st, keys[cur], n, seg, nkeys);
   return EXPB200_OK;
 }
 

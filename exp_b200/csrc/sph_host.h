@@ -32,6 +32,7 @@ inline SphGeom make_sph_geom(const expb200_sphere_config &cfg)
     g.dxi = (cfg.rmax_grid - cfg.rmin_grid) / (R - 1);
   }
   g.scale = cfg.scale; g.rmin = cfg.rmin; g.rmax = cfg.rmax;
+  g.inv_rmap = 1.0 / g.rmap; g.inv_dxi = 1.0 / g.dxi; g.inv_scale = 1.0 / g.scale;
   g.cx = g.cy = g.cz = 0.0; g.rtrunc2 = 1.0e300;
   return g;
 }
@@ -52,7 +53,7 @@ inline void make_sph_constants(std::vector<double> &K, std::vector<double> &inv)
 
 struct SphMaps {
   std::vector<int> row_l, row_m;          // coefficient row -> (l, m)
-  std::vector<int> slot_l, rowc, rows;    // field slot -> l, cos row, sin row (-1: no term)
+  std::vector<int> slot_l, slot_m, rowc, rows;   // field slot -> l, m, cos row, sin row (-1: no term)
 };
 
 // The force loop's slot -> coefficient-row map, following the reference's loop literally
@@ -70,9 +71,9 @@ inline SphMaps make_sph_maps(const expb200_sphere_config &cfg)
       M.row_l[r] = l; M.row_m[r] = m;
       if (m) { M.row_l[r + 1] = l; M.row_m[r + 1] = m; }
     }
-  M.slot_l.resize(nslot); M.rowc.assign(nslot, -1); M.rows.assign(nslot, -1);
+  M.slot_l.resize(nslot); M.slot_m.resize(nslot); M.rowc.assign(nslot, -1); M.rows.assign(nslot, -1);
   for (int l = 0; l <= L; l++)
-    for (int m = 0; m <= l; m++) M.slot_l[sph_slot(L, l, m)] = l;
+    for (int m = 0; m <= l; m++) { M.slot_l[sph_slot(L, l, m)] = l; M.slot_m[sph_slot(L, l, m)] = m; }
   if (!cfg.NO_L0) M.rowc[sph_slot(L, 0, 0)] = 0;
   for (int l = 1, loffset = 1; l <= L; loffset += (2 * l + 1), l++) {
     if (cfg.NO_L1 && l == 1) continue;

@@ -11,14 +11,23 @@
 // nodes, the particle sum and the n sum commute:
 //
 //   coef[row][n] = sum_p Y_p[row] w_p potd_p(l,n)
-//                = sum_i E[l,n,i] * G[i][row],   G[i][row] = sum_p Y_p[row] w_p P0_p (x1_p [i_p=i] + x2_p [i_p=i-1])
+//                = K_row sum_i E[l,n,i] * G[row][i],
+//   G[row][i]    = sum_p P_p[row] w_p P0_p (x1_p [i_p=i] + x2_p [i_p=i-1])   (P = Y / K)
 //
 //   sum_n coef[row][n] potd(l,n) = P0 (x1 H[i][row] + x2 H[i+1][row]),  H[i][row] = sum_n E[l,n,i] coef[row][n]
-//   sum_n coef[row][n] dpot(l,n) = fac ((p-1/2) p0[j-1] H[j-1] - 2p p0[j] H[j] + (p+1/2) p0[j+1] H[j+1])
+//   sum_n coef[row][n] dpot(l,n) = fac ((q-1/2) p0[j-1] H[j-1] - 2q p0[j] H[j] + (q+1/2) p0[j+1] H[j+1])
 //
 // so a particle costs O((L+1)^2) instead of O((L+1)^2 nmax) and the nmax-contractions
-// become two tiny dense products per step.  The result differs from the reference only by
-// floating-point re-association (~1e-15 relative).
+// become two tiny dense products per step.  Within a radial cell both sums are
+// polynomials in the cell coordinate (x2 = p, x1 = 1-p):
+//
+//   P0 (x1 H_i + x2 H_{i+1}) = c0 + c1 p + c2 p^2        (cell i, p in [0,1))
+//   dpot-sum / fac           = d0 + d1 q                 (stencil centre j, q = p when j == i)
+//
+// and the field table stores (c0,c1,c2,d0,d1) per (cell, l, m) with the normalisation
+// K_lm and the 1/scale factors folded in: the force costs 3 FMAs per term for the radial
+// part.  The result differs from the reference only by floating-point re-association
+// and by reciprocal-multiplies in place of divisions (~1e-13 relative; budget 1e-10/1e-8).
 #pragma once
 
 #include "common.cuh"
@@ -41,64 +50,64 @@ namespace expb200 {
 using std::exp; using std::fabs; using std::log; using std::sqrt;
 #endif
 
+HD double fast_rsqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // Geometry + grid constants of one Sphere, passed to kernels by value.
 struct SphGeom {
   int lmax, nmax, numr, cmap;
   int nrow;                 // (lmax+1)^2
   int nslot;                // (lmax+1)(lmax+2)/2
   double rmap, xmin, dxi;   // SLGridSph grid (exputil/SLGridMP2.cc:1355-1382)
+  double inv_rmap, inv_dxi, inv_scale;
   double scale, rmin, rmax; // SphericalBasis scale and expansion radii
   double cx, cy, cz, rtrunc2;
 };
 
+constexpr int kSphPoly = 5;   // double2 entries per (cell, slot): c0 c1 c2 d0 d1, each (cos, sin)
+
 // slot of (l,m) in the m-major order used by the field table: m outer, l inner
-HD int sph_slot(int lmax, int l, int m) { return m * (lmax + 1) - m * (m - 1) / 2 + (l - m); }
+HD constexpr int sph_slot(int lmax, int l, int m) { return m * (lmax + 1) - m * (m - 1) / 2 + (l - m); }
 // row of (l,m) in the reference's coefficient layout (cos row; sin row is +1 for m>0)
-HD int sph_row(int l, int m) { return l * l + (m ? 2 * m - 1 : 0); }
+HD constexpr int sph_row(int l, int m) { return l * l + (m ? 2 * m - 1 : 0); }
 
 // a5: SLGridSph::r_to_xi / d_xi_to_r (exputil/SLGridMP2.cc:711-726, 748-765)
 HD double sph_r_to_xi(const SphGeom &g, double r)
 {
-  if (g.cmap == 1) return (r / g.rmap - 1.0) / (r / g.rmap + 1.0);
+  if (g.cmap == 1) {
+    double q = r * g.inv_rmap;
+    return (q - 1.0) * (1.0 / (q + 1.0));
+  }
   if (g.cmap == 2) return log(r);
   return r;
 }
 HD double sph_d_xi_to_r(const SphGeom &g, double xi)
 {
-  if (g.cmap == 1) return 0.5 * (1.0 - xi) * (1.0 - xi) / g.rmap;
+  if (g.cmap == 1) return 0.5 * (1.0 - xi) * (1.0 - xi) * g.inv_rmap;
   if (g.cmap == 2) return exp(-xi);
   return 1.0;
 }
 
-// Interpolation stencil of one radius: nodes j-1, j, j+1 (j = the reference's force
-// index, clamped to [1,numr-2]); bw = weights of the potential (a6), aw = weights of
-// the radial derivative (a7), both with p0 folded in.
-struct SphStencil {
-  int j;
-  int cell;        // the reference's potential index (clamped to [0,numr-2])
-  double x1, x2;   // linear weights on (cell, cell+1)
-};
-
-HD SphStencil sph_stencil(const SphGeom &g, double rs, double &xi_out)
+// Position of a radius on the table: t = (xi - xmin)/dxi, so that the reference's
+// indx = (int)t (exputil/SLGridMP2.cc:887, 969), x2 = t - indx, x1 = 1 - x2.
+HD double sph_grid_coord(const SphGeom &g, double rs, double &xi)
 {
-  double xi = sph_r_to_xi(g, rs);
-  int raw = (int)((xi - g.xmin) / g.dxi);
-  int cell = raw < 0 ? 0 : raw;
-  if (cell > g.numr - 2) cell = g.numr - 2;
-  int j = raw < 1 ? 1 : raw;
-  if (j > g.numr - 2) j = g.numr - 2;
-  SphStencil s;
-  s.j = j;
-  s.cell = cell;
-  s.x1 = ((g.xmin + g.dxi * (cell + 1)) - xi) / g.dxi;
-  s.x2 = (xi - (g.xmin + g.dxi * cell)) / g.dxi;
-  xi_out = xi;
-  return s;
+  xi = sph_r_to_xi(g, rs);
+  return (xi - g.xmin) * g.inv_dxi;
+}
+HD int sph_clamp_cell(const SphGeom &g, double t, int lo)
+{
+  int raw = (int)t;
+  int c = raw < lo ? lo : raw;
+  return c > g.numr - 2 ? g.numr - 2 : c;
 }
 
-// Radial-cell key of a particle for the coefficient pass: its potential cell when it
-// contributes (not frozen, rmin <= r <= rmax: src/SphericalBasis.cc:489,
-// src/Component.cc:4194-4202), else the dead cell numr-1.
 // mode 0: coefficient accumulation (rmin <= r <= rmax, src/SphericalBasis.cc:489);
 // mode 1: multistep_update (r < rmax only, src/SphericalBasis.cc:1177).
 HD bool sph_in_range(const SphGeom &g, double r, int mode)
@@ -106,6 +115,9 @@ HD bool sph_in_range(const SphGeom &g, double r, int mode)
   return mode == 0 ? (r >= g.rmin && r <= g.rmax) : (r < g.rmax);
 }
 
+// Radial-cell key of a particle for the coefficient pass: its potential cell when it
+// contributes (not frozen, in range: src/SphericalBasis.cc:489, src/Component.cc:4194-4202),
+// else the dead cell numr-1.  The deposit takes the cell from this key.
 HD uint32_t sph_cell_of(const SphGeom &g, const rec4 &pm, int mode = 0)
 {
   double x = pm.x - g.cx, y = pm.y - g.cy, z = pm.z - g.cz;
@@ -114,25 +126,45 @@ HD uint32_t sph_cell_of(const SphGeom &g, const rec4 &pm, int mode = 0)
   double r = sqrt(r2) + EXPB200_DSMALL;
   if (!sph_in_range(g, r, mode)) return (uint32_t)(g.numr - 1);
   double xi;
-  SphStencil s = sph_stencil(g, r / g.scale, xi);
-  return (uint32_t)s.cell;
+  double t = sph_grid_coord(g, r * g.inv_scale, xi);
+  return (uint32_t)sph_clamp_cell(g, t, 0);
+}
+
+// Azimuth: cos(phi), sin(phi) of phi = atan2(y,x) without the transcendental
+// (src/SphericalBasis.cc:493 then src/Basis.cc:104-105).  iR2 = 1/(x^2+y^2).
+HD void sph_azimuth(double x, double y, double &c1, double &s1, double &R2, double &iR2)
+{
+  R2 = x * x + y * y;
+  if (R2 > 0.0) {
+    double Ri = fast_rsqrt(R2);
+    c1 = x * Ri;
+    s1 = y * Ri;
+    iR2 = Ri * Ri;
+  } else {
+    c1 = 1.0;
+    s1 = 0.0;
+    iR2 = 0.0;
+  }
 }
 
 // Visits the associated Legendre functions in m-outer / l-inner order, calling
 // f(l, m, P_l^m, P_{l-1}^m) with the recursion of Basis::legendre_R (src/Basis.cc:14-52);
-// on_m(m) is called once at the head of every m column.  inv[k] = 1/k.
-template <int L, class M, class F>
-HD void sph_for_each_plm(double x, const double *inv, M &&on_m, F &&f)
+// on_m(m) is called once at the head of every m column and end_m(m) at its end.
+// Only the columns M0 <= m <= M1 are expanded (on_m still runs for m < M0, so that a
+// caller's azimuthal recursion advances).  inv[k] = 1/k.
+template <int L, int M0, int M1, class M, class F, class E>
+HD void sph_for_each_plm(double x, const double *inv, M &&on_m, F &&f, E &&end_m)
 {
   double somx2 = sqrt((1.0 - x) * (1.0 + x));
   double pmm = 1.0, fact = 1.0;
 #pragma unroll
-  for (int m = 0; m <= L; m++) {
+  for (int m = 0; m <= M1; m++) {
     if (m > 0) {
       pmm *= -fact * somx2;
       fact += 2.0;
     }
     on_m(m);
+    if (m < M0) continue;
     f(m, m, pmm, 0.0);
     if (m < L) {
       double pl2 = pmm;
@@ -146,190 +178,236 @@ HD void sph_for_each_plm(double x, const double *inv, M &&on_m, F &&f)
         pl1 = pll;
       }
     }
-  }
-}
-
-// Azimuth: cos(phi), sin(phi) of phi = atan2(y,x) without the transcendental
-// (src/SphericalBasis.cc:493 then src/Basis.cc:104-105).
-HD void sph_azimuth(double x, double y, double &c1, double &s1, double &R2)
-{
-  R2 = x * x + y * y;
-  if (R2 > 0.0) {
-    double Ri = 1.0 / sqrt(R2);
-    c1 = x * Ri;
-    s1 = y * Ri;
-  } else {
-    c1 = 1.0;
-    s1 = 0.0;
+    end_m(m);
   }
 }
 
 // ---------------------------------------------------------------------------
-// Coefficient pass, per particle (a8): fills yv[row] = K_lm P_lm {1,cos,sin}(m phi)
-// and returns the two node weights w1 (node cell) and w2 (node cell+1), which carry
-// mass * adb * (-4 pi) * P0(xi).  Returns false when the particle does not contribute.
+// Coefficient pass, per particle (a8).  The particle's radial cell comes from its
+// sort key.  Produces the two node weights w1 (node cell) and w2 (node cell+1), which
+// carry mass * adb * (-4 pi) * P0(xi), and the angular arguments.
 // ---------------------------------------------------------------------------
-template <int L, class Store>
-HD bool sph_deposit_particle(const SphGeom &g, const double *K, const double *inv,
-                             const double *p0, const rec4 &pm, double adb,
-                             int &cell, double &w1, double &w2, Store &&store, int mode = 0)
+struct SphDep { double w1, w2, costh, c1, s1; };
+
+HD void sph_deposit_setup(const SphGeom &g, const double *p0, const rec4 &pm, double adb,
+                          int cell, SphDep &d)
 {
   double x = pm.x - g.cx, y = pm.y - g.cy, z = pm.z - g.cz;
   double r2 = x * x + y * y + z * z;
-  if (r2 > g.rtrunc2) return false;
   double r = sqrt(r2) + EXPB200_DSMALL;
-  if (!sph_in_range(g, r, mode)) return false;
-
-  double costh = z / r;
-  double c1, s1, R2;
-  sph_azimuth(x, y, c1, s1, R2);
-
+  d.costh = z * (1.0 / r);
+  double R2, iR2;
+  sph_azimuth(x, y, d.c1, d.s1, R2, iR2);
   double xi;
-  SphStencil st = sph_stencil(g, r / g.scale, xi);
-  double P0 = st.x1 * EXPB200_LDG(p0 + st.cell) + st.x2 * EXPB200_LDG(p0 + st.cell + 1);
+  double t = sph_grid_coord(g, r * g.inv_scale, xi);
+  double x2 = t - cell, x1 = 1.0 - x2;
+  double P0 = x1 * EXPB200_LDG(p0 + cell) + x2 * EXPB200_LDG(p0 + cell + 1);
   double wgt = pm.w * adb * (-4.0 * M_PI) * P0;
-  cell = st.cell;
-  w1 = wgt * st.x1;
-  w2 = wgt * st.x2;
+  d.w1 = wgt * x1;
+  d.w2 = wgt * x2;
+}
 
+// Visits yv[row] = P_lm {1,cos,sin}(m phi) (without the normalisation K_lm, which the
+// contraction applies per row) for every coefficient row of the columns M0 <= m <= M1.
+template <int L, int M0, int M1, class Store>
+HD void sph_deposit_rows(const SphDep &d, const double *inv, Store &&store)
+{
   double cm = 1.0, sm = 0.0, cm1 = 0.0, sm1 = 0.0;   // cos/sin(m phi), (m-1) phi
-  sph_for_each_plm<L>(costh, inv, [&](int m) {
+  sph_for_each_plm<L, M0, M1>(d.costh, inv, [&](int m) {
     if (m == 0) return;       // advance the Chebyshev recursion (src/Basis.cc:107-110)
     double cn, sn;
-    if (m == 1) { cn = c1; sn = s1; }
-    else { cn = 2.0 * c1 * cm - cm1; sn = 2.0 * c1 * sm - sm1; }
+    if (m == 1) { cn = d.c1; sn = d.s1; }
+    else { cn = 2.0 * d.c1 * cm - cm1; sn = 2.0 * d.c1 * sm - sm1; }
     cm1 = cm; sm1 = sm; cm = cn; sm = sn;
   }, [&](int l, int m, double plm, double) {
-    double f = K[l * (kMaxL + 1) + m] * plm;
-    int row = sph_row(l, m);
-    if (m == 0) store(row, f);
-    else { store(row, f * cm); store(row + 1, f * sm); }
-  });
+    if (m == 0) store(l, 0, 0, plm);
+    else { store(l, m, 0, plm * cm); store(l, m, 1, plm * sm); }
+  }, [](int) {});
+}
+
+// Compact index of (l, m, cos/sin) among the rows of the columns M0..M1 (the register
+// accumulators of one deposit sweep), and their number.
+template <int L, int M0>
+HD constexpr int sph_compact(int l, int m, int cs)
+{
+  return M0 == 0 ? (m == 0 ? l : (L + 1) + 2 * (sph_slot(L, l, m) - (L + 1)) + cs)
+                 : 2 * (sph_slot(L, l, m) - sph_slot(L, M0, M0)) + cs;
+}
+template <int L, int M0, int M1>
+HD constexpr int sph_compact_count()
+{
+  return sph_compact<L, M0>(L, M1, M1 > 0 ? 1 : 0) + 1;
+}
+
+// ---------------------------------------------------------------------------
+// Field table entry of (row i, one slot) from the node values of H at i-1, i, i+1
+// (K_lm already folded in): out[0..2] = c0,c1,c2 of cell i, out[3..4] = d0,d1 of the
+// stencil centred on i; cos in .x, sin in .y.  1/scale (potential) and 1/scale^2
+// (radial derivative) are folded in (src/SphericalBasis.cc:1640-1643).
+// ---------------------------------------------------------------------------
+HD void sph_poly_entry(const SphGeom &g, const double *p0, int i, double2 Hm, double2 Hc, double2 Hp,
+                       double2 *out)
+{
+  const double is = g.inv_scale, is2 = g.inv_scale * g.inv_scale;
+  double2 z2; z2.x = 0.0; z2.y = 0.0;
+  for (int k = 0; k < kSphPoly; k++) out[k] = z2;
+  if (i <= g.numr - 2) {
+    double p0c = p0[i], dp0 = p0[i + 1] - p0[i];
+    double dHx = Hp.x - Hc.x, dHy = Hp.y - Hc.y;
+    out[0].x = p0c * Hc.x * is;                 out[0].y = p0c * Hc.y * is;
+    out[1].x = (p0c * dHx + dp0 * Hc.x) * is;   out[1].y = (p0c * dHy + dp0 * Hc.y) * is;
+    out[2].x = dp0 * dHx * is;                  out[2].y = dp0 * dHy * is;
+  }
+  if (i >= 1 && i <= g.numr - 2) {
+    double wm = p0[i - 1], wc = p0[i], wp = p0[i + 1];
+    double Wmx = wm * Hm.x, Wcx = wc * Hc.x, Wpx = wp * Hp.x;
+    double Wmy = wm * Hm.y, Wcy = wc * Hc.y, Wpy = wp * Hp.y;
+    out[3].x = 0.5 * (Wpx - Wmx) * is2;         out[3].y = 0.5 * (Wpy - Wmy) * is2;
+    out[4].x = (Wmx - 2.0 * Wcx + Wpx) * is2;   out[4].y = (Wmy - 2.0 * Wcy + Wpy) * is2;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Force pass, per particle (a11).  T is the field table [numr][nslot][kSphPoly] of
+// (cos,sin) pairs (see sph_poly_entry).  sph_force_setup does the per-particle geometry
+// (returns false for frozen particles) and tells which table rows the particle reads
+// (S.cell for c0..c2, S.j for d0,d1); sph_force_eval walks the (l,m) terms given pointers
+// to those two rows (global memory, or a shared-memory copy) and adds into
+// (ax,ay,az,pot).  OFF = true compiles the r > rmax multipole continuation
+// (src/SphericalBasis.cc:1555-1560, 1605-1628) in; with OFF = false the caller
+// guarantees r <= rmax.
+// ---------------------------------------------------------------------------
+struct SphForce {
+  double x, y, z, ir, costh, c1, s1, R2, iR2;
+  double ratio, r0i;          // r > rmax continuation
+  double p, q, fac, xd, somx2i;
+  int cell, j;
+  bool ioff;
+};
+
+template <bool OFF>
+HD bool sph_force_setup(const SphGeom &g, const rec4 &pm, SphForce &S)
+{
+  S.x = pm.x - g.cx; S.y = pm.y - g.cy; S.z = pm.z - g.cz;
+  double r2 = S.x * S.x + S.y * S.y + S.z * S.z;
+  if (r2 > g.rtrunc2) return false;
+
+  double r = sqrt(r2) + EXPB200_DSMALL;
+  S.ir = 1.0 / r;
+  S.costh = S.z * S.ir;
+  sph_azimuth(S.x, S.y, S.c1, S.s1, S.R2, S.iR2);
+
+  S.ioff = OFF && r > g.rmax;
+  S.ratio = 1.0; S.r0i = 0.0;
+  if (OFF && S.ioff) {               // evaluate at rmax, continue outwards
+    S.ratio = g.rmax * S.ir;
+    S.r0i = S.ir * g.inv_scale;
+    r = g.rmax;
+    S.ir = 1.0 / r;
+  }
+
+  double xi;
+  const double t = sph_grid_coord(g, r * g.inv_scale, xi);
+  S.cell = sph_clamp_cell(g, t, 0);
+  S.j = sph_clamp_cell(g, t, 1);
+  S.p = t - S.cell;
+  S.q = t - S.j;
+  S.fac = sph_d_xi_to_r(g, xi) * g.inv_dxi;
+
+  // Legendre derivative clamp (src/Basis.cc:81-86)
+  double xd = S.costh;
+  if (1.0 - fabs(xd) < EXPB200_MINEPS) xd = xd > 0 ? 1.0 - EXPB200_MINEPS : -(1.0 - EXPB200_MINEPS);
+  S.xd = xd;
+  S.somx2i = 1.0 / (xd * xd - 1.0);
   return true;
 }
 
-// ---------------------------------------------------------------------------
-// Force pass, per particle (a11).  H is the field table [numr][nslot] of
-// (cos,sin) pairs built from the coefficients (see sphere.cu: sph_field_kernel).
-// Adds into (ax,ay,az,pot).  Returns false for frozen particles.
-// ---------------------------------------------------------------------------
-template <int L>
-HD bool sph_force_particle(const SphGeom &g, const double *K, const double *inv,
-                           const double *p0, const double2 *H, const rec4 &pm,
-                           double &ax, double &ay, double &az, double &pot)
+template <int L, bool OFF, class LD>
+HD void sph_force_eval(const double *inv, const SphForce &S, const double2 *Tc, const double2 *Td,
+                       LD &&ld, double &ax, double &ay, double &az, double &pot)
 {
-  double x = pm.x - g.cx, y = pm.y - g.cy, z = pm.z - g.cz;
-  double r2 = x * x + y * y + z * z;
-  if (r2 > g.rtrunc2) return false;
-
-  double r = sqrt(r2) + EXPB200_DSMALL;
-  double costh = z / r;
-  double rs = r / g.scale;
-  double c1, s1, R2;
-  sph_azimuth(x, y, c1, s1, R2);
-
-  bool ioff = r > g.rmax;
-  double r0 = r;
-  if (ioff) {                       // src/SphericalBasis.cc:1555-1560
-    r = g.rmax;
-    rs = r / g.scale;
-  }
-
-  double xi;
-  SphStencil st = sph_stencil(g, rs, xi);
-  const int j = st.j;
-  double p0m = EXPB200_LDG(p0 + j - 1), p0c = EXPB200_LDG(p0 + j), p0p = EXPB200_LDG(p0 + j + 1);
-
-  // potential weights on nodes j-1, j, j+1
-  double b0, b1, b2;
-  if (st.cell == j) {
-    double P0 = st.x1 * p0c + st.x2 * p0p;
-    b0 = 0.0; b1 = P0 * st.x1; b2 = P0 * st.x2;
-  } else {                          // cell == j-1 (only at the inner edge)
-    double P0 = st.x1 * p0m + st.x2 * p0c;
-    b0 = P0 * st.x1; b1 = P0 * st.x2; b2 = 0.0;
-  }
-  // derivative weights (exputil/SLGridMP2.cc:975-986)
-  double p = (xi - (g.xmin + g.dxi * j)) / g.dxi;
-  double fac = sph_d_xi_to_r(g, xi) / g.dxi;
-  double a0 = fac * (p - 0.5) * p0m, a1 = -2.0 * fac * p * p0c, a2 = fac * (p + 0.5) * p0p;
-
-  // Legendre derivative clamp (src/Basis.cc:81-86)
-  double xd = costh;
-  if (1.0 - fabs(xd) < EXPB200_MINEPS) xd = xd > 0 ? 1.0 - EXPB200_MINEPS : -(1.0 - EXPB200_MINEPS);
-  double somx2i = 1.0 / (xd * xd - 1.0);
-
-  // exterior multipole continuation factors (src/SphericalBasis.cc:1605-1628)
-  double ratio = ioff ? g.rmax / r0 : 1.0;
-  double r0i = ioff ? 1.0 / r0 : 0.0;
-
-  const double2 *Hm = H + (size_t)(j - 1) * g.nslot;
-  const double2 *Hc = Hm + g.nslot;
-  const double2 *Hp = Hc + g.nslot;
-
+  const double p = S.p, q = S.q, xd = S.xd;
+  const bool ioff = OFF && S.ioff;
   double potl = 0.0, potr = 0.0, pott = 0.0, potp = 0.0;
   double cm = 1.0, sm = 0.0, cm1 = 0.0, sm1 = 0.0;
-  double pw_m = 1.0;                // ratio^m; the column head needs ratio^(m+1)
-  double pw = 1.0;
-  int slot = 0;
+  double Cc, Cs, Dc, Ds, Uc, Us;     // column sums over l of P pc, P ps, P dpc, P dps, P' pc, P' ps
+  double pw_m = 1.0, pw = 1.0;       // ratio^m at the column head; ratio^(l+1) per term
 
-  sph_for_each_plm<L>(costh, inv, [&](int m) {
+  sph_for_each_plm<L, 0, L>(S.costh, inv, [&](int m) {
     if (m > 0) {
       double cn, sn;
-      if (m == 1) { cn = c1; sn = s1; }
-      else { cn = 2.0 * c1 * cm - cm1; sn = 2.0 * c1 * sm - sm1; }
+      if (m == 1) { cn = S.c1; sn = S.s1; }
+      else { cn = 2.0 * S.c1 * cm - cm1; sn = 2.0 * S.c1 * sm - sm1; }
       cm1 = cm; sm1 = sm; cm = cn; sm = sn;
-      pw_m *= ratio;
+      if (OFF) pw_m *= S.ratio;
     }
-    pw = pw_m;
+    if (OFF) pw = pw_m;
+    Cc = Cs = Dc = Ds = Uc = Us = 0.0;
   }, [&](int l, int m, double plm, double plm1) {
-    pw *= ratio;                    // ratio^(l+1)
-    double dplm = somx2i * (xd * l * plm - (l + m) * plm1);
-    double k = K[l * (kMaxL + 1) + m];
-    double facL = k * plm, facD = k * dplm;
-
-    double2 v0 = EXPB200_LDG(Hm + slot), v1 = EXPB200_LDG(Hc + slot), v2 = EXPB200_LDG(Hp + slot);
-    slot++;
-    double pc = b0 * v0.x + b1 * v1.x + b2 * v2.x;
-    double dpc = a0 * v0.x + a1 * v1.x + a2 * v2.x;
-    if (ioff) {
-      pc *= pw;
-      dpc = -pc * r0i * (l + 1);
-    }
-    if (m == 0) {
-      potl += facL * pc;
-      potr += facL * dpc;
-      pott += facD * pc;
-    } else {
-      double ps = b0 * v0.y + b1 * v1.y + b2 * v2.y;
-      double dps = a0 * v0.y + a1 * v1.y + a2 * v2.y;
+    const int o = sph_slot(L, l, m) * kSphPoly;
+    double2 c0 = ld(Tc + o), c1p = ld(Tc + o + 1), c2 = ld(Tc + o + 2);
+    double2 d0 = ld(Td + o + 3), d1 = ld(Td + o + 4);
+    double dpl = (xd * l) * plm - (l + m) * plm1;      // (x^2-1) dP/dx
+    double pc = (c2.x * p + c1p.x) * p + c0.x;
+    double dpc = d1.x * q + d0.x;
+    if (OFF) {
+      pw *= S.ratio;                // ratio^(l+1)
       if (ioff) {
-        ps *= pw;
-        dps = -ps * r0i * (l + 1);
+        pc *= pw;
+        dpc = -pc * S.r0i * (l + 1);
       }
-      double A = pc * cm + ps * sm;
-      potl += facL * A;
-      potr += facL * (dpc * cm + dps * sm);
-      pott += facD * A;
-      potp += facL * (-pc * sm + ps * cm) * m;
+    }
+    Cc += plm * pc;
+    Dc += plm * dpc;
+    Uc += dpl * pc;
+    if (m > 0) {
+      double ps = (c2.y * p + c1p.y) * p + c0.y;
+      double dps = d1.y * q + d0.y;
+      if (OFF && ioff) {
+        ps *= pw;
+        dps = -ps * S.r0i * (l + 1);
+      }
+      Cs += plm * ps;
+      Ds += plm * dps;
+      Us += dpl * ps;
+    }
+  }, [&](int m) {
+    if (m == 0) {
+      potl += Cc;
+      potr += Dc;
+      pott += Uc;
+    } else {
+      potl += Cc * cm + Cs * sm;
+      potr += Dc * cm + Ds * sm;
+      pott += Uc * cm + Us * sm;
+      potp += (Cs * cm - Cc * sm) * m;
     }
   });
 
-  // src/SphericalBasis.cc:1636-1653 (note: r is the clamped radius when r0 > rmax)
-  potr /= g.scale * g.scale;
-  potl /= g.scale;
-  pott /= g.scale;
-  potp /= g.scale;
+  pott *= S.somx2i;
+  if (!ioff) potr *= S.fac;
 
-  double r3 = r * r * r;
-  ax += -(potr * x / r - pott * x * z / r3);
-  ay += -(potr * y / r - pott * y * z / r3);
-  az += -(potr * z / r + pott * R2 / r3);
-  if (R2 > EXPB200_DSMALL) {
-    ax += potp * y / R2;
-    ay += -potp * x / R2;
+  // src/SphericalBasis.cc:1645-1653 (note: r is the clamped radius when r0 > rmax)
+  const double ir = S.ir, ir3 = ir * ir * ir;
+  ax += -(potr * S.x * ir - pott * S.x * S.z * ir3);
+  ay += -(potr * S.y * ir - pott * S.y * S.z * ir3);
+  az += -(potr * S.z * ir + pott * S.R2 * ir3);
+  if (S.R2 > EXPB200_DSMALL) {
+    ax += potp * S.y * S.iR2;
+    ay += -potp * S.x * S.iR2;
   }
   pot += potl;
+}
+
+template <int L, bool OFF>
+HD bool sph_force_particle(const SphGeom &g, const double *inv, const double2 *T, const rec4 &pm,
+                           double &ax, double &ay, double &az, double &pot)
+{
+  SphForce S;
+  if (!sph_force_setup<OFF>(g, pm, S)) return false;
+  sph_force_eval<L, OFF>(inv, S, T + (size_t)S.cell * g.nslot * kSphPoly,
+                         T + (size_t)S.j * g.nslot * kSphPoly,
+                         [](const double2 *a) { return EXPB200_LDG(a); }, ax, ay, az, pot);
   return true;
 }
 

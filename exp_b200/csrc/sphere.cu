@@ -7,14 +7,17 @@
 //
 // Per coefficient call (levlist[mlevel]):
 //   key      : radial cell (and level) of every particle            [HBM stream]
-//   sort     : stable radix sort -> permutation + cell offsets      [HBM stream]
-//   deposit  : per particle Y_lm(theta,phi) * node weights, reduced per radial cell
-//              in sorted order by one warp per chunk (fixed order => deterministic)
+//   sort     : one-pass stable radix binning -> permutation, cell offsets and a copy
+//              of the position records in sorted order              [HBM stream]
+//   deposit  : per particle P_lm(theta) {cos,sin}(m phi) * node weights; lane = particle
+//              with the (lmax+1)^2 x 2 sums of a radial cell in registers, reduced across
+//              the warp by a fixed butterfly when the cell changes   [FP64 pipe]
 //   combine  : per-cell partials -> node sums G[row][i]              [tiny]
-//   contract : coef[row][n] = sum_i E[l][n][i] G[row][i]             [tiny]
+//   contract : coef[row][n] = K_row sum_i E[l][n][i] G[row][i]       [tiny]
 // Per force call:
-//   field    : H[i][slot] = sum_n E[l][n][i] coef[row][n]            [tiny]
-//   force    : per particle 3-node stencil on H, Legendre + derivative, acc/pot
+//   field    : T[i][slot] = per-cell polynomial coefficients of sum_n E coef   [tiny]
+//   force    : per particle Horner forms on T, Legendre + derivative, acc/pot  [FP64 pipe]
+// The single-level step additionally fuses kick+drift+key and force+kick.
 #include "common.cuh"
 #include "sort.cuh"
 #include "sph_math.cuh"
@@ -23,6 +26,7 @@
 #include "profile.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace expb200 {
@@ -34,6 +38,7 @@ namespace {
 
 constexpr int kDepositWarps = 4;
 constexpr int kForceThreads = 128;
+constexpr int kRegDepositMaxL = 6;     // (L+1)^2 x 2 register accumulators fit up to here
 
 template <int L> struct DepositShape {
   static constexpr int NROW = (L + 1) * (L + 1);
@@ -59,6 +64,27 @@ sph_key_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restr
       if (lev > (uint32_t)maxlev) lev = maxlev;
     }
     keys[i] = lev * (uint32_t)g.numr + cell;
+  }
+}
+
+// Single-level step: first half kick, drift and the radial key of the new position in one
+// pass over the particle records (src/step.cc:272-290; arithmetic of src/incvel.cc:68-69,
+// src/incpos.cc:63-66).
+__global__ void __launch_bounds__(256)
+sph_kick_drift_key_kernel(SphGeom g, rec4 *__restrict__ posm, rec4 *__restrict__ vel,
+                          const rec4 *__restrict__ accp, size_t n, double dtk, double dtd,
+                          uint32_t *__restrict__ keys)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    rec4 v = ld_rec_rw(&vel[i]);
+    rec4 a = ld_rec(&accp[i]);
+    rec4 p = ld_rec_rw(&posm[i]);
+    v.x = fma(a.x, dtk, v.x); v.y = fma(a.y, dtk, v.y); v.z = fma(a.z, dtk, v.z);
+    p.x = fma(v.x, dtd, p.x); p.y = fma(v.y, dtd, p.y); p.z = fma(v.z, dtd, p.z);
+    st_rec(&vel[i], v);
+    st_rec(&posm[i], p);
+    keys[i] = sph_cell_of(g, p);
   }
 }
 
@@ -104,17 +130,154 @@ __global__ void multistep_interp_kernel(const double *__restrict__ cL, const dou
 }
 
 // ---------------------------------------------------------------------------
-// deposit: one warp per chunk of CH sorted particles.
-// phase 1 (lane = particle): Y rows -> shared tile; phase 2 (lane = row): walk the 32
+// Warp reduce-scatter of N per-lane values: five butterfly steps, each lane keeps one
+// half of its array and sends the other, so that afterwards lane L holds the full
+// 32-lane sums of RS<N>::FIN rows (rs_row tells which).  N + ... shuffles instead of
+// 5 N, and the summation tree is fixed.
+// ---------------------------------------------------------------------------
+template <int N, int S> struct RS {
+  static constexpr int H = (N + 1) / 2;
+  static constexpr int FIN = RS<H, S + 1>::FIN;
+  static __device__ __forceinline__ void run(double *v, int lane)
+  {
+    const bool up = (lane >> (4 - S)) & 1;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      const double lo = v[i];
+      const double hi = (i + H < N) ? v[i + H] : 0.0;
+      const double send = up ? lo : hi;
+      const double keep = up ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16 >> S);
+    }
+    RS<H, S + 1>::run(v, lane);
+  }
+  // original index of entry i held by `lane` after the remaining steps S..4 (or -1)
+  static __device__ __forceinline__ int row(int lane, int i)
+  {
+    int idx = RS<H, S + 1>::row(lane, i);
+    if (idx < 0) return -1;
+    if ((lane >> (4 - S)) & 1) idx += H;
+    return idx < N ? idx : -1;
+  }
+};
+template <int N> struct RS<N, 5> {
+  static constexpr int FIN = N;
+  static __device__ __forceinline__ void run(double *, int) {}
+  static __device__ __forceinline__ int row(int, int i) { return i < N ? i : -1; }
+};
+
+// ---------------------------------------------------------------------------
+// deposit (lmax <= 6): one warp per chunk of CH sorted particles, lane = particle.
+// Every lane keeps the 2 x NACC sums of the current radial cell in registers; when the
+// cell changes (at most numr times over the whole array) or the chunk ends they are
+// reduced across the warp and written to partial slot (chunk + cell), which is unique
+// because both chunk and cell are non-decreasing along the sorted order.
+// One launch ("sweep") covers the azimuthal columns M0..M1 so that the accumulators fit
+// the register file without spilling: lmax = 6 takes two sweeps (m <= 2: 58 sums,
+// m >= 3: 40 sums).
+// ---------------------------------------------------------------------------
+template <int L, int M0, int M1>
+__device__ __forceinline__ int deposit_row_of(int idx)
+{
+  int row = -1;
+#pragma unroll
+  for (int m = M0; m <= M1; m++)
+#pragma unroll
+    for (int l = m; l <= L; l++) {
+      const int c = sph_compact<L, M0>(l, m, 0);
+      if (idx == c) row = sph_row(l, m);
+      if (m > 0 && idx == c + 1) row = sph_row(l, m) + 1;
+    }
+  return row;
+}
+
+template <int L, int M0, int M1, int MINB>
+__global__ void __launch_bounds__(kDepositWarps * 32, MINB)
+sph_deposit_reg_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ ps,
+                       const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg,
+                       int keybase, int CH, double adb, double *__restrict__ PA,
+                       double *__restrict__ PB)
+{
+  constexpr int NROW = (L + 1) * (L + 1);
+  constexpr int NACC = sph_compact_count<L, M0, M1>();
+  using R = RS<NACC, 0>;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lo = seg[keybase], hi = seg[keybase + g.numr - 1];
+  const size_t chunk = (size_t)blockIdx.x * kDepositWarps + w;
+  const size_t beg = (size_t)lo + chunk * (size_t)CH;
+  if (beg >= hi) return;
+  const size_t end = beg + CH < hi ? beg + CH : hi;
+
+  double A[NACC], B[NACC];
+#pragma unroll
+  for (int r = 0; r < NACC; r++) A[r] = B[r] = 0.0;
+  int cur = -1;
+
+  auto flush = [&](int c) {
+    const size_t slot = (chunk + (size_t)c) * NROW;
+    R::run(A, lane);
+    R::run(B, lane);
+#pragma unroll
+    for (int i = 0; i < R::FIN; i++) {
+      const int idx = R::row(lane, i);
+      const int row = idx >= 0 ? deposit_row_of<L, M0, M1>(idx) : -1;
+      if (row >= 0) {
+        PA[slot + row] = A[i];
+        PB[slot + row] = B[i];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NACC; r++) A[r] = B[r] = 0.0;
+  };
+
+  rec4 nxt = rec4{1.0, 0.0, 0.0, 0.0};
+  uint32_t nkey = 0;
+  if (beg + lane < end) { nxt = ld_rec(&ps[beg + lane]); nkey = skeys[beg + lane]; }
+
+  for (size_t k0 = beg; k0 < end; k0 += 32) {
+    const bool valid = k0 + lane < end;
+    const rec4 pm = nxt;
+    int cell = valid ? (int)nkey - keybase : 0x7fffffff;
+    {
+      const size_t kn = k0 + 32 + lane;      // prefetch the next batch
+      if (kn < end) { nxt = ld_rec(&ps[kn]); nkey = skeys[kn]; }
+    }
+    SphDep d;
+    sph_deposit_setup(g, p0, pm, adb, valid ? cell : 0, d);
+    if (!valid) d.w1 = d.w2 = 0.0;
+
+    // distinct cells of this batch in increasing order (almost always exactly one)
+    int c = __reduce_min_sync(0xffffffffu, cell);
+    while (true) {
+      if (c != cur) {
+        if (cur >= 0) flush(cur);
+        cur = c;
+      }
+      const bool mine = cell == c;
+      const double a = mine ? d.w1 : 0.0, b = mine ? d.w2 : 0.0;
+      sph_deposit_rows<L, M0, M1>(d, c_inv, [&](int l, int m, int cs, double v) {
+        const int q = sph_compact<L, M0>(l, m, cs);
+        A[q] = fma(a, v, A[q]);
+        B[q] = fma(b, v, B[q]);
+      });
+      const int nc = __reduce_min_sync(0xffffffffu, (cell > c && valid) ? cell : 0x7fffffff);
+      if (nc == 0x7fffffff) break;
+      c = nc;
+    }
+  }
+  if (cur >= 0) flush(cur);
+}
+
+// ---------------------------------------------------------------------------
+// deposit (lmax > 6): one warp per chunk of CH sorted particles.
+// phase 1 (lane = particle): rows -> shared tile; phase 2 (lane = row): walk the 32
 // particles in order, accumulate w1*Y and w2*Y, flush when the radial cell changes.
-// A flush goes to partial slot (chunk + cell), which is unique because both chunk and
-// cell are non-decreasing along the sorted order.
 // ---------------------------------------------------------------------------
 template <int L>
 __global__ void __launch_bounds__(kDepositWarps * 32)
-sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ posm,
-                   const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg,
-                   int keybase, int CH, double adb, int mode,
+sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ ps,
+                   const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg,
+                   int keybase, int CH, double adb,
                    double *__restrict__ PA, double *__restrict__ PB)
 {
   using S = DepositShape<L>;
@@ -152,15 +315,14 @@ sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restr
     const size_t k = k0 + lane;
     int cell = -1;
     double w1 = 0.0, w2 = 0.0;
-    bool used = false;
     if (k < end) {
-      rec4 pm = ld_rec(&posm[perm[k]]);
-      used = sph_deposit_particle<L>(g, c_K, c_inv, p0, pm, adb, cell, w1, w2,
-                                     [&](int row, double v) { my[row] = v; }, mode);
-    }
-    if (!used) {
-      cell = -1;
-      w1 = w2 = 0.0;
+      rec4 pm = ld_rec(&ps[k]);
+      cell = (int)skeys[k] - keybase;
+      SphDep d;
+      sph_deposit_setup(g, p0, pm, adb, cell, d);
+      w1 = d.w1; w2 = d.w2;
+      sph_deposit_rows<L, 0, L>(d, c_inv, [&](int l, int m, int cs, double v) { my[sph_row(l, m) + cs] = v; });
+    } else {
       for (int r = 0; r < S::NROW; r++) my[r] = 0.0;
     }
     my[S::NROW] = w1;
@@ -242,96 +404,209 @@ __device__ __forceinline__ double block_sum_256(double v, double *sh)
   return t;   // valid in thread 0
 }
 
-// contract: coef[row][n] = sum_i E[l][n][i] * G[row][i]; one CTA per row.
+// contract: coef[row][n] = K_lm sum_i E[l][n][i] * G[row][i]; one CTA per (row, n).
 __global__ void __launch_bounds__(256)
 sph_contract_kernel(SphGeom g, const double *__restrict__ Ep, const double *__restrict__ G,
                     const int *__restrict__ row_l, const int *__restrict__ row_m, int M0_only,
                     double *__restrict__ coef)
 {
   __shared__ double sh[8];
-  const int row = blockIdx.x;
-  const int l = row_l[row];
-  const bool dead = M0_only && row_m[row] != 0;     // src/SphericalBasis.cc:549
+  const int row = blockIdx.x, n = blockIdx.y;
+  const int l = row_l[row], m = row_m[row];
+  const bool dead = M0_only && m != 0;              // src/SphericalBasis.cc:549
   const double *Gr = G + (size_t)row * g.numr;
-  for (int n = 0; n < g.nmax; n++) {
-    const double *E = Ep + ((size_t)l * g.nmax + n) * g.numr;
-    double s = 0.0;
-    for (int i = threadIdx.x; i < g.numr; i += 256) s += E[i] * Gr[i];
-    double t = block_sum_256(s, sh);
-    if (threadIdx.x == 0) coef[(size_t)row * g.nmax + n] = dead ? 0.0 : t;
-  }
+  const double *E = Ep + ((size_t)l * g.nmax + n) * g.numr;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < g.numr; i += 256) s += E[i] * Gr[i];
+  double t = block_sum_256(s, sh);
+  if (threadIdx.x == 0) coef[(size_t)row * g.nmax + n] = dead ? 0.0 : c_K[l * (kMaxL + 1) + m] * t;
 }
 
-// field: H[i][slot] = (sum_n E[l][n][i] coef[rowc][n], sum_n E[l][n][i] coef[rows][n]).
+// field: T[i][slot][0..4] from H[i][slot] = K_lm (sum_n E[l][n][i] coef[rowc][n],
+// sum_n E[l][n][i] coef[rows][n]) at nodes i-1, i, i+1 (sph_poly_entry).
 // slot_rowc/slot_rows encode which coefficient rows the reference's force loop reads for
 // this (l,m), including its NO_L0/NO_L1/EVEN_L/EVEN_M/M0_only behaviour; -1 = no term.
 __global__ void __launch_bounds__(128)
-sph_field_kernel(SphGeom g, const double *__restrict__ Ep, const double *__restrict__ coef,
-                 const int *__restrict__ slot_l, const int *__restrict__ slot_rowc,
-                 const int *__restrict__ slot_rows, double2 *__restrict__ H)
+sph_field_kernel(SphGeom g, const double *__restrict__ Ep, const double *__restrict__ p0,
+                 const double *__restrict__ coef, const int *__restrict__ slot_l,
+                 const int *__restrict__ slot_m, const int *__restrict__ slot_rowc,
+                 const int *__restrict__ slot_rows, double2 *__restrict__ T)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int slot = blockIdx.y;
   if (i >= g.numr) return;
-  const int l = slot_l[slot], rc = slot_rowc[slot], rs = slot_rows[slot];
-  double c = 0.0, s = 0.0;
+  const int l = slot_l[slot], m = slot_m[slot], rc = slot_rowc[slot], rs = slot_rows[slot];
+  double2 H[3];
+  for (int k = 0; k < 3; k++) H[k] = make_double2(0.0, 0.0);
   if (rc >= 0) {
-    const double *E = Ep + (size_t)l * g.nmax * g.numr + i;
+    const double K = c_K[l * (kMaxL + 1) + m];
     const double *cc = coef + (size_t)rc * g.nmax;
     const double *cs = rs >= 0 ? coef + (size_t)rs * g.nmax : nullptr;
-    for (int n = 0; n < g.nmax; n++) {
-      double e = E[(size_t)n * g.numr];
-      c += e * cc[n];
-      if (cs) s += e * cs[n];
+    for (int k = 0; k < 3; k++) {
+      const int node = i - 1 + k;
+      if (node < 0 || node >= g.numr) continue;
+      const double *E = Ep + (size_t)l * g.nmax * g.numr + node;
+      double c = 0.0, s = 0.0;
+      for (int n = 0; n < g.nmax; n++) {
+        double e = E[(size_t)n * g.numr];
+        c += e * cc[n];
+        if (cs) s += e * cs[n];
+      }
+      H[k] = make_double2(K * c, K * s);
     }
   }
-  H[(size_t)i * g.nslot + slot] = make_double2(c, s);
+  double2 out[kSphPoly];
+  sph_poly_entry(g, p0, i, H[0], H[1], H[2], out);
+  double2 *dst = T + ((size_t)i * g.nslot + slot) * kSphPoly;
+  for (int k = 0; k < kSphPoly; k++) dst[k] = out[k];
 }
 
-// force: one thread per particle, sorted order (neighbouring lanes share table rows).
-template <int L>
-__global__ void __launch_bounds__(kForceThreads)
-sph_force_kernel(SphGeom g, const double *__restrict__ p0, const double2 *__restrict__ H,
-                 const rec4 *__restrict__ posm, rec4 *__restrict__ accp,
-                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg,
-                 int keybase, size_t n)
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
-  const size_t lo = seg ? seg[keybase] : 0;
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+constexpr int kForceRows = 6;     // table rows (radial cells) a CTA stages in shared memory
+
+// force: one thread per particle, sorted order (the 128 particles of a CTA span a few
+// radial cells), positions streamed from the sorted copy.  The CTA finds the range of
+// table rows its particles read and, when it is at most kForceRows, stages those rows of T
+// (contiguous, 2240 B each at lmax=6) into shared memory with one TMA bulk copy; otherwise
+// (sparse outskirts, the unsorted dead-cell tail) it reads T through L1.
+// mode 0: acc/pot += (Component::AddAcc); mode 1 (fused step): acc/pot = value (they would
+// have been zeroed first).
+template <int L>
+__global__ void __launch_bounds__(kForceThreads, 4)
+sph_force_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *__restrict__ ps,
+                 rec4 *__restrict__ accp, const uint32_t *__restrict__ perm,
+                 const uint32_t *__restrict__ seg, int keybase, size_t n, int mode)
+{
+  constexpr int ROW = (L + 1) * (L + 2) / 2 * kSphPoly;      // double2 per table row
+  __shared__ __align__(128) double2 rows[kForceRows * ROW];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_lo, s_hi;
+
+  if (threadIdx.x == 0) {
+    s_lo = 0x7fffffff;
+    s_hi = -1;
+    mbar_init(&bar, 1);
+  }
+  __syncthreads();
+
+  const size_t lo = seg[keybase];
   const size_t k = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const size_t i = perm ? perm[k] : k;
-  rec4 pm = ld_rec(&posm[i]);
+  const bool valid = k < n;
+  rec4 pm = rec4{g.cx + 1.0, g.cy, g.cz, 0.0};
+  uint32_t i = 0;
+  if (valid) { pm = ld_rec(&ps[k]); i = perm[k]; }
+
+  SphForce S;
+  const bool ok = sph_force_setup<true>(g, pm, S) && valid;
+  {
+    int wmin = __reduce_min_sync(0xffffffffu, ok ? S.cell : 0x7fffffff);
+    int wmax = __reduce_max_sync(0xffffffffu, ok ? S.j : -1);      // j >= cell
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&s_lo, wmin);
+      atomicMax(&s_hi, wmax);
+    }
+  }
+  __syncthreads();
+  const int rlo = s_lo, rhi = s_hi;
+  const bool staged = rhi >= rlo && rhi - rlo < kForceRows;
+  const double2 *Tc, *Td;
+  if (staged) {
+    if (threadIdx.x == 0)
+      tma_bulk_load(rows, T + (size_t)rlo * ROW, (uint32_t)((rhi - rlo + 1) * ROW * sizeof(double2)), &bar);
+    Tc = rows + (ok ? S.cell - rlo : 0) * ROW;
+    Td = rows + (ok ? S.j - rlo : 0) * ROW;
+    mbar_wait(&bar, 0);
+  } else {
+    Tc = T + (size_t)(ok ? S.cell : 0) * ROW;
+    Td = T + (size_t)(ok ? S.j : 0) * ROW;
+  }
+
   double ax = 0.0, ay = 0.0, az = 0.0, pot = 0.0;
-  if (!sph_force_particle<L>(g, c_K, c_inv, p0, H, pm, ax, ay, az, pot)) return;
-  rec4 a = ld_rec_rw(&accp[i]);
-  a.x += ax; a.y += ay; a.z += az; a.w += pot;
-  st_rec(&accp[i], a);
+  const bool far = __any_sync(0xffffffffu, ok && S.ioff);
+  if (ok) {
+    if (staged) {
+      auto ld = [](const double2 *a) { return *a; };
+      if (far) sph_force_eval<L, true>(c_inv, S, Tc, Td, ld, ax, ay, az, pot);
+      else     sph_force_eval<L, false>(c_inv, S, Tc, Td, ld, ax, ay, az, pot);
+    } else {
+      auto ld = [](const double2 *a) { return __ldg(a); };
+      if (far) sph_force_eval<L, true>(c_inv, S, Tc, Td, ld, ax, ay, az, pot);
+      else     sph_force_eval<L, false>(c_inv, S, Tc, Td, ld, ax, ay, az, pot);
+    }
+  }
+  if (!valid) return;
+  if (mode == 0) {
+    if (!ok) return;
+    rec4 a = ld_rec_rw(&accp[i]);
+    a.x += ax; a.y += ay; a.z += az; a.w += pot;
+    st_rec(&accp[i], a);
+  } else {
+    st_rec(&accp[i], rec4{0.0 + ax, 0.0 + ay, 0.0 + az, 0.0 + pot});
+  }
 }
 
 template <int L> struct Launch {
-  static int deposit(cudaStream_t st, unsigned nblocks, const SphGeom &g, const double *p0,
-                     const rec4 *posm, const uint32_t *perm, const uint32_t *seg, int keybase,
-                     int CH, double adb, int mode, double *PA, double *PB)
+  static int deposit(cudaStream_t st, unsigned nchunks, const SphGeom &g, const double *p0,
+                     const rec4 *ps, const uint32_t *skeys, const uint32_t *seg, int keybase,
+                     int CH, double adb, double *PA, double *PB)
   {
-    size_t sm = kDepositWarps * DepositShape<L>::WARP_DOUBLES * sizeof(double);
-    static bool attr[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr[dev & 63]) {
-      CU_TRY(cudaFuncSetAttribute(sph_deposit_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      attr[dev & 63] = true;
+    const unsigned nblocks = div_up(nchunks, kDepositWarps);
+    if constexpr (L <= 4) {
+      sph_deposit_reg_kernel<L, 0, L, 3><<<nblocks, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg,
+                                                                                 keybase, CH, adb, PA, PB);
+    } else if constexpr (L <= kRegDepositMaxL) {
+      static const int variant = getenv("EXPB200_DEPOSIT_VARIANT") ? atoi(getenv("EXPB200_DEPOSIT_VARIANT")) : 1;
+#define DEP(M0, M1, MB) sph_deposit_reg_kernel<L, M0, M1, MB><<<nblocks, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg, keybase, CH, adb, PA, PB)
+      if (variant == 0) { DEP(0, 2, 3); DEP(3, L, 3); }
+      else if (variant == 1) { DEP(0, 2, 2); DEP(3, L, 3); }
+      else if (variant == 2) { DEP(0, 1, 3); DEP(2, 3, 3); DEP(4, L, 3); }
+      else { DEP(0, 1, 4); DEP(2, 3, 4); DEP(4, L, 4); }
+#undef DEP
+    } else {
+      size_t sm = kDepositWarps * DepositShape<L>::WARP_DOUBLES * sizeof(double);
+      static bool attr[64] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr[dev & 63]) {
+        CU_TRY(cudaFuncSetAttribute(sph_deposit_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attr[dev & 63] = true;
+      }
+      sph_deposit_kernel<L><<<nblocks, kDepositWarps * 32, sm, st>>>(g, p0, ps, skeys, seg, keybase,
+                                                                      CH, adb, PA, PB);
     }
-    sph_deposit_kernel<L><<<nblocks, kDepositWarps * 32, sm, st>>>(g, p0, posm, perm, seg, keybase,
-                                                                    CH, adb, mode, PA, PB);
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
-  static int force(cudaStream_t st, const SphGeom &g, const double *p0, const double2 *H,
-                   const rec4 *posm, rec4 *accp, const uint32_t *perm, const uint32_t *seg,
-                   int keybase, size_t n)
+  static int force(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps, rec4 *accp,
+                   const uint32_t *perm, const uint32_t *seg, int keybase, size_t n, int mode)
   {
-    sph_force_kernel<L><<<div_up(n, kForceThreads), kForceThreads, 0, st>>>(g, p0, H, posm, accp,
-                                                                           perm, seg, keybase, n);
+    sph_force_kernel<L><<<div_up(n, kForceThreads), kForceThreads, 0, st>>>(g, T, ps, accp, perm, seg,
+                                                                           keybase, n, mode);
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
@@ -349,18 +624,17 @@ template <int L> struct Launch {
     default: set_error("lmax=%d not instantiated (max %d)", lmax, kMaxL); return EXPB200_EINVAL; \
   }
 
-int launch_deposit(int lmax, cudaStream_t st, unsigned nblocks, const SphGeom &g, const double *p0,
-                   const rec4 *posm, const uint32_t *perm, const uint32_t *seg, int keybase, int CH,
-                   double adb, int mode, double *PA, double *PB)
+int launch_deposit(int lmax, cudaStream_t st, unsigned nchunks, const SphGeom &g, const double *p0,
+                   const rec4 *ps, const uint32_t *skeys, const uint32_t *seg, int keybase, int CH,
+                   double adb, double *PA, double *PB)
 {
-  DISPATCH_L(lmax, deposit(st, nblocks, g, p0, posm, perm, seg, keybase, CH, adb, mode, PA, PB))
+  DISPATCH_L(lmax, deposit(st, nchunks, g, p0, ps, skeys, seg, keybase, CH, adb, PA, PB))
 }
 
-int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double *p0, const double2 *H,
-                 const rec4 *posm, rec4 *accp, const uint32_t *perm, const uint32_t *seg,
-                 int keybase, size_t n)
+int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
+                 rec4 *accp, const uint32_t *perm, const uint32_t *seg, int keybase, size_t n, int mode)
 {
-  DISPATCH_L(lmax, force(st, g, p0, H, posm, accp, perm, seg, keybase, n))
+  DISPATCH_L(lmax, force(st, g, T, ps, accp, perm, seg, keybase, n, mode))
 }
 
 } // namespace
@@ -379,12 +653,12 @@ struct expb200_sphere_s {
   double *p0 = nullptr;      // [numr]
   double *coef = nullptr;    // device expcoef0: last accumulated vector
   double *coef_use = nullptr;// coefficients installed for the force
-  double2 *H = nullptr;      // field table [numr][nslot]
+  double2 *T = nullptr;      // field table [numr][nslot][kSphPoly] (sph_poly_entry)
   double *G = nullptr;       // node sums [nrow][numr]
   double *PA = nullptr, *PB = nullptr;
   size_t part_slots = 0;
   int *row_l = nullptr, *row_m = nullptr;
-  int *slot_l = nullptr, *slot_rowc = nullptr, *slot_rows = nullptr;
+  int *slot_l = nullptr, *slot_m = nullptr, *slot_rowc = nullptr, *slot_rows = nullptr;
   bool field_valid = false;
   bool have_accum = false;
   uint32_t *used_dev = nullptr;
@@ -405,10 +679,11 @@ namespace {
 
 int deposit_chunk(size_t n)
 {
-  // one warp per chunk; enough chunks to fill 148 SMs x 32 warps, at most 1024 particles each
-  size_t q = n / ((size_t)kSMsB200 * 32 * 32);
+  // one warp per chunk; 12 warps are resident per SM (register-limited), aim at >= 4 waves
+  // of chunks and at most 4096 particles each
+  size_t q = n / ((size_t)kSMsB200 * 12 * 4 * 32);
   if (q < 1) q = 1;
-  if (q > 32) q = 32;
+  if (q > 128) q = 128;
   return (int)q * 32;
 }
 
@@ -420,6 +695,50 @@ SphGeom geom_for(const expb200_sphere_s *s, const expb200_component_s *c)
   return g;
 }
 
+// Bins the keys in c->keys[0]: permutation, cell offsets and the sorted copy of posm.
+// With allow_reorder the particle store is physically re-ordered into this order when it has
+// never been (random order: every access through the permutation would be a random
+// 32-byte DRAM transaction) or every kReorderEvery sorts (particles drift across cells).
+int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool allow_reorder)
+{
+  (void)s;
+  int cur = 0;
+  {
+    ProfRegion pr(K_SORT, c->stream, radix_sort_launches(c->n, nkeys, true));
+    SortPayload pl;
+    pl.src = c->posm;
+    pl.dst = c->posm_sorted;
+    int rc = radix_sort_pairs(c->stream, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur, c->seg, pl);
+    if (rc) return rc;
+  }
+  c->cur = cur;
+  c->psort = c->posm_sorted;
+  c->sorts_since_reorder++;
+  if (allow_reorder && (c->never_reordered || c->sorts_since_reorder >= kReorderEvery))
+    return component_reorder(c);
+  return EXPB200_OK;
+}
+
+void mark_sorted(expb200_sphere_s *s, expb200_component_s *c)
+{
+  c->sort_kind = 2;
+  c->sort_owner = s;
+  c->keys_per_level = s->cfg.numr;
+  c->sort_pos_ver = c->pos_ver;
+  c->sort_lev_ver = c->lev_ver;
+}
+
+int ensure_seg(expb200_component_s *c, uint32_t nkeys)
+{
+  if (c->seg_cap < (size_t)nkeys + 2) {
+    if (c->seg) cudaFree(c->seg);
+    c->seg = nullptr;
+    CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
+    c->seg_cap = (size_t)nkeys + 2;
+  }
+  return EXPB200_OK;
+}
+
 // (level, radial cell) sort of component c for sphere s, reused while neither positions
 // nor levels changed.
 int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
@@ -428,12 +747,7 @@ int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
       c->sort_lev_ver == c->lev_ver)
     return EXPB200_OK;
   const uint32_t nkeys = (uint32_t)s->nlev * (uint32_t)s->cfg.numr;
-  if (c->seg_cap < (size_t)nkeys + 2) {
-    if (c->seg) cudaFree(c->seg);
-    c->seg = nullptr;
-    CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
-    c->seg_cap = (size_t)nkeys + 2;
-  }
+  { int rc = ensure_seg(c, nkeys); if (rc) return rc; }
   SphGeom g = geom_for(s, c);
   if (c->n) {
     { ProfRegion pr(K_KEY, c->stream);
@@ -441,23 +755,12 @@ int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
                                                                s->nlev > 1, s->nlev - 1, c->keys[0]);
     }
     CU_LAUNCH_CHECK();
-    int cur = 0;
-    int npass = 0;
-    { int nbits = 1; while ((1ull << nbits) < nkeys) nbits++; npass = (nbits + 7) / 8; }
-    ProfRegion pr(K_SORT, c->stream, 3 * npass);
-    int rc = radix_sort_pairs(c->stream, c->keys, c->perm, c->hist, c->n, nkeys, &cur);
+    int rc = sort_keyed(s, c, nkeys, true);
     if (rc) return rc;
-    c->cur = cur;
+  } else {
+    CU_TRY(cudaMemsetAsync(c->seg, 0, ((size_t)nkeys + 1) * sizeof(uint32_t), c->stream));
   }
-  int rc;
-  { ProfRegion pr(K_SEG, c->stream);
-    rc = segment_offsets(c->stream, c->keys[c->cur], c->n, c->seg, nkeys); }
-  if (rc) return rc;
-  c->sort_kind = 2;
-  c->sort_owner = s;
-  c->keys_per_level = s->cfg.numr;
-  c->sort_pos_ver = c->pos_ver;
-  c->sort_lev_ver = c->lev_ver;
+  mark_sorted(s, c);
   return EXPB200_OK;
 }
 
@@ -480,10 +783,36 @@ int build_field(expb200_sphere_s *s, cudaStream_t st)
   const SphGeom &g = s->geom;
   dim3 grid(div_up(g.numr, 128), g.nslot);
   ProfRegion pr(K_FIELD, st);
-  sph_field_kernel<<<grid, 128, 0, st>>>(g, s->Ep, s->coef_use, s->slot_l, s->slot_rowc,
-                                         s->slot_rows, s->H);
+  sph_field_kernel<<<grid, 128, 0, st>>>(g, s->Ep, s->p0, s->coef_use, s->slot_l, s->slot_m,
+                                         s->slot_rowc, s->slot_rows, s->T);
   CU_LAUNCH_CHECK();
   s->field_valid = true;
+  return EXPB200_OK;
+}
+
+// deposit + combine + contract of levlist[mlevel] on an already sorted component -> s->coef
+int accumulate_sorted(expb200_sphere_s *s, expb200_component_s *c, int mlevel, double adb)
+{
+  const int CH = deposit_chunk(c->n);
+  int rc = ensure_partials(s, c->n, CH);
+  if (rc) return rc;
+  SphGeom g = geom_for(s, c);
+  const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
+  if (c->n) {
+    unsigned nchunks = div_up(c->n, CH);
+    ProfRegion pr(K_DEPOSIT, c->stream);
+    rc = launch_deposit(s->cfg.lmax, c->stream, nchunks, g, s->p0, c->psort, c->keys[c->cur],
+                        c->seg, keybase, CH, adb, s->PA, s->PB);
+    if (rc) return rc;
+  }
+  { ProfRegion pr(K_COMBINE, c->stream);
+    sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, s->PA, s->PB, s->G); }
+  { ProfRegion pr(K_CONTRACT, c->stream);
+    sph_contract_kernel<<<dim3(g.nrow, g.nmax), 256, 0, c->stream>>>(g, s->Ep, s->G, s->row_l, s->row_m,
+                                                                     s->cfg.M0_only, s->coef); }
+  CU_LAUNCH_CHECK();
+  s->have_accum = true;
+  s->last_stream = c->stream;
   return EXPB200_OK;
 }
 
@@ -492,27 +821,7 @@ int accumulate(expb200_sphere_s *s, expb200_component_s *c, int mlevel, double a
   { cudaStream_t ws = s->work_stream(); if (ws != c->stream) CU_TRY(cudaStreamSynchronize(ws)); }
   int rc = ensure_sorted(s, c);
   if (rc) return rc;
-  const int CH = deposit_chunk(c->n);
-  rc = ensure_partials(s, c->n, CH);
-  if (rc) return rc;
-  SphGeom g = geom_for(s, c);
-  const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
-  if (c->n) {
-    unsigned nchunks = div_up(c->n, CH);
-    ProfRegion pr(K_DEPOSIT, c->stream);
-    rc = launch_deposit(s->cfg.lmax, c->stream, div_up(nchunks, kDepositWarps), g, s->p0, c->posm,
-                        c->perm[c->cur], c->seg, keybase, CH, adb, 0, s->PA, s->PB);
-    if (rc) return rc;
-  }
-  { ProfRegion pr(K_COMBINE, c->stream);
-    sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, s->PA, s->PB, s->G); }
-  { ProfRegion pr(K_CONTRACT, c->stream);
-    sph_contract_kernel<<<g.nrow, 256, 0, c->stream>>>(g, s->Ep, s->G, s->row_l, s->row_m,
-                                                       s->cfg.M0_only, s->coef); }
-  CU_LAUNCH_CHECK();
-  s->have_accum = true;
-  s->last_stream = c->stream;
-  return EXPB200_OK;
+  return accumulate_sorted(s, c, mlevel, adb);
 }
 
 } // namespace
@@ -577,6 +886,7 @@ int expb200_sphere_create(int device, const expb200_sphere_config *cfg, const do
     };
     int rc;
     if ((rc = up(&s->row_l, M.row_l)) || (rc = up(&s->row_m, M.row_m)) || (rc = up(&s->slot_l, M.slot_l)) ||
+        (rc = up(&s->slot_m, M.slot_m)) ||
         (rc = up(&s->slot_rowc, M.rowc)) || (rc = up(&s->slot_rows, M.rows)))
       return rc;
   }
@@ -585,7 +895,7 @@ int expb200_sphere_create(int device, const expb200_sphere_config *cfg, const do
   CU_TRY(cudaMalloc(&s->coef_use, s->ncoef * sizeof(double)));
   CU_TRY(cudaMemset(s->coef, 0, s->ncoef * sizeof(double)));
   CU_TRY(cudaMemset(s->coef_use, 0, s->ncoef * sizeof(double)));
-  CU_TRY(cudaMalloc(&s->H, (size_t)R * g.nslot * sizeof(double2)));
+  CU_TRY(cudaMalloc(&s->T, (size_t)R * g.nslot * kSphPoly * sizeof(double2)));
   CU_TRY(cudaMalloc(&s->G, (size_t)g.nrow * R * sizeof(double)));
   CU_TRY(cudaMalloc(&s->used_dev, 2 * sizeof(uint32_t)));
   CU_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
@@ -608,9 +918,9 @@ int expb200_sphere_destroy(expb200_sphere s)
   if (!s) return EXPB200_OK;
   DeviceGuard g(s->device);
   cudaDeviceSynchronize();
-  cudaFree(s->Ep); cudaFree(s->p0); cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->H);
+  cudaFree(s->Ep); cudaFree(s->p0); cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->T);
   cudaFree(s->G); cudaFree(s->PA); cudaFree(s->PB); cudaFree(s->row_l); cudaFree(s->row_m);
-  cudaFree(s->slot_l); cudaFree(s->slot_rowc); cudaFree(s->slot_rows); cudaFree(s->used_dev);
+  cudaFree(s->slot_l); cudaFree(s->slot_m); cudaFree(s->slot_rowc); cudaFree(s->slot_rows); cudaFree(s->used_dev);
   cudaFree(s->coefN); cudaFree(s->coefL); cudaFree(s->differ); cudaFree(s->tmp);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
@@ -683,8 +993,8 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   SphGeom gm = geom_for(s, c);
   const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
   ProfRegion pr(K_FORCE, c->stream);
-  return launch_force(s->cfg.lmax, c->stream, gm, s->p0, s->H, c->posm, c->accp, c->perm[c->cur],
-                      c->seg, keybase, c->n);
+  return launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, c->accp, c->perm[c->cur],
+                      c->seg, keybase, c->n, 0);
 }
 
 // ---- multistep coefficient tables -------------------------------------------------
@@ -773,31 +1083,23 @@ int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, doubl
   if (c->n && s->nlev > 1) {
     SphGeom gm = geom_for(s, c);
     const uint32_t nkeys = (uint32_t)s->nlev * (uint32_t)s->cfg.numr + 1;
-    if (c->seg_cap < (size_t)nkeys + 2) {
-      if (c->seg) cudaFree(c->seg);
-      c->seg = nullptr;
-      CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
-      c->seg_cap = (size_t)nkeys + 2;
-    }
-    const int CH = deposit_chunk(c->n);
-    int rc = ensure_partials(s, c->n, CH);
+    int rc = ensure_seg(c, nkeys);
     if (rc) return rc;
+    const int CH = deposit_chunk(c->n);
+    if ((rc = ensure_partials(s, c->n, CH))) return rc;
     for (int side = 0; side < 2; side++) {          // 0: "to" (+), 1: "from" (-)
       sph_switch_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(gm, c->posm, c->level, c->prev_level,
                                                                  c->n, side, s->nlev, c->keys[0]);
       CU_LAUNCH_CHECK();
-      int cur = 0;
-      if ((rc = radix_sort_pairs(st, c->keys, c->perm, c->hist, c->n, nkeys, &cur))) return rc;
-      c->cur = cur;
-      if ((rc = segment_offsets(st, c->keys[cur], c->n, c->seg, nkeys))) return rc;
+      if ((rc = sort_keyed(s, c, nkeys, false))) return rc;
       for (int M = 0; M < s->nlev; M++) {
         const int keybase = M * s->cfg.numr;
         unsigned nchunks = div_up(c->n, CH);
-        rc = launch_deposit(s->cfg.lmax, st, div_up(nchunks, kDepositWarps), gm, s->p0, c->posm,
-                            c->perm[cur], c->seg, keybase, CH, adb, 1, s->PA, s->PB);
+        rc = launch_deposit(s->cfg.lmax, st, nchunks, gm, s->p0, c->psort, c->keys[c->cur],
+                            c->seg, keybase, CH, adb, s->PA, s->PB);
         if (rc) return rc;
         sph_combine_kernel<<<gm.numr, 64, 0, st>>>(gm, c->seg, keybase, CH, s->PA, s->PB, s->G);
-        sph_contract_kernel<<<gm.nrow, 256, 0, st>>>(gm, s->Ep, s->G, s->row_l, s->row_m, 0, s->tmp);
+        sph_contract_kernel<<<dim3(gm.nrow, gm.nmax), 256, 0, st>>>(gm, s->Ep, s->G, s->row_l, s->row_m, 0, s->tmp);
         axpy_kernel<<<div_up(s->ncoef, 256), 256, 0, st>>>(s->differ + (size_t)M * s->ncoef, s->tmp,
                                                           side == 0 ? 1.0 : -1.0, s->ncoef);
         CU_LAUNCH_CHECK();
@@ -834,20 +1136,33 @@ int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double
   REQUIRE(s->nlev == 1, "expb200_sphere_step is the single-level driver (multistep=0)");
   DeviceGuard g(s->device);
   int rc;
-  // do_step, multistep == 0 branch (src/step.cc:272-322)
-  if ((rc = expb200_incr_velocity(c, 0.5 * dt, -1))) return rc;
-  if ((rc = expb200_incr_position(c, dt, -1))) return rc;
-  if ((rc = accumulate(s, c, 0, adb))) return rc;
+  // do_step, multistep == 0 branch (src/step.cc:272-322), fused:
+  //   kick(dt/2) + drift(dt) + key | sort | deposit/combine/contract | [all-reduce] |
+  //   field | force (overwriting acc/pot: no zero pass) | kick(dt/2)
+  { cudaStream_t ws = s->work_stream(); if (ws != c->stream) CU_TRY(cudaStreamSynchronize(ws)); }
+  const uint32_t nkeys = (uint32_t)s->cfg.numr;
+  if ((rc = ensure_seg(c, nkeys))) return rc;
+  if (c->n == 0) return EXPB200_OK;
+  SphGeom gm = geom_for(s, c);
+  { ProfRegion pr(K_KDK, c->stream);
+    sph_kick_drift_key_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(gm, c->posm, c->vel, c->accp, c->n,
+                                                                          0.5 * dt, dt, c->keys[0]);
+    CU_LAUNCH_CHECK(); }
+  c->pos_ver++;
+  if ((rc = sort_keyed(s, c, nkeys, true))) return rc;
+  mark_sorted(s, c);
+  if ((rc = accumulate_sorted(s, c, 0, adb))) return rc;
   if (nccl_comm) {
     ProfRegion pr(K_ALLREDUCE, c->stream, 0);
     if ((rc = nccl_allreduce_sum_f64(nccl_comm, s->coef, s->ncoef, c->stream))) return rc;
   }
   CU_TRY(cudaMemcpyAsync(s->coef_use, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  s->field_valid = false;
-  if ((rc = expb200_component_zero_pot_acc(c, 0))) return rc;
-  if ((rc = expb200_sphere_determine_acceleration(s, c, 0))) return rc;
-  if ((rc = expb200_incr_velocity(c, 0.5 * dt, -1))) return rc;
-  return EXPB200_OK;
+  if ((rc = build_field(s, c->stream))) return rc;
+  { ProfRegion pr(K_FORCE, c->stream);
+    rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, c->accp, c->perm[c->cur],
+                      c->seg, 0, c->n, 1); }
+  if (rc) return rc;
+  return expb200_incr_velocity(c, 0.5 * dt, -1);
 }
 
 } // extern "C"

@@ -200,8 +200,11 @@ int expb200_sphere_get_level_coefficients(expb200_sphere s, int which, int mleve
 int expb200_sphere_set_level_coefficients(expb200_sphere s, int which, int mlevel, const double *host);
 
 /* One fused single-level KDK step for a self-gravitating component, the
- * sequence of do_step (src/step.cc:272-322) with results identical to the
+ * sequence of do_step (src/step.cc:272-322) with the arithmetic of the
  * separate calls: kick(dt/2) drift(dt) coefficients force kick(dt/2).
+ * (Coefficient sums run in the component's storage order, so two components
+ * with different call histories agree to rounding, ~1e-14 relative; the same
+ * history always gives the same bits.)
  * If comm != NULL it is an ncclComm_t and the coefficient vector is summed
  * across ranks (the reference's MPI_Allreduce, src/SphericalBasis.cc:864-903). */
 int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb,

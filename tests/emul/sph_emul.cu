@@ -30,14 +30,15 @@ void coef_impl(const SphGeom &g, const double *K, const double *inv, const doubl
   for (long k = 0; k < n; k++) {
     long i = perm[k];
     if ((int)cell[i] == g.numr - 1) continue;
-    int c; double w1, w2;
+    const int c = (int)cell[i];
     rec4 pm{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]};
-    if (!sph_deposit_particle<L>(g, K, inv, p0, pm, adb, c, w1, w2,
-                                 [&](int row, double v) { yv[row] = v; })) continue;
+    SphDep d;
+    sph_deposit_setup(g, p0, pm, adb, c, d);
+    sph_deposit_rows<L, 0, L>(d, inv, [&](int l, int m, int cs, double v) { yv[sph_row(l, m) + cs] = v; });
     nused++;
     for (int r = 0; r < nrow; r++) {
-      G[(size_t)r * g.numr + c] += w1 * yv[r];
-      G[(size_t)r * g.numr + c + 1] += w2 * yv[r];
+      G[(size_t)r * g.numr + c] += d.w1 * yv[r];
+      G[(size_t)r * g.numr + c + 1] += d.w2 * yv[r];
     }
   }
   SphMaps M;
@@ -45,12 +46,12 @@ void coef_impl(const SphGeom &g, const double *K, const double *inv, const doubl
   cfg.lmax = g.lmax;
   M = make_sph_maps(cfg);
   for (int row = 0; row < nrow; row++) {
-    int l = M.row_l[row];
+    int l = M.row_l[row], m = M.row_m[row];
     for (int nn = 0; nn < g.nmax; nn++) {
       const double *E = Ep + ((size_t)l * g.nmax + nn) * g.numr;
       double s = 0.0;
       for (int i = 0; i < g.numr; i++) s += E[i] * G[(size_t)row * g.numr + i];
-      coef[(size_t)row * g.nmax + nn] = (M0_only && M.row_m[row]) ? 0.0 : s;
+      coef[(size_t)row * g.nmax + nn] = (M0_only && m) ? 0.0 : K[l * (kMaxL + 1) + m] * s;
     }
   }
   *used = nused;
@@ -58,13 +59,13 @@ void coef_impl(const SphGeom &g, const double *K, const double *inv, const doubl
 
 template <int L>
 void accel_impl(const SphGeom &g, const double *K, const double *inv, const double *p0,
-                const double2 *H, long n, const double *pos, const double *mass, double *acc,
+                const double2 *T, long n, const double *pos, const double *mass, double *acc,
                 double *pot)
 {
   for (long i = 0; i < n; i++) {
     rec4 pm{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]};
     double ax = 0, ay = 0, az = 0, pp = 0;
-    if (!sph_force_particle<L>(g, K, inv, p0, H, pm, ax, ay, az, pp)) continue;
+    if (!sph_force_particle<L, true>(g, inv, T, pm, ax, ay, az, pp)) continue;
     acc[3 * i] += ax; acc[3 * i + 1] += ay; acc[3 * i + 2] += az; pot[i] += pp;
   }
 }
@@ -110,10 +111,10 @@ int emul_sph_accel(const expb200_sphere_config *cfg, const double *ev, const dou
   make_sph_constants(K, inv);
   SphMaps M = make_sph_maps(*cfg);
   const int L = cfg->lmax, N = cfg->nmax, R = cfg->numr;
-  std::vector<double2> H((size_t)R * g.nslot);
+  std::vector<double2> H((size_t)R * g.nslot), T((size_t)R * g.nslot * kSphPoly);
   for (int i = 0; i < R; i++)
     for (int slot = 0; slot < g.nslot; slot++) {
-      int l = M.slot_l[slot], rc = M.rowc[slot], rs = M.rows[slot];
+      int l = M.slot_l[slot], m = M.slot_m[slot], rc = M.rowc[slot], rs = M.rows[slot];
       double c = 0, s = 0;
       if (rc >= 0)
         for (int nn = 0; nn < N; nn++) {
@@ -121,9 +122,18 @@ int emul_sph_accel(const expb200_sphere_config *cfg, const double *ev, const dou
           c += e * coef[(size_t)rc * N + nn];
           if (rs >= 0) s += e * coef[(size_t)rs * N + nn];
         }
-      H[(size_t)i * g.nslot + slot] = make_double2(c, s);
+      const double Kf = K[l * (kMaxL + 1) + m];
+      H[(size_t)i * g.nslot + slot] = make_double2(Kf * c, Kf * s);
     }
-  DISPATCH(L, accel_impl, g, K.data(), inv.data(), p0, H.data(), n, pos, mass, acc, pot)
+  const double2 zero = make_double2(0.0, 0.0);
+  for (int i = 0; i < R; i++)
+    for (int slot = 0; slot < g.nslot; slot++) {
+      double2 Hm = i > 0 ? H[(size_t)(i - 1) * g.nslot + slot] : zero;
+      double2 Hp = i < R - 1 ? H[(size_t)(i + 1) * g.nslot + slot] : zero;
+      sph_poly_entry(g, p0, i, Hm, H[(size_t)i * g.nslot + slot], Hp,
+                     &T[((size_t)i * g.nslot + slot) * kSphPoly]);
+    }
+  DISPATCH(L, accel_impl, g, K.data(), inv.data(), p0, T.data(), n, pos, mass, acc, pot)
   return 0;
 }
 }
