@@ -31,6 +31,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# Algorithmic HBM bytes per particle-step: binning 100 (histogram 4,
+# rank 8, apply 88), deposit 2 x 36, force + kicks + drift + key 168.
+STEP_BYTES = 340
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0          # B200_PROFILING.md fallback
+
+
+HBM_PEAK_GBS = _hbm_peak()
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+# capture of this workload (profiles/r01_ncu_*): bytes per launch at 1e7 particles
+NCU_TRAFFIC = {"force": None, "deposit": None}
+
 METRIC = "particle-steps/sec (coef+force+kick-drift) sphereSL"
 UNIT = "particle-steps/s"
 LMAX, NMAX, NUMR = 6, 18, 2000
@@ -40,13 +57,18 @@ DT = 1.0e-3
 
 # ---- algorithmic work per particle (DESIGN.md section "Work model") ----------
 def flops_force(L):
-    """sph_force_kernel: 52 flop per (l,m>0), 29 per (l,0), trig recursion, pro/epilogue"""
-    return 52 * L * (L + 1) // 2 + 29 * (L + 1) + 6 * max(L - 1, 0) + 100
+    """sph_force2_kernel: 31 flop per (l,m>0) term (Legendre recursion 4,
+    derivative 3, Horner forms 12, column sums 12), 19 per (l,0) term, 21 per m>0 column
+    (azimuthal recursion + combination), 120 for geometry, coordinate map and the Cartesian
+    projection; FMA = 2."""
+    return 31 * L * (L + 1) // 2 + 19 * (L + 1) + 21 * L + 120
 
 
 def flops_deposit(L):
-    """sph_deposit_kernel: 17 flop per (l,m>0) (Legendre + 2 rows x 2 node FMAs), 11 per (l,0)"""
-    return 17 * L * (L + 1) // 2 + 11 * (L + 1) + 6 * max(L - 1, 0) + 60
+    """sph_deposit_reg_kernel: 14 flop per (l,m>0) term (recursion 4, 2 products, 4 node FMAs),
+    8 per (l,0) term, 4 per m>0 column, 60 for geometry and weights (counted once although the
+    two register sweeps both evaluate it)."""
+    return 14 * L * (L + 1) // 2 + 8 * (L + 1) + 4 * L + 60
 
 
 def flops_reference(L, N):
@@ -189,7 +211,7 @@ def workload_config(args, world):
             "particles_per_gpu": args.particles_per_gpu, "particles_total": args.particles_per_gpu * world,
             "lmax": LMAX, "nmax": NMAX, "numr": NUMR, "dt": DT,
             "parallelism": f"particles sharded over {world} GPU(s), coefficient all-reduce",
-            "cache": "inputs larger than L2 (96 B/particle resident state >> 126 MB)"}
+            "cache": "inputs larger than L2 (>= 140 B/particle resident state >> 126 MB)"}
 
 
 # ---- our arm ------------------------------------------------------------------------
@@ -255,8 +277,7 @@ def run_ours(args):
     c.sync()
 
     # ---------------- resident throughput: K fused steps, device-timed ----------------
-    for _ in range(args.warmup):
-        s.step(c, DT, comm=comm)
+    s.steps(c, DT, args.warmup, comm=comm)
     c.sync()
     clocks = ClockSampler(local) if rank == 0 else None
     _lib.check(L.expb200_profile_reset())
@@ -266,8 +287,7 @@ def run_ours(args):
     if clocks:
         clocks.start()
     c.event_record(0)
-    for _ in range(args.steps):
-        s.step(c, DT, comm=comm)
+    s.steps(c, DT, args.steps, comm=comm)          # K KDK steps (expb200_sphere_steps)
     c.event_record(1)
     c.sync()
     barrier()
@@ -281,16 +301,7 @@ def run_ours(args):
     # ---------------- end to end through the plugin calls, host buffers ----------------
     def e2e_step():
         c.upload_range(0, hpos, hvel, hmass)                 # H2D of the step's inputs
-        c.incr_velocity(0.5 * DT)
-        c.incr_position(DT)
-        s.determine_coefficients(c, to_host=False)
-        if comm:
-            p, st = s.coef_device()
-            _lib.check(L.expb200_allreduce_sum(comm, p, s.nrow * s.nmax, st))
-        s.set_coefficients(None)
-        c.zero_pot_acc()
-        s.get_acceleration_and_potential(c)
-        c.incr_velocity(0.5 * DT)
+        s.step(c, DT, comm=comm)
         c.download_range(0, n, hpos, hvel, hacc, hpot)       # D2H of the step's result
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -321,19 +332,28 @@ def run_ours(args):
     tot = sum(v[1] for v in prof.values()) or 1.0
     shares = {k: round(v[1] / tot, 4) for k, v in prof.items() if v[2]}
     dom = max(("force", "deposit"), key=lambda k: kern_ms.get(k, 0.0))
-    fl = flops_force(LMAX) if dom == "force" else flops_deposit(LMAX)
-    achieved = fl * n / (kern_ms[dom] * 1e-3) / 1e12
+    # the force launch of a multi-step call also does both half kicks and the drift (18 flop)
+    fl = flops_force(LMAX) + 18 if dom == "force" else flops_deposit(LMAX)
+    ms_dom = prof[dom][1] / args.steps          # per step (the deposit is two launches per step)
+    achieved = fl * n / (ms_dom * 1e-3) / 1e12
+    step_fl = flops_force(LMAX) + flops_deposit(LMAX) + 18
     roofline = {
-        "bound": "fp64", "kernel": f"sph_{dom}_kernel<{LMAX}>", "achieved": achieved,
-        "peak": peak_tf.value, "unit": "TFLOP/s", "frac": achieved / peak_tf.value,
+        "bound": "fp64", "kernel": {"force": f"sph_force2_kernel<{LMAX}>",
+                                    "deposit": f"sph_deposit_reg_kernel<{LMAX},*> (2 sweeps)"}[dom],
+        "achieved": achieved, "peak": peak_tf.value, "unit": "TFLOP/s", "frac": achieved / peak_tf.value,
         "peak_source": "measured: dependency-free DFMA microbenchmark on this device "
                        "(MEASURED_PEAKS.json has no FP64 figure)",
-        "flop_per_particle": fl, "avg_launch_ms": kern_ms[dom], "traffic": None,
+        "flop_per_particle": fl, "avg_launch_ms": ms_dom, "traffic": NCU_TRAFFIC.get(dom),
+        "flop_model": "flops of the factorised formulation this kernel executes (DESIGN.md section 4), "
+                      "not SURVEY 8d's reference-formulation count",
+        "frac_survey_8d_formula": flops_reference(LMAX, NMAX) * n / (ms / args.steps * 1e-3) / 1e12 / peak_tf.value,
         "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in prof.items() if v[2]},
         "kernel_share": shares,
-        "step_flop_per_particle": flops_force(LMAX) + flops_deposit(LMAX) + 18,
+        "step_flop_per_particle": step_fl,
+        "step_fp64_frac": step_fl * n / (ms / args.steps * 1e-3) / 1e12 / peak_tf.value,
         "reference_flop_per_particle": flops_reference(LMAX, NMAX),
-        "hbm_gbs_step": 160.0 * n / (ms / args.steps * 1e-3) / 1e9,
+        "step_hbm_bytes_per_particle": STEP_BYTES,
+        "step_hbm_frac": STEP_BYTES * n / (ms / args.steps * 1e-3) / 1e9 / HBM_PEAK_GBS,
     }
 
     # ---------------- CPU baseline (oracle port of the reference CPU path) ----------------
@@ -356,9 +376,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.e2e_steps,
                 "steps": args.e2e_steps,
-                "path": "Component.upload_range -> incr_velocity -> incr_position -> "
-                        "Sphere.determine_coefficients -> get_acceleration_and_potential -> "
-                        "incr_velocity -> Component.download_range, pinned host buffers"},
+                "path": "Component.upload_range -> Sphere.step (kick, drift, coefficients, force, kick) "
+                        "-> Component.download_range, pinned host buffers"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -399,6 +399,103 @@ HD void sph_force_eval(const double *inv, const SphForce &S, const double2 *Tc, 
   pot += potl;
 }
 
+// Two particles that read the same two table rows (same cell and stencil centre) evaluated
+// together, so that every table entry is delivered to the lane once for both: the register
+// file's input bandwidth, not the FP64 pipe, bounds the single-particle form (a table entry
+// is 16 B per lane per term).  r <= rmax for both (no continuation).
+template <int L, class LD>
+HD void sph_force_eval2(const double *inv, const SphForce &A, const SphForce &B, const double2 *Tc,
+                        const double2 *Td, LD &&ld, double *oa, double *ob)
+{
+  double potl[2] = {0.0, 0.0}, potr[2] = {0.0, 0.0}, pott[2] = {0.0, 0.0}, potp[2] = {0.0, 0.0};
+  double cm[2] = {1.0, 1.0}, sm[2] = {0.0, 0.0}, cm1[2] = {0.0, 0.0}, sm1[2] = {0.0, 0.0};
+  const double x[2] = {A.costh, B.costh}, xd[2] = {A.xd, B.xd};
+  const double c1[2] = {A.c1, B.c1}, s1[2] = {A.s1, B.s1};
+  const double p[2] = {A.p, B.p}, q[2] = {A.q, B.q};
+  double somx2[2], pmm[2] = {1.0, 1.0};
+#pragma unroll
+  for (int k = 0; k < 2; k++) somx2[k] = sqrt((1.0 - x[k]) * (1.0 + x[k]));
+  double fact = 1.0;
+
+#pragma unroll
+  for (int m = 0; m <= L; m++) {
+    if (m > 0) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        pmm[k] *= -fact * somx2[k];
+        double cn, sn;
+        if (m == 1) { cn = c1[k]; sn = s1[k]; }
+        else { cn = 2.0 * c1[k] * cm[k] - cm1[k]; sn = 2.0 * c1[k] * sm[k] - sm1[k]; }
+        cm1[k] = cm[k]; sm1[k] = sm[k]; cm[k] = cn; sm[k] = sn;
+      }
+      fact += 2.0;
+    }
+    double Cc[2] = {0.0, 0.0}, Cs[2] = {0.0, 0.0}, Dc[2] = {0.0, 0.0}, Ds[2] = {0.0, 0.0},
+           Uc[2] = {0.0, 0.0}, Us[2] = {0.0, 0.0};
+    double pl1[2], pl2[2] = {0.0, 0.0};
+#pragma unroll
+    for (int l = m; l <= L; l++) {
+      double plm[2], plm1[2];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (l == m) { plm[k] = pmm[k]; plm1[k] = 0.0; }
+        else if (l == m + 1) { plm[k] = x[k] * (2 * m + 1) * pmm[k]; plm1[k] = pmm[k]; }
+        else { plm[k] = (x[k] * (2 * l - 1) * pl1[k] - (l + m - 1) * pl2[k]) * inv[l - m]; plm1[k] = pl1[k]; }
+      }
+      const int o = sph_slot(L, l, m) * kSphPoly;
+      const double2 c0 = ld(Tc + o), c1p = ld(Tc + o + 1), c2 = ld(Tc + o + 2);
+      const double2 d0 = ld(Td + o + 3), d1 = ld(Td + o + 4);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const double dpl = (xd[k] * l) * plm[k] - (l + m) * plm1[k];
+        const double pc = (c2.x * p[k] + c1p.x) * p[k] + c0.x;
+        const double dpc = d1.x * q[k] + d0.x;
+        Cc[k] += plm[k] * pc;
+        Dc[k] += plm[k] * dpc;
+        Uc[k] += dpl * pc;
+        if (m > 0) {
+          const double ps = (c2.y * p[k] + c1p.y) * p[k] + c0.y;
+          const double dps = d1.y * q[k] + d0.y;
+          Cs[k] += plm[k] * ps;
+          Ds[k] += plm[k] * dps;
+          Us[k] += dpl * ps;
+        }
+        pl2[k] = plm1[k];
+        pl1[k] = plm[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (m == 0) {
+        potl[k] += Cc[k];
+        potr[k] += Dc[k];
+        pott[k] += Uc[k];
+      } else {
+        potl[k] += Cc[k] * cm[k] + Cs[k] * sm[k];
+        potr[k] += Dc[k] * cm[k] + Ds[k] * sm[k];
+        pott[k] += Uc[k] * cm[k] + Us[k] * sm[k];
+        potp[k] += (Cs[k] * cm[k] - Cc[k] * sm[k]) * m;
+      }
+    }
+  }
+
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const SphForce &S = k ? B : A;
+    double *o = k ? ob : oa;
+    const double tt = pott[k] * S.somx2i, rr = potr[k] * S.fac;
+    const double ir = S.ir, ir3 = ir * ir * ir;
+    o[0] += -(rr * S.x * ir - tt * S.x * S.z * ir3);
+    o[1] += -(rr * S.y * ir - tt * S.y * S.z * ir3);
+    o[2] += -(rr * S.z * ir + tt * S.R2 * ir3);
+    if (S.R2 > EXPB200_DSMALL) {
+      o[0] += potp[k] * S.y * S.iR2;
+      o[1] += -potp[k] * S.x * S.iR2;
+    }
+    o[3] += potl[k];
+  }
+}
+
 template <int L, bool OFF>
 HD bool sph_force_particle(const SphGeom &g, const double *inv, const double2 *T, const rec4 &pm,
                            double &ax, double &ay, double &az, double &pot)

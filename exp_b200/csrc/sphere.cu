@@ -489,6 +489,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase)
 
 constexpr int kForceRows = 6;     // table rows (radial cells) a CTA stages in shared memory
 
+// What the force kernels do with a particle's result.
+//   mode 0: acc/pot += (Component::AddAcc)
+//   mode 1: fused single-level step: acc/pot = value (they would have been zeroed first) and
+//           the second half kick vel += acc*dtk
+//   mode 2: mode 1, then the NEXT step's first half kick, drift and radial key (the step
+//           driver runs several steps back to back: src/step.cc:272-322 in a loop)
+struct ForceOut {
+  rec4 *accp, *vel, *posm;
+  uint32_t *keys;
+  double dtk, dtd;
+  int mode;
+};
+
+// pm: the particle's position record (already in registers); v: its velocity record,
+// loaded by the caller before the evaluation so that its latency is hidden (modes 1, 2).
+__device__ __forceinline__ void force_store(const SphGeom &g, const ForceOut &F, uint32_t i, bool ok,
+                                            const double *o, rec4 pm, rec4 v)
+{
+  if (F.mode == 0) {
+    if (!ok) return;
+    rec4 a = ld_rec_rw(&F.accp[i]);
+    a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3];
+    st_rec(&F.accp[i], a);
+    return;
+  }
+  const rec4 a = rec4{0.0 + o[0], 0.0 + o[1], 0.0 + o[2], 0.0 + o[3]};
+  st_rec(&F.accp[i], a);
+  v.x = fma(a.x, F.dtk, v.x); v.y = fma(a.y, F.dtk, v.y); v.z = fma(a.z, F.dtk, v.z);
+  if (F.mode == 2) {
+    v.x = fma(a.x, F.dtk, v.x); v.y = fma(a.y, F.dtk, v.y); v.z = fma(a.z, F.dtk, v.z);
+    rec4 p = pm;
+    p.x = fma(v.x, F.dtd, p.x); p.y = fma(v.y, F.dtd, p.y); p.z = fma(v.z, F.dtd, p.z);
+    st_rec(&F.posm[i], p);
+    F.keys[i] = sph_cell_of(g, p);
+  }
+  st_rec(&F.vel[i], v);
+}
+
 // force: one thread per particle, sorted order (the 128 particles of a CTA span a few
 // radial cells), positions streamed from the sorted copy.  The CTA finds the range of
 // table rows its particles read and, when it is at most kForceRows, stages those rows of T
@@ -498,9 +536,9 @@ constexpr int kForceRows = 6;     // table rows (radial cells) a CTA stages in s
 // have been zeroed first).
 template <int L>
 __global__ void __launch_bounds__(kForceThreads, 4)
-sph_force_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *__restrict__ ps,
-                 rec4 *__restrict__ accp, const uint32_t *__restrict__ perm,
-                 const uint32_t *__restrict__ seg, int keybase, size_t n, int mode)
+sph_force_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, ForceOut F,
+                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg, int keybase,
+                 size_t n)
 {
   constexpr int ROW = (L + 1) * (L + 2) / 2 * kSphPoly;      // double2 per table row
   __shared__ __align__(128) double2 rows[kForceRows * ROW];
@@ -519,7 +557,12 @@ sph_force_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *__restric
   const bool valid = k < n;
   rec4 pm = rec4{g.cx + 1.0, g.cy, g.cz, 0.0};
   uint32_t i = 0;
-  if (valid) { pm = ld_rec(&ps[k]); i = perm[k]; }
+  rec4 vv = rec4{0.0, 0.0, 0.0, 0.0};
+  if (valid) {
+    pm = ld_rec_rw(&ps[k]);
+    i = perm[k];
+    if (F.mode) vv = ld_rec_rw(&F.vel[i]);
+  }
 
   SphForce S;
   const bool ok = sph_force_setup<true>(g, pm, S) && valid;
@@ -560,14 +603,85 @@ sph_force_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *__restric
     }
   }
   if (!valid) return;
-  if (mode == 0) {
-    if (!ok) return;
-    rec4 a = ld_rec_rw(&accp[i]);
-    a.x += ax; a.y += ay; a.z += az; a.w += pot;
-    st_rec(&accp[i], a);
-  } else {
-    st_rec(&accp[i], rec4{0.0 + ax, 0.0 + ay, 0.0 + az, 0.0 + pot});
+  const double o[4] = {ax, ay, az, pot};
+  force_store(g, F, i, ok, o, pm, vv);
+}
+
+// force, two particles per lane (adjacent in the sorted order, so they almost always read the
+// same table rows): halves the table bytes delivered per particle, which is what bounds the
+// one-particle form.  CTAs of 64 threads = 128 particles, staging as in sph_force_kernel.
+constexpr int kForce2Threads = 64;
+
+template <int L>
+__global__ void __launch_bounds__(kForce2Threads, 5)
+sph_force2_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, ForceOut F,
+                  const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg, int keybase,
+                  size_t n)
+{
+  constexpr int ROW = (L + 1) * (L + 2) / 2 * kSphPoly;      // double2 per table row
+  __shared__ __align__(128) double2 rows[kForceRows * ROW];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_lo, s_hi;
+
+  if (threadIdx.x == 0) {
+    s_lo = 0x7fffffff;
+    s_hi = -1;
+    mbar_init(&bar, 1);
   }
+  __syncthreads();
+
+  const size_t lo = seg[keybase];
+  const size_t k0 = lo + (blockIdx.x * (size_t)kForce2Threads + threadIdx.x) * 2;
+  const bool validA = k0 < n, validB = k0 + 1 < n;
+  rec4 pmA = rec4{g.cx + 1.0, g.cy, g.cz, 0.0}, pmB = pmA;
+  uint32_t iA = 0, iB = 0;
+  rec4 vA = rec4{0.0, 0.0, 0.0, 0.0}, vB = vA;
+  if (validA) { pmA = ld_rec_rw(&ps[k0]); iA = perm[k0]; if (F.mode) vA = ld_rec_rw(&F.vel[iA]); }
+  if (validB) { pmB = ld_rec_rw(&ps[k0 + 1]); iB = perm[k0 + 1]; if (F.mode) vB = ld_rec_rw(&F.vel[iB]); }
+
+  SphForce A, B;
+  const bool okA = sph_force_setup<true>(g, pmA, A) && validA;
+  const bool okB = sph_force_setup<true>(g, pmB, B) && validB;
+  {
+    int mn = min(okA ? A.cell : 0x7fffffff, okB ? B.cell : 0x7fffffff);
+    int mx = max(okA ? A.j : -1, okB ? B.j : -1);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&s_lo, mn);
+      atomicMax(&s_hi, mx);
+    }
+  }
+  __syncthreads();
+  const int rlo = s_lo, rhi = s_hi;
+  const bool staged = rhi >= rlo && rhi - rlo < kForceRows;
+  if (staged) {
+    if (threadIdx.x == 0)
+      tma_bulk_load(rows, T + (size_t)rlo * ROW, (uint32_t)((rhi - rlo + 1) * ROW * sizeof(double2)), &bar);
+    mbar_wait(&bar, 0);
+  }
+
+  double oa[4] = {0.0, 0.0, 0.0, 0.0}, ob[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool pair = okA && okB && A.cell == B.cell && A.j == B.j && !A.ioff && !B.ioff;
+  if (pair) {
+    if (staged)
+      sph_force_eval2<L>(c_inv, A, B, rows + (A.cell - rlo) * ROW, rows + (A.j - rlo) * ROW,
+                         [](const double2 *a) { return *a; }, oa, ob);
+    else
+      sph_force_eval2<L>(c_inv, A, B, T + (size_t)A.cell * ROW, T + (size_t)A.j * ROW,
+                         [](const double2 *a) { return __ldg(a); }, oa, ob);
+  } else {
+    // rare: the pair straddles a cell boundary, or a particle beyond rmax (generic loads)
+    const double2 *base = staged ? rows - (size_t)rlo * ROW : T;
+    auto ld = [](const double2 *a) { return *a; };
+    if (okA) sph_force_eval<L, true>(c_inv, A, base + (size_t)A.cell * ROW, base + (size_t)A.j * ROW, ld,
+                                     oa[0], oa[1], oa[2], oa[3]);
+    if (okB) sph_force_eval<L, true>(c_inv, B, base + (size_t)B.cell * ROW, base + (size_t)B.j * ROW, ld,
+                                     ob[0], ob[1], ob[2], ob[3]);
+  }
+
+  if (validA) force_store(g, F, iA, okA, oa, pmA, vA);
+  if (validB) force_store(g, F, iB, okB, ob, pmB, vB);
 }
 
 template <int L> struct Launch {
@@ -602,11 +716,16 @@ template <int L> struct Launch {
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
-  static int force(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps, rec4 *accp,
-                   const uint32_t *perm, const uint32_t *seg, int keybase, size_t n, int mode)
+  static int force(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps, const ForceOut &F,
+                   const uint32_t *perm, const uint32_t *seg, int keybase, size_t n)
   {
-    sph_force_kernel<L><<<div_up(n, kForceThreads), kForceThreads, 0, st>>>(g, T, ps, accp, perm, seg,
-                                                                           keybase, n, mode);
+    static const int variant = getenv("EXPB200_FORCE_VARIANT") ? atoi(getenv("EXPB200_FORCE_VARIANT")) : 1;
+    if (variant == 1 && L <= 8)
+      sph_force2_kernel<L><<<div_up(n, 2 * kForce2Threads), kForce2Threads, 0, st>>>(g, T, ps, F, perm, seg,
+                                                                                   keybase, n);
+    else
+      sph_force_kernel<L><<<div_up(n, kForceThreads), kForceThreads, 0, st>>>(g, T, ps, F, perm, seg,
+                                                                             keybase, n);
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
@@ -632,9 +751,9 @@ int launch_deposit(int lmax, cudaStream_t st, unsigned nchunks, const SphGeom &g
 }
 
 int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
-                 rec4 *accp, const uint32_t *perm, const uint32_t *seg, int keybase, size_t n, int mode)
+                 const ForceOut &F, const uint32_t *perm, const uint32_t *seg, int keybase, size_t n)
 {
-  DISPATCH_L(lmax, force(st, g, T, ps, accp, perm, seg, keybase, n, mode))
+  DISPATCH_L(lmax, force(st, g, T, ps, F, perm, seg, keybase, n))
 }
 
 } // namespace
@@ -993,8 +1112,9 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   SphGeom gm = geom_for(s, c);
   const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
   ProfRegion pr(K_FORCE, c->stream);
-  return launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, c->accp, c->perm[c->cur],
-                      c->seg, keybase, c->n, 0);
+  ForceOut F{c->accp, c->vel, c->posm, c->keys[0], 0.0, 0.0, 0};
+  return launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->seg, keybase,
+                      c->n);
 }
 
 // ---- multistep coefficient tables -------------------------------------------------
@@ -1130,39 +1250,53 @@ int expb200_sphere_multistep_update_finish(expb200_sphere s)
   return EXPB200_OK;
 }
 
-int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb, void *nccl_comm)
+// nsteps single-level KDK steps of a self-gravitating component back to back
+// (do_step, multistep == 0 branch, src/step.cc:272-322, in the main loop of src/expand.cc).
+// Per step: [kick(dt/2) + drift(dt) + key] | bin | deposit/combine/contract | [all-reduce] |
+// field | force (overwriting acc/pot: no zero pass) + kick(dt/2); between two steps of the
+// same call the first bracket rides in the previous step's force kernel.
+int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int nsteps, double adb,
+                         void *nccl_comm)
 {
   REQUIRE(s && c, "NULL argument");
-  REQUIRE(s->nlev == 1, "expb200_sphere_step is the single-level driver (multistep=0)");
+  REQUIRE(s->nlev == 1, "expb200_sphere_step(s) is the single-level driver (multistep=0)");
+  REQUIRE(nsteps >= 0, "nsteps=%d", nsteps);
   DeviceGuard g(s->device);
   int rc;
-  // do_step, multistep == 0 branch (src/step.cc:272-322), fused:
-  //   kick(dt/2) + drift(dt) + key | sort | deposit/combine/contract | [all-reduce] |
-  //   field | force (overwriting acc/pot: no zero pass) | kick(dt/2)
   { cudaStream_t ws = s->work_stream(); if (ws != c->stream) CU_TRY(cudaStreamSynchronize(ws)); }
   const uint32_t nkeys = (uint32_t)s->cfg.numr;
   if ((rc = ensure_seg(c, nkeys))) return rc;
-  if (c->n == 0) return EXPB200_OK;
+  if (c->n == 0 || nsteps == 0) return EXPB200_OK;
   SphGeom gm = geom_for(s, c);
-  { ProfRegion pr(K_KDK, c->stream);
-    sph_kick_drift_key_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(gm, c->posm, c->vel, c->accp, c->n,
-                                                                          0.5 * dt, dt, c->keys[0]);
-    CU_LAUNCH_CHECK(); }
-  c->pos_ver++;
-  if ((rc = sort_keyed(s, c, nkeys, true))) return rc;
-  mark_sorted(s, c);
-  if ((rc = accumulate_sorted(s, c, 0, adb))) return rc;
-  if (nccl_comm) {
-    ProfRegion pr(K_ALLREDUCE, c->stream, 0);
-    if ((rc = nccl_allreduce_sum_f64(nccl_comm, s->coef, s->ncoef, c->stream))) return rc;
+  for (int step = 0; step < nsteps; step++) {
+    if (step == 0) {
+      ProfRegion pr(K_KDK, c->stream);
+      sph_kick_drift_key_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(gm, c->posm, c->vel, c->accp, c->n,
+                                                                            0.5 * dt, dt, c->keys[0]);
+      CU_LAUNCH_CHECK();
+    }
+    c->pos_ver++;
+    if ((rc = sort_keyed(s, c, nkeys, true))) return rc;
+    mark_sorted(s, c);
+    if ((rc = accumulate_sorted(s, c, 0, adb))) return rc;
+    if (nccl_comm) {
+      ProfRegion pr(K_ALLREDUCE, c->stream, 0);
+      if ((rc = nccl_allreduce_sum_f64(nccl_comm, s->coef, s->ncoef, c->stream))) return rc;
+    }
+    CU_TRY(cudaMemcpyAsync(s->coef_use, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = build_field(s, c->stream))) return rc;
+    const bool last = step == nsteps - 1;
+    ForceOut F{c->accp, c->vel, c->posm, c->keys[0], 0.5 * dt, dt, last ? 1 : 2};
+    ProfRegion pr(K_FORCE, c->stream);
+    rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->seg, 0, c->n);
+    if (rc) return rc;
   }
-  CU_TRY(cudaMemcpyAsync(s->coef_use, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  if ((rc = build_field(s, c->stream))) return rc;
-  { ProfRegion pr(K_FORCE, c->stream);
-    rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, c->accp, c->perm[c->cur],
-                      c->seg, 0, c->n, 1); }
-  if (rc) return rc;
-  return expb200_incr_velocity(c, 0.5 * dt, -1);
+  return EXPB200_OK;
+}
+
+int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb, void *nccl_comm)
+{
+  return expb200_sphere_steps(s, c, dt, 1, adb, nccl_comm);
 }
 
 } // extern "C"

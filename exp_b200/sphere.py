@@ -82,6 +82,10 @@ class Sphere:
     def step(self, c: Component, dt: float, adb: float = 1.0, comm=None):
         check(_lib.lib().expb200_sphere_step(self._h, c._h, float(dt), float(adb), comm))
 
+    def steps(self, c: Component, dt: float, nsteps: int, adb: float = 1.0, comm=None):
+        """nsteps single-level KDK steps back to back (same arithmetic as step() in a loop)."""
+        check(_lib.lib().expb200_sphere_steps(self._h, c._h, float(dt), int(nsteps), float(adb), comm))
+
     def coef_device(self):
         p = c_dp()
         st = C.c_void_p()

@@ -209,6 +209,10 @@ int expb200_sphere_set_level_coefficients(expb200_sphere s, int which, int mleve
  * across ranks (the reference's MPI_Allreduce, src/SphericalBasis.cc:864-903). */
 int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb,
                         void *nccl_comm);
+/* nsteps such steps back to back (the main loop of src/expand.cc around do_step): the same
+ * arithmetic, with the first kick + drift of step k+1 riding in the force kernel of step k. */
+int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int nsteps, double adb,
+                         void *nccl_comm);
 
 /* ------------------------------------------------------------------------
  * Cylinder (force id "cylinder"): Cylinder + EmpCylSL tables.

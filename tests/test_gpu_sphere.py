@@ -200,6 +200,15 @@ def test_leapfrog_and_step():
     for k in ("pos", "vel", "acc", "pot"):
         assert fused[k].tobytes() == again[k].tobytes(), k
 
+    # several steps in one call (first kick + drift of step k+1 fused into the force pass of
+    # step k) == the same number of single-step calls, bit for bit
+    for _ in range(3):
+        s2.step(c2, dt)
+    s3.steps(c3, dt, 3)
+    one, many = c2.download(), c3.download()
+    for k in ("pos", "vel", "acc", "pot"):
+        assert one[k].tobytes() == many[k].tobytes(), k
+
 
 def test_empty_and_tiny():
     tab = get_table("hernquist", 2, 10)
