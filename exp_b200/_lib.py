@@ -146,6 +146,8 @@ SIGNATURES = {
     "expb200_sphere_differ_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]),
     "expb200_sphere_get_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_sphere_set_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
+    "expb200_sphere_covariance": (C.c_int, [_H, _H, C.c_int, C.c_double, C.c_int, C.c_uint64, c_up, c_dp,
+                                            c_dp, c_dp]),
     "expb200_sphere_step": (C.c_int, [_H, _H, C.c_double, C.c_double, C.c_void_p]),
     "expb200_sphere_steps": (C.c_int, [_H, _H, C.c_double, C.c_int, C.c_double, C.c_void_p]),
     "expb200_cylinder_create": (C.c_int, [C.c_int, C.POINTER(CylinderConfig), c_dp, c_dp, c_dp, c_dp,

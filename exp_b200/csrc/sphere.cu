@@ -195,14 +195,17 @@ template <int L, int M0, int M1, int MINB>
 __global__ void __launch_bounds__(kDepositWarps * 32, MINB)
 sph_deposit_reg_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ ps,
                        const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg,
-                       int keybase, int CH, double adb, double *__restrict__ PA,
+                       int keybase0, int CH, double adb, int batched, double *__restrict__ PA,
                        double *__restrict__ PB)
 {
   constexpr int NROW = (L + 1) * (L + 1);
   constexpr int NACC = sph_compact_count<L, M0, M1>();
   using R = RS<NACC, 0>;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // batched: blockIdx.y selects one of several consecutive key groups (covariance bins)
+  const int keybase = keybase0 + blockIdx.y * g.numr;
   const uint32_t lo = seg[keybase], hi = seg[keybase + g.numr - 1];
+  const size_t sbase = batched ? (size_t)blockIdx.y * (g.numr + 2) + (lo - seg[keybase0]) / CH : 0;
   const size_t chunk = (size_t)blockIdx.x * kDepositWarps + w;
   const size_t beg = (size_t)lo + chunk * (size_t)CH;
   if (beg >= hi) return;
@@ -214,7 +217,7 @@ sph_deposit_reg_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__r
   int cur = -1;
 
   auto flush = [&](int c) {
-    const size_t slot = (chunk + (size_t)c) * NROW;
+    const size_t slot = (sbase + chunk + (size_t)c) * NROW;
     R::run(A, lane);
     R::run(B, lane);
 #pragma unroll
@@ -277,7 +280,7 @@ template <int L>
 __global__ void __launch_bounds__(kDepositWarps * 32)
 sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ ps,
                    const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg,
-                   int keybase, int CH, double adb,
+                   int keybase0, int CH, double adb, int batched,
                    double *__restrict__ PA, double *__restrict__ PB)
 {
   using S = DepositShape<L>;
@@ -286,7 +289,9 @@ sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restr
   double *tile = smem + (size_t)w * S::WARP_DOUBLES;
   int *cells = reinterpret_cast<int *>(tile + 32 * S::STRIDE);
 
+  const int keybase = keybase0 + blockIdx.y * g.numr;
   const uint32_t lo = seg[keybase], hi = seg[keybase + g.numr - 1];
+  const size_t sbase = batched ? (size_t)blockIdx.y * (g.numr + 2) + (lo - seg[keybase0]) / CH : 0;
   const size_t chunk = (size_t)blockIdx.x * kDepositWarps + w;
   const size_t beg = (size_t)lo + chunk * (size_t)CH;
   if (beg >= hi) return;
@@ -298,7 +303,7 @@ sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restr
   int cur = -1;
 
   auto flush = [&](int c) {
-    size_t slot = (chunk + (size_t)c) * S::NROW;
+    size_t slot = (sbase + chunk + (size_t)c) * S::NROW;
 #pragma unroll
     for (int q = 0; q < S::RPL; q++) {
       int r = lane + 32 * q;
@@ -357,13 +362,18 @@ sph_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restr
 // combine: G[row][i] = sum over the chunks holding cell i of PA + same for cell i-1 of PB,
 // chunks visited in increasing order (fixed order).
 // ---------------------------------------------------------------------------
-__global__ void sph_combine_kernel(SphGeom g, const uint32_t *__restrict__ seg, int keybase, int CH,
-                                   const double *__restrict__ PA, const double *__restrict__ PB,
-                                   double *__restrict__ G)
+__global__ void sph_combine_kernel(SphGeom g, const uint32_t *__restrict__ seg, int keybase0, int CH,
+                                   int batched, const double *__restrict__ PA,
+                                   const double *__restrict__ PB, double *__restrict__ G)
 {
   const int i = blockIdx.x;
   const int nrow = g.nrow;
+  const int keybase = keybase0 + blockIdx.y * g.numr;
   const uint32_t lo = seg[keybase];
+  const size_t sbase = batched ? (size_t)blockIdx.y * (g.numr + 2) + (lo - seg[keybase0]) / CH : 0;
+  PA += sbase * nrow;
+  PB += sbase * nrow;
+  G += (size_t)blockIdx.y * nrow * g.numr;
   for (int row = threadIdx.x; row < nrow; row += blockDim.x) {
     double sum = 0.0;
     if (i <= g.numr - 2) {
@@ -414,6 +424,8 @@ sph_contract_kernel(SphGeom g, const double *__restrict__ Ep, const double *__re
   const int row = blockIdx.x, n = blockIdx.y;
   const int l = row_l[row], m = row_m[row];
   const bool dead = M0_only && m != 0;              // src/SphericalBasis.cc:549
+  G += (size_t)blockIdx.z * g.nrow * g.numr;        // batched over covariance bins
+  coef += (size_t)blockIdx.z * g.nrow * g.nmax;
   const double *Gr = G + (size_t)row * g.numr;
   const double *E = Ep + ((size_t)l * g.nmax + n) * g.numr;
   double s = 0.0;
@@ -684,18 +696,285 @@ sph_force2_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, Forc
   if (validB) force_store(g, F, iB, okB, ob, pmB, vB);
 }
 
+// ===========================================================================
+// Covariance (pcavar), src/SphericalBasis.cc:501-509, 525-545, 563-581.
+// Per jackknife bin T = indx % sampT the reference accumulates, over the bin's particles,
+//   coefT[T][lm](n)   = the bin's share of the coefficients (complex: cos + i sin)
+//   coefM[T][lm](n,o) = sum_p mass fac0^2 (K_lm P_lm)^2 potd(l,n) potd(l,o)
+// potd is linear in the two table nodes of the particle's radial cell, so coefM factorises
+// like the coefficients do: with a = P0 x1, b = P0 x2 and W = mass fac0^2 (K P)^2
+//   Saa[i] = sum_{p in cell i} W a^2,  Sab[i] = sum W a b,  Sbb[i] = sum W b^2
+//   coefM(n,o) = sum_i E_n(i) [ D_i E_o(i) + O_i E_o(i+1) + O_{i-1} E_o(i-1) ]
+//   D_i = Saa[i] + Sbb[i-1],  O_i = Sab[i]
+// i.e. one dense  E^T (Tri E)  product per (T, l, m) with K = numr: the DMMA tensor cores
+// do it (mma.sync m8n8k4 f64).  The per-particle work is 3 sums per (l,m).
+// ===========================================================================
+
+// keys (T, cell): T = host slot % sampT; particles of other levels -> sentinel
+__global__ void __launch_bounds__(256)
+sph_cov_key_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                   const uint32_t *__restrict__ slot_of, size_t n, int use_levels, int mlevel,
+                   uint32_t sampT, uint64_t indx_base, uint32_t *__restrict__ keys)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t key = sampT * (uint32_t)g.numr;
+    if (!use_levels || level[i] == (unsigned)mlevel) {
+      const uint64_t indx = indx_base + (slot_of ? slot_of[i] : (uint32_t)i);
+      key = (uint32_t)(indx % sampT) * (uint32_t)g.numr + sph_cell_of(g, ld_rec(&posm[i]));
+    }
+    keys[i] = key;
+  }
+}
+
+// quadratic deposit: lane = particle, 3 sums per (l,m) + the mass in registers, flushed
+// (fixed butterfly) when the (T, cell) key changes.  Partial slot layout as the deposit's.
+template <int L>
+__global__ void __launch_bounds__(kDepositWarps * 32, 2)
+sph_cov_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ ps,
+                       const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg,
+                       int keybase0, int CH, double adb, double *__restrict__ PS)
+{
+  constexpr int NS = (L + 1) * (L + 2) / 2;
+  constexpr int NACC = 3 * NS + 1;
+  using R = RS<NACC, 0>;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int keybase = keybase0 + blockIdx.y * g.numr;
+  const uint32_t lo = seg[keybase], hi = seg[keybase + g.numr - 1];
+  const size_t sbase = (size_t)blockIdx.y * (g.numr + 2) + (lo - seg[keybase0]) / CH;
+  const size_t chunk = (size_t)blockIdx.x * kDepositWarps + w;
+  const size_t beg = (size_t)lo + chunk * (size_t)CH;
+  if (beg >= hi) return;
+  const size_t end = beg + CH < hi ? beg + CH : hi;
+
+  double A[NACC];
+#pragma unroll
+  for (int r = 0; r < NACC; r++) A[r] = 0.0;
+  int cur = -1;
+  auto flush = [&](int c) {
+    const size_t slot = (sbase + chunk + (size_t)c) * NACC;
+    R::run(A, lane);
+#pragma unroll
+    for (int i = 0; i < R::FIN; i++) {
+      const int idx = R::row(lane, i);
+      if (idx >= 0) PS[slot + idx] = A[i];
+    }
+#pragma unroll
+    for (int r = 0; r < NACC; r++) A[r] = 0.0;
+  };
+
+  for (size_t k0 = beg; k0 < end; k0 += 32) {
+    const bool valid = k0 + lane < end;
+    rec4 pm = rec4{1.0, 0.0, 0.0, 0.0};
+    int cell = 0x7fffffff;
+    if (valid) { pm = ld_rec(&ps[k0 + lane]); cell = (int)skeys[k0 + lane] - keybase; }
+    SphDep d;
+    sph_deposit_setup(g, p0, pm, adb, valid ? cell : 0, d);
+    // d.w1 = mass adb fac0 P0 x1 = mass adb fac0 a: W a^2 = w1^2 / (mass adb), etc.
+    const double mass = pm.w * adb;
+    const double im = valid && mass != 0.0 ? 1.0 / mass : 0.0;
+    const double waa = valid ? d.w1 * d.w1 * im : 0.0, wab = valid ? d.w1 * d.w2 * im : 0.0,
+                 wbb = valid ? d.w2 * d.w2 * im : 0.0;
+    int c = __reduce_min_sync(0xffffffffu, cell);
+    while (true) {
+      if (c != cur) {
+        if (cur >= 0) flush(cur);
+        cur = c;
+      }
+      const bool mine = cell == c;
+      const double aa = mine ? waa : 0.0, ab = mine ? wab : 0.0, bb = mine ? wbb : 0.0;
+      sph_for_each_plm<L, 0, L>(d.costh, c_inv, [](int) {}, [&](int l, int m, double plm, double) {
+        const double f = c_K[l * (kMaxL + 1) + m] * plm;
+        const double f2 = f * f;
+        const int q = 3 * sph_slot(L, l, m);
+        A[q] = fma(aa, f2, A[q]);
+        A[q + 1] = fma(ab, f2, A[q + 1]);
+        A[q + 2] = fma(bb, f2, A[q + 2]);
+      }, [](int) {});
+      A[3 * NS] += mine ? mass : 0.0;
+      const int nc = __reduce_min_sync(0xffffffffu, (cell > c && valid) ? cell : 0x7fffffff);
+      if (nc == 0x7fffffff) break;
+      c = nc;
+    }
+  }
+  if (cur >= 0) flush(cur);
+}
+
+// combine: D[ty][slot][i] = Saa[i] + Sbb[i-1], O[ty][slot][i] = Sab[i]; the mass of cell i
+// goes to Mc[ty][i].  Chunks visited in increasing order.
+__global__ void sph_cov_combine_kernel(SphGeom g, const uint32_t *__restrict__ seg, int keybase0, int CH,
+                                       const double *__restrict__ PS, double *__restrict__ DO,
+                                       double *__restrict__ Mc)
+{
+  const int i = blockIdx.x, ty = blockIdx.y;
+  const int ns = g.nslot, nacc = 3 * ns + 1;
+  const int keybase = keybase0 + ty * g.numr;
+  const uint32_t lo = seg[keybase];
+  const size_t sbase = (size_t)ty * (g.numr + 2) + (lo - seg[keybase0]) / CH;
+  PS += sbase * nacc;
+  double *D = DO + (size_t)ty * ns * g.numr * 2, *O = D + (size_t)ns * g.numr;
+  auto cell_sum = [&](int c, int idx) {
+    double sum = 0.0;
+    if (c < 0 || c > g.numr - 2) return sum;
+    uint32_t s0 = seg[keybase + c], s1 = seg[keybase + c + 1];
+    if (s1 > s0) {
+      size_t j0 = (s0 - lo) / CH, j1 = (s1 - 1 - lo) / CH;
+      for (size_t j = j0; j <= j1; j++) sum += PS[(j + c) * nacc + idx];
+    }
+    return sum;
+  };
+  for (int slot = threadIdx.x; slot < ns; slot += blockDim.x) {
+    D[(size_t)slot * g.numr + i] = cell_sum(i, 3 * slot) + cell_sum(i - 1, 3 * slot + 2);
+    O[(size_t)slot * g.numr + i] = cell_sum(i, 3 * slot + 1);
+  }
+  if (threadIdx.x == blockDim.x - 1) Mc[(size_t)ty * g.numr + i] = cell_sum(i, 3 * ns);
+}
+
+__global__ void sph_cov_mass_kernel(SphGeom g, const double *__restrict__ Mc, double *__restrict__ massT)
+{
+  if (threadIdx.x) return;
+  double t = 0.0;
+  for (int i = 0; i < g.numr; i++) t += Mc[(size_t)blockIdx.x * g.numr + i];
+  massT[blockIdx.x] = t;
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// contraction on the FP64 tensor cores: one CTA per (slot, T); warp w takes the nodes
+// i = 4 (w + 4 s), s = 0, 1, ...; the four partial nmax x nmax tiles are summed in warp order.
+// A fragment (row n = 8 rt + lane/4, k = lane%4) is E[l][n][i]; the B fragment of column tile
+// ct is the tridiagonally weighted E of the same lane mapping, so one set of loads serves both.
+constexpr int kCovTiles = 4;          // nmax <= 32
+__global__ void __launch_bounds__(128)
+sph_cov_contract_kernel(SphGeom g, const double *__restrict__ Ep, const double *__restrict__ DO,
+                        const int *__restrict__ slot_l, const int *__restrict__ slot_m, int M0_only,
+                        double *__restrict__ Mout)
+{
+  __shared__ double part[4][kCovTiles * 8][kCovTiles * 8 + 1];
+  const int slot = blockIdx.x, ty = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int N = g.nmax, R = g.numr, NT = (N + 7) / 8;
+  const int l = slot_l[slot];
+  const double *D = DO + ((size_t)ty * g.nslot * 2 + slot) * R;
+  const double *O = D + (size_t)g.nslot * R;
+  const double *E = Ep + (size_t)l * N * R;
+  double acc[kCovTiles][kCovTiles][2];
+#pragma unroll
+  for (int a = 0; a < kCovTiles; a++)
+#pragma unroll
+    for (int b = 0; b < kCovTiles; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  const bool dead = M0_only && slot_m[slot] != 0;
+  if (!dead) {
+    for (int i0 = 4 * w; i0 < R; i0 += 16) {
+      const int i = i0 + t;
+      const bool in = i < R;
+      const double Di = in ? D[i] : 0.0;
+      const double Oi = (in && i <= R - 2) ? O[i] : 0.0;
+      const double Om = (in && i >= 1) ? O[i - 1] : 0.0;
+      double af[kCovTiles], bf[kCovTiles];
+#pragma unroll
+      for (int r = 0; r < kCovTiles; r++) {
+        const int n = 8 * r + gq;
+        double ec = 0.0, em = 0.0, ep = 0.0;
+        if (r < NT && n < N && in) {
+          const double *e = E + (size_t)n * R + i;
+          ec = e[0];
+          if (i >= 1) em = e[-1];
+          if (i <= R - 2) ep = e[1];
+        }
+        af[r] = ec;
+        bf[r] = Di * ec + Oi * ep + Om * em;
+      }
+#pragma unroll
+      for (int a = 0; a < kCovTiles; a++)
+#pragma unroll
+        for (int b = 0; b < kCovTiles; b++)
+          if (a < NT && b < NT) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < kCovTiles; a++)
+#pragma unroll
+    for (int b = 0; b < kCovTiles; b++) {
+      part[w][8 * a + gq][8 * b + 2 * t] = acc[a][b][0];
+      part[w][8 * a + gq][8 * b + 2 * t + 1] = acc[a][b][1];
+    }
+  __syncthreads();
+  double *M = Mout + ((size_t)ty * g.nslot + slot) * N * N;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int n = e / N, o = e % N;
+    M[e] = ((part[0][n][o] + part[1][n][o]) + part[2][n][o]) + part[3][n][o];
+  }
+}
+
+// host layout: coefT[T][iC][n][2] (iC = l(l+1)/2 + m; re = cos row, im = sin row),
+// coefM[T][iC][n][o]
+__global__ void sph_cov_pack_kernel(SphGeom g, const double *__restrict__ coefT_rows,
+                                    const double *__restrict__ Mslots, double *__restrict__ outT,
+                                    double *__restrict__ outM)
+{
+  const int iC = blockIdx.x, ty = blockIdx.y;
+  const int N = g.nmax, ldim = g.nslot;
+  int l = 0;
+  while ((l + 1) * (l + 2) / 2 <= iC) l++;
+  const int m = iC - l * (l + 1) / 2;
+  const int row = sph_row(l, m), slot = sph_slot(g.lmax, l, m);
+  const double *rows = coefT_rows + (size_t)ty * g.nrow * N;
+  double *T = outT + ((size_t)ty * ldim + iC) * N * 2;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    T[2 * n] = rows[(size_t)row * N + n];
+    T[2 * n + 1] = m ? rows[(size_t)(row + 1) * N + n] : 0.0;
+  }
+  const double *Ms = Mslots + ((size_t)ty * ldim + slot) * N * N;
+  double *M = outM + ((size_t)ty * ldim + iC) * N * N;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) M[e] = Ms[e];
+}
+
+template <int L> struct LaunchCov {
+  static int run(cudaStream_t st, dim3 grid, const SphGeom &g, const double *p0, const rec4 *ps,
+                 const uint32_t *skeys, const uint32_t *seg, int keybase, int CH, double adb, double *PS)
+  {
+    sph_cov_deposit_kernel<L><<<grid, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    CU_LAUNCH_CHECK();
+    return EXPB200_OK;
+  }
+};
+
+int launch_cov_deposit(int lmax, cudaStream_t st, dim3 grid, const SphGeom &g, const double *p0,
+                       const rec4 *ps, const uint32_t *skeys, const uint32_t *seg, int keybase, int CH,
+                       double adb, double *PS)
+{
+  switch (lmax) {
+    case 0: return LaunchCov<0>::run(st, grid, g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    case 1: return LaunchCov<1>::run(st, grid, g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    case 2: return LaunchCov<2>::run(st, grid, g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    case 3: return LaunchCov<3>::run(st, grid, g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    case 4: return LaunchCov<4>::run(st, grid, g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    case 5: return LaunchCov<5>::run(st, grid, g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    case 6: return LaunchCov<6>::run(st, grid, g, p0, ps, skeys, seg, keybase, CH, adb, PS);
+    default: set_error("covariance: lmax=%d not instantiated (max 6)", lmax); return EXPB200_EINVAL;
+  }
+}
+
 template <int L> struct Launch {
   static int deposit(cudaStream_t st, unsigned nchunks, const SphGeom &g, const double *p0,
                      const rec4 *ps, const uint32_t *skeys, const uint32_t *seg, int keybase,
-                     int CH, double adb, double *PA, double *PB)
+                     int CH, double adb, double *PA, double *PB, int nbatch)
   {
-    const unsigned nblocks = div_up(nchunks, kDepositWarps);
+    const dim3 nblocks(div_up(nchunks, kDepositWarps), nbatch > 0 ? nbatch : 1);
+    const int batched = nbatch > 0;
     if constexpr (L <= 4) {
       sph_deposit_reg_kernel<L, 0, L, 3><<<nblocks, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg,
-                                                                                 keybase, CH, adb, PA, PB);
+                                                                                 keybase, CH, adb, batched, PA, PB);
     } else if constexpr (L <= kRegDepositMaxL) {
       static const int variant = getenv("EXPB200_DEPOSIT_VARIANT") ? atoi(getenv("EXPB200_DEPOSIT_VARIANT")) : 1;
-#define DEP(M0, M1, MB) sph_deposit_reg_kernel<L, M0, M1, MB><<<nblocks, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg, keybase, CH, adb, PA, PB)
+#define DEP(M0, M1, MB) sph_deposit_reg_kernel<L, M0, M1, MB><<<nblocks, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg, keybase, CH, adb, batched, PA, PB)
       if (variant == 0) { DEP(0, 2, 3); DEP(3, L, 3); }
       else if (variant == 1) { DEP(0, 2, 2); DEP(3, L, 3); }
       else if (variant == 2) { DEP(0, 1, 3); DEP(2, 3, 3); DEP(4, L, 3); }
@@ -711,7 +990,7 @@ template <int L> struct Launch {
         attr[dev & 63] = true;
       }
       sph_deposit_kernel<L><<<nblocks, kDepositWarps * 32, sm, st>>>(g, p0, ps, skeys, seg, keybase,
-                                                                      CH, adb, PA, PB);
+                                                                      CH, adb, batched, PA, PB);
     }
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
@@ -745,9 +1024,9 @@ template <int L> struct Launch {
 
 int launch_deposit(int lmax, cudaStream_t st, unsigned nchunks, const SphGeom &g, const double *p0,
                    const rec4 *ps, const uint32_t *skeys, const uint32_t *seg, int keybase, int CH,
-                   double adb, double *PA, double *PB)
+                   double adb, double *PA, double *PB, int nbatch = 0)
 {
-  DISPATCH_L(lmax, deposit(st, nchunks, g, p0, ps, skeys, seg, keybase, CH, adb, PA, PB))
+  DISPATCH_L(lmax, deposit(st, nchunks, g, p0, ps, skeys, seg, keybase, CH, adb, PA, PB, nbatch))
 }
 
 int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
@@ -925,7 +1204,7 @@ int accumulate_sorted(expb200_sphere_s *s, expb200_component_s *c, int mlevel, d
     if (rc) return rc;
   }
   { ProfRegion pr(K_COMBINE, c->stream);
-    sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, s->PA, s->PB, s->G); }
+    sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, 0, s->PA, s->PB, s->G); }
   { ProfRegion pr(K_CONTRACT, c->stream);
     sph_contract_kernel<<<dim3(g.nrow, g.nmax), 256, 0, c->stream>>>(g, s->Ep, s->G, s->row_l, s->row_m,
                                                                      s->cfg.M0_only, s->coef); }
@@ -1218,7 +1497,7 @@ int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, doubl
         rc = launch_deposit(s->cfg.lmax, st, nchunks, gm, s->p0, c->psort, c->keys[c->cur],
                             c->seg, keybase, CH, adb, s->PA, s->PB);
         if (rc) return rc;
-        sph_combine_kernel<<<gm.numr, 64, 0, st>>>(gm, c->seg, keybase, CH, s->PA, s->PB, s->G);
+        sph_combine_kernel<<<gm.numr, 64, 0, st>>>(gm, c->seg, keybase, CH, 0, s->PA, s->PB, s->G);
         sph_contract_kernel<<<dim3(gm.nrow, gm.nmax), 256, 0, st>>>(gm, s->Ep, s->G, s->row_l, s->row_m, 0, s->tmp);
         axpy_kernel<<<div_up(s->ncoef, 256), 256, 0, st>>>(s->differ + (size_t)M * s->ncoef, s->tmp,
                                                           side == 0 ? 1.0 : -1.0, s->ncoef);
@@ -1297,6 +1576,120 @@ int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int n
 int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double adb, void *nccl_comm)
 {
   return expb200_sphere_steps(s, c, dt, 1, adb, nccl_comm);
+}
+
+// ~ the `compute && pcavar` branch of determine_coefficients_thread
+// (src/SphericalBasis.cc:501-509, 525-545, 563-581) for levlist[mlevel]: per jackknife bin
+// T = (indx_base + host slot) % sampT the number, mass, coefficient share and covariance
+// matrices of the bin's particles.  Host outputs (any may be NULL):
+//   countT[sampT], massT[sampT], coefT[sampT][ldim][nmax][2], coefM[sampT][ldim][nmax][nmax]
+// with ldim = (lmax+1)(lmax+2)/2, index l(l+1)/2 + m (the reference's iC).
+int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel, double adb, int sampT,
+                              uint64_t indx_base, unsigned *countT, double *massT, double *coefT,
+                              double *coefM)
+{
+  REQUIRE(s && c, "NULL argument");
+  REQUIRE(s->device == c->device, "device mismatch");
+  REQUIRE(mlevel >= 0 && mlevel < s->nlev, "mlevel=%d outside [0,%d]", mlevel, s->nlev - 1);
+  REQUIRE(sampT >= 1 && (uint64_t)sampT * s->cfg.numr < 0x7fffffffull, "sampT=%d out of range", sampT);
+  REQUIRE(s->cfg.nmax <= 8 * kCovTiles, "covariance supports nmax <= %d", 8 * kCovTiles);
+  REQUIRE(s->cfg.lmax <= 6, "covariance supports lmax <= 6");
+  DeviceGuard gd(s->device);
+  cudaStream_t st = c->stream;
+  { cudaStream_t ws = s->work_stream(); if (ws != st) CU_TRY(cudaStreamSynchronize(ws)); }
+  s->last_stream = st;
+  const SphGeom gm = geom_for(s, c);
+  const int R = gm.numr, N = gm.nmax, ldim = gm.nslot;
+  const uint32_t nkeys = (uint32_t)sampT * R + 1;
+  int rc = ensure_seg(c, nkeys);
+  if (rc) return rc;
+  if (countT) for (int T = 0; T < sampT; T++) countT[T] = 0;
+  if (massT) for (int T = 0; T < sampT; T++) massT[T] = 0.0;
+  if (coefT) memset(coefT, 0, (size_t)sampT * ldim * N * 2 * sizeof(double));
+  if (coefM) memset(coefM, 0, (size_t)sampT * ldim * N * N * sizeof(double));
+  if (c->n == 0) return EXPB200_OK;
+
+  ProfRegion pr(K_COV, st, 0);
+  sph_cov_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(gm, c->posm, c->level,
+                                                          c->identity_order ? nullptr : c->slot_of, c->n,
+                                                          s->nlev > 1, mlevel, (uint32_t)sampT, indx_base,
+                                                          c->keys[0]);
+  CU_LAUNCH_CHECK();
+  if ((rc = sort_keyed(s, c, nkeys, false))) return rc;
+  c->sort_kind = 0;                       // the component's regular sort was overwritten
+
+  // bin boundaries on the host: seg[T*R] (first particle of bin T) and seg[T*R + R - 1]
+  std::vector<uint32_t> hseg((size_t)nkeys + 1);
+  CU_TRY(cudaMemcpyAsync(hseg.data(), c->seg, hseg.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  size_t maxlen = 1;
+  for (int T = 0; T < sampT; T++) {
+    size_t len = hseg[(size_t)T * R + R - 1] - hseg[(size_t)T * R];
+    if (countT) countT[T] = (unsigned)len;
+    if (len > maxlen) maxlen = len;
+  }
+  int CH = (int)(maxlen / 8 / 32) * 32;
+  if (CH < 32) CH = 32;
+  if (CH > 2048) CH = 2048;
+  const unsigned nchunks = div_up(maxlen, CH);
+
+  // bins are processed TB at a time; scratch sized for one batch
+  const size_t per_bin = (size_t)(R + 2) + nchunks + 1;              // partial slots per bin
+  const size_t bytes_per_bin = per_bin * (2 * gm.nrow + 3 * ldim + 1) * sizeof(double) +
+                               ((size_t)gm.nrow * R + 2 * (size_t)ldim * R + R + (size_t)gm.nrow * N +
+                                (size_t)ldim * N * N) * sizeof(double);
+  int TB = (int)((size_t)1 << 30) / (int)(bytes_per_bin > ((size_t)1 << 30) ? ((size_t)1 << 30) : bytes_per_bin);
+  if (TB < 1) TB = 1;
+  if (TB > sampT) TB = sampT;
+  if (TB > 65535) TB = 65535;
+  double *PA = nullptr, *PB = nullptr, *PS = nullptr, *G = nullptr, *DO = nullptr, *Mc = nullptr,
+         *rows = nullptr, *Ms = nullptr, *mT = nullptr, *outT = nullptr, *outM = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(PA); cudaFree(PB); cudaFree(PS); cudaFree(G); cudaFree(DO); cudaFree(Mc); cudaFree(rows);
+    cudaFree(Ms); cudaFree(mT); cudaFree(outT); cudaFree(outM);
+  };
+#define COV_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
+  const size_t slots = per_bin * TB + 2;
+  COV_TRY(cudaMalloc(&PA, slots * gm.nrow * sizeof(double)));
+  COV_TRY(cudaMalloc(&PB, slots * gm.nrow * sizeof(double)));
+  COV_TRY(cudaMalloc(&PS, slots * (3 * ldim + 1) * sizeof(double)));
+  COV_TRY(cudaMalloc(&G, (size_t)TB * gm.nrow * R * sizeof(double)));
+  COV_TRY(cudaMalloc(&DO, (size_t)TB * 2 * ldim * R * sizeof(double)));
+  COV_TRY(cudaMalloc(&Mc, (size_t)TB * R * sizeof(double)));
+  COV_TRY(cudaMalloc(&rows, (size_t)TB * gm.nrow * N * sizeof(double)));
+  COV_TRY(cudaMalloc(&Ms, (size_t)TB * ldim * N * N * sizeof(double)));
+  COV_TRY(cudaMalloc(&mT, (size_t)TB * sizeof(double)));
+  COV_TRY(cudaMalloc(&outT, (size_t)TB * ldim * N * 2 * sizeof(double)));
+  COV_TRY(cudaMalloc(&outM, (size_t)TB * ldim * N * N * sizeof(double)));
+
+  for (int T0 = 0; T0 < sampT; T0 += TB) {
+    const int nb = sampT - T0 < TB ? sampT - T0 : TB;
+    const int keybase = T0 * R;
+    // linear sums of every bin: the ordinary deposit, batched over the bins
+    rc = launch_deposit(s->cfg.lmax, st, nchunks, gm, s->p0, c->psort, c->keys[c->cur], c->seg, keybase, CH,
+                        adb, PA, PB, nb);
+    if (rc) { cleanup(); return rc; }
+    sph_combine_kernel<<<dim3(R, nb), 64, 0, st>>>(gm, c->seg, keybase, CH, 1, PA, PB, G);
+    sph_contract_kernel<<<dim3(gm.nrow, N, nb), 256, 0, st>>>(gm, s->Ep, G, s->row_l, s->row_m,
+                                                              s->cfg.M0_only, rows);
+    // quadratic sums, then the E^T (Tri E) products on the tensor cores
+    rc = launch_cov_deposit(s->cfg.lmax, st, dim3(div_up(nchunks, kDepositWarps), nb), gm, s->p0, c->psort,
+                            c->keys[c->cur], c->seg, keybase, CH, adb, PS);
+    if (rc) { cleanup(); return rc; }
+    sph_cov_combine_kernel<<<dim3(R, nb), 32, 0, st>>>(gm, c->seg, keybase, CH, PS, DO, Mc);
+    sph_cov_mass_kernel<<<nb, 32, 0, st>>>(gm, Mc, mT);
+    sph_cov_contract_kernel<<<dim3(ldim, nb), 128, 0, st>>>(gm, s->Ep, DO, s->slot_l, s->slot_m,
+                                                            s->cfg.M0_only, Ms);
+    sph_cov_pack_kernel<<<dim3(ldim, nb), 128, 0, st>>>(gm, rows, Ms, outT, outM);
+    COV_TRY(cudaGetLastError());
+    if (massT) COV_TRY(cudaMemcpyAsync(massT + T0, mT, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (coefT) COV_TRY(cudaMemcpyAsync(coefT + (size_t)T0 * ldim * N * 2, outT, (size_t)nb * ldim * N * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (coefM) COV_TRY(cudaMemcpyAsync(coefM + (size_t)T0 * ldim * N * N, outM, (size_t)nb * ldim * N * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    COV_TRY(cudaStreamSynchronize(st));
+  }
+#undef COV_TRY
+  cleanup();
+  return EXPB200_OK;
 }
 
 } // extern "C"

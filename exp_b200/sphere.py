@@ -64,6 +64,21 @@ class Sphere:
         self.used = used.value
         return coef
 
+    def covariance(self, c: Component, sampT: int, adb: float = 1.0, indx_base: int = 0):
+        """The pcavar accumulation (src/SphericalBasis.cc:501-581) of levlist[mlevel]: per
+        jackknife bin T = indx % sampT returns countT, massT, coefT (complex, [T][ldim][nmax])
+        and coefM ([T][ldim][nmax][nmax]), ldim index l(l+1)/2 + m."""
+        ldim = (self.lmax + 1) * (self.lmax + 2) // 2
+        countT = np.zeros(sampT, dtype=np.uint32)
+        massT = np.zeros(sampT)
+        coefT = np.zeros((sampT, ldim, self.nmax, 2))
+        coefM = np.zeros((sampT, ldim, self.nmax, self.nmax))
+        check(_lib.lib().expb200_sphere_covariance(
+            self._h, c._h, self.mlevel, float(adb), int(sampT), int(indx_base),
+            countT.ctypes.data_as(_lib.c_up), massT.ctypes.data_as(c_dp), coefT.ctypes.data_as(c_dp),
+            coefM.ctypes.data_as(c_dp)))
+        return dict(countT=countT, massT=massT, coefT=coefT[..., 0] + 1j * coefT[..., 1], coefM=coefM)
+
     def set_coefficients(self, coef=None):
         """HtoD_coefs: install the coefficients the force evaluation uses (None: the
         vector accumulated on the device)."""

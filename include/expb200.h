@@ -199,6 +199,19 @@ int expb200_sphere_differ_device(expb200_sphere s, double **dptr, size_t *count,
 int expb200_sphere_get_level_coefficients(expb200_sphere s, int which, int mlevel, double *host);
 int expb200_sphere_set_level_coefficients(expb200_sphere s, int which, int mlevel, const double *host);
 
+/* Covariance of the coefficients (pcavar), the `compute` branch of
+ * determine_coefficients_thread (src/SphericalBasis.cc:501-509, 525-545, 563-581;
+ * ~ the covariance part of determine_coefficients_cuda, src/cudaSphericalBasis.cu) for
+ * levlist[mlevel].  Bin T = (indx_base + host slot) % sampT.  Host outputs, any may be NULL:
+ *   countT[sampT], massT[sampT]                    countT1 / massT1
+ *   coefT[sampT][ldim][nmax][2]                    expcoefT1 (re, im)
+ *   coefM[sampT][ldim][nmax][nmax]                 expcoefM1 (real; imaginary part is 0)
+ * ldim = (lmax+1)(lmax+2)/2, index l(l+1)/2 + m.  lmax <= 6, nmax <= 32.  The component's
+ * cell sort is replaced by the (bin, cell) sort of this call. */
+int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel, double adb,
+                              int sampT, uint64_t indx_base, unsigned *countT, double *massT,
+                              double *coefT, double *coefM);
+
 /* One fused single-level KDK step for a self-gravitating component, the
  * sequence of do_step (src/step.cc:272-322) with the arithmetic of the
  * separate calls: kick(dt/2) drift(dt) coefficients force kick(dt/2).
