@@ -162,6 +162,11 @@ SIGNATURES = {
     "expb200_cylinder_determine_acceleration": (C.c_int, [_H, _H, C.c_int]),
     "expb200_cylinder_multistep_commit": (C.c_int, [_H, C.c_int]),
     "expb200_cylinder_compute_multistep_coefficients": (C.c_int, [_H, C.c_int, C.c_double]),
+    "expb200_cylinder_multistep_update": (C.c_int, [_H, _H, C.c_double, C.c_int]),
+    "expb200_cylinder_multistep_update_finish": (C.c_int, [_H]),
+    "expb200_cylinder_differ_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_size_t),
+                                                 C.POINTER(C.c_void_p)]),
+    "expb200_cylinder_get_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp, c_dp]),
     "expb200_profile_enable": (C.c_int, [C.c_int]),
     "expb200_profile_reset": (C.c_int, []),
     "expb200_profile_kernels": (C.c_int, []),

@@ -88,26 +88,27 @@ HDC void cyl_rot(const double *R, double &x, double &y, double &z)
 // Classification of a particle for the coefficient pass
 // (src/Cylinder.cc:836-858, exputil/EmpCylSL.cc:4062-4063):
 //   returns 0 = unused, 1 = used but off the table (counts + mass only), 2 = deposits.
+// mode 1 = multistep_update (src/Cylinder.cc:1751-1773): no orientation, no rcylmax gate.
 HDC int cyl_classify(const CylGeom &g, const rec4 &pm, double &x, double &y, double &z,
-                     double &r)
+                     double &r, int mode = 0)
 {
   x = pm.x - g.cx; y = pm.y - g.cy; z = pm.z - g.cz;
   if (x * x + y * y + z * z > g.rtrunc2) return 0;          // Component::freeze
-  if (g.rotate) cyl_rot(g.body, x, y, z);
+  if (g.rotate && mode == 0) cyl_rot(g.body, x, y, z);
   double r2 = x * x + y * y;
   r = sqrt(r2);
   double R2 = r2 + z * z;
-  if (!(R2 < g.rmax2)) return 0;
+  if (mode == 0 && !(R2 < g.rmax2)) return 0;
   double rr = sqrt(r * r + z * z);
   if (rr / g.ascale > g.rtable) return 1;
   return 2;
 }
 
 // key within a level: cell index, ncell (used, off table) or ncell+1 (unused)
-HDC uint32_t cyl_cell_key(const CylGeom &g, const rec4 &pm)
+HDC uint32_t cyl_cell_key(const CylGeom &g, const rec4 &pm, int mode = 0)
 {
   double x, y, z, r;
-  int cls = cyl_classify(g, pm, x, y, z, r);
+  int cls = cyl_classify(g, pm, x, y, z, r, mode);
   if (cls == 0) return (uint32_t)g.ncell + 1u;
   if (cls == 1) return (uint32_t)g.ncell;
   double zz = z;
@@ -138,10 +139,10 @@ HDC void cyl_trig(int mmax, double x, double y, double r, F &&f)
 // -4 pi * mass * adb, and the cell with its four corner weights.
 template <class Store>
 HDC bool cyl_deposit_particle(const CylGeom &g, const rec4 &pm, double adb, CylCell &cell,
-                              Store &&store)
+                              Store &&store, int mode = 0)
 {
   double x, y, z, r;
-  if (cyl_classify(g, pm, x, y, z, r) != 2) return false;
+  if (cyl_classify(g, pm, x, y, z, r, mode) != 2) return false;
   double zz = z;
   if (zz / g.ascale > g.rtable) zz = g.rtable * g.ascale;       // EmpCylSL::get_pot clamp
   if (zz / g.ascale < -g.rtable) zz = -g.rtable * g.ascale;

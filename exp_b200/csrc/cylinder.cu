@@ -66,12 +66,39 @@ __global__ void cyl_mass_kernel(const double *__restrict__ block_mass, int nbloc
   }
 }
 
+// keys for multistep_update: particles whose level changed get (side level, cell with the
+// update's own gating), everything else the sentinel key nlev*(ncell+2).
+__global__ void __launch_bounds__(256)
+cyl_switch_key_kernel(CylGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                      const unsigned *__restrict__ prev, size_t n, int use_prev, int nlev,
+                      uint32_t *__restrict__ keys)
+{
+  const uint32_t kpl = (uint32_t)g.ncell + 2u;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    unsigned a = prev[i], b = level[i];
+    uint32_t key = (uint32_t)nlev * kpl;
+    if (a != b) {
+      uint32_t lev = use_prev ? a : b;
+      if (lev >= (uint32_t)nlev) lev = nlev - 1;
+      key = lev * kpl + cyl_cell_key(g, ld_rec(&posm[i]), 1);
+    }
+    keys[i] = key;
+  }
+}
+
+__global__ void cyl_axpy_kernel(double *__restrict__ dst, const double *__restrict__ src, double sign, size_t n)
+{
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k < n) dst[k] += sign * src[k];
+}
+
 // deposit: see sphere.cu::sph_deposit_kernel for the scheme.  Here a particle carries nk
 // azimuthal terms and four corner weights; lane q owns accumulators (k, corner) = (q>>2, q&3).
 __global__ void __launch_bounds__(kCylDepositWarps * 32)
 cyl_deposit_kernel(CylGeom g, const rec4 *__restrict__ posm, const uint32_t *__restrict__ perm,
                    const uint32_t *__restrict__ seg, int keybase, int CH, double adb,
-                   int stride, double *__restrict__ PA)
+                   int stride, int mode, double *__restrict__ PA)
 {
   // per warp: 32 rows of `stride` doubles (nk azimuthal terms + 4 corner weights, odd
   // stride => conflict-free 64-bit lanes) + 32 cell ids
@@ -111,7 +138,7 @@ cyl_deposit_kernel(CylGeom g, const rec4 *__restrict__ posm, const uint32_t *__r
     if (k < end) {
       rec4 pm = ld_rec(&posm[perm[k]]);
       CylCell c;
-      used = cyl_deposit_particle(g, pm, adb, c, [&](int kk, double v) { my[kk] = v; });
+      used = cyl_deposit_particle(g, pm, adb, c, [&](int kk, double v) { my[kk] = v; }, mode);
       if (used) {
         cellid = c.ix * g.numy + c.iy;
         my[nk] = c.c00; my[nk + 1] = c.c10; my[nk + 2] = c.c01; my[nk + 3] = c.c11;
@@ -273,6 +300,7 @@ struct expb200_cylinder_s {
   double *coef = nullptr;           // accumulated [cos | sin | mass]   (ncoef + 1 doubles)
   double *coef_use = nullptr;       // installed   [cos | sin | cylmass]
   double *coefN = nullptr, *coefL = nullptr;      // [nlev][ncoef+1]
+  double *differ = nullptr, *tmp = nullptr;       // level-switch differences [nlev][ncoef+1], scratch
   double *G = nullptr;              // [nk][nnode]
   double *F = nullptr;              // [nnode][3][nkpad]
   double *PA = nullptr;
@@ -420,6 +448,9 @@ int expb200_cylinder_create(int device, const expb200_cylinder_config *cfg,
   CU_TRY(cudaMemset(s->coef_use, 0, cb));
   CU_TRY(cudaMemset(s->coefN, 0, s->nlev * cb));
   CU_TRY(cudaMemset(s->coefL, 0, s->nlev * cb));
+  CU_TRY(cudaMalloc(&s->differ, s->nlev * cb));
+  CU_TRY(cudaMalloc(&s->tmp, cb));
+  CU_TRY(cudaMemset(s->differ, 0, s->nlev * cb));
   CU_TRY(cudaMalloc(&s->G, (size_t)g.nk * g.nnode * sizeof(double)));
   CU_TRY(cudaMalloc(&s->F, (size_t)g.nnode * 3 * s->nkpad * sizeof(double)));
   CU_TRY(cudaMalloc(&s->block_mass, (size_t)kSMsB200 * 8 * sizeof(double)));
@@ -435,6 +466,7 @@ int expb200_cylinder_destroy(expb200_cylinder s)
   cudaDeviceSynchronize();
   for (int k = 0; k < 3; k++) for (int cs = 0; cs < 2; cs++) cudaFree(s->tab[k][cs]);
   cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->coefN); cudaFree(s->coefL);
+  cudaFree(s->differ); cudaFree(s->tmp);
   cudaFree(s->G); cudaFree(s->F); cudaFree(s->PA); cudaFree(s->block_mass);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
@@ -483,7 +515,7 @@ int expb200_cylinder_determine_coefficients(expb200_cylinder s, expb200_componen
     const int stride = (g.nk + 4) | 1;
     const size_t sm = (size_t)kCylDepositWarps * (32 * stride + 16) * sizeof(double);
     cyl_deposit_kernel<<<div_up(nchunks, kCylDepositWarps), kCylDepositWarps * 32, sm, st>>>(
-        g, c->posm, c->perm[c->cur], c->seg, keybase, CH, adb, stride, s->PA);
+        g, c->posm, c->perm[c->cur], c->seg, keybase, CH, adb, stride, 0, s->PA);
     CU_LAUNCH_CHECK();
   }
   { ProfRegion pr(K_COMBINE, st);
@@ -603,6 +635,106 @@ int expb200_cylinder_compute_multistep_coefficients(expb200_cylinder s, int mdrf
     CU_TRY(cudaMemcpy(s->coef_use + s->ncoef, &cylmass, sizeof(double), cudaMemcpyHostToDevice));
   }
   s->field_valid = false;
+  return EXPB200_OK;
+}
+
+// ~ CylEXP::multistep_update_begin / multistep_update (per switching particle) /
+// multistep_update_finish (src/CylEXP.cc:45-157, 159-188; src/Cylinder.cc:1751-1773): for every
+// particle whose level changed in the last expb200_adjust_multistep_level, subtract its
+// contribution from differ[old level] and add it to differ[new level]; with finish != 0 also
+// cosN/sinN[M] += differ[M] (single rank; with several ranks all-reduce the differ buffer
+// first, then call expb200_cylinder_multistep_update_finish).
+int expb200_cylinder_multistep_update(expb200_cylinder s, expb200_component c, double adb, int finish)
+{
+  REQUIRE(s && c, "NULL argument");
+  REQUIRE(s->device == c->device, "device mismatch");
+  DeviceGuard gd(s->device);
+  cudaStream_t st = c->stream;
+  { cudaStream_t ws = s->work_stream(); if (ws != st) CU_TRY(cudaStreamSynchronize(ws)); }
+  s->last_stream = st;
+  const size_t n1 = s->ncoef + 1, all = (size_t)s->nlev * n1;
+  CU_TRY(cudaMemsetAsync(s->differ, 0, all * sizeof(double), st));
+  if (c->n && s->nlev > 1) {
+    CylGeom g = geom_for(s, c);
+    g.rotate = 0;                                   // the update uses the unrotated position
+    const uint32_t kpl = (uint32_t)g.ncell + 2u;
+    const uint32_t nkeys = (uint32_t)s->nlev * kpl + 1;
+    if (c->seg_cap < (size_t)nkeys + 2) {
+      if (c->seg) cudaFree(c->seg);
+      c->seg = nullptr;
+      CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
+      c->seg_cap = (size_t)nkeys + 2;
+    }
+    const int CH = cyl_chunk(c->n);
+    const size_t slots = (c->n + CH - 1) / CH + (size_t)g.ncell + 1;
+    if (slots > s->part_slots) {
+      if (s->PA) cudaFree(s->PA);
+      s->PA = nullptr; s->part_slots = 0;
+      CU_TRY(cudaMalloc(&s->PA, slots * 4 * g.nk * sizeof(double)));
+      s->part_slots = slots;
+    }
+    const int stride = (g.nk + 4) | 1;
+    const size_t sm = (size_t)kCylDepositWarps * (32 * stride + 16) * sizeof(double);
+    const unsigned nchunks = div_up(c->n, CH);
+    for (int side = 0; side < 2; side++) {          // 0: "to" (+), 1: "from" (-)
+      cyl_switch_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(g, c->posm, c->level, c->prev_level, c->n,
+                                                                 side, s->nlev, c->keys[0]);
+      CU_LAUNCH_CHECK();
+      int cur = 0;
+      int rc = radix_sort_pairs(st, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur, c->seg);
+      if (rc) return rc;
+      c->cur = cur;
+      for (int M = 0; M < s->nlev; M++) {
+        const int keybase = M * (int)kpl;
+        cyl_deposit_kernel<<<div_up(nchunks, kCylDepositWarps), kCylDepositWarps * 32, sm, st>>>(
+            g, c->posm, c->perm[cur], c->seg, keybase, CH, adb, stride, 1, s->PA);
+        cyl_combine_kernel<<<div_up(g.nnode, 128), 128, 0, st>>>(g, c->seg, keybase, CH, s->PA, s->G);
+        // rows get_pot does not fill (m > MLIM, odd m with EVEN_M) stay zero, as in the
+        // coefficient pass (src/CylEXP.cc:170-186 loops mm = 0..MMAX over what get_pot filled)
+        cyl_contract_kernel<<<(unsigned)s->ncoef, 256, 0, st>>>(g, s->tab[0][0], s->tab[0][1], s->G,
+                                                                s->cfg.MLIM, s->cfg.EVEN_M, s->tmp);
+        cyl_axpy_kernel<<<div_up(s->ncoef, 256), 256, 0, st>>>(s->differ + (size_t)M * n1, s->tmp,
+                                                              side == 0 ? 1.0 : -1.0, s->ncoef);
+        CU_LAUNCH_CHECK();
+      }
+    }
+    c->sort_kind = 0;          // the component's regular sort was overwritten
+  }
+  if (finish) return expb200_cylinder_multistep_update_finish(s);
+  return EXPB200_OK;
+}
+
+int expb200_cylinder_differ_device(expb200_cylinder s, double **dptr, size_t *count, void **stream)
+{
+  REQUIRE(s && dptr, "NULL argument");
+  *dptr = s->differ;
+  if (count) *count = (size_t)s->nlev * (s->ncoef + 1);
+  if (stream) *stream = s->work_stream();
+  return EXPB200_OK;
+}
+
+int expb200_cylinder_multistep_update_finish(expb200_cylinder s)
+{
+  REQUIRE(s, "cylinder is NULL");
+  DeviceGuard gd(s->device);
+  const size_t all = (size_t)s->nlev * (s->ncoef + 1);
+  cyl_axpy_kernel<<<div_up(all, 256), 256, 0, s->work_stream()>>>(s->coefN, s->differ, 1.0, all);
+  CU_LAUNCH_CHECK();
+  return EXPB200_OK;
+}
+
+// Host access to the per-level tables: which = 0: cosN/sinN, 1: cosL/sinL, 2: differ;
+// cos_host, sin_host [(mmax+1)][norder].
+int expb200_cylinder_get_level_coefficients(expb200_cylinder s, int which, int mlevel, double *cos_host,
+                                            double *sin_host)
+{
+  REQUIRE(s && cos_host && sin_host && which >= 0 && which <= 2 && mlevel >= 0 && mlevel < s->nlev, "bad argument");
+  DeviceGuard gd(s->device);
+  CU_TRY(cudaStreamSynchronize(s->work_stream()));
+  const size_t n1 = s->ncoef + 1, half = s->ncoef / 2;
+  const double *src = (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * n1;
+  CU_TRY(cudaMemcpy(cos_host, src, half * sizeof(double), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(sin_host, src + half, half * sizeof(double), cudaMemcpyDeviceToHost));
   return EXPB200_OK;
 }
 

@@ -90,6 +90,23 @@ class Cylinder:
     def compute_multistep_coefficients(self, mdrft, cylmass=-1.0):
         check(_lib.lib().expb200_cylinder_compute_multistep_coefficients(self._h, int(mdrft), float(cylmass)))
 
+    def multistep_update(self, c: Component, adb=1.0, finish=True):
+        """Move the contribution of every particle whose level changed in the last
+        adjust_multistep_level from its old to its new level table."""
+        check(_lib.lib().expb200_cylinder_multistep_update(self._h, c._h, float(adb), int(finish)))
+
+    def multistep_update_finish(self):
+        check(_lib.lib().expb200_cylinder_multistep_update_finish(self._h))
+
+    def level_coefficients(self, which, mlevel):
+        """(cos, sin) of level mlevel: which = "N" (cosN/sinN), "L" or "differ"."""
+        shape = (self.mmax + 1, self.norder)
+        cs, sn = np.zeros(shape), np.zeros(shape)
+        check(_lib.lib().expb200_cylinder_get_level_coefficients(
+            self._h, {"N": 0, "L": 1, "differ": 2}[which], int(mlevel), cs.ctypes.data_as(c_dp),
+            sn.ctypes.data_as(c_dp)))
+        return cs, sn
+
     def coef_device(self):
         p = c_dp()
         n = C.c_size_t(0)

@@ -269,6 +269,15 @@ int expb200_cylinder_determine_acceleration(expb200_cylinder s, expb200_componen
 /* multistep tables cosL/cosN (exputil/EmpCylSL.cc:2004-2014, src/CylEXP.cc:192-282) */
 int expb200_cylinder_multistep_commit(expb200_cylinder s, int mlevel);
 int expb200_cylinder_compute_multistep_coefficients(expb200_cylinder s, int mdrft, double cylmass);
+/* ~ CylEXP::multistep_update_begin/update/finish (src/CylEXP.cc:45-188,
+ * src/Cylinder.cc:1751-1773), as expb200_sphere_multistep_update.  The differ buffer is
+ * [nlev][cos | sin | pad] (count doubles) for one all-reduce before _finish. */
+int expb200_cylinder_multistep_update(expb200_cylinder s, expb200_component c, double adb, int finish);
+int expb200_cylinder_multistep_update_finish(expb200_cylinder s);
+int expb200_cylinder_differ_device(expb200_cylinder s, double **dptr, size_t *count, void **stream);
+/* which = 0: cosN/sinN, 1: cosL/sinL, 2: differ; cos_host, sin_host [(mmax+1)][norder] */
+int expb200_cylinder_get_level_coefficients(expb200_cylinder s, int which, int mlevel,
+                                            double *cos_host, double *sin_host);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU: one process (MPI rank) per GPU; NCCL is loaded with dlopen.

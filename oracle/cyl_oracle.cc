@@ -245,6 +245,45 @@ long orc_cyl_coefficients_cov(const orc_cylgrid *g, const orc_cyl_params *P, con
   return cyl_coef_slice(g, P, S, list, 0, nlist, adb, cosN, sinN, cylmass, &cov);
 }
 
+// Cylinder::multistep_update (src/Cylinder.cc:1751-1773) + CylEXP::multistep_update
+// (src/CylEXP.cc:159-188) for one particle: its contribution moves from level `from` to
+// level `to` in differC/differS [(multistep+1)][(MMAX+1)][NORDER].  Note: no orientation
+// rotation and no rcylmax gate here, unlike the coefficient pass.
+void orc_cyl_multistep_update(const orc_cylgrid *g, const orc_particles *S, int indx, double adb,
+                              int from, int to, double *differC, double *differS)
+{
+  const int MMAX = g->MMAX, rank3 = g->NORDER;
+  double pos[3], r2f = 0.0;
+  for (int k = 0; k < 3; k++) {
+    pos[k] = S->pos[3 * (long)indx + k] - S->center[k];
+    r2f += pos[k] * pos[k];
+  }
+  if (r2f > S->rtrunc * S->rtrunc) return;              // c->freeze(i)
+  double mass = S->mass[indx] * adb;
+  double xx = pos[0], yy = pos[1], zz = pos[2];
+  double r = std::sqrt(xx * xx + yy * yy);
+  double phi = std::atan2(yy, xx);
+  double rr = std::sqrt(r * r + zz * zz);
+  if (rr / g->ASCALE > g->Rtable) return;
+  const double norm = -4.0 * M_PI;
+  std::vector<double> vc((std::max(1, MMAX) + 1) * rank3), vs((std::max(1, MMAX) + 1) * rank3);
+  orc_cyl_get_pot(g, r, zz, vc.data(), vs.data());
+  const long lev = (long)(MMAX + 1) * rank3;
+  for (int mm = 0; mm <= MMAX; mm++) {
+    double mcos = std::cos(phi * mm), msin = std::sin(phi * mm);
+    for (int nn = 0; nn < rank3; nn++) {
+      double hold = norm * mass * mcos * vc[mm * rank3 + nn];
+      differC[from * lev + mm * rank3 + nn] -= hold;
+      differC[to * lev + mm * rank3 + nn] += hold;
+      if (mm > 0) {
+        hold = norm * mass * msin * vs[mm * rank3 + nn];
+        differS[from * lev + mm * rank3 + nn] -= hold;
+        differS[to * lev + mm * rank3 + nn] += hold;
+      }
+    }
+  }
+}
+
 void orc_cyl_accumulated_eval(const orc_cylgrid *g, const double *accum_cos, const double *accum_sin,
                               double r, double z, double phi,
                               double *p0, double *p_, double *fr_, double *fz_, double *fp_)

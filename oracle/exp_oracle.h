@@ -178,6 +178,10 @@ long orc_cyl_coefficients_cov(const orc_cylgrid *g, const orc_cyl_params *P, con
                               const int *list, long nlist, double adb, int sampT,
                               double *cosN, double *sinN, double *cylmass,
                               double *massT, unsigned *numbT, double *VC, double *MV);
+/* Cylinder::multistep_update + CylEXP::multistep_update (src/Cylinder.cc:1751-1773,
+ * src/CylEXP.cc:159-188): differC, differS [(multistep+1)][(MMAX+1)][NORDER] */
+void orc_cyl_multistep_update(const orc_cylgrid *g, const orc_particles *S, int indx, double adb,
+                              int from, int to, double *differC, double *differS);
 /* EmpCylSL::accumulated_eval (exputil/EmpCylSL.cc:5256-5410) */
 void orc_cyl_accumulated_eval(const orc_cylgrid *g, const double *accum_cos, const double *accum_sin,
                               double r, double z, double phi,

@@ -121,6 +121,8 @@ def lib() -> C.CDLL:
         L.orc_cyl_coefficients_cov.argtypes = [C.POINTER(CylGrid), C.POINTER(CylParams), C.POINTER(Particles),
                                                c_ip, C.c_long, C.c_double, C.c_int, c_dp, c_dp, c_dp,
                                                c_dp, c_up, c_dp, c_dp]
+        L.orc_cyl_multistep_update.argtypes = [C.POINTER(CylGrid), C.POINTER(Particles), C.c_int, C.c_double,
+                                               C.c_int, C.c_int, c_dp, c_dp]
         L.orc_cyl_accel.argtypes = [C.POINTER(CylGrid), C.POINTER(CylParams), C.POINTER(Particles),
                                     c_ip, C.c_long, c_dp, c_dp, C.c_double, C.c_int]
         _LIB = L
@@ -355,6 +357,12 @@ def cyl_coefficients_cov(g: CylGridPy, P, S: ParticleSet, sampT, lst=None, adb=1
                                           numbT.ctypes.data_as(c_up), _dp(VC), _dp(MV))
     return dict(cos=cs, sin=sn, used=used, mass=mass[0], massT=massT, numbT=numbT,
                 VC=VC[..., 0] + 1j * VC[..., 1], MV=MV[..., 0] + 1j * MV[..., 1])
+
+
+def cyl_multistep_update(g: CylGridPy, S: ParticleSet, indx, frm, to, differC, differS, adb=1.0):
+    sc = S.c()
+    lib().orc_cyl_multistep_update(C.byref(g.c), C.byref(sc), int(indx), adb, int(frm), int(to),
+                                   _dp(differC), _dp(differS))
 
 
 def cyl_accel(g: CylGridPy, P, S: ParticleSet, cos, sin, cylmass, lst=None, nthreads=1):

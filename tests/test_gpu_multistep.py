@@ -159,3 +159,50 @@ def test_full_step_against_reference_ordering(multistep):
     if multistep:
         for M in range(multistep + 1):
             assert rel_rms(s.level_coefficients("N", M), ref.coefN[M]) <= 1e-9, M
+
+
+def test_cylinder_multistep_update():
+    """CylEXP::multistep_update (src/CylEXP.cc:159-188, src/Cylinder.cc:1751-1773): level switches
+    move each particle's contribution between the per-level cos/sin tables."""
+    from exp_b200 import cyltable
+    from exp_b200.cylinder import Cylinder
+    from test_emul_cyl import disk, rotations
+    tab = cyltable.synthetic_cyl_table(mmax=4, norder=6, numx=48, numy=24)
+    n, ms = 20000, 3
+    pos, vel, mass = disk(n)
+    rng = np.random.default_rng(11)
+    cyl = Cylinder(tab, multistep=ms)
+    body, orig = rotations()
+    cyl.set_orientation(body, orig)            # the update ignores the orientation (reference)
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    old = rng.integers(0, ms + 1, n).astype(np.uint32)
+    c.set_levels(old)
+    acc = rng.normal(size=(n, 3)) * np.exp(rng.normal(size=(n, 1)) * 2.0)
+    c.set_acc_pot(acc, -np.ones(n))
+    # per-level tables before the update
+    cN = []
+    for M in range(ms + 1):
+        cyl.set_multistep_level(M)
+        cyl.determine_coefficients(c, to_host=False)
+        cyl.multistep_commit(M)
+        cN.append(cyl.level_coefficients("N", M))
+    c.adjust_multistep_level(0.05, ms)
+    new = c.download(pos=False, vel=False, acc=False, pot=False, level=True)["level"]
+    assert (new != old).sum() > 100
+    cyl.multistep_update(c, finish=False)
+    g = O.CylGridPy(tab)
+    S = O.ParticleSet(pos, vel, mass)
+    shape = (ms + 1, tab.mmax + 1, tab.norder)
+    dC, dS = np.zeros(shape), np.zeros(shape)
+    for i in np.nonzero(new != old)[0]:
+        O.cyl_multistep_update(g, S, int(i), int(old[i]), int(new[i]), dC, dS)
+    scale = np.abs(dC).max()
+    for M in range(ms + 1):
+        gc, gs = cyl.level_coefficients("differ", M)
+        assert np.abs(gc - dC[M]).max() <= 1e-10 * scale, M
+        assert np.abs(gs[1:] - dS[M][1:]).max() <= 1e-10 * scale, M
+    cyl.multistep_update_finish()
+    for M in range(ms + 1):
+        gc, gs = cyl.level_coefficients("N", M)
+        assert np.abs(gc - (cN[M][0] + dC[M])).max() <= 1e-10 * max(scale, np.abs(cN[M][0]).max())
