@@ -202,7 +202,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -382,9 +382,20 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def emit(line):
+    """the ONE JSON line, on the process's original stdout"""
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
+# Libraries (NCCL's version banner, torchrun) write to fd 1; keep the contract's single JSON
+# line clean by pointing fd 1 at stderr for everything except emit().
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
