@@ -101,6 +101,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_DIR = os.path.join(_HERE, "host")
+HOST_LIB_PATH = os.path.join(_HERE, "lib", "libexphost.so")
+
+
+def build_host(force: bool = False, verbose: bool = False) -> str:
+    """Compile the C++ host driver (exp_b200/host/*.cc: Component, PotAccel, SphericalBasis,
+    Cylinder, ComponentContainer, do_step ...) into exp_b200/lib/libexphost.so, linked
+    against libexpb200.so ($ORIGIN rpath)."""
+    srcs = sorted(os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith(".cc"))
+    deps = srcs + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith((".H", ".h"))]
+    deps += [os.path.join(_HERE, "..", "include", "expb200.h"), LIB_PATH]
+    if (not force and os.path.exists(HOST_LIB_PATH)
+            and os.path.getmtime(HOST_LIB_PATH) >= max(os.path.getmtime(d) for d in deps)):
+        return HOST_LIB_PATH
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-I" + os.path.join(_HERE, "..", "include"),
+           "-o", HOST_LIB_PATH] + srcs + ["-L" + os.path.dirname(LIB_PATH), "-lexpb200",
+                                          "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise Expb200Error("host build failed:\n" + r.stdout + r.stderr)
+    return HOST_LIB_PATH
+
+
 # symbol -> (restype, argtypes); every symbol include/expb200.h declares
 _H = C.c_void_p
 SIGNATURES = {
@@ -167,6 +192,7 @@ SIGNATURES = {
     "expb200_cylinder_differ_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_size_t),
                                                  C.POINTER(C.c_void_p)]),
     "expb200_cylinder_get_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp, c_dp]),
+    "expb200_cylinder_get_mass": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_profile_enable": (C.c_int, [C.c_int]),
     "expb200_profile_reset": (C.c_int, []),
     "expb200_profile_kernels": (C.c_int, []),

@@ -728,13 +728,28 @@ int expb200_cylinder_multistep_update_finish(expb200_cylinder s)
 int expb200_cylinder_get_level_coefficients(expb200_cylinder s, int which, int mlevel, double *cos_host,
                                             double *sin_host)
 {
-  REQUIRE(s && cos_host && sin_host && which >= 0 && which <= 2 && mlevel >= 0 && mlevel < s->nlev, "bad argument");
+  REQUIRE(s && cos_host && sin_host && which >= 0 && which <= 4, "bad argument");
+  REQUIRE(which >= 3 || (mlevel >= 0 && mlevel < s->nlev), "mlevel=%d outside [0,%d)", mlevel, s->nlev);
   DeviceGuard gd(s->device);
   CU_TRY(cudaStreamSynchronize(s->work_stream()));
   const size_t n1 = s->ncoef + 1, half = s->ncoef / 2;
-  const double *src = (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * n1;
+  const double *src = which == 3 ? s->coef_use : which == 4 ? s->coef
+                    : (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * n1;
   CU_TRY(cudaMemcpy(cos_host, src, half * sizeof(double), cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(sin_host, src + half, half * sizeof(double), cudaMemcpyDeviceToHost));
+  return EXPB200_OK;
+}
+
+int expb200_cylinder_get_mass(expb200_cylinder s, int which, int mlevel, double *mass)
+{
+  REQUIRE(s && mass && which >= 0 && which <= 4, "bad argument");
+  REQUIRE(which >= 3 || (mlevel >= 0 && mlevel < s->nlev), "mlevel=%d outside [0,%d)", mlevel, s->nlev);
+  DeviceGuard gd(s->device);
+  CU_TRY(cudaStreamSynchronize(s->work_stream()));
+  const size_t n1 = s->ncoef + 1;
+  const double *src = which == 3 ? s->coef_use : which == 4 ? s->coef
+                    : (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * n1;
+  CU_TRY(cudaMemcpy(mass, src + s->ncoef, sizeof(double), cudaMemcpyDeviceToHost));
   return EXPB200_OK;
 }
 

@@ -1445,10 +1445,12 @@ int expb200_sphere_compute_multistep_coefficients(expb200_sphere s, int mdrft)
 // Host access to the per-level tables (which = 0: expcoefN, 1: expcoefL, 2: differ).
 int expb200_sphere_get_level_coefficients(expb200_sphere s, int which, int mlevel, double *host)
 {
-  REQUIRE(s && host && which >= 0 && which <= 2 && mlevel >= 0 && mlevel < s->nlev, "bad argument");
+  REQUIRE(s && host && which >= 0 && which <= 4, "bad argument");
+  REQUIRE(which >= 3 || (mlevel >= 0 && mlevel < s->nlev), "mlevel=%d outside [0,%d)", mlevel, s->nlev);
   DeviceGuard g(s->device);
   CU_TRY(cudaStreamSynchronize(s->work_stream()));
-  const double *src = (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * s->ncoef;
+  const double *src = which == 3 ? s->coef_use : which == 4 ? s->coef
+                    : (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * s->ncoef;
   CU_TRY(cudaMemcpy(host, src, s->ncoef * sizeof(double), cudaMemcpyDeviceToHost));
   return EXPB200_OK;
 }

@@ -1,0 +1,171 @@
+"""ctypes view of the C++ host driver (exp_b200/host/, libexphost.so): the reference's
+engine-side objects for the force loop -- Component, PotAccel (Sphere, Cylinder),
+ComponentContainer, begin_run, do_step, adjust_multistep_level -- written in C++ over the C
+ABI.  This module only assembles a run and reads results back; all stepping logic is C++."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_dp
+
+_HOST = None
+
+
+class SphereDesc(C.Structure):
+    _fields_ = [("lmax", C.c_int), ("nmax", C.c_int), ("numr", C.c_int), ("cmap", C.c_int),
+                ("rmin", C.c_double), ("rmax", C.c_double), ("rmap", C.c_double),
+                ("ev", c_dp), ("ef", c_dp), ("p0", c_dp),
+                ("scale", C.c_double), ("rmin_exp", C.c_double), ("rmax_exp", C.c_double),
+                ("NO_L0", C.c_int), ("NO_L1", C.c_int), ("EVEN_L", C.c_int), ("EVEN_M", C.c_int),
+                ("M0_only", C.c_int), ("self_consistent", C.c_int)]
+
+
+class CylinderDesc(C.Structure):
+    _fields_ = [("mmax", C.c_int), ("norder", C.c_int), ("numx", C.c_int), ("numy", C.c_int),
+                ("cmapr", C.c_int), ("cmapz", C.c_int),
+                ("ascale", C.c_double), ("hscale", C.c_double), ("rmin", C.c_double), ("rmax", C.c_double),
+                ("potC", c_dp), ("potS", c_dp), ("rforceC", c_dp), ("rforceS", c_dp),
+                ("zforceC", c_dp), ("zforceS", c_dp),
+                ("rcylmax", C.c_double), ("acyl", C.c_double),
+                ("EVEN_M", C.c_int), ("MMIN", C.c_int), ("MLIM", C.c_int), ("NMIN", C.c_int),
+                ("NLIM", C.c_int), ("self_consistent", C.c_int), ("body", c_dp), ("orig", c_dp)]
+
+
+def host():
+    global _HOST
+    if _HOST is None:
+        _lib.lib()                                   # libexpb200.so first (fails loudly if missing)
+        import os
+        if not os.path.exists(_lib.HOST_LIB_PATH):
+            raise _lib.Expb200Error(f"{_lib.HOST_LIB_PATH} is missing: run __graft_entry__.build()")
+        H = C.CDLL(_lib.HOST_LIB_PATH)
+        H.exphost_last_error.restype = C.c_char_p
+        H.exphost_set_params.argtypes = [C.c_double, C.c_int] + [C.c_double] * 5 + [C.c_int]
+        H.exphost_set_comm.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        H.exphost_add_component.argtypes = [C.c_char_p, C.c_size_t, c_dp, c_dp, c_dp, C.c_int,
+                                            C.POINTER(C.c_int)]
+        H.exphost_component_options.argtypes = [C.c_int, c_dp, C.c_double, C.c_int, C.c_int, C.c_int]
+        H.exphost_set_sphere.argtypes = [C.c_int, C.POINTER(SphereDesc)]
+        H.exphost_set_cylinder.argtypes = [C.c_int, C.POINTER(CylinderDesc)]
+        H.exphost_add_interaction.argtypes = [C.c_int, C.c_int]
+        H.exphost_do_steps.argtypes = [C.c_int]
+        H.exphost_do_steps_timed.argtypes = [C.c_int, c_dp]
+        H.exphost_get_particles.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, _lib.c_up, _lib.c_fp]
+        H.exphost_get_sphere_coefs.argtypes = [C.c_int, C.c_int, C.c_int, c_dp]
+        H.exphost_get_cylinder_coefs.argtypes = [C.c_int, c_dp, c_dp, c_dp]
+        H.exphost_level_report.argtypes = [C.c_int] + [_lib.c_u64p] * 5
+        H.exphost_state.argtypes = [c_dp, C.POINTER(C.c_int), c_dp, c_dp]
+        _HOST = H
+    return _HOST
+
+
+def _check(rc):
+    if rc != 0:
+        raise _lib.Expb200Error(f"exphost error {rc}: {host().exphost_last_error().decode()}")
+
+
+def _p(a):
+    return a.ctypes.data_as(c_dp)
+
+
+class Simulation:
+    """One run of the C++ host driver (the process-wide `comp` container of the reference)."""
+
+    def __init__(self, dtime, multistep=0, dynfracS=1.0, dynfracD=1.0e32, dynfracV=0.01,
+                 dynfracA=0.03, dynfracP=0.05, shiftlevl=0, comm=None, myid=0, numprocs=1, device=0):
+        self.H = host()
+        self.device, self.multistep = device, multistep
+        self._keep = []
+        self.kinds = []
+        _check(self.H.exphost_reset())
+        _check(self.H.exphost_set_params(dtime, multistep, dynfracS, dynfracD, dynfracV, dynfracA,
+                                         dynfracP, shiftlevl))
+        _check(self.H.exphost_set_comm(comm, myid, numprocs))
+
+    def add_component(self, name, pos, vel, mass, center=None, rtrunc=1.0e20, noswitch=False,
+                      freezeLev=False, dtreset=True):
+        pos, vel, mass = (np.ascontiguousarray(a, dtype=np.float64) for a in (pos, vel, mass))
+        idx = C.c_int(-1)
+        _check(self.H.exphost_add_component(name.encode(), len(pos), _p(pos), _p(vel), _p(mass),
+                                            self.device, C.byref(idx)))
+        ctr = None if center is None else np.ascontiguousarray(center, dtype=np.float64)
+        _check(self.H.exphost_component_options(idx.value, None if ctr is None else _p(ctr), rtrunc,
+                                                int(noswitch), int(freezeLev), int(dtreset)))
+        self.kinds.append(None)
+        return idx.value
+
+    def set_sphere(self, idx, tab, scale=1.0, rmin=-1.0, rmax=-1.0, NO_L0=False, NO_L1=False,
+                   EVEN_L=False, EVEN_M=False, M0_only=False, self_consistent=True):
+        arr = [np.ascontiguousarray(getattr(tab, k), dtype=np.float64) for k in ("ev", "ef", "p0")]
+        self._keep.append(arr)
+        d = SphereDesc(tab.lmax, tab.nmax, tab.numr, tab.cmap, tab.rmin, tab.rmax, tab.rmap,
+                       _p(arr[0]), _p(arr[1]), _p(arr[2]), scale, rmin, rmax, int(NO_L0), int(NO_L1),
+                       int(EVEN_L), int(EVEN_M), int(M0_only), int(self_consistent))
+        _check(self.H.exphost_set_sphere(idx, C.byref(d)))
+        self.kinds[idx] = ("sphere", (tab.lmax + 1) ** 2, tab.nmax)
+
+    def set_cylinder(self, idx, tab, rcylmax=20.0, acyl=-1.0, EVEN_M=False, MMIN=0, MLIM=2 ** 30,
+                     NMIN=0, NLIM=2 ** 30, self_consistent=True, body=None, orig=None):
+        arr = [np.ascontiguousarray(getattr(tab, k), dtype=np.float64)
+               for k in ("potC", "potS", "rforceC", "rforceS", "zforceC", "zforceS")]
+        rot = [None if body is None else np.ascontiguousarray(body, dtype=np.float64),
+               None if orig is None else np.ascontiguousarray(orig, dtype=np.float64)]
+        self._keep.append(arr + rot)
+        d = CylinderDesc(tab.mmax, tab.norder, tab.numx, tab.numy, tab.cmapr, tab.cmapz, tab.ascale,
+                         tab.hscale, tab.rmin, tab.rmax, *[_p(a) for a in arr], rcylmax, acyl,
+                         int(EVEN_M), MMIN, MLIM, NMIN, NLIM, int(self_consistent),
+                         None if rot[0] is None else _p(rot[0]), None if rot[1] is None else _p(rot[1]))
+        _check(self.H.exphost_set_cylinder(idx, C.byref(d)))
+        self.kinds[idx] = ("cylinder", tab.mmax + 1, tab.norder)
+
+    def add_interaction(self, frm, on):
+        _check(self.H.exphost_add_interaction(frm, on))
+
+    def begin_run(self):
+        _check(self.H.exphost_begin_run())
+
+    def do_steps(self, n=1):
+        _check(self.H.exphost_do_steps(n))
+
+    def do_steps_timed(self, n):
+        ms = C.c_double(0.0)
+        _check(self.H.exphost_do_steps_timed(n, C.byref(ms)))
+        return ms.value
+
+    def particles(self, idx, n):
+        out = dict(pos=np.empty((n, 3)), vel=np.empty((n, 3)), acc=np.empty((n, 3)), pot=np.empty(n),
+                   level=np.empty(n, dtype=np.uint32), dtreq=np.empty(n, dtype=np.float32))
+        _check(self.H.exphost_get_particles(idx, _p(out["pos"]), _p(out["vel"]), _p(out["acc"]),
+                                            _p(out["pot"]), out["level"].ctypes.data_as(_lib.c_up),
+                                            out["dtreq"].ctypes.data_as(_lib.c_fp)))
+        return out
+
+    def sphere_coefs(self, idx, which=3, M=0):
+        _, nrow, nmax = self.kinds[idx]
+        out = np.empty((nrow, nmax))
+        _check(self.H.exphost_get_sphere_coefs(idx, which, M, _p(out)))
+        return out
+
+    def cylinder_coefs(self, idx):
+        _, m1, n = self.kinds[idx]
+        cs, sn = np.empty((m1, n)), np.empty((m1, n))
+        mass = C.c_double(0.0)
+        _check(self.H.exphost_get_cylinder_coefs(idx, _p(cs), _p(sn), C.byref(mass)))
+        return cs, sn, mass.value
+
+    def level_report(self, idx):
+        v = [C.c_uint64(0) for _ in range(4)]
+        counts = np.zeros(self.multistep + 1, dtype=np.uint64)
+        _check(self.H.exphost_level_report(idx, *[C.byref(x) for x in v],
+                                           counts.ctypes.data_as(_lib.c_u64p)))
+        return dict(examined=v[0].value, switched=v[1].value, offlo=v[2].value, offhi=v[3].value,
+                    counts=counts)
+
+    def state(self):
+        t, k = C.c_double(0.0), C.c_int(0)
+        pc, vc = np.zeros(self.multistep + 1), np.zeros(self.multistep + 1)
+        _check(self.H.exphost_state(C.byref(t), C.byref(k), _p(pc), _p(vc)))
+        return dict(tnow=t.value, this_step=k.value, pos_check=pc, vel_check=vc)

@@ -1,0 +1,105 @@
+// SphericalBasis.cc -- see SphericalBasis.H
+#include "SphericalBasis.H"
+
+#include "global.H"
+
+namespace exphost {
+
+SphericalBasis::SphericalBasis(const SLGridSphTables &t, int device, double scale_, double rmin_,
+                               double rmax_, bool no_l0, bool no_l1, bool even_l, bool even_m,
+                               bool m0_only)
+  : Lmax(t.lmax), nmax(t.nmax), scale(scale_), NO_L0(no_l0), NO_L1(no_l1), EVEN_L(even_l),
+    EVEN_M(even_m), M0_only(m0_only)
+{
+  id = "sphereSL";
+  // rmin/rmax default to the table's range, as the Sphere constructor does (src/Sphere.cc:65-66)
+  rmin = rmin_ < 0.0 ? t.rmin : rmin_;
+  rmax = rmax_ < 0.0 ? t.rmax : rmax_;
+  expb200_sphere_config cfg = {t.lmax, t.nmax, t.numr, t.cmap, t.rmin, t.rmax, t.rmap, scale, rmin, rmax,
+                               NO_L0, NO_L1, EVEN_L, EVEN_M, M0_only, (int)multistep};
+  EXPHOST_CHECK(expb200_sphere_create(device, &cfg, t.ev, t.ef, t.p0, &b200s));
+}
+
+SphericalBasis::~SphericalBasis()
+{
+  if (b200s) expb200_sphere_destroy(b200s);
+}
+
+void SphericalBasis::determine_coefficients(Component *c)
+{
+  // src/SphericalBasis.cc:694: a fixed (not self-consistent) basis is computed once
+  if (!self_consistent && !firstime_coef && !initializing) return;
+
+  uint64_t use1 = 0;
+  EXPHOST_CHECK(expb200_sphere_determine_coefficients(b200s, c->b200, (int)mlevel, c->Adiabatic(),
+                                                      nullptr, &use1));
+  // the reference's (Lmax+1)^2 host MPI_Allreduce calls (:864-903) -> one device all-reduce
+  if (nccl_comm) {
+    double *d = nullptr; void *st = nullptr;
+    EXPHOST_CHECK(expb200_sphere_coef_device(b200s, &d, &st));
+    EXPHOST_CHECK(expb200_allreduce_sum(nccl_comm, d, ncoef(), st));
+  }
+  if (multistep) {
+    // swap expcoefL <-> expcoefN[mlevel], store the new vector as expcoefN[mlevel] (:785-788)
+    EXPHOST_CHECK(expb200_sphere_multistep_commit(b200s, (int)mlevel));
+  } else {
+    EXPHOST_CHECK(expb200_sphere_set_coefficients(b200s, nullptr));
+  }
+  if (multistep == 0 || tnow == resetT) used += (int)use1;          // :905-907
+  firstime_coef = false;
+}
+
+void SphericalBasis::compute_multistep_coefficients()
+{
+  EXPHOST_CHECK(expb200_sphere_compute_multistep_coefficients(b200s, mdrft));
+}
+
+void SphericalBasis::get_acceleration_and_potential(Component *cC)
+{
+  if (!use_external) {
+    if (multistep && (self_consistent || initializing)) compute_multistep_coefficients();
+  }
+  EXPHOST_CHECK(expb200_sphere_determine_acceleration(b200s, cC->b200, (int)mlevel));
+}
+
+void SphericalBasis::multistep_reset()
+{
+  used = 0;
+  resetT = tnow;
+}
+
+void SphericalBasis::multistep_update(Component *c)
+{
+  if (!self_consistent) return;
+  // differences stay on the device; with several ranks they are all-reduced in _finish
+  EXPHOST_CHECK(expb200_sphere_multistep_update(b200s, c->b200, c->Adiabatic(), 0));
+  pending_update = true;
+}
+
+void SphericalBasis::multistep_update_finish()
+{
+  if (!pending_update) return;
+  if (nccl_comm) {
+    double *d = nullptr; size_t n = 0; void *st = nullptr;
+    EXPHOST_CHECK(expb200_sphere_differ_device(b200s, &d, &n, &st));
+    EXPHOST_CHECK(expb200_allreduce_sum(nccl_comm, d, n, st));
+  }
+  EXPHOST_CHECK(expb200_sphere_multistep_update_finish(b200s));
+  pending_update = false;
+}
+
+std::vector<double> SphericalBasis::get_coefs()
+{
+  std::vector<double> v(ncoef());
+  EXPHOST_CHECK(expb200_sphere_get_level_coefficients(b200s, 3, 0, v.data()));
+  return v;
+}
+
+std::vector<double> SphericalBasis::get_level_coefs(int which, int M)
+{
+  std::vector<double> v(ncoef());
+  EXPHOST_CHECK(expb200_sphere_get_level_coefficients(b200s, which, M, v.data()));
+  return v;
+}
+
+} // namespace exphost

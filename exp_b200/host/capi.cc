@@ -1,0 +1,238 @@
+// capi.cc -- see capi.h
+#include "capi.h"
+
+#include <cstring>
+#include <string>
+
+#include "Cylinder.H"
+#include "SphericalBasis.H"
+#include "expand.H"
+
+using namespace exphost;
+
+namespace {
+
+thread_local std::string g_err;
+ComponentContainer *g_comp = nullptr;
+
+Component *component_at(int index)
+{
+  if (!g_comp || index < 0 || index >= (int)g_comp->owned.size())
+    throw GenericError("no such component", __FILE__, __LINE__);
+  return g_comp->owned[index].get();
+}
+
+template <class F> int guarded(F &&f)
+{
+  try { f(); return 0; }
+  catch (const GenericError &e) { g_err = e.what(); return e.errcode ? e.errcode : -1; }
+  catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+} // namespace
+
+extern "C" {
+
+const char *exphost_last_error(void) { return g_err.c_str(); }
+
+int exphost_reset(void)
+{
+  return guarded([] {
+    delete g_comp;
+    g_comp = new ComponentContainer();
+    comp = g_comp;
+    level_report.clear();
+    reset_globals();
+  });
+}
+
+int exphost_set_params(double dtime_, int multistep_, double S, double D, double V, double A, double P,
+                       int shift)
+{
+  return guarded([&] {
+    if (multistep_ < 0 || multistep_ > 20) throw GenericError("multistep out of range", __FILE__, __LINE__);
+    dtime = dtime_; multistep = (unsigned)multistep_;
+    dynfracS = S; dynfracD = D; dynfracV = V; dynfracA = A; dynfracP = P; shiftlevl = shift;
+  });
+}
+
+int exphost_set_comm(void *c, int id, int np)
+{
+  nccl_comm = c; myid = id; numprocs = np;
+  return 0;
+}
+
+int exphost_add_component(const char *name, size_t n, const double *pos, const double *vel,
+                          const double *mass, int device, int *index)
+{
+  return guarded([&] {
+    if (!g_comp) throw GenericError("call exphost_reset first", __FILE__, __LINE__);
+    auto c = std::make_unique<Component>(name, n, device);
+    for (size_t i = 0; i < n; i++) {
+      Particle &p = c->particles[i];
+      p.mass = mass[i];
+      for (int k = 0; k < 3; k++) { p.pos[k] = pos[3 * i + k]; p.vel[k] = vel ? vel[3 * i + k] : 0.0; }
+    }
+    c->ParticlesToCuda();
+    g_comp->add(std::move(c));
+    if (index) *index = (int)g_comp->owned.size() - 1;
+  });
+}
+
+int exphost_component_options(int index, const double center[3], double rtrunc, int noswitch,
+                              int freezeLev, int dtreset)
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    if (center) for (int k = 0; k < 3; k++) c->center[k] = center[k];
+    c->rtrunc = rtrunc; c->noswitch = noswitch; c->freezeLev = freezeLev; c->dtreset = dtreset;
+    c->update_center();
+  });
+}
+
+int exphost_set_sphere(int index, const exphost_sphere_desc *d)
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    SLGridSphTables t;
+    t.lmax = d->lmax; t.nmax = d->nmax; t.numr = d->numr; t.cmap = d->cmap;
+    t.rmin = d->rmin; t.rmax = d->rmax; t.rmap = d->rmap; t.ev = d->ev; t.ef = d->ef; t.p0 = d->p0;
+    auto f = std::make_shared<Sphere>(t, c->cudaDevice, d->scale, d->rmin_exp, d->rmax_exp, d->NO_L0,
+                                      d->NO_L1, d->EVEN_L, d->EVEN_M, d->M0_only);
+    f->self_consistent = d->self_consistent;
+    c->set_force(f);
+  });
+}
+
+int exphost_set_cylinder(int index, const exphost_cylinder_desc *d)
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    EmpCylSLTables t;
+    t.mmax = d->mmax; t.norder = d->norder; t.numx = d->numx; t.numy = d->numy;
+    t.cmapr = d->cmapr; t.cmapz = d->cmapz; t.ascale = d->ascale; t.hscale = d->hscale;
+    t.rmin = d->rmin; t.rmax = d->rmax;
+    t.potC = d->potC; t.potS = d->potS; t.rforceC = d->rforceC; t.rforceS = d->rforceS;
+    t.zforceC = d->zforceC; t.zforceS = d->zforceS;
+    auto f = std::make_shared<Cylinder>(t, c->cudaDevice, d->rcylmax, d->acyl, d->EVEN_M, d->MMIN,
+                                        d->MLIM, d->NMIN, d->NLIM);
+    f->self_consistent = d->self_consistent;
+    if (d->body && d->orig) f->set_orientation(d->body, d->orig);
+    c->set_force(f);
+  });
+}
+
+int exphost_add_interaction(int from, int on)
+{
+  return guarded([&] { g_comp->add_interaction(component_at(from), component_at(on)); });
+}
+
+int exphost_begin_run(void) { return guarded([] { begin_run(); }); }
+
+int exphost_do_steps(int nsteps)
+{
+  return guarded([&] { for (int i = 0; i < nsteps; i++) do_step(this_step); });
+}
+
+int exphost_do_steps_timed(int nsteps, double *ms)
+{
+  return guarded([&] {
+    Component *c0 = component_at(0);
+    for (auto &c : g_comp->owned) EXPHOST_CHECK(expb200_component_sync(c->b200));
+    EXPHOST_CHECK(expb200_component_event_record(c0->b200, 6));
+    for (int i = 0; i < nsteps; i++) do_step(this_step);
+    for (auto &c : g_comp->owned) EXPHOST_CHECK(expb200_component_sync(c->b200));
+    EXPHOST_CHECK(expb200_component_event_record(c0->b200, 7));
+    EXPHOST_CHECK(expb200_component_sync(c0->b200));
+    EXPHOST_CHECK(expb200_component_event_elapsed(c0->b200, 6, 7, ms));
+  });
+}
+
+int exphost_get_particles(int index, double *pos, double *vel, double *acc, double *pot,
+                          unsigned *level, float *dtreq)
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    c->CudaToParticles();
+    const size_t n = c->Number();
+    for (size_t i = 0; i < n; i++) {
+      const Particle &p = c->particles[i];
+      for (int k = 0; k < 3; k++) {
+        if (pos) pos[3 * i + k] = p.pos[k];
+        if (vel) vel[3 * i + k] = p.vel[k];
+        if (acc) acc[3 * i + k] = p.acc[k];
+      }
+      if (pot) pot[i] = p.pot;
+      if (level) level[i] = p.level;
+      if (dtreq) dtreq[i] = p.dtreq;
+    }
+  });
+}
+
+int exphost_get_sphere_coefs(int index, int which, int M, double *coef)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<SphericalBasis *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not sphereSL", __FILE__, __LINE__);
+    auto v = which == 3 ? s->get_coefs() : s->get_level_coefs(which, M);
+    std::memcpy(coef, v.data(), v.size() * sizeof(double));
+  });
+}
+
+int exphost_get_cylinder_coefs(int index, double *cosv, double *sinv, double *cylmass)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<Cylinder *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not cylinder", __FILE__, __LINE__);
+    std::vector<double> a, b;
+    s->get_coefs(a, b);
+    std::memcpy(cosv, a.data(), a.size() * sizeof(double));
+    std::memcpy(sinv, b.data(), b.size() * sizeof(double));
+    if (cylmass) *cylmass = s->get_cylmass();
+  });
+}
+
+int exphost_level_report(int index, uint64_t *examined, uint64_t *switched, uint64_t *offlo,
+                         uint64_t *offhi, uint64_t *counts)
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    const LevelReport &r = level_report[c];
+    if (examined) *examined = r.examined;
+    if (switched) *switched = r.switched;
+    if (offlo) *offlo = r.offlo;
+    if (offhi) *offhi = r.offhi;
+    if (counts) {
+      auto v = c->level_counts();
+      for (size_t i = 0; i < v.size(); i++) counts[i] = v[i];
+    }
+  });
+}
+
+int exphost_multistep_tables(int ms, int *mintvl_, int *mfirst_, int *dL, int *dN)
+{
+  return guarded([&] {
+    if (ms < 0 || ms > 20) throw GenericError("multistep out of range", __FILE__, __LINE__);
+    const unsigned keep = multistep;
+    multistep = (unsigned)ms;
+    initialize_multistep();
+    for (int i = 0; i <= ms; i++) mintvl_[i] = mintvl[i];
+    for (int i = 0; i <= Mstep; i++) mfirst_[i] = mfirst[i];
+    for (int l = 0; l <= ms; l++)
+      for (int n = 0; n < Mstep; n++) { dL[l * Mstep + n] = dstepL[l][n]; dN[l * Mstep + n] = dstepN[l][n]; }
+    multistep = keep;
+  });
+}
+
+int exphost_state(double *tnow_, int *this_step_, double *pc, double *vc)
+{
+  if (tnow_) *tnow_ = tnow;
+  if (this_step_) *this_step_ = this_step;
+  for (size_t i = 0; i < pos_check.size(); i++) {
+    if (pc) pc[i] = pos_check[i];
+    if (vc) vc[i] = vel_check[i];
+  }
+  return 0;
+}
+
+} // extern "C"

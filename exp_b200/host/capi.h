@@ -1,0 +1,63 @@
+/* capi.h -- flat C entry points of the C++ host driver (libexphost.so) so that the parity
+ * tests and bench.py can assemble and run a simulation (components + forces + interactions,
+ * begin_run, do_step) from Python.  This is a harness around the C++ classes, not a second
+ * boundary: the drop-in boundary of the GPU path is include/expb200.h.
+ * Every function returns 0 or a negative status; exphost_last_error() has the message. */
+#ifndef EXPHOST_CAPI_H
+#define EXPHOST_CAPI_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int lmax, nmax, numr, cmap;
+  double rmin, rmax, rmap;             /* SLGridSph grid */
+  const double *ev, *ef, *p0;
+  double scale, rmin_exp, rmax_exp;    /* < 0: table range */
+  int NO_L0, NO_L1, EVEN_L, EVEN_M, M0_only, self_consistent;
+} exphost_sphere_desc;
+
+typedef struct {
+  int mmax, norder, numx, numy, cmapr, cmapz;
+  double ascale, hscale, rmin, rmax;
+  const double *potC, *potS, *rforceC, *rforceS, *zforceC, *zforceS;
+  double rcylmax, acyl;                /* acyl < 0: ascale */
+  int EVEN_M, MMIN, MLIM, NMIN, NLIM, self_consistent;
+  const double *body, *orig;           /* orientation or NULL */
+} exphost_cylinder_desc;
+
+const char *exphost_last_error(void);
+int exphost_reset(void);
+/* globals of src/global.cc: dtime, multistep, dynfrac{S,D,V,A,P}, shiftlevl */
+int exphost_set_params(double dtime, int multistep, double dynfracS, double dynfracD, double dynfracV,
+                       double dynfracA, double dynfracP, int shiftlevl);
+int exphost_set_comm(void *nccl_comm, int myid, int numprocs);
+int exphost_add_component(const char *name, size_t n, const double *pos, const double *vel,
+                          const double *mass, int device, int *index);
+int exphost_component_options(int index, const double center[3], double rtrunc, int noswitch,
+                              int freezeLev, int dtreset);
+int exphost_set_sphere(int index, const exphost_sphere_desc *d);
+int exphost_set_cylinder(int index, const exphost_cylinder_desc *d);
+int exphost_add_interaction(int from, int on);
+int exphost_begin_run(void);
+int exphost_do_steps(int nsteps);
+/* device-timed: nsteps of do_step between two events on component 0's stream */
+int exphost_do_steps_timed(int nsteps, double *ms);
+int exphost_get_particles(int index, double *pos, double *vel, double *acc, double *pot,
+                          unsigned *level, float *dtreq);
+int exphost_get_sphere_coefs(int index, int which, int M, double *coef);
+int exphost_get_cylinder_coefs(int index, double *cosv, double *sinv, double *cylmass);
+int exphost_level_report(int index, uint64_t *examined, uint64_t *switched, uint64_t *offlo,
+                         uint64_t *offhi, uint64_t *counts /* [multistep+1] */);
+/* initialize_multistep tables for `multistep` levels (no GPU needed): mintvl[multistep+1],
+ * mfirst[Mstep+1], dstepL/dstepN[(multistep+1)][Mstep] */
+int exphost_multistep_tables(int multistep, int *mintvl, int *mfirst, int *dstepL, int *dstepN);
+int exphost_state(double *tnow, int *this_step, double *pos_check, double *vel_check);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

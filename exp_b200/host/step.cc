@@ -1,0 +1,59 @@
+// step.cc -- do_step (src/step.cc:67-323): one K(1/2) D K(1/2) leapfrog step; with
+// multistep > 0 the hierarchy of 2^multistep sub-steps in which level M moves every
+// mintvl[M] sub-steps and the inactive levels' coefficients are interpolated.
+#include <cmath>
+
+#include "expand.H"
+
+namespace exphost {
+
+std::vector<double> pos_check, vel_check;
+
+void do_step(int n)
+{
+  (void)n;
+  comp->multistep_reset();
+
+  if (multistep) {
+    const double dt = dtime / Mstep;                   // smallest time step
+    pos_check.assign(multistep + 1, 0.0);
+    vel_check.assign(multistep + 1, 0.0);
+
+    for (mstep = 0; mstep < Mstep; mstep++) {
+      mdrft = mstep;
+
+      // coefficients of the levels that move on this sub-step
+      for (unsigned M = (unsigned)mfirst[mstep]; M <= multistep; M++) {
+        const double DT = dt * mintvl[M];
+        incr_velocity(0.5 * DT, (int)M);               // first half kick
+        vel_check[M] += 0.5 * DT;
+        incr_position(DT, (int)M);                     // drift
+        pos_check[M] += DT;
+        comp->compute_expansion(M);                    // coefficients at the drifted position
+      }
+
+      tnow += dt;
+
+      mdrft = mstep + 1;                               // drifted position in the level tables
+      comp->compute_potential((unsigned)mfirst[mstep]);
+
+      // second half kick for the levels active at the next sub-step
+      for (unsigned M = (unsigned)mfirst[mdrft]; M <= multistep; M++) {
+        incr_velocity(0.5 * dt * mintvl[M], (int)M);
+        vel_check[M] += 0.5 * dt * mintvl[M];
+      }
+
+      adjust_multistep_level();
+    }
+  } else {
+    tnow += dtime;
+    incr_velocity(0.5 * dtime);
+    incr_position(dtime);
+    comp->compute_expansion(0);
+    comp->compute_potential();
+    incr_velocity(0.5 * dtime);
+  }
+  this_step++;
+}
+
+} // namespace exphost

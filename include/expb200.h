@@ -195,7 +195,8 @@ int expb200_sphere_compute_multistep_coefficients(expb200_sphere s, int mdrft);
 int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, double adb, int finish);
 int expb200_sphere_multistep_update_finish(expb200_sphere s);
 int expb200_sphere_differ_device(expb200_sphere s, double **dptr, size_t *count, void **stream);
-/* which = 0: expcoefN, 1: expcoefL, 2: differ */
+/* which = 0: expcoefN, 1: expcoefL, 2: differ (of level mlevel); 3: the installed vector
+ * (expcoef, what the force uses), 4: the last accumulated vector (after any all-reduce) */
 int expb200_sphere_get_level_coefficients(expb200_sphere s, int which, int mlevel, double *host);
 int expb200_sphere_set_level_coefficients(expb200_sphere s, int which, int mlevel, const double *host);
 
@@ -275,9 +276,12 @@ int expb200_cylinder_compute_multistep_coefficients(expb200_cylinder s, int mdrf
 int expb200_cylinder_multistep_update(expb200_cylinder s, expb200_component c, double adb, int finish);
 int expb200_cylinder_multistep_update_finish(expb200_cylinder s);
 int expb200_cylinder_differ_device(expb200_cylinder s, double **dptr, size_t *count, void **stream);
-/* which = 0: cosN/sinN, 1: cosL/sinL, 2: differ; cos_host, sin_host [(mmax+1)][norder] */
+/* which = 0: cosN/sinN, 1: cosL/sinL, 2: differ (of level mlevel); 3: installed accum_cos/sin,
+ * 4: last accumulated (after any all-reduce); cos_host, sin_host [(mmax+1)][norder] */
 int expb200_cylinder_get_level_coefficients(expb200_cylinder s, int which, int mlevel,
                                             double *cos_host, double *sin_host);
+/* the mass slot of the same vectors (cylmass0 summed; src/Cylinder.cc:1081-1098) */
+int expb200_cylinder_get_mass(expb200_cylinder s, int which, int mlevel, double *mass);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU: one process (MPI rank) per GPU; NCCL is loaded with dlopen.

@@ -1,0 +1,98 @@
+"""The C++ host driver (exp_b200/host/: Component, PotAccel -> Sphere / Cylinder,
+ComponentContainer, begin_run, do_step, adjust_multistep_level) over the C ABI, against the
+same ordering driven with the CPU oracle (tests/ref_stepper.py): single level, multistep,
+and a disk+halo pair with mutual interactions (BASELINE configs[3] in miniature)."""
+import numpy as np
+import pytest
+
+from conftest import acc_rel_err, get_table, rel_rms
+from exp_b200 import cyltable, ics
+from exp_b200.exphost import Simulation
+from ref_stepper import RefSim, RefSphereStepper
+from test_emul_cyl import disk
+
+pytestmark = pytest.mark.gpu
+
+
+def _halo(n, seed=31):
+    pos, vel, mass = ics.hernquist_halo(n, seed=seed)
+    return pos + np.array([0.01, -0.02, 0.005]), vel, mass
+
+
+@pytest.mark.parametrize("multistep,dtime,nsteps", [(0, 0.005, 3), (3, 0.04, 2)])
+def test_sphere_do_step(multistep, dtime, nsteps):
+    tab = get_table("hernquist", 4, 10)
+    n = 30000
+    pos, vel, mass = _halo(n)
+    dyn = dict(dynfracV=0.02, dynfracA=0.06)
+    ref = RefSphereStepper(tab, pos, vel, mass, dtime, multistep, **dyn)
+    ref.initialize()
+    sim = Simulation(dtime, multistep, **dyn)
+    h = sim.add_component("halo", pos, vel, mass)
+    sim.set_sphere(h, tab)
+    sim.begin_run()
+    for _ in range(nsteps):
+        ref.step()
+    sim.do_steps(nsteps)
+    out = sim.particles(h, n)
+    assert np.array_equal(out["level"], ref.S.level)
+    if multistep:
+        assert len(np.unique(ref.S.level)) >= 3
+        st = sim.state()
+        assert np.allclose(st["pos_check"], dtime, rtol=1e-12)      # CHK_STEP identity
+        assert np.allclose(st["vel_check"], dtime, rtol=1e-12)
+        assert sim.level_report(h)["counts"].sum() == n
+    assert np.abs(out["pos"] - ref.S.pos).max() <= 1e-10 * np.abs(ref.S.pos).max()
+    assert np.abs(out["vel"] - ref.S.vel).max() <= 1e-9 * np.abs(ref.S.vel).max()
+    assert acc_rel_err(out["acc"], ref.S.acc).max() <= 1e-8
+    assert rel_rms(sim.sphere_coefs(h), ref.expcoef) <= 1e-10
+    assert abs(sim.state()["tnow"] - nsteps * dtime) < 1e-12
+
+
+@pytest.mark.parametrize("multistep", [0, 2])
+def test_disk_halo_interactions(multistep):
+    """two components, each force acting on both (the reference's interaction list)"""
+    tabS = get_table("hernquist", 4, 10)
+    tabC = cyltable.synthetic_cyl_table(mmax=4, norder=6, numx=48, numy=24)
+    nh, nd = 20000, 12000
+    ph, vh, mh = _halo(nh, seed=7)
+    ph *= 0.05                                   # bring part of the halo onto the disk's grid
+    pd, vd, md = disk(nd, seed=8)
+    md *= 0.05
+    dtime = 0.002
+    dyn = dict(dynfracV=0.05, dynfracA=0.2, dynfracP=0.3)
+    ref = RefSim(dtime, multistep, **dyn)
+    rh = ref.add("sphere", tabS, ph, vh, mh)
+    rd = ref.add("cylinder", tabC, pd, vd, md)
+    ref.add_interaction(rh, rd)
+    ref.add_interaction(rd, rh)
+    ref.initialize()
+
+    sim = Simulation(dtime, multistep, **dyn)
+    h = sim.add_component("halo", ph, vh, mh)
+    d = sim.add_component("disk", pd, vd, md)
+    sim.set_sphere(h, tabS)
+    sim.set_cylinder(d, tabC)
+    sim.add_interaction(h, d)
+    sim.add_interaction(d, h)
+    sim.begin_run()
+
+    nsteps = 2
+    for _ in range(nsteps):
+        ref.step()
+    sim.do_steps(nsteps)
+    for idx, S, n in ((h, ref.S[rh], nh), (d, ref.S[rd], nd)):
+        out = sim.particles(idx, n)
+        assert np.array_equal(out["level"], S.level)
+        assert np.abs(out["pos"] - S.pos).max() <= 1e-10 * np.abs(S.pos).max()
+        assert np.abs(out["vel"] - S.vel).max() <= 1e-9 * np.abs(S.vel).max()
+        assert acc_rel_err(out["acc"], S.acc).max() <= 1e-8
+        assert np.abs(out["pot"] - S.pot).max() <= 1e-8 * np.abs(S.pot).max()
+    if multistep:
+        lv = np.concatenate([ref.S[rh].level, ref.S[rd].level])
+        assert len(np.unique(lv)) >= 2
+    assert rel_rms(sim.sphere_coefs(h), ref.F[rh].use[0]) <= 1e-10
+    cs, sn, cm = sim.cylinder_coefs(d)
+    assert rel_rms(cs, ref.F[rd].use[0]) <= 1e-10
+    assert rel_rms(sn[1:], ref.F[rd].use[1][1:]) <= 1e-10
+    assert abs(cm - ref.F[rd].cylmass) <= 1e-11 * cm
