@@ -193,6 +193,8 @@ SIGNATURES = {
                                                  C.POINTER(C.c_void_p)]),
     "expb200_cylinder_get_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp, c_dp]),
     "expb200_cylinder_get_mass": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
+    "expb200_cylinder_covariance": (C.c_int, [_H, _H, C.c_int, C.c_double, C.c_int, C.c_uint64, c_up, c_dp,
+                                              c_dp, c_dp]),
     "expb200_profile_enable": (C.c_int, [C.c_int]),
     "expb200_profile_reset": (C.c_int, []),
     "expb200_profile_kernels": (C.c_int, []),

@@ -88,6 +88,13 @@ __device__ __forceinline__ void st_rec(rec4 *p, const rec4 &v)
   q[0] = make_double2(v.x, v.y);
   q[1] = make_double2(v.z, v.w);
 }
+// FP64 tensor-core tile product D(8x8) += A(8x4) B(4x8): lane (g = lane/4, t = lane%4) holds
+// a = A[g][t], b = B[t][g], d0 = D[g][2t], d1 = D[g][2t+1].
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 #endif
 
 } // namespace expb200

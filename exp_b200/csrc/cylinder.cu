@@ -276,6 +276,303 @@ __global__ void cyl_interp_kernel(const double *__restrict__ cL, const double *_
   out[k] = s;
 }
 
+// ===========================================================================
+// Covariance (`covar`), EmpCylSL::accumulate (exputil/EmpCylSL.cc:4069-4074, 4123-4141).
+// Per jackknife bin T = indx % sampT and harmonic m the reference accumulates
+//   VC[T][m]   += mass vec,            vec_n = norm [(Vc_n cos + Vs_n sin) + i (Vc_n sin - Vs_n cos)]
+//   MV[T][m]   += mass vec vec^H       (Hermitian norder x norder)
+// with Vc/Vs the bilinear table values of get_pot (Vs = 0 for m = 0).  Unlike the
+// coefficients this is quadratic in the particle, so there is nothing to factorise across
+// particles: it is a genuine SYRK.  With u = sqrt(mass) [Re vec ; Im vec] (2 norder reals)
+//   U U^T = [[aa^T, ab^T],[ba^T, bb^T]],   Re MV = aa^T + bb^T,   Im MV = ba^T - ab^T
+// so one real rank-k update per (T, m) on the FP64 tensor cores (DMMA m8n8k4) gives both.
+//
+// Particles are sorted by (T, cell).  A CTA owns a chunk of consecutive sorted particles and
+// the harmonics m = 8 blockIdx.y + warp; it walks the chunk in tiles of 16 particles of one
+// bin: every thread evaluates one (m, n) entry of u for the tile's particles from the
+// node-major complex pot table Zt[node][m][n] = (potC, potS) (4 coalesced 16-byte loads per
+// particle), then warp m multiplies its 2 norder x 16 panel into register accumulators.
+// When the bin changes the accumulators go to partial slot (chunk + T) -- unique, because
+// both are non-decreasing along the sorted order -- and a second kernel adds a bin's
+// partials in chunk order: no atomics, bit-reproducible.
+// ===========================================================================
+constexpr int kCovP = 16;             // particles per tile
+constexpr int kCovLD = 20;            // leading dimension of a panel row (doubles): 2-way = minimal
+                                      // bank conflicts for the 64-bit fragment loads
+constexpr int kCovMG = 8;             // harmonics per CTA (one per warp)
+constexpr int kCovSplit = 4;          // particle interleave of the panel evaluation (max)
+
+__global__ void __launch_bounds__(256)
+cyl_cov_table_kernel(CylGeom g, const double *__restrict__ potC, const double *__restrict__ potS,
+                     int mlim, int even_m, double2 *__restrict__ Zt)
+{
+  const int MN = (g.mmax + 1) * g.norder;
+  const size_t total = (size_t)g.nnode * MN;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int node = (int)(e / MN), mn = (int)(e % MN), m = mn / g.norder;
+    // rows get_pot never fills (m > MLIM, odd m with EVEN_M) count as zero
+    const bool off = m > mlim || (even_m && (m & 1));
+    double2 z = make_double2(0.0, 0.0);
+    if (!off) {
+      z.x = potC[(size_t)mn * g.nnode + node];
+      if (m) z.y = potS[(size_t)mn * g.nnode + node];
+    }
+    Zt[e] = z;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cyl_cov_key_kernel(CylGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                   const uint32_t *__restrict__ slot_of, size_t n, int use_levels, int mlevel,
+                   uint32_t sampT, uint64_t indx_base, uint32_t *__restrict__ keys)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t key = sampT * (uint32_t)g.ncell;
+    if (!use_levels || level[i] == (unsigned)mlevel) {
+      const uint32_t ck = cyl_cell_key(g, ld_rec(&posm[i]));
+      if (ck < (uint32_t)g.ncell) {
+        const uint64_t indx = indx_base + (slot_of ? slot_of[i] : (uint32_t)i);
+        key = (uint32_t)(indx % sampT) * (uint32_t)g.ncell + ck;
+      }
+    }
+    keys[i] = key;
+  }
+}
+
+// bstart[T] = first sorted position whose bin is >= T, T in [0, sampT]
+__global__ void cyl_cov_bounds_kernel(const uint32_t *__restrict__ skeys, size_t n, uint32_t ncell,
+                                      int sampT, uint32_t *__restrict__ bstart)
+{
+  const int T = blockIdx.x * blockDim.x + threadIdx.x;
+  if (T > sampT) return;
+  const uint64_t want = (uint64_t)T * ncell;
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    size_t mid = (lo + hi) / 2;
+    if ((uint64_t)skeys[mid] < want) lo = mid + 1; else hi = mid;
+  }
+  bstart[T] = (uint32_t)lo;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, NT <= 5 ? 2 : 1)
+cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict__ posm,
+               const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skeys,
+               const uint32_t *__restrict__ bstart, int sampT, int CH, double adb, int nsplit,
+               double *__restrict__ PC, double *__restrict__ PV, double *__restrict__ PM)
+{
+  extern __shared__ double cov_smem[];
+  const int N = g.norder, R2 = 2 * N, M1 = g.mmax + 1, MN = M1 * N;
+  const int mg0 = blockIdx.y * kCovMG;
+  const int nml = M1 - mg0 < kCovMG ? M1 - mg0 : kCovMG;       // harmonics of this CTA
+  const int items = nml * N;
+  double *U = cov_smem;                                        // [kCovMG][R2][kCovLD]
+  double *wgt = U + (size_t)kCovMG * R2 * kCovLD;              // [kCovP][4]
+  double *trg = wgt + kCovP * 4;                               // [kCovP][M1][2]
+  double *sqm = trg + (size_t)kCovP * M1 * 2;                  // [kCovP]
+  double *pms = sqm + kCovP;                                   // [kCovP]
+  int *nbs = reinterpret_cast<int *>(pms + kCovP);             // [kCovP]
+  int *info = nbs + kCovP;                                     // cnt, T
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const size_t nused = bstart[sampT];
+  const size_t chunk = blockIdx.x;
+  const size_t beg = chunk * (size_t)CH;
+  if (beg >= nused) return;
+  const size_t end = beg + CH < nused ? beg + CH : nused;
+
+  // panel evaluation: thread -> (split, local m, n)
+  const int split = tid / items, it = tid % items;
+  const bool evalr = split < nsplit;
+  const int ml = it / N, nn = it % N;
+  const int mn = (mg0 + ml) * N + nn;
+
+  double acc[NT][NT][2];
+#pragma unroll
+  for (int a = 0; a < NT; a++)
+#pragma unroll
+    for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+  double vcr = 0.0, vci = 0.0;            // this thread's share of VC[T][m][n]
+  double bmass = 0.0, bcount = 0.0;       // thread 0: massT / numbT of the current bin
+  int curT = -1;
+
+  auto flush = [&](int T) {
+    const size_t slot = chunk + (size_t)T;
+    if (w < nml) {
+      double *P = PC + ((slot * M1 + (mg0 + w)) * R2) * R2;
+#pragma unroll
+      for (int a = 0; a < NT; a++)
+#pragma unroll
+        for (int b = a; b < NT; b++) {         // U U^T is symmetric: tiles on and above the diagonal
+          const int row = 8 * a + gq, col = 8 * b + 2 * t;
+          if (row < R2 && col < R2) {          // R2 is even: col + 1 < R2 as well
+            P[(size_t)row * R2 + col] = acc[a][b][0];
+            P[(size_t)row * R2 + col + 1] = acc[a][b][1];
+          }
+          acc[a][b][0] = acc[a][b][1] = 0.0;
+        }
+    }
+    if (evalr) {
+      double *V = PV + ((slot * kCovSplit + split) * MN + mn) * 2;
+      V[0] = vcr; V[1] = vci;
+      vcr = vci = 0.0;
+    }
+    if (tid == 0 && mg0 == 0) {
+      PM[slot * 2] = bmass; PM[slot * 2 + 1] = bcount;
+      bmass = bcount = 0.0;
+    }
+  };
+
+  for (size_t k0 = beg; k0 < end;) {
+    // ---- per-particle geometry of the tile (warp 0, lane = particle)
+    if (w == 0) {
+      const size_t k = k0 + lane;
+      const bool valid = lane < kCovP && k < end;
+      const uint32_t key = valid ? skeys[k] : 0xffffffffu;
+      const int Tj = (int)(key / (uint32_t)g.ncell);
+      const int T0 = __shfl_sync(0xffffffffu, Tj, 0);
+      const unsigned mask = __ballot_sync(0xffffffffu, valid && Tj == T0);
+      const int cnt = __ffs(~mask) - 1;                    // leading run of the same bin
+      if (lane == 0) { info[0] = cnt; info[1] = T0; }
+      if (lane < cnt) {
+        const rec4 pm = ld_rec(&posm[perm[k]]);
+        double x, y, z, r;
+        cyl_classify(g, pm, x, y, z, r, 0);
+        double zz = z;
+        if (zz / g.ascale > g.rtable) zz = g.rtable * g.ascale;       // EmpCylSL::get_pot clamp
+        if (zz / g.ascale < -g.rtable) zz = -g.rtable * g.ascale;
+        const CylCell c = cyl_locate(g, r, zz);
+        const double mass = pm.w * adb;
+        const double sq = sqrt(mass), sw = -4.0 * M_PI * sq;
+        wgt[lane * 4 + 0] = sw * c.c00; wgt[lane * 4 + 1] = sw * c.c10;
+        wgt[lane * 4 + 2] = sw * c.c01; wgt[lane * 4 + 3] = sw * c.c11;
+        nbs[lane] = c.ix * (g.numy + 1) + c.iy;
+        sqm[lane] = sq;
+        pms[lane] = mass;
+        cyl_trig(g.mmax, x, y, r, [&](int m, double cm, double sm) {
+          trg[(lane * M1 + m) * 2] = cm;
+          trg[(lane * M1 + m) * 2 + 1] = sm;
+        });
+      }
+    }
+    __syncthreads();
+    const int cnt = info[0], T0 = info[1];
+    if (T0 != curT) {
+      if (curT >= 0) flush(curT);
+      curT = T0;
+    }
+    if (tid == 0) {
+      for (int j = 0; j < cnt; j++) { bmass += pms[j]; bcount += 1.0; }
+    }
+    // ---- panel: u[m][n][j], u[m][N+n][j] for the tile's particles (zero beyond cnt)
+    const int kpad = (cnt + 3) & ~3;
+    if (evalr) {
+      double *ua = U + ((size_t)ml * R2 + nn) * kCovLD, *ub = ua + (size_t)N * kCovLD;
+      for (int j = split; j < kpad; j += nsplit) {
+        double a = 0.0, b = 0.0;
+        if (j < cnt) {
+          const double2 *z = Zt + (size_t)nbs[j] * MN + mn;
+          const double2 z00 = __ldg(z), z01 = __ldg(z + MN);
+          const double2 z10 = __ldg(z + (size_t)(g.numy + 1) * MN), z11 = __ldg(z + (size_t)(g.numy + 2) * MN);
+          const double *wj = wgt + j * 4;
+          const double vc = z00.x * wj[0] + z10.x * wj[1] + z01.x * wj[2] + z11.x * wj[3];
+          const double vs = z00.y * wj[0] + z10.y * wj[1] + z01.y * wj[2] + z11.y * wj[3];
+          const double cm = trg[(j * M1 + mg0 + ml) * 2], sm = trg[(j * M1 + mg0 + ml) * 2 + 1];
+          a = vc * cm + vs * sm;
+          b = vc * sm - vs * cm;
+          vcr += sqm[j] * a;
+          vci += sqm[j] * b;
+        }
+        ua[j] = a;
+        ub[j] = b;
+      }
+    }
+    __syncthreads();
+    // ---- rank-k update on the tensor cores: warp w owns harmonic mg0 + w
+    if (w < nml) {
+      const double *Um = U + (size_t)w * R2 * kCovLD;
+      for (int kk = 0; kk < kpad; kk += 4) {
+        double af[NT];
+#pragma unroll
+        for (int r = 0; r < NT; r++) {
+          const int row = 8 * r + gq;
+          af[r] = row < R2 ? Um[(size_t)row * kCovLD + kk + t] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < NT; a++)
+#pragma unroll
+          for (int b = a; b < NT; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], af[b]);
+      }
+    }
+    k0 += cnt;
+    // the next tile's geometry is written by warp 0 only after it finished its own update;
+    // the barrier after it orders the panel rewrite against every warp's update
+  }
+  if (curT >= 0) flush(curT);
+}
+
+// MV / VC / massT / numbT of bin T = sum over the chunks that overlap it, in chunk order
+__global__ void __launch_bounds__(128)
+cyl_cov_combine_kernel(CylGeom g, const uint32_t *__restrict__ bstart, int CH, int nsplit,
+                       const double *__restrict__ PC, const double *__restrict__ PV,
+                       const double *__restrict__ PM, double *__restrict__ outMV,
+                       double *__restrict__ outVC, double *__restrict__ outMass,
+                       unsigned *__restrict__ outCount)
+{
+  const int T = blockIdx.x, m = blockIdx.y;
+  const int N = g.norder, R2 = 2 * N, M1 = g.mmax + 1, MN = M1 * N;
+  const uint32_t b0 = bstart[T], b1 = bstart[T + 1];
+  const bool any = b1 > b0;
+  const size_t c0 = any ? b0 / CH : 1, c1 = any ? (b1 - 1) / CH : 0;
+  double *MV = outMV + ((size_t)T * M1 + m) * N * N * 2;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int n = e / N, o = e % N;
+    double re = 0.0, im = 0.0;
+    for (size_t c = c0; c <= c1; c++) {
+      const double *P = PC + (((c + T) * M1 + m) * R2) * R2;
+      // only the 8x8 tiles on and above the diagonal were stored; the rest by symmetry
+      auto at = [&](int r, int q) { return (r >> 3) <= (q >> 3) ? P[(size_t)r * R2 + q] : P[(size_t)q * R2 + r]; };
+      re += at(n, o) + at(N + n, N + o);
+      im += at(N + n, o) - at(n, N + o);
+    }
+    MV[2 * e] = re;
+    MV[2 * e + 1] = im;
+  }
+  double *VC = outVC + ((size_t)T * M1 + m) * N * 2;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    double re = 0.0, im = 0.0;
+    for (size_t c = c0; c <= c1; c++)
+      for (int sp = 0; sp < nsplit; sp++) {
+        const double *V = PV + (((c + T) * kCovSplit + sp) * MN + (size_t)m * N + n) * 2;
+        re += V[0];
+        im += V[1];
+      }
+    VC[2 * n] = re;
+    VC[2 * n + 1] = im;
+  }
+  if (m == 0 && threadIdx.x == 0) {
+    double ms = 0.0, ct = 0.0;
+    for (size_t c = c0; c <= c1; c++) { ms += PM[(c + T) * 2]; ct += PM[(c + T) * 2 + 1]; }
+    outMass[T] = ms;
+    outCount[T] = (unsigned)(ct + 0.5);
+  }
+}
+
+template <int NT>
+int launch_cyl_cov(cudaStream_t st, dim3 grid, size_t smem, const CylGeom &g, const double2 *Zt,
+                   const rec4 *posm, const uint32_t *perm, const uint32_t *skeys, const uint32_t *bstart,
+                   int sampT, int CH, double adb, int nsplit, double *PC, double *PV, double *PM)
+{
+  CU_TRY(cudaFuncSetAttribute(cyl_cov_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cyl_cov_kernel<NT><<<grid, 256, smem, st>>>(g, Zt, posm, perm, skeys, bstart, sampT, CH, adb, nsplit,
+                                              PC, PV, PM);
+  CU_LAUNCH_CHECK();
+  return EXPB200_OK;
+}
+
 int cyl_chunk(size_t n)
 {
   size_t q = n / ((size_t)kSMsB200 * 32 * 32);
@@ -306,6 +603,7 @@ struct expb200_cylinder_s {
   double *PA = nullptr;
   size_t part_slots = 0;
   double *block_mass = nullptr;
+  double2 *Zt = nullptr;            // covariance: node-major complex pot table [nnode][(mmax+1)*norder]
   bool field_valid = false, have_accum = false;
   cudaStream_t last_stream = nullptr, own_stream = nullptr;
   cudaStream_t work_stream()
@@ -467,7 +765,7 @@ int expb200_cylinder_destroy(expb200_cylinder s)
   for (int k = 0; k < 3; k++) for (int cs = 0; cs < 2; cs++) cudaFree(s->tab[k][cs]);
   cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->coefN); cudaFree(s->coefL);
   cudaFree(s->differ); cudaFree(s->tmp);
-  cudaFree(s->G); cudaFree(s->F); cudaFree(s->PA); cudaFree(s->block_mass);
+  cudaFree(s->G); cudaFree(s->F); cudaFree(s->PA); cudaFree(s->block_mass); cudaFree(s->Zt);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
   return EXPB200_OK;
@@ -737,6 +1035,109 @@ int expb200_cylinder_get_level_coefficients(expb200_cylinder s, int which, int m
                     : (which == 0 ? s->coefN : which == 1 ? s->coefL : s->differ) + (size_t)mlevel * n1;
   CU_TRY(cudaMemcpy(cos_host, src, half * sizeof(double), cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(sin_host, src + half, half * sizeof(double), cudaMemcpyDeviceToHost));
+  return EXPB200_OK;
+}
+
+// ~ the covariance branch of EmpCylSL::accumulate for levlist[mlevel] (see the kernels above)
+int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mlevel, double adb,
+                                int sampT, uint64_t indx_base, unsigned *numbT, double *massT,
+                                double *VC, double *MV)
+{
+  REQUIRE(s && c, "NULL argument");
+  REQUIRE(s->device == c->device, "device mismatch");
+  REQUIRE(mlevel >= 0 && mlevel < s->nlev, "mlevel=%d outside [0,%d]", mlevel, s->nlev - 1);
+  const CylGeom &g0 = s->geom;
+  REQUIRE(sampT >= 1 && (uint64_t)sampT * g0.ncell < 0x7fffffffull, "sampT=%d out of range", sampT);
+  REQUIRE(g0.norder <= 32, "covariance supports norder <= 32");
+  DeviceGuard gd(s->device);
+  cudaStream_t st = c->stream;
+  { cudaStream_t ws = s->work_stream(); if (ws != st) CU_TRY(cudaStreamSynchronize(ws)); }
+  s->last_stream = st;
+  const int N = g0.norder, R2 = 2 * N, M1 = g0.mmax + 1, MN = M1 * N;
+  if (numbT) memset(numbT, 0, (size_t)sampT * sizeof(unsigned));
+  if (massT) memset(massT, 0, (size_t)sampT * sizeof(double));
+  if (VC) memset(VC, 0, (size_t)sampT * MN * 2 * sizeof(double));
+  if (MV) memset(MV, 0, (size_t)sampT * MN * N * 2 * sizeof(double));
+  if (c->n == 0) return EXPB200_OK;
+
+  CylGeom g = geom_for(s, c);
+  g.rotate = s->geom.rotate;
+  ProfRegion pr(K_COV, st, 0);
+  if (!s->Zt) {
+    CU_TRY(cudaMalloc(&s->Zt, (size_t)g.nnode * MN * sizeof(double2)));
+    cyl_cov_table_kernel<<<grid_for((size_t)g.nnode * MN, 256), 256, 0, st>>>(g, s->tab[0][0], s->tab[0][1],
+                                                                              s->cfg.MLIM, s->cfg.EVEN_M, s->Zt);
+    CU_LAUNCH_CHECK();
+  }
+  // (T, cell) keys -> stable sort; the component's own sort is replaced
+  const uint32_t nkeys = (uint32_t)sampT * (uint32_t)g.ncell + 1;
+  cyl_cov_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(g, c->posm, c->level,
+                                                          c->identity_order ? nullptr : c->slot_of, c->n,
+                                                          s->nlev > 1, mlevel, (uint32_t)sampT, indx_base,
+                                                          c->keys[0]);
+  CU_LAUNCH_CHECK();
+  int cur = 0;
+  int rc = radix_sort_pairs(st, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur);
+  if (rc) return rc;
+  c->cur = cur;
+  c->sort_kind = 0;
+
+  uint32_t *bstart = nullptr;
+  double *PC = nullptr, *PV = nullptr, *PM = nullptr, *dMV = nullptr, *dVC = nullptr, *dMass = nullptr;
+  unsigned *dCount = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(bstart); cudaFree(PC); cudaFree(PV); cudaFree(PM); cudaFree(dMV); cudaFree(dVC);
+    cudaFree(dMass); cudaFree(dCount);
+  };
+#define COV_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
+  COV_TRY(cudaMalloc(&bstart, ((size_t)sampT + 1) * sizeof(uint32_t)));
+  cyl_cov_bounds_kernel<<<div_up((size_t)sampT + 1, 128), 128, 0, st>>>(c->keys[c->cur], c->n, (uint32_t)g.ncell,
+                                                                        sampT, bstart);
+  uint32_t nused = 0;
+  COV_TRY(cudaMemcpyAsync(&nused, bstart + sampT, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  COV_TRY(cudaStreamSynchronize(st));
+  if (nused == 0) { cleanup(); return EXPB200_OK; }
+
+  // chunk: a few waves of CTAs over the 148 SMs, 256..4096 particles each
+  size_t chq = nused / ((size_t)kSMsB200 * 8);
+  int CH = (int)(chq < 256 ? 256 : chq > 4096 ? 4096 : chq);
+  const unsigned nchunks = div_up(nused, CH);
+  const size_t slots = (size_t)nchunks + sampT + 1;
+  const int mgroups = (M1 + kCovMG - 1) / kCovMG;
+  const int items = (M1 < kCovMG ? M1 : kCovMG) * N;
+  int nsplit = 256 / items;
+  if (nsplit > kCovSplit) nsplit = kCovSplit;
+  COV_TRY(cudaMalloc(&PC, slots * M1 * R2 * R2 * sizeof(double)));
+  COV_TRY(cudaMalloc(&PV, slots * kCovSplit * MN * 2 * sizeof(double)));
+  COV_TRY(cudaMalloc(&PM, slots * 2 * sizeof(double)));
+  COV_TRY(cudaMemsetAsync(PV, 0, slots * kCovSplit * MN * 2 * sizeof(double), st));
+  COV_TRY(cudaMalloc(&dMV, (size_t)sampT * MN * N * 2 * sizeof(double)));
+  COV_TRY(cudaMalloc(&dVC, (size_t)sampT * MN * 2 * sizeof(double)));
+  COV_TRY(cudaMalloc(&dMass, (size_t)sampT * sizeof(double)));
+  COV_TRY(cudaMalloc(&dCount, (size_t)sampT * sizeof(unsigned)));
+
+  const size_t smem = ((size_t)kCovMG * R2 * kCovLD + kCovP * 4 + (size_t)kCovP * M1 * 2 + 2 * kCovP) * sizeof(double) +
+                      (kCovP + 4) * sizeof(int);
+  const dim3 grid(nchunks, mgroups);
+  const int NT = (R2 + 7) / 8;
+#define COV_LAUNCH(K) rc = launch_cyl_cov<K>(st, grid, smem, g, s->Zt, c->posm, c->perm[c->cur], c->keys[c->cur], \
+                                             bstart, sampT, CH, adb, nsplit, PC, PV, PM)
+  switch (NT) {
+    case 1: COV_LAUNCH(1); break;  case 2: COV_LAUNCH(2); break;  case 3: COV_LAUNCH(3); break;
+    case 4: COV_LAUNCH(4); break;  case 5: COV_LAUNCH(5); break;  case 6: COV_LAUNCH(6); break;
+    default: COV_LAUNCH(8); break;
+  }
+#undef COV_LAUNCH
+  if (rc) { cleanup(); return rc; }
+  cyl_cov_combine_kernel<<<dim3(sampT, M1), 128, 0, st>>>(g, bstart, CH, nsplit, PC, PV, PM, dMV, dVC, dMass, dCount);
+  COV_TRY(cudaGetLastError());
+  if (MV) COV_TRY(cudaMemcpyAsync(MV, dMV, (size_t)sampT * MN * N * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (VC) COV_TRY(cudaMemcpyAsync(VC, dVC, (size_t)sampT * MN * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (massT) COV_TRY(cudaMemcpyAsync(massT, dMass, (size_t)sampT * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (numbT) COV_TRY(cudaMemcpyAsync(numbT, dCount, (size_t)sampT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  COV_TRY(cudaStreamSynchronize(st));
+#undef COV_TRY
+  cleanup();
   return EXPB200_OK;
 }
 

@@ -838,12 +838,6 @@ __global__ void sph_cov_mass_kernel(SphGeom g, const double *__restrict__ Mc, do
   massT[blockIdx.x] = t;
 }
 
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
-{
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
 // contraction on the FP64 tensor cores: one CTA per (slot, T); warp w takes the nodes
 // i = 4 (w + 4 s), s = 0, 1, ...; the four partial nmax x nmax tiles are summed in warp order.
 // A fragment (row n = 8 rt + lane/4, k = lane%4) is E[l][n][i]; the B fragment of column tile

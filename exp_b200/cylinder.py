@@ -72,6 +72,22 @@ class Cylinder:
         self.used, self.cylmass = used.value, mass.value
         return cs, sn
 
+    def covariance(self, c: Component, sampT: int, adb: float = 1.0, indx_base: int = 0):
+        """The `covar` accumulation of EmpCylSL::accumulate (exputil/EmpCylSL.cc:4123-4141) for
+        levlist[mlevel]: per jackknife bin T = indx % sampT returns numbT, massT, VC (complex,
+        [T][m][n]) and MV (complex Hermitian, [T][m][n][o])."""
+        M1, N = self.mmax + 1, self.norder
+        numbT = np.zeros(sampT, dtype=np.uint32)
+        massT = np.zeros(sampT)
+        VC = np.zeros((sampT, M1, N, 2))
+        MV = np.zeros((sampT, M1, N, N, 2))
+        check(_lib.lib().expb200_cylinder_covariance(
+            self._h, c._h, self.mlevel, float(adb), int(sampT), int(indx_base),
+            numbT.ctypes.data_as(_lib.c_up), massT.ctypes.data_as(c_dp), VC.ctypes.data_as(c_dp),
+            MV.ctypes.data_as(c_dp)))
+        return dict(numbT=numbT, massT=massT, VC=VC[..., 0] + 1j * VC[..., 1],
+                    MV=MV[..., 0] + 1j * MV[..., 1])
+
     def set_coefficients(self, cos=None, sin=None, cylmass=-1.0):
         if cos is None:
             check(_lib.lib().expb200_cylinder_set_coefficients(self._h, None, None, float(cylmass)))

@@ -283,6 +283,19 @@ int expb200_cylinder_get_level_coefficients(expb200_cylinder s, int which, int m
 /* the mass slot of the same vectors (cylmass0 summed; src/Cylinder.cc:1081-1098) */
 int expb200_cylinder_get_mass(expb200_cylinder s, int which, int mlevel, double *mass);
 
+/* Covariance of the coefficients (`covar`), the compute branch of EmpCylSL::accumulate
+ * (exputil/EmpCylSL.cc:4069-4074, 4123-4141; ~ the covariance part of
+ * Cylinder::determine_coefficients_cuda, results as EmpCylSL::set_massT/set_numbT/set_VC/
+ * set_MV take them, include/EmpCylSL.H:996-1110) for levlist[mlevel].
+ * Bin T = (indx_base + host slot) % sampT.  Host outputs, any may be NULL:
+ *   numbT[sampT], massT[sampT]
+ *   VC[sampT][(mmax+1)][norder][2]                 mass * vec             (re, im)
+ *   MV[sampT][(mmax+1)][norder][norder][2]         mass * vec vec^H       (re, im)
+ * norder <= 32.  The component's cell sort is replaced by the (bin, cell) sort of this call. */
+int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mlevel, double adb,
+                                int sampT, uint64_t indx_base, unsigned *numbT, double *massT,
+                                double *VC, double *MV);
+
 /* ------------------------------------------------------------------------
  * Multi-GPU: one process (MPI rank) per GPU; NCCL is loaded with dlopen.
  * Replaces the host MPI_Allreduce of the coefficient vector

@@ -72,3 +72,47 @@ def test_covariance_after_reordering_uses_host_slots():
     out = s.covariance(c, sampT)
     assert np.array_equal(out["countT"], ref["countT"])
     assert _rel(out["coefM"], ref["coefM"]) <= 1e-10
+
+
+# ---- cylinder (`covar` branch of EmpCylSL::accumulate, exputil/EmpCylSL.cc:4123-4141) ----
+@pytest.mark.parametrize("shape,n,sampT,rot", [
+    ((4, 6, 48, 24), 20000, 1, False),
+    ((4, 6, 48, 24), 20000, 7, True),
+    ((6, 18, 64, 32), 30000, 3, False),
+    ((6, 18, 64, 32), 30000, 173, False),      # ~ sqrt(N) bins: most (bin, cell) groups are singletons
+    ((0, 4, 16, 8), 3000, 2, False),
+    ((9, 5, 24, 12), 6000, 4, False),          # two harmonic groups (mmax + 1 > 8)
+])
+def test_cylinder_covariance_parity(shape, n, sampT, rot):
+    from exp_b200 import cyltable
+    from exp_b200.cylinder import Cylinder
+    from test_emul_cyl import disk, rotations
+    tab = cyltable.synthetic_cyl_table(mmax=shape[0], norder=shape[1], numx=shape[2], numy=shape[3])
+    pos, vel, mass = disk(n, seed=61)
+    body, orig = rotations() if rot else (None, None)
+    g = O.CylGridPy(tab)
+    P = O.cyl_params(rcylmax=20.0, acyl=tab.ascale, body=body, orig=orig)
+    S = O.ParticleSet(pos, vel, mass)
+    ref = O.cyl_coefficients_cov(g, P, S, sampT)
+
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    cyl = Cylinder(tab)
+    if rot:
+        cyl.set_orientation(body, orig)
+    cs, sn = cyl.determine_coefficients(c)          # sorts (and may re-order) the store first
+    out = cyl.covariance(c, sampT)
+    assert np.array_equal(out["numbT"], ref["numbT"])
+    assert out["numbT"].sum() <= ref["used"]      # `used` also counts particles off the table
+    assert _rel(out["massT"], ref["massT"]) <= 1e-10
+    assert _rel(out["VC"], ref["VC"]) <= 1e-10
+    assert _rel(out["MV"], ref["MV"]) <= 1e-10
+    # Hermitian, and the bins add up to the coefficients: Re vec = vC cos + vS sin, so
+    # sum_T Re VC = cosN + sinN (a checksum of checksums)
+    assert np.abs(out["MV"] - np.conj(np.swapaxes(out["MV"], -1, -2))).max() <= 1e-14 * np.abs(out["MV"]).max()
+    tot = out["VC"].sum(axis=0)
+    sn0 = sn.copy()
+    sn0[0] = 0.0
+    assert np.abs(tot.real - (cs + sn0)).max() <= 1e-11 * np.abs(cs).max()
+    again = cyl.covariance(c, sampT)
+    assert again["MV"].tobytes() == out["MV"].tobytes()      # reproducible bit for bit
