@@ -50,12 +50,53 @@ namespace expb200 {
 using std::exp; using std::fabs; using std::log; using std::sqrt;
 #endif
 
+// Branch-free device forms of 1/sqrt(x), sqrt(x) and 1/x for the normal-range arguments of
+// this path (radii, cylindrical radii, grid coordinates): the hardware seed (MUFU.RSQ64H /
+// MUFU.RCP64H) and the same Newton polish the CUDA library routines use, without their
+// denormal/inf/nan slow-path branch.  The branch costs a convergence barrier per call, which
+// keeps the compiler from interleaving the set-up chains of the two particles a lane handles
+// (the set-up is latency-bound).  Results are within 1 ulp of the IEEE operations (the host
+// emulation uses those).
 HD double fast_rsqrt(double x)
 {
 #if defined(__CUDA_ARCH__)
-  return rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);              // 1 - x y^2
+  const double t = fma(e, 0.375, 0.5);               // y (1 + e/2 + 3 e^2/8)
+  y = fma(t, y * e, y);
+  const double e2 = fma(-x * y, y, 1.0);
+  return fma(0.5 * y, e2, y);
 #else
   return 1.0 / sqrt(x);
+#endif
+}
+HD double fast_sqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+  const double xs = x > 2.3e-308 ? x : 2.3e-308;     // sqrt(0) = 0 without a branch
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+  const double e = fma(-xs * y, y, 1.0);
+  const double t = fma(e, 0.375, 0.5);
+  y = fma(t, y * e, y);
+  const double s = x * y;
+  return fma(fma(-s, s, x), 0.5 * y, s);
+#else
+  return sqrt(x);
+#endif
+}
+HD double fast_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, fma(e, e, e), y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
 #endif
 }
 
@@ -65,7 +106,7 @@ struct SphGeom {
   int nrow;                 // (lmax+1)^2
   int nslot;                // (lmax+1)(lmax+2)/2
   double rmap, xmin, dxi;   // SLGridSph grid (exputil/SLGridMP2.cc:1355-1382)
-  double inv_rmap, inv_dxi, inv_scale;
+  double inv_rmap, inv_dxi, inv_scale, inv_rmax;
   double scale, rmin, rmax; // SphericalBasis scale and expansion radii
   double cx, cy, cz, rtrunc2;
 };
@@ -82,7 +123,7 @@ HD double sph_r_to_xi(const SphGeom &g, double r)
 {
   if (g.cmap == 1) {
     double q = r * g.inv_rmap;
-    return (q - 1.0) * (1.0 / (q + 1.0));
+    return (q - 1.0) * fast_rcp(q + 1.0);
   }
   if (g.cmap == 2) return log(r);
   return r;
@@ -123,7 +164,7 @@ HD uint32_t sph_cell_of(const SphGeom &g, const rec4 &pm, int mode = 0)
   double x = pm.x - g.cx, y = pm.y - g.cy, z = pm.z - g.cz;
   double r2 = x * x + y * y + z * z;
   if (r2 > g.rtrunc2) return (uint32_t)(g.numr - 1);
-  double r = sqrt(r2) + EXPB200_DSMALL;
+  double r = fast_sqrt(r2) + EXPB200_DSMALL;
   if (!sph_in_range(g, r, mode)) return (uint32_t)(g.numr - 1);
   double xi;
   double t = sph_grid_coord(g, r * g.inv_scale, xi);
@@ -155,7 +196,7 @@ HD void sph_azimuth(double x, double y, double &c1, double &s1, double &R2, doub
 template <int L, int M0, int M1, class M, class F, class E>
 HD void sph_for_each_plm(double x, const double *inv, M &&on_m, F &&f, E &&end_m)
 {
-  double somx2 = sqrt((1.0 - x) * (1.0 + x));
+  double somx2 = fast_sqrt((1.0 - x) * (1.0 + x));
   double pmm = 1.0, fact = 1.0;
 #pragma unroll
   for (int m = 0; m <= M1; m++) {
@@ -194,8 +235,8 @@ HD void sph_deposit_setup(const SphGeom &g, const double *p0, const rec4 &pm, do
 {
   double x = pm.x - g.cx, y = pm.y - g.cy, z = pm.z - g.cz;
   double r2 = x * x + y * y + z * z;
-  double r = sqrt(r2) + EXPB200_DSMALL;
-  d.costh = z * (1.0 / r);
+  double r = fast_sqrt(r2) + EXPB200_DSMALL;
+  d.costh = z * fast_rcp(r);
   double R2, iR2;
   sph_azimuth(x, y, d.c1, d.s1, R2, iR2);
   double xi;
@@ -292,8 +333,8 @@ HD bool sph_force_setup(const SphGeom &g, const rec4 &pm, SphForce &S)
   double r2 = S.x * S.x + S.y * S.y + S.z * S.z;
   if (r2 > g.rtrunc2) return false;
 
-  double r = sqrt(r2) + EXPB200_DSMALL;
-  S.ir = 1.0 / r;
+  double r = fast_sqrt(r2) + EXPB200_DSMALL;
+  S.ir = fast_rcp(r);
   S.costh = S.z * S.ir;
   sph_azimuth(S.x, S.y, S.c1, S.s1, S.R2, S.iR2);
 
@@ -303,7 +344,7 @@ HD bool sph_force_setup(const SphGeom &g, const rec4 &pm, SphForce &S)
     S.ratio = g.rmax * S.ir;
     S.r0i = S.ir * g.inv_scale;
     r = g.rmax;
-    S.ir = 1.0 / r;
+    S.ir = g.inv_rmax;
   }
 
   double xi;
@@ -318,7 +359,7 @@ HD bool sph_force_setup(const SphGeom &g, const rec4 &pm, SphForce &S)
   double xd = S.costh;
   if (1.0 - fabs(xd) < EXPB200_MINEPS) xd = xd > 0 ? 1.0 - EXPB200_MINEPS : -(1.0 - EXPB200_MINEPS);
   S.xd = xd;
-  S.somx2i = 1.0 / (xd * xd - 1.0);
+  S.somx2i = fast_rcp(xd * xd - 1.0);
   return true;
 }
 
@@ -414,7 +455,7 @@ HD void sph_force_eval2(const double *inv, const SphForce &A, const SphForce &B,
   const double p[2] = {A.p, B.p}, q[2] = {A.q, B.q};
   double somx2[2], pmm[2] = {1.0, 1.0};
 #pragma unroll
-  for (int k = 0; k < 2; k++) somx2[k] = sqrt((1.0 - x[k]) * (1.0 + x[k]));
+  for (int k = 0; k < 2; k++) somx2[k] = fast_sqrt((1.0 - x[k]) * (1.0 + x[k]));
   double fact = 1.0;
 
 #pragma unroll

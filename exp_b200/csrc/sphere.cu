@@ -539,6 +539,20 @@ __device__ __forceinline__ void force_store(const SphGeom &g, const ForceOut &F,
   st_rec(&F.vel[i], v);
 }
 
+// force_store with the record to combine with (mode 0: acc/pot, modes 1-2: velocity) already
+// fetched by the caller
+__device__ __forceinline__ void force_store_side(const SphGeom &g, const ForceOut &F, uint32_t i, bool ok,
+                                                 const double *o, rec4 pm, rec4 v)
+{
+  if (F.mode == 0) {
+    if (!ok) return;
+    v.x += o[0]; v.y += o[1]; v.z += o[2]; v.w += o[3];
+    st_rec(&F.accp[i], v);
+    return;
+  }
+  force_store(g, F, i, ok, o, pm, v);
+}
+
 // force: one thread per particle, sorted order (the 128 particles of a CTA span a few
 // radial cells), positions streamed from the sorted copy.  The CTA finds the range of
 // table rows its particles read and, when it is at most kForceRows, stages those rows of T
@@ -694,6 +708,196 @@ sph_force2_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, Forc
 
   if (validA) force_store(g, F, iA, okA, oa, pmA, vA);
   if (validB) force_store(g, F, iB, okB, ob, pmB, vB);
+}
+
+// force, persistent and software-pipelined (the default): a CTA walks tiles of 2*kFPThreads
+// sorted particles (tile t = absolute sorted positions [t*TILE, (t+1)*TILE), so every bulk
+// copy is 16-byte aligned) and keeps a two-stage ring in shared memory.  While the lanes
+// evaluate tile t from stage s, three TMA bulk copies fill stage s^1 for the CTA's next
+// tile: the position records (contiguous in the sorted copy), the permutation slice, and
+// the table rows the tile reads.  The row range is known WITHOUT looking at the particles:
+// the tile is sorted by key, so its first and last sorted key bound the radial cells
+// (thread 0 fetches those two keys one iteration ahead).  Nothing the evaluation needs is
+// then a dependent global load: the long-scoreboard stalls that capped the one-shot kernel
+// (sph_force2_kernel: positions -> cells -> atomics -> TMA -> wait, all serial, per CTA)
+// are off the critical path.  Every lane still checks its own rows against the staged range
+// and falls back to global loads when outside (tiles that straddle levels, dead-cell tail).
+template <int L, int TH, int ROWS> struct FPStage {
+  static constexpr int kFPTile = 2 * TH;
+  static constexpr int ROW = (L + 1) * (L + 2) / 2 * kSphPoly;
+  double2 rows[ROWS * ROW];
+  rec4 ps[kFPTile];
+  uint32_t perm[kFPTile];
+};
+template <int L, int TH, int ROWS> struct FPShared {
+  FPStage<L, TH, ROWS> stage[2];
+  rec4 vbuf[2 * TH];            // the lane's two velocity (mode 0: acc/pot) records, via cp.async
+};
+struct FPDesc { int rlo, nrows, full; };
+
+__device__ __forceinline__ void tma_bulk_copy(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// register-free global -> shared copies (LDGSTS): the data lands in shared memory while the
+// lane computes, so no register (and no spill) waits on the load
+__device__ __forceinline__ void cp_async_rec(rec4 *dst_smem, const rec4 *src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+               "cp.async.cg.shared.global [%2], [%3], 16;"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(smem_u32(dst_smem) + 16),
+                 "l"(reinterpret_cast<const char *>(src) + 16) : "memory");
+}
+__device__ __forceinline__ void cp_async_u64(void *dst_smem, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+// Row range of every tile of the pipelined force kernel, from the first and last sorted key of
+// the tile (the tile is sorted by key): out[t] = (first table row, number of rows), rows = 0
+// when the tile straddles two levels, touches the dead cell or needs more than `rows_max` rows
+// (its lanes then read the table through L1/L2).
+__global__ void __launch_bounds__(256)
+sph_tile_desc_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg, int keybase,
+                     size_t n, int tile, int numr, int rows_max, int2 *__restrict__ out)
+{
+  const size_t lo = seg[keybase];
+  const size_t t_end = (n + tile - 1) / tile;
+  const size_t t = lo / tile + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= t_end) return;
+  const size_t a = t * tile < lo ? lo : t * tile;
+  const size_t b = (t + 1) * tile <= n ? (t + 1) * tile - 1 : n - 1;
+  const uint32_t kf = skeys[a < b ? a : b], kl = skeys[b];
+  const int lf = (int)(kf / (uint32_t)numr), ll = (int)(kl / (uint32_t)numr);
+  const int cf = (int)(kf - (uint32_t)lf * numr), cl = (int)(kl - (uint32_t)ll * numr);
+  const int rlo = cf, rhi = cl < 1 ? 1 : cl;       // stencil centre j = max(cell, 1)
+  int nrows = rhi - rlo + 1;
+  if (lf != ll || cl >= numr - 1 || nrows > rows_max || nrows < 1) nrows = 0;
+  out[t] = make_int2(rlo, nrows);
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int L, int TH, int MINB, int ROWS>
+__global__ void __launch_bounds__(TH, MINB)
+sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, ForceOut F,
+                   const uint32_t *__restrict__ perm, const int2 *__restrict__ tdesc,
+                   const uint32_t *__restrict__ seg, int keybase, size_t n)
+{
+  using Stage = FPStage<L, TH, ROWS>;
+  constexpr int kFPTile = 2 * TH;
+  constexpr int ROW = Stage::ROW;
+  extern __shared__ __align__(128) unsigned char fp_smem[];
+  FPShared<L, TH, ROWS> &SH = *reinterpret_cast<FPShared<L, TH, ROWS> *>(fp_smem);
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ FPDesc desc[2];
+  __shared__ __align__(8) int2 ndesc;    // descriptor of the tile after next (cp.async)
+
+  const size_t lo = seg[keybase];
+  const size_t t_end = (n + kFPTile - 1) / kFPTile;
+  const size_t t0 = lo / kFPTile + blockIdx.x;
+  const size_t stride = gridDim.x;
+  if (t0 >= t_end) return;
+  const int tid = threadIdx.x;
+
+  // thread 0: the row range of a tile comes from sph_tile_desc_kernel (fetched one iteration
+  // ahead into shared memory); issue() starts the copies of a tile into a stage
+  auto fetch_desc = [&](size_t t) {
+    if (t < t_end) cp_async_u64(&ndesc, tdesc + t);
+  };
+  auto issue = [&](int s, size_t t) {
+    cp_async_wait_all();
+    const int2 nd = ndesc;
+    const int rlo = nd.x, nrows = nd.y;
+    const size_t k0 = t * kFPTile;
+    const int full = k0 >= lo && k0 + kFPTile <= n;
+    desc[s].rlo = rlo;
+    desc[s].nrows = nrows;
+    desc[s].full = full;
+    uint32_t bytes = (uint32_t)nrows * ROW * (uint32_t)sizeof(double2);
+    if (full) bytes += kFPTile * (uint32_t)(sizeof(rec4) + sizeof(uint32_t));
+    mbar_expect(&bar[s], bytes);
+    if (nrows) tma_bulk_copy(SH.stage[s].rows, T + (size_t)rlo * ROW, (uint32_t)nrows * ROW * (uint32_t)sizeof(double2), &bar[s]);
+    if (full) {
+      tma_bulk_copy(SH.stage[s].ps, ps + k0, kFPTile * (uint32_t)sizeof(rec4), &bar[s]);
+      tma_bulk_copy(SH.stage[s].perm, perm + k0, kFPTile * (uint32_t)sizeof(uint32_t), &bar[s]);
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fetch_desc(t0);
+    issue(0, t0);
+    fetch_desc(t0 + stride);
+  }
+
+  const rec4 *side = F.mode ? F.vel : F.accp;     // the record force_store combines the result with
+  rec4 *myv = &SH.vbuf[2 * tid];
+  int it = 0;
+  for (size_t t = t0; t < t_end; t += stride, it++) {
+    const int s = it & 1;
+    __syncthreads();               // stage s^1 is drained (iteration it-1), desc[s] is published
+    if (tid == 0 && t + stride < t_end) {
+      issue(s ^ 1, t + stride);
+      fetch_desc(t + 2 * stride);
+    }
+    const FPDesc d = desc[s];
+    const Stage &S = SH.stage[s];
+    mbar_wait(&bar[s], (it >> 1) & 1);
+
+    const size_t k0 = t * kFPTile + 2 * (size_t)tid;
+    const bool validA = k0 >= lo && k0 < n, validB = k0 + 1 >= lo && k0 + 1 < n;
+    uint32_t iA = 0, iB = 0;
+    SphForce A, B;
+    bool okA, okB;
+    {
+      rec4 pmA = rec4{g.cx + 1.0, g.cy, g.cz, 0.0}, pmB = pmA;
+      if (d.full) {
+        pmA = S.ps[2 * tid]; pmB = S.ps[2 * tid + 1];
+        const uint2 ii = *reinterpret_cast<const uint2 *>(&S.perm[2 * tid]);
+        iA = ii.x; iB = ii.y;
+      } else {
+        if (validA) { pmA = ld_rec_rw(&ps[k0]); iA = perm[k0]; }
+        if (validB) { pmB = ld_rec_rw(&ps[k0 + 1]); iB = perm[k0 + 1]; }
+      }
+      if (validA) cp_async_rec(myv, side + iA);
+      if (validB) cp_async_rec(myv + 1, side + iB);
+      okA = sph_force_setup<true>(g, pmA, A) && validA;
+      okB = sph_force_setup<true>(g, pmB, B) && validB;
+    }
+    const int rlo = d.rlo, rhi = d.rlo + d.nrows - 1;
+    const bool inA = A.cell >= rlo && A.j <= rhi, inB = B.cell >= rlo && B.j <= rhi;
+
+    double oa[4] = {0.0, 0.0, 0.0, 0.0}, ob[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool pair = okA && okB && A.cell == B.cell && A.j == B.j && !A.ioff && !B.ioff;
+    if (pair && inA) {
+      sph_force_eval2<L>(c_inv, A, B, S.rows + (A.cell - rlo) * ROW, S.rows + (A.j - rlo) * ROW,
+                         [](const double2 *a) { return *a; }, oa, ob);
+    } else if (pair) {
+      sph_force_eval2<L>(c_inv, A, B, T + (size_t)A.cell * ROW, T + (size_t)A.j * ROW,
+                         [](const double2 *a) { return __ldg(a); }, oa, ob);
+    } else {
+      // rare: the pair straddles a cell boundary, or a particle beyond rmax (generic loads)
+      auto ld = [](const double2 *a) { return *a; };
+      const double2 *bA = inA ? S.rows - (ptrdiff_t)rlo * ROW : T;
+      const double2 *bB = inB ? S.rows - (ptrdiff_t)rlo * ROW : T;
+      if (okA) sph_force_eval<L, true>(c_inv, A, bA + (size_t)A.cell * ROW, bA + (size_t)A.j * ROW, ld,
+                                       oa[0], oa[1], oa[2], oa[3]);
+      if (okB) sph_force_eval<L, true>(c_inv, B, bB + (size_t)B.cell * ROW, bB + (size_t)B.j * ROW, ld,
+                                       ob[0], ob[1], ob[2], ob[3]);
+    }
+
+    // the position records are re-read (shared memory, or L2 for a ragged tile) rather than
+    // held in registers across the evaluation
+    cp_async_wait_all();
+    if (validA) force_store_side(g, F, iA, okA, oa, d.full ? S.ps[2 * tid] : ld_rec_rw(&ps[k0]), myv[0]);
+    if (validB) force_store_side(g, F, iB, okB, ob, d.full ? S.ps[2 * tid + 1] : ld_rec_rw(&ps[k0 + 1]), myv[1]);
+  }
 }
 
 // ===========================================================================
@@ -989,11 +1193,46 @@ template <int L> struct Launch {
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
-  static int force(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps, const ForceOut &F,
-                   const uint32_t *perm, const uint32_t *seg, int keybase, size_t n)
+  template <int TH, int MINB, int ROWS>
+  static int force_pipelined(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
+                             const ForceOut &F, const uint32_t *perm, const uint32_t *skeys,
+                             const uint32_t *seg, int keybase, size_t n, int2 *tdesc)
   {
-    static const int variant = getenv("EXPB200_FORCE_VARIANT") ? atoi(getenv("EXPB200_FORCE_VARIANT")) : 1;
-    if (variant == 1 && L <= 8)
+    constexpr size_t sm = sizeof(FPShared<L, TH, ROWS>);
+    static int ctas[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &occ = ctas[dev & 63];
+    if (!occ) {
+      CU_TRY(cudaFuncSetAttribute(sph_force2p_kernel<L, TH, MINB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      int nb = 0, nsm = 0;
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sph_force2p_kernel<L, TH, MINB, ROWS>, TH, sm));
+      CU_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      occ = (nb > 0 ? nb : 1) * nsm;
+    }
+    const size_t ntiles = div_up(n, (size_t)(2 * TH));
+    const unsigned grid = (unsigned)(ntiles < (size_t)occ ? ntiles : (size_t)occ);
+    sph_tile_desc_kernel<<<div_up(ntiles, 256), 256, 0, st>>>(skeys, seg, keybase, n, 2 * TH, g.numr, ROWS, tdesc);
+    sph_force2p_kernel<L, TH, MINB, ROWS><<<grid, TH, sm, st>>>(g, T, ps, F, perm, tdesc, seg, keybase, n);
+    CU_LAUNCH_CHECK();
+    return EXPB200_OK;
+  }
+  static int force(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps, const ForceOut &F,
+                   const uint32_t *perm, const uint32_t *skeys, const uint32_t *seg, int keybase, size_t n,
+                   int2 *tdesc)
+  {
+    // 2: persistent pipelined kernel (default), 1: one-shot two-particle kernel, 0: one particle per lane
+    static const int variant = getenv("EXPB200_FORCE_VARIANT") ? atoi(getenv("EXPB200_FORCE_VARIANT")) : 2;
+    if constexpr (L <= 8) {
+      // the pipelined kernel reads the sorted keys while (mode 2) writing the next step's keys:
+      // they must be different buffers
+      if (variant >= 2 && skeys && tdesc && !(F.mode == 2 && skeys == F.keys)) {
+        if (variant == 3) return force_pipelined<128, 4, 4>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        if (variant == 4) return force_pipelined<128, 3, 4>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        return force_pipelined<128, 3, 6>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+      }
+    }
+    if (variant >= 1 && L <= 8)
       sph_force2_kernel<L><<<div_up(n, 2 * kForce2Threads), kForce2Threads, 0, st>>>(g, T, ps, F, perm, seg,
                                                                                    keybase, n);
     else
@@ -1024,9 +1263,10 @@ int launch_deposit(int lmax, cudaStream_t st, unsigned nchunks, const SphGeom &g
 }
 
 int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
-                 const ForceOut &F, const uint32_t *perm, const uint32_t *seg, int keybase, size_t n)
+                 const ForceOut &F, const uint32_t *perm, const uint32_t *skeys, const uint32_t *seg,
+                 int keybase, size_t n, int2 *tdesc)
 {
-  DISPATCH_L(lmax, force(st, g, T, ps, F, perm, seg, keybase, n))
+  DISPATCH_L(lmax, force(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc))
 }
 
 } // namespace
@@ -1049,6 +1289,8 @@ struct expb200_sphere_s {
   double *G = nullptr;       // node sums [nrow][numr]
   double *PA = nullptr, *PB = nullptr;
   size_t part_slots = 0;
+  int2 *tdesc = nullptr;     // per-tile row ranges of the pipelined force kernel
+  size_t tdesc_cap = 0;
   int *row_l = nullptr, *row_m = nullptr;
   int *slot_l = nullptr, *slot_m = nullptr, *slot_rowc = nullptr, *slot_rows = nullptr;
   bool field_valid = false;
@@ -1167,6 +1409,18 @@ int ensure_partials(expb200_sphere_s *s, size_t n, int CH)
   CU_TRY(cudaMalloc(&s->PA, slots * s->geom.nrow * sizeof(double)));
   CU_TRY(cudaMalloc(&s->PB, slots * s->geom.nrow * sizeof(double)));
   s->part_slots = slots;
+  return EXPB200_OK;
+}
+
+int ensure_tdesc(expb200_sphere_s *s, size_t n)
+{
+  const size_t need = n / 128 + 2;          // tiles are >= 128 particles
+  if (need <= s->tdesc_cap) return EXPB200_OK;
+  if (s->tdesc) cudaFree(s->tdesc);
+  s->tdesc = nullptr;
+  s->tdesc_cap = 0;
+  CU_TRY(cudaMalloc(&s->tdesc, need * sizeof(int2)));
+  s->tdesc_cap = need;
   return EXPB200_OK;
 }
 
@@ -1313,7 +1567,7 @@ int expb200_sphere_destroy(expb200_sphere s)
   cudaFree(s->Ep); cudaFree(s->p0); cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->T);
   cudaFree(s->G); cudaFree(s->PA); cudaFree(s->PB); cudaFree(s->row_l); cudaFree(s->row_m);
   cudaFree(s->slot_l); cudaFree(s->slot_m); cudaFree(s->slot_rowc); cudaFree(s->slot_rows); cudaFree(s->used_dev);
-  cudaFree(s->coefN); cudaFree(s->coefL); cudaFree(s->differ); cudaFree(s->tmp);
+  cudaFree(s->coefN); cudaFree(s->coefL); cudaFree(s->differ); cudaFree(s->tmp); cudaFree(s->tdesc);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
   return EXPB200_OK;
@@ -1386,8 +1640,9 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
   ProfRegion pr(K_FORCE, c->stream);
   ForceOut F{c->accp, c->vel, c->posm, c->keys[0], 0.0, 0.0, 0};
-  return launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->seg, keybase,
-                      c->n);
+  if ((rc = ensure_tdesc(s, c->n))) return rc;
+  return launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->keys[c->cur],
+                      c->seg, keybase, c->n, s->tdesc);
 }
 
 // ---- multistep coefficient tables -------------------------------------------------
@@ -1542,6 +1797,7 @@ int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int n
   const uint32_t nkeys = (uint32_t)s->cfg.numr;
   if ((rc = ensure_seg(c, nkeys))) return rc;
   if (c->n == 0 || nsteps == 0) return EXPB200_OK;
+  if ((rc = ensure_tdesc(s, c->n))) return rc;
   SphGeom gm = geom_for(s, c);
   for (int step = 0; step < nsteps; step++) {
     if (step == 0) {
@@ -1563,7 +1819,8 @@ int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int n
     const bool last = step == nsteps - 1;
     ForceOut F{c->accp, c->vel, c->posm, c->keys[0], 0.5 * dt, dt, last ? 1 : 2};
     ProfRegion pr(K_FORCE, c->stream);
-    rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->seg, 0, c->n);
+    rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->keys[c->cur],
+                      c->seg, 0, c->n, s->tdesc);
     if (rc) return rc;
   }
   return EXPB200_OK;
