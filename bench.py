@@ -46,7 +46,7 @@ def _hbm_peak():
 HBM_PEAK_GBS = _hbm_peak()
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # capture of this workload (profiles/r01_ncu_*): bytes per launch at 1e7 particles
-NCU_TRAFFIC = {"force": None, "deposit": None}
+NCU_TRAFFIC = {"force": 1.645e9, "deposit": 7.42e8}   # profiles/r01e_ncu_full_summary.txt
 
 METRIC = "particle-steps/sec (coef+force+kick-drift) sphereSL"
 UNIT = "particle-steps/s"
@@ -57,7 +57,7 @@ DT = 1.0e-3
 
 # ---- algorithmic work per particle (DESIGN.md section "Work model") ----------
 def flops_force(L):
-    """sph_force2_kernel: 31 flop per (l,m>0) term (Legendre recursion 4,
+    """sph_force2p_kernel: 31 flop per (l,m>0) term (Legendre recursion 4,
     derivative 3, Horner forms 12, column sums 12), 19 per (l,0) term, 21 per m>0 column
     (azimuthal recursion + combination), 120 for geometry, coordinate map and the Cartesian
     projection; FMA = 2."""
@@ -338,7 +338,7 @@ def run_ours(args):
     achieved = fl * n / (ms_dom * 1e-3) / 1e12
     step_fl = flops_force(LMAX) + flops_deposit(LMAX) + 18
     roofline = {
-        "bound": "fp64", "kernel": {"force": f"sph_force2_kernel<{LMAX}>",
+        "bound": "fp64", "kernel": {"force": f"sph_force2p_kernel<{LMAX},64,6,4,2>",
                                     "deposit": f"sph_deposit_reg_kernel<{LMAX},*> (2 sweeps)"}[dom],
         "achieved": achieved, "peak": peak_tf.value, "unit": "TFLOP/s", "frac": achieved / peak_tf.value,
         "peak_source": "measured: dependency-free DFMA microbenchmark on this device "

@@ -464,23 +464,26 @@ int expb200_component_create(int device, size_t capacity, expb200_component *out
   CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   stream_register(c->stream, true);
   CU_TRY(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
-  CU_TRY(cudaMalloc(&c->posm, capacity * sizeof(rec4)));
-  CU_TRY(cudaMalloc(&c->vel, capacity * sizeof(rec4)));
-  CU_TRY(cudaMalloc(&c->accp, capacity * sizeof(rec4)));
-  CU_TRY(cudaMalloc(&c->posm_sorted, capacity * sizeof(rec4)));
-  CU_TRY(cudaMalloc(&c->spare, capacity * sizeof(rec4)));
-  CU_TRY(cudaMalloc(&c->slot_of, capacity * sizeof(uint32_t)));
-  CU_TRY(cudaMalloc(&c->where, capacity * sizeof(uint32_t)));
+  // every per-particle array is allocated in whole tiles of 512 entries: the pipelined force
+  // kernel copies sorted positions and the permutation a tile at a time (TMA bulk copies)
+  const size_t padcap = (capacity + 511) / 512 * 512;
+  CU_TRY(cudaMalloc(&c->posm, padcap * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->vel, padcap * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->accp, padcap * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->posm_sorted, padcap * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->spare, padcap * sizeof(rec4)));
+  CU_TRY(cudaMalloc(&c->slot_of, padcap * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&c->where, padcap * sizeof(uint32_t)));
   c->psort = c->posm_sorted;
-  CU_TRY(cudaMalloc(&c->level, capacity * sizeof(unsigned)));
-  CU_TRY(cudaMalloc(&c->prev_level, capacity * sizeof(unsigned)));
-  CU_TRY(cudaMalloc(&c->dtreq, capacity * sizeof(float)));
-  CU_TRY(cudaMalloc(&c->scale, capacity * sizeof(float)));
+  CU_TRY(cudaMalloc(&c->level, padcap * sizeof(unsigned)));
+  CU_TRY(cudaMalloc(&c->prev_level, padcap * sizeof(unsigned)));
+  CU_TRY(cudaMalloc(&c->dtreq, padcap * sizeof(float)));
+  CU_TRY(cudaMalloc(&c->scale, padcap * sizeof(float)));
   for (int k = 0; k < 2; k++) {
-    CU_TRY(cudaMalloc(&c->keys[k], capacity * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&c->perm[k], capacity * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->keys[k], padcap * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->perm[k], padcap * sizeof(uint32_t)));
   }
-  CU_TRY(cudaMalloc(&c->rank, capacity * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&c->rank, padcap * sizeof(uint32_t)));
   c->hist_cap = sort_hist_words(capacity);
   CU_TRY(cudaMalloc(&c->hist, c->hist_cap * sizeof(uint32_t)));
   c->stage_chunk = capacity < kStageChunk ? capacity : kStageChunk;

@@ -710,18 +710,21 @@ sph_force2_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, Forc
   if (validB) force_store(g, F, iB, okB, ob, pmB, vB);
 }
 
-// force, persistent and software-pipelined (the default): a CTA walks tiles of 2*kFPThreads
+// force, persistent and software-pipelined (the default): a CTA walks tiles of TILE = 2*TH
 // sorted particles (tile t = absolute sorted positions [t*TILE, (t+1)*TILE), so every bulk
-// copy is 16-byte aligned) and keeps a two-stage ring in shared memory.  While the lanes
-// evaluate tile t from stage s, three TMA bulk copies fill stage s^1 for the CTA's next
-// tile: the position records (contiguous in the sorted copy), the permutation slice, and
-// the table rows the tile reads.  The row range is known WITHOUT looking at the particles:
-// the tile is sorted by key, so its first and last sorted key bound the radial cells
-// (thread 0 fetches those two keys one iteration ahead).  Nothing the evaluation needs is
-// then a dependent global load: the long-scoreboard stalls that capped the one-shot kernel
-// (sph_force2_kernel: positions -> cells -> atomics -> TMA -> wait, all serial, per CTA)
-// are off the critical path.  Every lane still checks its own rows against the staged range
-// and falls back to global loads when outside (tiles that straddle levels, dead-cell tail).
+// copy is 16-byte aligned) and keeps a ring of NST stages in shared memory.  While the lanes
+// evaluate tile t from one stage, three TMA bulk copies fill the next stage for the CTA's
+// next tile: the position records (contiguous in the sorted copy), the permutation slice,
+// and the table rows the tile reads.  The row range is known WITHOUT looking at the
+// particles: the tile is sorted by key, so its first and last sorted key bound the radial
+// cells (sph_tile_desc_kernel, a pre-pass of one thread per tile).  The lane's two velocity
+// records are gathered with cp.async into shared memory, and the position records are
+// re-read from the stage after the evaluation, so no register (and no spill) waits on a
+// load.  Nothing the evaluation needs is then a dependent global load: the long-scoreboard
+// stalls of the one-shot kernel (sph_force2_kernel: positions -> cells -> atomics -> TMA ->
+// wait, all serial, per CTA) are off the critical path.  Every lane still checks its own
+// rows against the staged range and falls back to global loads when outside (tiles that
+// straddle levels, the dead-cell tail).
 template <int L, int TH, int ROWS> struct FPStage {
   static constexpr int kFPTile = 2 * TH;
   static constexpr int ROW = (L + 1) * (L + 2) / 2 * kSphPoly;
@@ -729,11 +732,11 @@ template <int L, int TH, int ROWS> struct FPStage {
   rec4 ps[kFPTile];
   uint32_t perm[kFPTile];
 };
-template <int L, int TH, int ROWS> struct FPShared {
-  FPStage<L, TH, ROWS> stage[2];
+template <int L, int TH, int ROWS, int NST> struct FPShared {
+  FPStage<L, TH, ROWS> stage[NST];
   rec4 vbuf[2 * TH];            // the lane's two velocity (mode 0: acc/pot) records, via cp.async
 };
-struct FPDesc { int rlo, nrows, full; };
+struct FPDesc { int rlo, nrows; };
 
 __device__ __forceinline__ void tma_bulk_copy(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
@@ -782,7 +785,7 @@ sph_tile_desc_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restr
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int L, int TH, int MINB, int ROWS>
+template <int L, int TH, int MINB, int ROWS, int NST>
 __global__ void __launch_bounds__(TH, MINB)
 sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, ForceOut F,
                    const uint32_t *__restrict__ perm, const int2 *__restrict__ tdesc,
@@ -792,9 +795,9 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
   constexpr int kFPTile = 2 * TH;
   constexpr int ROW = Stage::ROW;
   extern __shared__ __align__(128) unsigned char fp_smem[];
-  FPShared<L, TH, ROWS> &SH = *reinterpret_cast<FPShared<L, TH, ROWS> *>(fp_smem);
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ FPDesc desc[2];
+  FPShared<L, TH, ROWS, NST> &SH = *reinterpret_cast<FPShared<L, TH, ROWS, NST> *>(fp_smem);
+  __shared__ __align__(8) uint64_t full[NST];
+  __shared__ FPDesc desc[NST];
   __shared__ __align__(8) int2 ndesc;    // descriptor of the tile after next (cp.async)
 
   const size_t lo = seg[keybase];
@@ -804,67 +807,60 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
   if (t0 >= t_end) return;
   const int tid = threadIdx.x;
 
-  // thread 0: the row range of a tile comes from sph_tile_desc_kernel (fetched one iteration
-  // ahead into shared memory); issue() starts the copies of a tile into a stage
-  auto fetch_desc = [&](size_t t) {
-    if (t < t_end) cp_async_u64(&ndesc, tdesc + t);
-  };
-  auto issue = [&](int s, size_t t) {
-    cp_async_wait_all();
-    const int2 nd = ndesc;
+  // thread 0 starts the copies of tile t into stage s.  The particle arrays are allocated in
+  // whole tiles (component.cu pads every array), so a tile is always copied in full; lanes
+  // outside [lo, n) ignore what they get.
+  auto issue = [&](int s, size_t t, int2 nd) {
     const int rlo = nd.x, nrows = nd.y;
     const size_t k0 = t * kFPTile;
-    const int full = k0 >= lo && k0 + kFPTile <= n;
     desc[s].rlo = rlo;
     desc[s].nrows = nrows;
-    desc[s].full = full;
-    uint32_t bytes = (uint32_t)nrows * ROW * (uint32_t)sizeof(double2);
-    if (full) bytes += kFPTile * (uint32_t)(sizeof(rec4) + sizeof(uint32_t));
-    mbar_expect(&bar[s], bytes);
-    if (nrows) tma_bulk_copy(SH.stage[s].rows, T + (size_t)rlo * ROW, (uint32_t)nrows * ROW * (uint32_t)sizeof(double2), &bar[s]);
-    if (full) {
-      tma_bulk_copy(SH.stage[s].ps, ps + k0, kFPTile * (uint32_t)sizeof(rec4), &bar[s]);
-      tma_bulk_copy(SH.stage[s].perm, perm + k0, kFPTile * (uint32_t)sizeof(uint32_t), &bar[s]);
-    }
+    const uint32_t rbytes = (uint32_t)nrows * ROW * (uint32_t)sizeof(double2);
+    mbar_expect(&full[s], rbytes + kFPTile * (uint32_t)(sizeof(rec4) + sizeof(uint32_t)));
+    if (nrows) tma_bulk_copy(SH.stage[s].rows, T + (size_t)rlo * ROW, rbytes, &full[s]);
+    tma_bulk_copy(SH.stage[s].ps, ps + k0, kFPTile * (uint32_t)sizeof(rec4), &full[s]);
+    tma_bulk_copy(SH.stage[s].perm, perm + k0, kFPTile * (uint32_t)sizeof(uint32_t), &full[s]);
   };
 
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    fetch_desc(t0);
-    issue(0, t0);
-    fetch_desc(t0 + stride);
+    for (int q = 0; q < NST; q++) {
+      mbar_init(&full[q], 1);
+    }
+    for (int q = 0; q < NST; q++)
+      if (t0 + q * stride < t_end) issue(q, t0 + q * stride, __ldg(tdesc + t0 + q * stride));
   }
+  __syncthreads();
 
   const rec4 *side = F.mode ? F.vel : F.accp;     // the record force_store combines the result with
   rec4 *myv = &SH.vbuf[2 * tid];
-  int it = 0;
-  for (size_t t = t0; t < t_end; t += stride, it++) {
-    const int s = it & 1;
-    __syncthreads();               // stage s^1 is drained (iteration it-1), desc[s] is published
-    if (tid == 0 && t + stride < t_end) {
-      issue(s ^ 1, t + stride);
-      fetch_desc(t + 2 * stride);
+  // The warps of a CTA stay in lockstep (one block barrier per tile): they run the same
+  // long straight-line code on the four sub-partitions at the same time and share its
+  // instruction fetches; letting them drift (per-stage "empty" barriers) measured slower.
+  int s = 0, ph = 0;
+  for (size_t t = t0; t < t_end; t += stride) {
+    __syncthreads();               // the stage used by the previous tile is drained
+    if (tid == 0) {
+      const size_t tn = t + (NST - 1) * stride;    // refill the stage the previous tile used
+      if (t != t0 && tn < t_end) {
+        cp_async_wait_all();
+        issue(s == 0 ? NST - 1 : s - 1, tn, ndesc);
+      }
+      if (tn + stride < t_end) cp_async_u64(&ndesc, tdesc + tn + stride);
     }
+    mbar_wait(&full[s], ph);
     const FPDesc d = desc[s];
     const Stage &S = SH.stage[s];
-    mbar_wait(&bar[s], (it >> 1) & 1);
 
     const size_t k0 = t * kFPTile + 2 * (size_t)tid;
     const bool validA = k0 >= lo && k0 < n, validB = k0 + 1 >= lo && k0 + 1 < n;
-    uint32_t iA = 0, iB = 0;
+    uint32_t iA, iB;
     SphForce A, B;
     bool okA, okB;
     {
-      rec4 pmA = rec4{g.cx + 1.0, g.cy, g.cz, 0.0}, pmB = pmA;
-      if (d.full) {
-        pmA = S.ps[2 * tid]; pmB = S.ps[2 * tid + 1];
-        const uint2 ii = *reinterpret_cast<const uint2 *>(&S.perm[2 * tid]);
-        iA = ii.x; iB = ii.y;
-      } else {
-        if (validA) { pmA = ld_rec_rw(&ps[k0]); iA = perm[k0]; }
-        if (validB) { pmB = ld_rec_rw(&ps[k0 + 1]); iB = perm[k0 + 1]; }
-      }
+      const rec4 dummy = rec4{g.cx + 1.0, g.cy, g.cz, 0.0};
+      const rec4 pmA = validA ? S.ps[2 * tid] : dummy, pmB = validB ? S.ps[2 * tid + 1] : dummy;
+      const uint2 ii = *reinterpret_cast<const uint2 *>(&S.perm[2 * tid]);
+      iA = validA ? ii.x : 0; iB = validB ? ii.y : 0;
       if (validA) cp_async_rec(myv, side + iA);
       if (validB) cp_async_rec(myv + 1, side + iB);
       okA = sph_force_setup<true>(g, pmA, A) && validA;
@@ -892,11 +888,12 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
                                        ob[0], ob[1], ob[2], ob[3]);
     }
 
-    // the position records are re-read (shared memory, or L2 for a ragged tile) rather than
-    // held in registers across the evaluation
+    // the position records are re-read from the stage rather than held in registers across
+    // the evaluation
     cp_async_wait_all();
-    if (validA) force_store_side(g, F, iA, okA, oa, d.full ? S.ps[2 * tid] : ld_rec_rw(&ps[k0]), myv[0]);
-    if (validB) force_store_side(g, F, iB, okB, ob, d.full ? S.ps[2 * tid + 1] : ld_rec_rw(&ps[k0 + 1]), myv[1]);
+    if (validA) force_store_side(g, F, iA, okA, oa, S.ps[2 * tid], myv[0]);
+    if (validB) force_store_side(g, F, iB, okB, ob, S.ps[2 * tid + 1], myv[1]);
+    if (++s == NST) { s = 0; ph ^= 1; }
   }
 }
 
@@ -1193,27 +1190,27 @@ template <int L> struct Launch {
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
-  template <int TH, int MINB, int ROWS>
+  template <int TH, int MINB, int ROWS, int NST>
   static int force_pipelined(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
                              const ForceOut &F, const uint32_t *perm, const uint32_t *skeys,
                              const uint32_t *seg, int keybase, size_t n, int2 *tdesc)
   {
-    constexpr size_t sm = sizeof(FPShared<L, TH, ROWS>);
+    constexpr size_t sm = sizeof(FPShared<L, TH, ROWS, NST>);
     static int ctas[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     int &occ = ctas[dev & 63];
     if (!occ) {
-      CU_TRY(cudaFuncSetAttribute(sph_force2p_kernel<L, TH, MINB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CU_TRY(cudaFuncSetAttribute(sph_force2p_kernel<L, TH, MINB, ROWS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       int nb = 0, nsm = 0;
-      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sph_force2p_kernel<L, TH, MINB, ROWS>, TH, sm));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sph_force2p_kernel<L, TH, MINB, ROWS, NST>, TH, sm));
       CU_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
       occ = (nb > 0 ? nb : 1) * nsm;
     }
     const size_t ntiles = div_up(n, (size_t)(2 * TH));
     const unsigned grid = (unsigned)(ntiles < (size_t)occ ? ntiles : (size_t)occ);
     sph_tile_desc_kernel<<<div_up(ntiles, 256), 256, 0, st>>>(skeys, seg, keybase, n, 2 * TH, g.numr, ROWS, tdesc);
-    sph_force2p_kernel<L, TH, MINB, ROWS><<<grid, TH, sm, st>>>(g, T, ps, F, perm, tdesc, seg, keybase, n);
+    sph_force2p_kernel<L, TH, MINB, ROWS, NST><<<grid, TH, sm, st>>>(g, T, ps, F, perm, tdesc, seg, keybase, n);
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
@@ -1227,9 +1224,9 @@ template <int L> struct Launch {
       // the pipelined kernel reads the sorted keys while (mode 2) writing the next step's keys:
       // they must be different buffers
       if (variant >= 2 && skeys && tdesc && !(F.mode == 2 && skeys == F.keys)) {
-        if (variant == 3) return force_pipelined<128, 4, 4>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
-        if (variant == 4) return force_pipelined<128, 3, 4>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
-        return force_pipelined<128, 3, 6>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        // CTAs of two warps (tiles of 128 particles), 6 per SM, 4 table rows per stage, two stages:
+        // the fastest of the shapes measured at 1e7 particles (128x3, 192x2, 384x1 were slower)
+        return force_pipelined<64, 6, 4, 2>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
       }
     }
     if (variant >= 1 && L <= 8)
@@ -1638,7 +1635,7 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   s->last_stream = c->stream;
   SphGeom gm = geom_for(s, c);
   const int keybase = (s->nlev > 1 ? mlevel : 0) * s->cfg.numr;
-  ProfRegion pr(K_FORCE, c->stream);
+  ProfRegion pr(K_FORCE, c->stream, 2);   // tile pre-pass + force
   ForceOut F{c->accp, c->vel, c->posm, c->keys[0], 0.0, 0.0, 0};
   if ((rc = ensure_tdesc(s, c->n))) return rc;
   return launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->keys[c->cur],
@@ -1818,7 +1815,7 @@ int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int n
     if ((rc = build_field(s, c->stream))) return rc;
     const bool last = step == nsteps - 1;
     ForceOut F{c->accp, c->vel, c->posm, c->keys[0], 0.5 * dt, dt, last ? 1 : 2};
-    ProfRegion pr(K_FORCE, c->stream);
+    ProfRegion pr(K_FORCE, c->stream, 2);   // tile pre-pass + force
     rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->keys[c->cur],
                       c->seg, 0, c->n, s->tdesc);
     if (rc) return rc;
