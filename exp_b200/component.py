@@ -134,3 +134,17 @@ class Component:
         check(_lib.lib().expb200_component_level_counts(self._h, multistep,
                                                         out.ctypes.data_as(_lib.c_u64p)))
         return out
+
+    def fix_positions(self, mlevel, multistep, lev_sums=None, dim=3, nccl_comm=None):
+        """Component::fix_positions (src/Component.cc:3354-3590) on the device: refreshes the rows
+        M >= mlevel of lev_sums[M] = [com_mas, com_lev[3], cov_lev[3], coa_lev[3]] and returns
+        (lev_sums, [mtot, com[3], cov[3], coa[3]])."""
+        if lev_sums is None:
+            lev_sums = np.zeros((multistep + 1, 10))
+        lev_sums = np.ascontiguousarray(lev_sums, dtype=np.float64)
+        check(_lib.lib().expb200_component_fix_positions(self._h, mlevel, multistep, dim,
+                                                         lev_sums.ctypes.data_as(_lib.c_dp), nccl_comm))
+        out = lev_sums.sum(axis=0)
+        if out[0] > 0.0:
+            out[1:] /= out[0]
+        return lev_sums, out

@@ -97,6 +97,46 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 }
 #endif
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// Warp reduce-scatter of N per-lane values: five butterfly steps, each lane keeps one
+// half of its array and sends the other, so that afterwards lane L holds the full
+// 32-lane sums of RS<N>::FIN rows (rs_row tells which).  N + ... shuffles instead of
+// 5 N, and the summation tree is fixed.
+// ---------------------------------------------------------------------------
+template <int N, int S> struct RS {
+  static constexpr int H = (N + 1) / 2;
+  static constexpr int FIN = RS<H, S + 1>::FIN;
+  static __device__ __forceinline__ void run(double *v, int lane)
+  {
+    const bool up = (lane >> (4 - S)) & 1;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      const double lo = v[i];
+      const double hi = (i + H < N) ? v[i + H] : 0.0;
+      const double send = up ? lo : hi;
+      const double keep = up ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16 >> S);
+    }
+    RS<H, S + 1>::run(v, lane);
+  }
+  // original index of entry i held by `lane` after the remaining steps S..4 (or -1)
+  static __device__ __forceinline__ int row(int lane, int i)
+  {
+    int idx = RS<H, S + 1>::row(lane, i);
+    if (idx < 0) return -1;
+    if ((lane >> (4 - S)) & 1) idx += H;
+    return idx < N ? idx : -1;
+  }
+};
+template <int N> struct RS<N, 5> {
+  static constexpr int FIN = N;
+  static __device__ __forceinline__ void run(double *, int) {}
+  static __device__ __forceinline__ int row(int, int i) { return i < N ? i : -1; }
+};
+
+#endif
+
 } // namespace expb200
 
 struct expb200_component_s;
@@ -158,4 +198,7 @@ struct expb200_component_s {
 
   // multistep statistics scratch
   unsigned long long *stats = nullptr;  // device, 8 words
+  // centre-of-mass sums scratch (expb200_component_fix_positions)
+  double *com_part = nullptr;
+  size_t com_part_cap = 0;
 };

@@ -7,7 +7,9 @@
 #include "common.cuh"
 #include "sort.cuh"
 #include "profile.cuh"
+#include "nccl_shim.h"
 
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -336,6 +338,76 @@ levels_kernel(const rec4 *__restrict__ vel, const rec4 *__restrict__ accp,
   }
 }
 
+// ---- centre of mass (Component::fix_positions) ------------------------------------
+// Per multistep level M >= mlevel the sums over the non-frozen particles of
+// {mass, mass*pos[k], mass*vel[k], mass*acc[k]} (k < dim), src/Component.cc:3280-3352.
+// One warp per tile of 32 particles; for every level present in the tile (ballot) the ten
+// values are reduced with the fixed reduce-scatter butterfly (RS<10>) and the lane that
+// ends up owning a value adds it to the warp's shared-memory accumulator.  CTA partials are
+// written to `part` and summed in block order by com_final_kernel: no atomics, so the
+// result is bit-reproducible.
+constexpr int kComWarps = 8;
+constexpr int kComVals = 10;
+constexpr int kComMaxLev = 16;
+
+__global__ void __launch_bounds__(kComWarps * 32)
+com_sum_kernel(const rec4 *__restrict__ posm, const rec4 *__restrict__ vel, const rec4 *__restrict__ accp,
+               const unsigned *__restrict__ level, size_t n, int mlevel, int nlev, int dim,
+               double cx, double cy, double cz, double rtrunc2, double *__restrict__ part)
+{
+  __shared__ double acc[kComWarps][kComMaxLev][kComVals];
+  using R = RS<kComVals, 0>;
+  static_assert(R::FIN == 1, "one value per lane after the reduce-scatter");
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = threadIdx.x; q < kComWarps * kComMaxLev * kComVals; q += blockDim.x) (&acc[0][0][0])[q] = 0.0;
+  __syncthreads();
+  const int myrow = R::row(lane, 0);
+  const size_t step = (size_t)gridDim.x * kComWarps * 32;
+  for (size_t base = ((size_t)blockIdx.x * kComWarps + w) * 32; base < n; base += step) {
+    const size_t i = base + lane;
+    int lev = -1;
+    rec4 p = rec4{0, 0, 0, 0}, v = p, a = p;
+    if (i < n) {
+      p = ld_rec(&posm[i]);
+      const double dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+      const int l = (int)level[i];
+      if (!(dx * dx + dy * dy + dz * dz > rtrunc2) && l >= mlevel && l < nlev) {   // Component::freeze
+        lev = l;
+        v = ld_rec(&vel[i]);
+        a = ld_rec(&accp[i]);
+      }
+    }
+    for (int mm = mlevel; mm < nlev; mm++) {
+      if (!__ballot_sync(0xffffffffu, lev == mm)) continue;
+      const double m = lev == mm ? p.w : 0.0;
+      double A[kComVals];
+      A[0] = m;
+      A[1] = m * p.x; A[2] = dim > 1 ? m * p.y : 0.0; A[3] = dim > 2 ? m * p.z : 0.0;
+      A[4] = m * v.x; A[5] = dim > 1 ? m * v.y : 0.0; A[6] = dim > 2 ? m * v.z : 0.0;
+      A[7] = m * a.x; A[8] = dim > 1 ? m * a.y : 0.0; A[9] = dim > 2 ? m * a.z : 0.0;
+      R::run(A, lane);
+      if (myrow >= 0) acc[w][mm][myrow] += A[0];
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < nlev * kComVals; q += blockDim.x) {
+    const int mm = q / kComVals, r = q % kComVals;
+    double t = 0.0;
+    for (int ww = 0; ww < kComWarps; ww++) t += acc[ww][mm][r];
+    part[(size_t)blockIdx.x * kComMaxLev * kComVals + q] = t;
+  }
+}
+
+__global__ void com_final_kernel(const double *__restrict__ part, int nblocks, int nlev, double *__restrict__ out)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nlev * kComVals) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; b++) t += part[(size_t)b * kComMaxLev * kComVals + q];
+  out[q] = t;
+}
+
+
 __global__ void __launch_bounds__(256)
 level_count_kernel(const unsigned *__restrict__ level, size_t n, int nlev,
                    unsigned long long *__restrict__ counts)
@@ -508,7 +580,7 @@ int expb200_component_destroy(expb200_component c)
   cudaFree(c->spare); cudaFree(c->slot_of); cudaFree(c->where);
   cudaFree(c->level); cudaFree(c->prev_level); cudaFree(c->dtreq); cudaFree(c->scale);
   for (int k = 0; k < 2; k++) { cudaFree(c->keys[k]); cudaFree(c->perm[k]); }
-  cudaFree(c->hist); cudaFree(c->rank); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats);
+  cudaFree(c->hist); cudaFree(c->rank); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats); cudaFree(c->com_part);
   cudaEventDestroy(c->copy_done);
   stream_register(c->stream, false);
   cudaStreamDestroy(c->stream);
@@ -841,6 +913,47 @@ int expb200_component_event_elapsed(expb200_component c, int slot_a, int slot_b,
   float f = 0.f;
   CU_TRY(cudaEventElapsedTime(&f, g_tev[slot_a], g_tev[slot_b]));
   *ms = f;
+  return EXPB200_OK;
+}
+
+// ~ Component::fix_positions_cuda (src/cudaComponent.cu:800-960); arithmetic of
+// fix_positions_thread (src/Component.cc:3280-3352) without the consp/tidal escape branch.
+int expb200_component_fix_positions(expb200_component c, int mlevel, int multistep, int dim, double *sums,
+                                    void *nccl_comm)
+{
+  REQUIRE(c && sums, "NULL argument");
+  REQUIRE(multistep >= 0 && multistep < kComMaxLev, "multistep=%d outside [0,%d)", multistep, kComMaxLev);
+  REQUIRE(mlevel >= 0 && mlevel <= multistep, "mlevel=%d outside [0,%d]", mlevel, multistep);
+  REQUIRE(dim >= 1 && dim <= 3, "dim=%d", dim);
+  DeviceGuard g(c->device);
+  const int nlev = multistep + 1;
+  int nblocks = (int)std::min<size_t>((c->n + kComWarps * 32 - 1) / (kComWarps * 32), (size_t)kSMsB200 * 8);
+  if (nblocks < 1) nblocks = 1;
+  const size_t need = ((size_t)nblocks + 1) * kComMaxLev * kComVals;
+  if (c->com_part_cap < need) {
+    if (c->com_part) cudaFree(c->com_part);
+    c->com_part = nullptr; c->com_part_cap = 0;
+    CU_TRY(cudaMalloc(&c->com_part, need * sizeof(double)));
+    c->com_part_cap = need;
+  }
+  double *out = c->com_part + (size_t)nblocks * kComMaxLev * kComVals;
+  {
+    ProfRegion pr(K_OTHER, c->stream, 2);
+    com_sum_kernel<<<nblocks, kComWarps * 32, 0, c->stream>>>(c->posm, c->vel, c->accp, c->level, c->n, mlevel,
+                                                             nlev, dim, c->center[0], c->center[1], c->center[2],
+                                                             c->rtrunc * c->rtrunc, c->com_part);
+    com_final_kernel<<<div_up(nlev * kComVals, 64), 64, 0, c->stream>>>(c->com_part, nblocks, nlev, out);
+    CU_LAUNCH_CHECK();
+  }
+  if (nccl_comm) {
+    int rc = nccl_allreduce_sum_f64(nccl_comm, out, (size_t)nlev * kComVals, c->stream);
+    if (rc) return rc;
+  }
+  double h[kComMaxLev * kComVals];
+  CU_TRY(cudaMemcpyAsync(h, out, (size_t)nlev * kComVals * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  for (int mm = mlevel; mm < nlev; mm++)
+    for (int r = 0; r < kComVals; r++) sums[mm * kComVals + r] = h[mm * kComVals + r];
   return EXPB200_OK;
 }
 

@@ -130,43 +130,6 @@ __global__ void multistep_interp_kernel(const double *__restrict__ cL, const dou
 }
 
 // ---------------------------------------------------------------------------
-// Warp reduce-scatter of N per-lane values: five butterfly steps, each lane keeps one
-// half of its array and sends the other, so that afterwards lane L holds the full
-// 32-lane sums of RS<N>::FIN rows (rs_row tells which).  N + ... shuffles instead of
-// 5 N, and the summation tree is fixed.
-// ---------------------------------------------------------------------------
-template <int N, int S> struct RS {
-  static constexpr int H = (N + 1) / 2;
-  static constexpr int FIN = RS<H, S + 1>::FIN;
-  static __device__ __forceinline__ void run(double *v, int lane)
-  {
-    const bool up = (lane >> (4 - S)) & 1;
-#pragma unroll
-    for (int i = 0; i < H; i++) {
-      const double lo = v[i];
-      const double hi = (i + H < N) ? v[i + H] : 0.0;
-      const double send = up ? lo : hi;
-      const double keep = up ? hi : lo;
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16 >> S);
-    }
-    RS<H, S + 1>::run(v, lane);
-  }
-  // original index of entry i held by `lane` after the remaining steps S..4 (or -1)
-  static __device__ __forceinline__ int row(int lane, int i)
-  {
-    int idx = RS<H, S + 1>::row(lane, i);
-    if (idx < 0) return -1;
-    if ((lane >> (4 - S)) & 1) idx += H;
-    return idx < N ? idx : -1;
-  }
-};
-template <int N> struct RS<N, 5> {
-  static constexpr int FIN = N;
-  static __device__ __forceinline__ void run(double *, int) {}
-  static __device__ __forceinline__ int row(int, int i) { return i < N ? i : -1; }
-};
-
-// ---------------------------------------------------------------------------
 // deposit (lmax <= 6): one warp per chunk of CH sorted particles, lane = particle.
 // Every lane keeps the 2 x NACC sums of the current radial cell in registers; when the
 // cell changes (at most numr times over the whole array) or the chunk ends they are

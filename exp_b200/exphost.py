@@ -58,6 +58,7 @@ def host():
         H.exphost_get_cylinder_coefs.argtypes = [C.c_int, c_dp, c_dp, c_dp]
         H.exphost_level_report.argtypes = [C.c_int] + [_lib.c_u64p] * 5
         H.exphost_state.argtypes = [c_dp, C.POINTER(C.c_int), c_dp, c_dp]
+        H.exphost_get_com.argtypes = [C.c_int, c_dp, c_dp]
         _HOST = H
     return _HOST
 
@@ -163,6 +164,13 @@ class Simulation:
                                            counts.ctypes.data_as(_lib.c_u64p)))
         return dict(examined=v[0].value, switched=v[1].value, offlo=v[2].value, offhi=v[3].value,
                     counts=counts)
+
+    def com(self, idx):
+        """[mtot, com[3], cov[3], coa[3]] of component idx after its last fix_positions, and the
+        per-level sums it keeps."""
+        out, lev = np.zeros(10), np.zeros((self.multistep + 1, 10))
+        _check(self.H.exphost_get_com(idx, _p(out), _p(lev)))
+        return out, lev
 
     def state(self):
         t, k = C.c_double(0.0), C.c_int(0)

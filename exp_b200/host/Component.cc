@@ -68,6 +68,52 @@ void Component::ZeroPotAccel(int minlev)
   EXPHOST_CHECK(expb200_component_zero_pot_acc(b200, minlev));
 }
 
+void Component::fix_positions(unsigned mlevel)
+{
+  const size_t nlev = multistep + 1;
+  if (com_mas.size() != nlev) {
+    com_lev.assign(3 * nlev, 0.0); cov_lev.assign(3 * nlev, 0.0); coa_lev.assign(3 * nlev, 0.0);
+    com_mas.assign(nlev, 0.0);
+    mlevel = 0;                           // no per-level history yet: sum every level
+  }
+  mtot = 0.0;
+  for (int k = 0; k < dim; k++) com[k] = cov[k] = coa[k] = 0.0;
+
+  // rows M >= mlevel: {com_mas, com_lev, cov_lev, coa_lev}, already summed over ranks
+  std::vector<double> sums(10 * nlev, 0.0);
+  EXPHOST_CHECK(expb200_component_fix_positions(b200, (int)mlevel, (int)multistep, dim, sums.data(), nccl_comm));
+  for (size_t mm = mlevel; mm < nlev; mm++) {
+    com_mas[mm] = sums[10 * mm];
+    for (int k = 0; k < 3; k++) {
+      com_lev[3 * mm + k] = sums[10 * mm + 1 + k];
+      cov_lev[3 * mm + k] = sums[10 * mm + 4 + k];
+      coa_lev[3 * mm + k] = sums[10 * mm + 7 + k];
+    }
+  }
+  // sum levels (:3484-3497); the rank sum was done per level on the device
+  for (size_t mm = 0; mm < nlev; mm++) {
+    for (int k = 0; k < 3; k++) {
+      com[k] += com_lev[3 * mm + k];
+      cov[k] += cov_lev[3 * mm + k];
+      coa[k] += coa_lev[3 * mm + k];
+    }
+    mtot += com_mas[mm];
+  }
+  if (mtot > 0.0) {
+    for (int k = 0; k < dim; k++) com[k] /= mtot;
+    for (int k = 0; k < dim; k++) cov[k] /= mtot;
+    for (int k = 0; k < dim; k++) coa[k] /= mtot;
+  }
+  if (com_system) {                       // :3555-3563 (consp is not mirrored)
+    for (int k = 0; k < dim; k++) com0[k] = com[k];
+    for (int k = 0; k < dim; k++) cov0[k] = cov[k];
+    for (int k = 0; k < dim; k++) acc0[k] = coa[k];
+    update_center();
+  } else {
+    for (int k = 0; k < dim; k++) acc0[k] = 0.0;
+  }
+}
+
 std::vector<unsigned long long> Component::level_counts() const
 {
   std::vector<uint64_t> c(multistep + 1, 0);

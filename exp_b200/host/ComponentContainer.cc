@@ -49,8 +49,23 @@ void ComponentContainer::compute_potential(unsigned mlevel)
       inter->c->force->ClearExternal();
     }
   }
-  // external forces and the centring pass (fix_positions) are outside the force loop proper
-  // 
+  // external forces are outside the force loop proper.
+  // Compute new centre(s) (src/ComponentContainer.cc:952-999)
+  int clev = centerlevl < 0 ? (int)multistep / 2 : centerlevl;      // :42-45
+  if (clev > (int)multistep) clev = (int)multistep;
+  if (mactive.empty() || mactive[mstep][clev]) fix_positions();
+}
+
+void ComponentContainer::fix_positions()
+{
+  mtot = 0.0;
+  for (int k = 0; k < 3; k++) gcom[k] = gcov[k] = 0.0;
+  for (auto c : components) {
+    c->fix_positions();
+    mtot += c->mtot;
+    for (int k = 0; k < 3; k++) gcom[k] += c->com[k];
+    for (int k = 0; k < 3; k++) gcov[k] += c->cov[k];
+  }
 }
 
 void ComponentContainer::multistep_reset()

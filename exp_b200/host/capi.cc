@@ -224,6 +224,26 @@ int exphost_multistep_tables(int ms, int *mintvl_, int *mfirst_, int *dL, int *d
   });
 }
 
+int exphost_get_com(int index, double *out, double *lev)
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    if (out) {
+      out[0] = c->mtot;
+      for (int k = 0; k < 3; k++) { out[1 + k] = c->com[k]; out[4 + k] = c->cov[k]; out[7 + k] = c->coa[k]; }
+    }
+    if (lev)
+      for (size_t mm = 0; mm < c->com_mas.size(); mm++) {
+        lev[10 * mm] = c->com_mas[mm];
+        for (int k = 0; k < 3; k++) {
+          lev[10 * mm + 1 + k] = c->com_lev[3 * mm + k];
+          lev[10 * mm + 4 + k] = c->cov_lev[3 * mm + k];
+          lev[10 * mm + 7 + k] = c->coa_lev[3 * mm + k];
+        }
+      }
+  });
+}
+
 int exphost_state(double *tnow_, int *this_step_, double *pc, double *vc)
 {
   if (tnow_) *tnow_ = tnow;

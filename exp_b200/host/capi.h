@@ -55,6 +55,9 @@ int exphost_level_report(int index, uint64_t *examined, uint64_t *switched, uint
 /* initialize_multistep tables for `multistep` levels (no GPU needed): mintvl[multistep+1],
  * mfirst[Mstep+1], dstepL/dstepN[(multistep+1)][Mstep] */
 int exphost_multistep_tables(int multistep, int *mintvl, int *mfirst, int *dstepL, int *dstepN);
+/* Component::mtot/com/cov/coa after the last fix_positions: out[10] = {mtot, com[3], cov[3],
+ * coa[3]}; lev[(multistep+1)][10] = {com_mas, com_lev, cov_lev, coa_lev} (may be NULL). */
+int exphost_get_com(int index, double *out, double *lev);
 int exphost_state(double *tnow, int *this_step, double *pos_check, double *vel_check);
 
 #ifdef __cplusplus

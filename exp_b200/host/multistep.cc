@@ -83,6 +83,7 @@ void adjust_multistep_level()
       c->force->multistep_update_finish();
       // reset_level_lists: the device store re-bins by level on its next sort
     }
+    c->fix_positions();                   // src/multistep.cc:543
   }
 }
 

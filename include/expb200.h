@@ -137,6 +137,18 @@ int expb200_adjust_multistep_level(expb200_component c, const expb200_level_para
  * (src/cudaComponent.cu:490-526). */
 int expb200_component_level_counts(expb200_component c, int multistep, uint64_t *counts);
 
+/* Centre-of-mass sums per multistep level of the non-frozen particles with
+ * level >= mlevel:  sums[M*10 + {0: mass, 1..3: mass*pos, 4..6: mass*vel,
+ * 7..9: mass*acc}] for M in [mlevel, multistep]; rows below mlevel are left
+ * untouched (the caller keeps com_lev/cov_lev/coa_lev/com_mas across calls).
+ * Components k >= dim stay 0.  With nccl_comm != NULL the rows are all-reduced
+ * (the reference's four MPI_Allreduce of src/Component.cc:3499-3502).
+ * ~ Component::fix_positions_cuda (src/cudaComponent.cu:800-960, src/Component.H:1133),
+ * arithmetic of fix_positions_thread (src/Component.cc:3280-3352); the consp/tidal
+ * escape branch (:3314-3334) is not on this path. */
+int expb200_component_fix_positions(expb200_component c, int mlevel, int multistep, int dim,
+                                    double *sums, void *nccl_comm);
+
 /* ------------------------------------------------------------------------
  * Sphere (force id "sphereSL"): SphericalBasis + SLGridSph tables.
  * ---------------------------------------------------------------------- */

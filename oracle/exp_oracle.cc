@@ -664,6 +664,46 @@ void orc_incr_velocity(orc_particles *S, const int *list, long nlist, double dt,
 }
 
 // ---------------------------------------------------------------------------
+// f1: Component::fix_positions_cpu / fix_positions_thread  (src/Component.cc:3280-3590)
+// without the consp/tidal escape branch (:3314-3334) and the EJ/c0/CF centre overrides
+// (:3570-3588), which are host-side policy.
+//   lev_sums[M][10] = {com_mas[M], com_lev[3M..], cov_lev[3M..], coa_lev[3M..]} is the
+//   state the reference keeps between calls: rows M >= mlevel are zeroed and re-summed
+//   (:3364-3368, :3310-3349), rows below keep their old values, then all levels are
+//   added (:3484-3497) and divided by the total mass (:3540-3544).
+//   out[10] = {mtot, com[3], cov[3], coa[3]}.
+// ---------------------------------------------------------------------------
+void orc_fix_positions(const orc_particles *S, int mlevel, int multistep, int dim,
+                       double *lev_sums, double *out)
+{
+  for (int mm = mlevel; mm <= multistep; mm++)
+    for (int r = 0; r < 10; r++) lev_sums[10 * mm + r] = 0.0;
+  for (int mm = mlevel; mm <= multistep; mm++) {
+    for (long i = 0; i < S->n; i++) {                   // levlist[mm] in index order
+      if ((int)S->level[i] != mm) continue;
+      double r2 = 0.0;                                   // Component::freeze, :4194-4202
+      for (int k = 0; k < 3; k++) {
+        double d = S->pos[3 * i + k] - S->center[k];
+        r2 += d * d;
+      }
+      if (r2 > S->rtrunc * S->rtrunc) continue;
+      double *L = lev_sums + 10 * mm;
+      L[0] += S->mass[i];
+      for (int k = 0; k < dim; k++) {
+        L[1 + k] += S->mass[i] * S->pos[3 * i + k];
+        L[4 + k] += S->mass[i] * S->vel[3 * i + k];
+        L[7 + k] += S->mass[i] * S->acc[3 * i + k];
+      }
+    }
+  }
+  for (int r = 0; r < 10; r++) out[r] = 0.0;
+  for (int mm = 0; mm <= multistep; mm++)
+    for (int r = 0; r < 10; r++) out[r] += lev_sums[10 * mm + r];
+  if (out[0] > 0.0)
+    for (int r = 1; r < 10; r++) out[r] /= out[0];
+}
+
+// ---------------------------------------------------------------------------
 // a22: adjust_multistep_level_thread  (src/multistep.cc:52-236)
 // ---------------------------------------------------------------------------
 long orc_adjust_levels(orc_particles *S, const int *list, long nlist,

@@ -143,6 +143,12 @@ long orc_adjust_levels(orc_particles *S, const int *list, long nlist,
 void orc_multistep_tables(int multistep, int *mintvl, int *mfirst,
                           int *dstepL, int *dstepN);
 
+/* f1: Component::fix_positions_cpu (src/Component.cc:3280-3590): lev_sums[(multistep+1)][10]
+ * = {com_mas, com_lev[3], cov_lev[3], coa_lev[3]} (rows >= mlevel recomputed),
+ * out[10] = {mtot, com[3], cov[3], coa[3]}. */
+void orc_fix_positions(const orc_particles *S, int mlevel, int multistep, int dim,
+                       double *lev_sums, double *out);
+
 /* ---- a14-a19: cylinder (EmpCylSL tables + Cylinder force)
  * Tables are six arrays [(MMAX+1)][NORDER][(NUMX+1)][(NUMY+1)] (ix major, iy minor); the
  * m=0 slabs of the S arrays are unused.  exputil/EmpCylSL.cc:2123-2187 (setup_table). */

@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         L.orc_adjust_levels.argtypes = [C.POINTER(Particles), c_ip, C.c_long,
                                         C.POINTER(LevelParams), c_ip, c_lp, c_lp]
         L.orc_multistep_tables.argtypes = [C.c_int, c_ip, c_ip, c_ip, c_ip]
+        L.orc_fix_positions.argtypes = [C.POINTER(Particles), C.c_int, C.c_int, C.c_int, c_dp, c_dp]
         L.orc_cyl_init.argtypes = [C.POINTER(CylGrid)]
         L.orc_cyl_get_pot.argtypes = [C.POINTER(CylGrid), C.c_double, C.c_double, c_dp, c_dp]
         L.orc_cyl_coefficients.restype = C.c_long
@@ -293,6 +294,19 @@ def incr_velocity(S: ParticleSet, dt, lst=None, dim=3):
     l = None if lst is None else _list(S, lst)
     lib().orc_incr_velocity(C.byref(sc), l.ctypes.data_as(c_ip) if l is not None else None,
                             S.n if l is None else len(l), dt, dim)
+
+
+def fix_positions(S: ParticleSet, mlevel, multistep, lev_sums=None, dim=3):
+    """Component::fix_positions_cpu (src/Component.cc:3354-3590): returns (lev_sums, out) with
+    lev_sums[M] = [com_mas, com_lev[3], cov_lev[3], coa_lev[3]] (updated for M >= mlevel) and
+    out = [mtot, com[3], cov[3], coa[3]]."""
+    if lev_sums is None:
+        lev_sums = np.zeros((multistep + 1, 10))
+    lev_sums = np.ascontiguousarray(lev_sums, dtype=np.float64)
+    out = np.zeros(10)
+    sc = S.c()
+    lib().orc_fix_positions(C.byref(sc), mlevel, multistep, dim, _dp(lev_sums), _dp(out))
+    return lev_sums, out
 
 
 def level_params(dtime, multistep, mfirst_mdrft=0, dynfracS=1.0, dynfracD=1.0e32, dynfracV=0.01,

@@ -163,6 +163,8 @@ class RefSim:
         self.Mstep = 1 << multistep
         self.S, self.F, self.inter = [], [], []
         self.this_step, self.tnow = 0, 0.0
+        self.com = {}                         # component -> [mtot, com, cov, coa] (fix_positions)
+        self.centerlevl = multistep // 2      # src/ComponentContainer.cc:42-45
 
     def add(self, kind, tab, pos, vel, mass, **kw):
         self.S.append(O.ParticleSet(pos, vel, mass))
@@ -179,7 +181,13 @@ class RefSim:
         for S, F in zip(self.S, self.F):
             F.coefficients(S, S.levlist(M), M, self.tnow)
 
-    def compute_potential(self, mlevel, mdrft):
+    def fix_positions(self):
+        # Component::fix_positions_cpu, default mlevel = 0 at both call sites
+        # (src/ComponentContainer.cc:1380, src/multistep.cc:543)
+        for k, S in enumerate(self.S):
+            _, self.com[k] = O.fix_positions(S, 0, self.multistep)
+
+    def compute_potential(self, mlevel, mdrft, mstep=0):
         for S, F in zip(self.S, self.F):
             act = self._lev(S, mlevel)
             S.acc[act] = 0.0
@@ -189,6 +197,9 @@ class RefSim:
             F.accel(S, act)
         for frm, on in self.inter:
             self.F[frm].accel(self.S[on], self._lev(self.S[on], mlevel))
+        # mactive[mstep][centerlevl] (src/ComponentContainer.cc:955, src/multistep.cc:646-654)
+        if mstep % (1 << (self.multistep - self.centerlevl)) == 0:
+            self.fix_positions()
 
     def adjust_multistep_level(self, mdrft, mstep):
         first_call = self.this_step == 0 and mdrft == 0
@@ -201,6 +212,7 @@ class RefSim:
             n, _, _, _ = O.adjust_levels(S, LP, lst=self._lev(S, first))
             F.switch(S, old, int(self.mfirst[mdrft]))
             nsw += n
+        self.fix_positions()
         return nsw
 
     def reset(self):
@@ -234,7 +246,7 @@ class RefSim:
                     self.compute_expansion(M)
                 self.tnow += dt
                 mdrft = mstep + 1
-                self.compute_potential(int(self.mfirst[mstep]), mdrft)
+                self.compute_potential(int(self.mfirst[mstep]), mdrft, mstep)
                 for M in range(int(self.mfirst[mdrft]), self.multistep + 1):
                     for S in self.S:
                         O.incr_velocity(S, 0.5 * dt * int(self.mintvl[M]), lst=S.levlist(M))

@@ -88,6 +88,14 @@ def test_disk_halo_interactions(multistep):
         assert np.abs(out["vel"] - S.vel).max() <= 1e-9 * np.abs(S.vel).max()
         assert acc_rel_err(out["acc"], S.acc).max() <= 1e-8
         assert np.abs(out["pot"] - S.pot).max() <= 1e-8 * np.abs(S.pot).max()
+        # centring pass (Component::fix_positions): mtot, com, cov, coa of each component
+        got, lev = sim.com(idx)
+        want = ref.com[{h: rh, d: rd}[idx]]
+        assert abs(got[0] - want[0]) <= 1e-12 * want[0]
+        assert np.abs(got[1:4] - want[1:4]).max() <= 1e-10 * np.abs(S.pos).max()
+        assert np.abs(got[4:7] - want[4:7]).max() <= 1e-9 * np.abs(S.vel).max()
+        assert np.abs(got[7:10] - want[7:10]).max() <= 1e-8 * np.abs(S.acc).max()
+        assert abs(lev[:, 0].sum() - want[0]) <= 1e-12 * want[0]
     if multistep:
         lv = np.concatenate([ref.S[rh].level, ref.S[rd].level])
         assert len(np.unique(lv)) >= 2

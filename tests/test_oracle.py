@@ -194,3 +194,26 @@ def test_leapfrog():
     assert np.array_equal(S.vel, v)
     p = pos.copy(); p[::2] += v[::2] * 0.25
     assert np.array_equal(S.pos, p)
+
+
+def test_fix_positions_restatement():
+    """Component::fix_positions_cpu (src/Component.cc:3280-3590): per-level sums of the
+    non-frozen particles, levels below mlevel carried over, totals divided by the mass."""
+    rng = np.random.default_rng(3)
+    n, multistep = 5000, 3
+    pos, vel = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    mass = rng.uniform(0.5, 1.5, n)
+    lev = rng.integers(0, multistep + 1, n).astype(np.uint32)
+    S = O.ParticleSet(pos, vel, mass, center=(0.1, 0.0, -0.1), rtrunc=2.0, level=lev)
+    S.acc[:] = rng.normal(size=(n, 3))
+    live = ((pos - np.array(S.center)) ** 2).sum(axis=1) <= 2.0 ** 2
+    prev = np.full((multistep + 1, 10), 7.0)
+    levs, out = O.fix_positions(S, 2, multistep, lev_sums=prev.copy())
+    assert np.array_equal(levs[:2], prev[:2])
+    for M in (2, 3):
+        sel = live & (lev == M)
+        want = np.concatenate([[mass[sel].sum()], (mass[sel, None] * pos[sel]).sum(0),
+                               (mass[sel, None] * vel[sel]).sum(0), (mass[sel, None] * S.acc[sel]).sum(0)])
+        assert np.allclose(levs[M], want, rtol=1e-12, atol=1e-12)
+    tot = levs.sum(axis=0)
+    assert np.allclose(out[0], tot[0]) and np.allclose(out[1:], tot[1:] / tot[0])
