@@ -59,6 +59,8 @@ def host():
         H.exphost_level_report.argtypes = [C.c_int] + [_lib.c_u64p] * 5
         H.exphost_state.argtypes = [c_dp, C.POINTER(C.c_int), c_dp, c_dp]
         H.exphost_get_com.argtypes = [C.c_int, c_dp, c_dp]
+        H.exphost_dump_coefs.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_long]
+        H.exphost_dump_coefs.restype = C.c_long
         _HOST = H
     return _HOST
 
@@ -164,6 +166,18 @@ class Simulation:
                                            counts.ctypes.data_as(_lib.c_u64p)))
         return dict(examined=v[0].value, switched=v[1].value, offlo=v[2].value, offhi=v[3].value,
                     counts=counts)
+
+    def dump_coefs(self, idx, kind=0):
+        """bytes of the force's dump_coefs stream (kind 0: NewCoefs, 1: old style) or of its
+        SphStruct/CylStruct complex array (kind 2)"""
+        n = self.H.exphost_dump_coefs(idx, kind, None, 0)
+        if n < 0:
+            _check(int(n))
+        buf = C.create_string_buffer(int(n))
+        n2 = self.H.exphost_dump_coefs(idx, kind, buf, n)
+        if n2 < 0:
+            _check(int(n2))
+        return buf.raw[:n2]
 
     def com(self, idx):
         """[mtot, com[3], cov[3], coa[3]] of component idx after its last fix_positions, and the

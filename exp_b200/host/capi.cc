@@ -1,6 +1,9 @@
 // capi.cc -- see capi.h
 #include "capi.h"
 
+#include <complex>
+#include <sstream>
+
 #include <cstring>
 #include <string>
 
@@ -222,6 +225,36 @@ int exphost_multistep_tables(int ms, int *mintvl_, int *mfirst_, int *dL, int *d
       for (int n = 0; n < Mstep; n++) { dL[l * Mstep + n] = dstepL[l][n]; dN[l * Mstep + n] = dstepN[l][n]; }
     multistep = keep;
   });
+}
+
+// Serialises the component's coefficients with the force's dump_coefs (kind 0: NewCoefs
+// stream, 1: old-style stream [sphere only], 2: the CoefStruct complex array as (re, im)
+// doubles).  Returns the number of bytes (buf may be NULL to query the size).
+long exphost_dump_coefs(int index, int kind, char *buf, long cap)
+{
+  long nbytes = -1;
+  int rc = guarded([&] {
+    PotAccel *f = component_at(index)->force.get();
+    std::ostringstream out;
+    if (auto *s = dynamic_cast<SphericalBasis *>(f)) {
+      if (kind == 2) {
+        SphStruct cs = s->coef_struct();
+        out.write(reinterpret_cast<const char *>(cs.coefs.data()), cs.coefs.size() * sizeof(std::complex<double>));
+      } else s->dump_coefs(out, kind == 0);
+    } else if (auto *cy = dynamic_cast<Cylinder *>(f)) {
+      if (kind == 2) {
+        CylStruct cs = cy->coef_struct();
+        out.write(reinterpret_cast<const char *>(cs.coefs.data()), cs.coefs.size() * sizeof(std::complex<double>));
+      } else cy->dump_coefs(out);
+    } else throw GenericError("component has no basis force", __FILE__, __LINE__);
+    const std::string str = out.str();
+    nbytes = (long)str.size();
+    if (buf) {
+      if (cap < nbytes) throw GenericError("buffer too small", __FILE__, __LINE__);
+      std::memcpy(buf, str.data(), str.size());
+    }
+  });
+  return rc ? rc : nbytes;
 }
 
 int exphost_get_com(int index, double *out, double *lev)

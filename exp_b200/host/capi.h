@@ -55,6 +55,10 @@ int exphost_level_report(int index, uint64_t *examined, uint64_t *switched, uint
 /* initialize_multistep tables for `multistep` levels (no GPU needed): mintvl[multistep+1],
  * mfirst[Mstep+1], dstepL/dstepN[(multistep+1)][Mstep] */
 int exphost_multistep_tables(int multistep, int *mintvl, int *mfirst, int *dstepL, int *dstepN);
+/* The force's coefficient output: kind 0 = dump_coefs stream (NewCoefs), 1 = old-style stream
+ * (sphere), 2 = the SphStruct/CylStruct complex array.  Returns the byte count (buf may be
+ * NULL) or a negative status. */
+long exphost_dump_coefs(int index, int kind, char *buf, long cap);
 /* Component::mtot/com/cov/coa after the last fix_positions: out[10] = {mtot, com[3], cov[3],
  * coa[3]}; lev[(multistep+1)][10] = {com_mas, com_lev, cov_lev, coa_lev} (may be NULL). */
 int exphost_get_com(int index, double *out, double *lev);

@@ -49,6 +49,30 @@ def test_sphere_do_step(multistep, dtime, nsteps):
     assert abs(sim.state()["tnow"] - nsteps * dtime) < 1e-12
 
 
+def _check_coef_output(sim, h, d, tnow):
+    """dump_coefs / coef_struct of both forces against the restated formats"""
+    import coef_format as CF
+    ex = sim.sphere_coefs(h)
+    lmax, nmax = int(round(np.sqrt(ex.shape[0]))) - 1, ex.shape[1]
+    buf = sim.dump_coefs(h, 0)
+    magic, node, off = CF.parse_header(buf)
+    assert magic == 0xc0a57a2
+    assert node["id"] == "sphereSL" and node["nmax"] == nmax and node["lmax"] == lmax and node["normed"] is True
+    assert node["time"] == tnow and node["scale"] == 1.0
+    assert np.array_equal(np.frombuffer(buf[off:]), CF.sphere_payload(ex, lmax, nmax))
+    assert sim.dump_coefs(h, 1) == CF.sphere_old_stream(ex, "sphereSL", tnow, 1.0, lmax, nmax)
+    cof = np.frombuffer(sim.dump_coefs(h, 2), dtype=np.complex128).reshape(-1, nmax)
+    assert np.array_equal(cof, CF.sphere_struct(ex, lmax, nmax))
+    cs, sn, _ = sim.cylinder_coefs(d)
+    buf = sim.dump_coefs(d, 0)
+    magic, node, off = CF.parse_header(buf)
+    assert magic == 0xc0a57a3
+    assert node == {"time": tnow, "mmax": cs.shape[0] - 1, "nmax": cs.shape[1]}
+    assert np.array_equal(np.frombuffer(buf[off:]), CF.cylinder_payload(cs, sn))
+    cof = np.frombuffer(sim.dump_coefs(d, 2), dtype=np.complex128).reshape(cs.shape)
+    assert np.array_equal(cof.real, cs) and np.array_equal(cof.imag[1:], sn[1:]) and not cof.imag[0].any()
+
+
 @pytest.mark.parametrize("multistep", [0, 2])
 def test_disk_halo_interactions(multistep):
     """two components, each force acting on both (the reference's interaction list)"""
@@ -100,6 +124,7 @@ def test_disk_halo_interactions(multistep):
         lv = np.concatenate([ref.S[rh].level, ref.S[rd].level])
         assert len(np.unique(lv)) >= 2
     assert rel_rms(sim.sphere_coefs(h), ref.F[rh].use[0]) <= 1e-10
+    _check_coef_output(sim, h, d, nsteps * dtime)
     cs, sn, cm = sim.cylinder_coefs(d)
     assert rel_rms(cs, ref.F[rd].use[0]) <= 1e-10
     assert rel_rms(sn[1:], ref.F[rd].use[1][1:]) <= 1e-10
