@@ -230,3 +230,101 @@ def test_empty_and_tiny():
     c.upload(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
     coef = s.determine_coefficients(c)
     assert np.all(coef == 0.0) and s.used == 0
+
+
+@pytest.mark.parametrize("n", [127, 128, 129, 255, 257, 1000, 4099])
+def test_force_tile_edges(n):
+    """The pipelined force kernel walks tiles of 128 sorted particles: counts around the tile
+    size, a sparse set (every tile spans more table rows than a stage holds, so the lanes read
+    the table through L2) and the fused multi-step driver on the same sets."""
+    tab = get_table("hernquist", 4, 10)
+    pos, vel, mass = _halo("hernquist", n, seed=100 + n)
+    pos[: max(1, n // 50)] *= 200.0              # a dead-cell tail beyond rmax
+    coef_o, used_o, acc_o, pot_o = _oracle_all(tab, pos, vel, mass)
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    s = Sphere(tab)
+    coef = s.determine_coefficients(c)
+    assert s.used == used_o and rel_rms(coef, coef_o) <= COEF_TOL
+    s.set_coefficients(coef_o)
+    c.zero_pot_acc()
+    s.get_acceleration_and_potential(c)
+    out = c.download()
+    assert acc_rel_err(out["acc"], acc_o).max() <= ACC_TOL
+    assert np.abs(out["pot"] - pot_o).max() <= ACC_TOL * np.abs(pot_o).max()
+    # fused steps == separate steps, bit for bit
+    dt = 1e-3
+    c2, c3 = Component(n), Component(n)
+    s2, s3 = Sphere(tab), Sphere(tab)
+    for cc, ss in ((c2, s2), (c3, s3)):
+        cc.upload(pos, vel, mass)
+        ss.determine_coefficients(cc, to_host=False)
+        ss.set_coefficients(None)
+        cc.zero_pot_acc()
+        ss.get_acceleration_and_potential(cc)
+    for _ in range(2):
+        s2.step(c2, dt)
+    s3.steps(c3, dt, 2)
+    one, many = c2.download(), c3.download()
+    for k in ("pos", "vel", "acc", "pot"):
+        assert one[k].tobytes() == many[k].tobytes(), k
+
+
+def test_force_all_dead_and_two_pass_keys():
+    """every particle outside [rmin, rmax] (no coefficients, continuation force only), and a
+    4000-node table: 12-bit keys take two radix passes, the sorted keys then share a buffer
+    with the next step's keys and the fused driver must fall back to the one-shot kernel."""
+    tab = get_table("hernquist", 2, 10)
+    n = 3000
+    pos, vel, mass = _halo("hernquist", n, seed=77)
+    far = pos * (60.0 / np.linalg.norm(pos, axis=1))[:, None]
+    coef_o, used_o, acc_o, pot_o = _oracle_all(tab, far, vel, mass)
+    assert used_o == 0
+    c = Component(n)
+    c.upload(far, vel, mass)
+    s = Sphere(tab)
+    coef = s.determine_coefficients(c)
+    assert s.used == 0 and not coef.any()
+    ref_coef, *_ = _oracle_all(tab, pos, vel, mass)
+    g, P = O.Grid(tab), O.sph_params(rmin=tab.rmin, rmax=tab.rmax)
+    S = O.ParticleSet(far, vel, mass)
+    O.sph_accel(g, P, S, ref_coef)
+    s.set_coefficients(ref_coef)
+    c.zero_pot_acc()
+    s.get_acceleration_and_potential(c)
+    out = c.download()
+    assert acc_rel_err(out["acc"], S.acc).max() <= ACC_TOL
+
+    tab4 = get_table("hernquist", 2, 8, numr=4000)
+    n = 20000
+    pos, vel, mass = _halo("hernquist", n, seed=78)
+    c2, c3 = Component(n), Component(n)
+    s2, s3 = Sphere(tab4), Sphere(tab4)
+    for cc, ss in ((c2, s2), (c3, s3)):
+        cc.upload(pos, vel, mass)
+        coef = ss.determine_coefficients(cc)
+        ss.set_coefficients(None)
+        cc.zero_pot_acc()
+        ss.get_acceleration_and_potential(cc)
+    coef_o, used_o, acc_o, pot_o = _oracle_all(tab4, pos, vel, mass)
+    assert rel_rms(coef, coef_o) <= COEF_TOL
+    assert acc_rel_err(c2.download()["acc"], acc_o).max() <= ACC_TOL
+    for _ in range(3):
+        s2.step(c2, 1e-3)
+    s3.steps(c3, 1e-3, 3)
+    one, many = c2.download(), c3.download()
+    for k in ("pos", "vel", "acc", "pot"):
+        assert one[k].tobytes() == many[k].tobytes(), k
+    # and the stepped state agrees with the oracle's leapfrog
+    S = O.ParticleSet(pos, vel, mass)
+    g, P = O.Grid(tab4), O.sph_params(rmin=tab4.rmin, rmax=tab4.rmax)
+    cf, _ = O.sph_coefficients(g, P, S)
+    O.sph_accel(g, P, S, cf)
+    for _ in range(3):
+        O.incr_velocity(S, 0.5e-3); O.incr_position(S, 1e-3)
+        S.acc[:] = 0.0; S.pot[:] = 0.0
+        cf, _ = O.sph_coefficients(g, P, S)
+        O.sph_accel(g, P, S, cf)
+        O.incr_velocity(S, 0.5e-3)
+    assert np.abs(many["pos"] - S.pos).max() <= 1e-11 * np.abs(S.pos).max()
+    assert acc_rel_err(many["acc"], S.acc).max() <= ACC_TOL
