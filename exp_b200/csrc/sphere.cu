@@ -1249,6 +1249,8 @@ struct expb200_sphere_s {
   double *G = nullptr;       // node sums [nrow][numr]
   double *PA = nullptr, *PB = nullptr;
   size_t part_slots = 0;
+  void *cov_buf[11] = {};    // cached scratch of the covariance call
+  size_t cov_cap[11] = {};
   int2 *tdesc = nullptr;     // per-tile row ranges of the pipelined force kernel
   size_t tdesc_cap = 0;
   int *row_l = nullptr, *row_m = nullptr;
@@ -1528,6 +1530,7 @@ int expb200_sphere_destroy(expb200_sphere s)
   cudaFree(s->G); cudaFree(s->PA); cudaFree(s->PB); cudaFree(s->row_l); cudaFree(s->row_m);
   cudaFree(s->slot_l); cudaFree(s->slot_m); cudaFree(s->slot_rowc); cudaFree(s->slot_rows); cudaFree(s->used_dev);
   cudaFree(s->coefN); cudaFree(s->coefL); cudaFree(s->differ); cudaFree(s->tmp); cudaFree(s->tdesc);
+  for (int q = 0; q < 11; q++) cudaFree(s->cov_buf[q]);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
   return EXPB200_OK;
@@ -1857,23 +1860,33 @@ int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel,
   if (TB > 65535) TB = 65535;
   double *PA = nullptr, *PB = nullptr, *PS = nullptr, *G = nullptr, *DO = nullptr, *Mc = nullptr,
          *rows = nullptr, *Ms = nullptr, *mT = nullptr, *outT = nullptr, *outM = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(PA); cudaFree(PB); cudaFree(PS); cudaFree(G); cudaFree(DO); cudaFree(Mc); cudaFree(rows);
-    cudaFree(Ms); cudaFree(mT); cudaFree(outT); cudaFree(outM);
+  // scratch is cached in the sphere (grow-only, freed with it): cudaMalloc/cudaFree of these
+  // buffers per call costs more than the kernels
+  auto cleanup = [&]() {};
+  auto cov_alloc = [&](double **ptr, size_t bytes, int slot) -> cudaError_t {
+    if (s->cov_cap[slot] < bytes) {
+      if (s->cov_buf[slot]) cudaFree(s->cov_buf[slot]);
+      s->cov_buf[slot] = nullptr; s->cov_cap[slot] = 0;
+      cudaError_t e = cudaMalloc(&s->cov_buf[slot], bytes);
+      if (e != cudaSuccess) return e;
+      s->cov_cap[slot] = bytes;
+    }
+    *ptr = static_cast<double *>(s->cov_buf[slot]);
+    return cudaSuccess;
   };
 #define COV_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
   const size_t slots = per_bin * TB + 2;
-  COV_TRY(cudaMalloc(&PA, slots * gm.nrow * sizeof(double)));
-  COV_TRY(cudaMalloc(&PB, slots * gm.nrow * sizeof(double)));
-  COV_TRY(cudaMalloc(&PS, slots * (3 * ldim + 1) * sizeof(double)));
-  COV_TRY(cudaMalloc(&G, (size_t)TB * gm.nrow * R * sizeof(double)));
-  COV_TRY(cudaMalloc(&DO, (size_t)TB * 2 * ldim * R * sizeof(double)));
-  COV_TRY(cudaMalloc(&Mc, (size_t)TB * R * sizeof(double)));
-  COV_TRY(cudaMalloc(&rows, (size_t)TB * gm.nrow * N * sizeof(double)));
-  COV_TRY(cudaMalloc(&Ms, (size_t)TB * ldim * N * N * sizeof(double)));
-  COV_TRY(cudaMalloc(&mT, (size_t)TB * sizeof(double)));
-  COV_TRY(cudaMalloc(&outT, (size_t)TB * ldim * N * 2 * sizeof(double)));
-  COV_TRY(cudaMalloc(&outM, (size_t)TB * ldim * N * N * sizeof(double)));
+  COV_TRY(cov_alloc(&PA, slots * gm.nrow * sizeof(double), 0));
+  COV_TRY(cov_alloc(&PB, slots * gm.nrow * sizeof(double), 1));
+  COV_TRY(cov_alloc(&PS, slots * (3 * ldim + 1) * sizeof(double), 2));
+  COV_TRY(cov_alloc(&G, (size_t)TB * gm.nrow * R * sizeof(double), 3));
+  COV_TRY(cov_alloc(&DO, (size_t)TB * 2 * ldim * R * sizeof(double), 4));
+  COV_TRY(cov_alloc(&Mc, (size_t)TB * R * sizeof(double), 5));
+  COV_TRY(cov_alloc(&rows, (size_t)TB * gm.nrow * N * sizeof(double), 6));
+  COV_TRY(cov_alloc(&Ms, (size_t)TB * ldim * N * N * sizeof(double), 7));
+  COV_TRY(cov_alloc(&mT, (size_t)TB * sizeof(double), 8));
+  COV_TRY(cov_alloc(&outT, (size_t)TB * ldim * N * 2 * sizeof(double), 9));
+  COV_TRY(cov_alloc(&outM, (size_t)TB * ldim * N * N * sizeof(double), 10));
 
   for (int T0 = 0; T0 < sampT; T0 += TB) {
     const int nb = sampT - T0 < TB ? sampT - T0 : TB;

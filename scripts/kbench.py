@@ -44,3 +44,12 @@ _lib.check(L.expb200_profile_enable(0))
 prof = _lib.profile_read()
 print(f"variant={os.environ.get('EXPB200_DEPOSIT_VARIANT', '0')} n={n} ms/step={ms:.4f} rate={n / ms * 1e3:.4e}")
 print("  " + " ".join(f"{k}={v[1] / steps:.4f}" for k, v in prof.items() if v[2]))
+if os.environ.get("KBENCH_COV"):
+    sampT = int(os.environ["KBENCH_COV"])
+    s.covariance(c, sampT)                      # warm-up (allocations)
+    for rep in range(3):
+        c.event_record(2)
+        s.covariance(c, sampT)
+        c.event_record(3)
+        c.sync()
+        print(f"  sphere covariance sampT={sampT}: {c.event_elapsed_ms(2, 3):.3f} ms (incl. D2H of the result)")
