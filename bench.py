@@ -242,6 +242,10 @@ def run_ours(args):
         raw = bytes(idbuf.cpu().numpy().tobytes())
         comm = C.c_void_p()
         _lib.check(L.expb200_comm_create(local, world, rank, raw, C.byref(comm)))
+        # the 882-double coefficient all-reduce by one kernel over NVLink peer memory (rank-ordered,
+        # bitwise identical on every rank) instead of ncclAllReduce; EXPB200_NO_PEER=1 keeps NCCL
+        if not os.environ.get("EXPB200_NO_PEER"):
+            _lib.connect_peers(comm, dist, world)
 
     def barrier():
         if dist is not None:

@@ -206,6 +206,8 @@ SIGNATURES = {
     "expb200_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "expb200_comm_destroy": (C.c_int, [C.c_void_p]),
     "expb200_allreduce_sum": (C.c_int, [C.c_void_p, c_dp, C.c_size_t, C.c_void_p]),
+    "expb200_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "expb200_comm_peer_connect": (C.c_int, [C.c_void_p, C.c_char_p]),
 }
 
 
@@ -240,3 +242,15 @@ def profile_read():
     tm = (C.c_ulonglong * k)()
     check(L.expb200_profile_read(la, ms, tm))
     return {L.expb200_profile_name(i).decode(): (int(la[i]), float(ms[i]), int(tm[i])) for i in range(k)}
+
+
+def connect_peers(comm, dist, world):
+    """Switch the small all-reduces of `comm` to the peer-memory kernel: gather every rank's
+    IPC handle with torch.distributed (any backend) and connect.  Ranks must share a node."""
+    L = lib()
+    raw = C.create_string_buffer(64)
+    check(L.expb200_comm_peer_handle(comm, raw))
+    got = [None] * world
+    dist.all_gather_object(got, bytes(raw.raw))
+    check(L.expb200_comm_peer_connect(comm, b"".join(got)))
+    dist.barrier()

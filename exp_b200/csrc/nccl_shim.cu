@@ -57,13 +57,101 @@ int fail(Api *a, int rc, const char *what)
   return EXPB200_ENCCL;
 }
 
+// ---------------------------------------------------------------------------
+// The communicator handed out by expb200_comm_create: the NCCL communicator plus,
+// once expb200_comm_peer_connect has run, peer-mapped receive buffers for the small
+// all-reduces of this path (882 doubles for sphereSL at L=6, nmax=18; 234 for the
+// cylinder; 10 per level for the centring pass).  For those NCCL's launch + protocol
+// latency (~50 us) is the whole cost, so they are done by ONE kernel over NVLink peer
+// memory: every rank stores its vector straight into slot [rank] of every peer's buffer
+// (P2P stores through NVSwitch), publishes a sequence number, waits for the others'
+// numbers and adds the world's vectors in rank order -- the result is therefore bitwise
+// identical on every rank and independent of arrival order, which ncclAllReduce does not
+// promise.  Buffers are double-buffered by the parity of the sequence number: a rank can
+// run at most one all-reduce ahead of the slowest (it needs that rank's data to finish).
+// ---------------------------------------------------------------------------
+constexpr int kPeerMaxWorld = 16;
+constexpr size_t kPeerCap = 16384;            // doubles per rank slot
+constexpr uint32_t kCommMagic = 0xb200c033u;
+
+struct PeerPtrs {
+  double *data[kPeerMaxWorld];                // rank r's receive area, [2][world][kPeerCap]
+  unsigned long long *flags[kPeerMaxWorld];   // rank r's flags, [2][world]
+};
+
+struct Comm {
+  uint32_t magic = kCommMagic;
+  void *nccl = nullptr;
+  int device = 0, world = 1, rank = 0;
+  void *local = nullptr;                      // this rank's allocation (flags, then data)
+  void *mapped[kPeerMaxWorld] = {};           // peers' allocations opened through CUDA IPC
+  PeerPtrs P = {};
+  bool connected = false;
+  unsigned long long seq = 0;
+  int *err_host = nullptr, *err_dev = nullptr;   // mapped pinned: set by a kernel that timed out
+};
+
+size_t peer_flag_bytes(int world) { return ((size_t)2 * world * sizeof(unsigned long long) + 255) / 256 * 256; }
+size_t peer_bytes(int world) { return peer_flag_bytes(world) + (size_t)2 * world * kPeerCap * sizeof(double); }
+
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(PeerPtrs P, int world, int rank, double *__restrict__ buf, size_t n,
+                      unsigned long long seq, int *err)
+{
+  const int par = (int)(seq & 1ull), tid = threadIdx.x;
+  // 1. my vector -> slot [par][rank] of every rank (P2P stores; the local one included)
+  for (int r = 0; r < world; r++) {
+    double *dst = P.data[r] + ((size_t)par * world + rank) * kPeerCap;
+    for (size_t i = tid; i < n; i += blockDim.x) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < world) {
+    volatile unsigned long long *f = P.flags[tid] + (size_t)par * world + rank;
+    *f = seq;
+  }
+  // 2. wait until every rank's vector of this sequence number has landed here
+  if (tid < world) {
+    volatile unsigned long long *f = P.flags[rank] + (size_t)par * world + tid;
+    const long long t0 = clock64();
+    while (*f < seq) {
+      if (clock64() - t0 > 8000000000ll) { *err = 1; break; }      // ~4 s: a peer died
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  // 3. sum in rank order (bypassing L1: the data was written by other GPUs)
+  const double *src = P.data[rank] + (size_t)par * world * kPeerCap;
+  for (size_t i = tid; i < n; i += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < world; r++) t += __ldcg(src + (size_t)r * kPeerCap + i);
+    buf[i] = t;
+  }
+}
+
+Comm *as_comm(void *comm)
+{
+  Comm *c = static_cast<Comm *>(comm);
+  return c && c->magic == kCommMagic ? c : nullptr;
+}
+
 } // namespace
 
 int nccl_allreduce_sum_f64(void *comm, double *buf, size_t n, cudaStream_t stream)
 {
+  Comm *c = as_comm(comm);
+  if (!c) { set_error("not an expb200 communicator"); return EXPB200_EINVAL; }
+  if (c->connected && n <= kPeerCap) {
+    if (*c->err_host) { set_error("peer all-reduce timed out waiting for another rank"); return EXPB200_ENCCL; }
+    DeviceGuard g(c->device);       // the stream belongs to the communicator's device
+    c->seq++;
+    peer_allreduce_kernel<<<1, 256, 0, stream>>>(c->P, c->world, c->rank, buf, n, c->seq, c->err_dev);
+    CU_LAUNCH_CHECK();
+    return EXPB200_OK;
+  }
   Api *a = api();
   if (!a) return EXPB200_ENCCL;
-  int rc = a->allreduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, stream);
+  int rc = a->allreduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, stream);
   if (rc) return fail(a, rc, "ncclAllReduce");
   return EXPB200_OK;
 }
@@ -87,28 +175,88 @@ int expb200_comm_unique_id(char id[128])
 int expb200_comm_create(int device, int nranks, int rank, const char id[128], void **comm)
 {
   REQUIRE(id && comm, "NULL argument");
+  REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "rank %d of %d", rank, nranks);
   Api *a = api();
   if (!a) return EXPB200_ENCCL;
   DeviceGuard g(device);
   uid128 u;
   memcpy(u.bytes, id, 128);
   typedef int (*fn)(void **, int, uid128, int);
-  int rc = ((fn)a->initrank)(comm, nranks, u, rank);
+  void *nc = nullptr;
+  int rc = ((fn)a->initrank)(&nc, nranks, u, rank);
   if (rc) return fail(a, rc, "ncclCommInitRank");
+  Comm *c = new Comm;
+  c->nccl = nc; c->device = device; c->world = nranks; c->rank = rank;
+  *comm = c;
   return EXPB200_OK;
 }
 
 int expb200_comm_destroy(void *comm)
 {
+  Comm *c = as_comm(comm);
+  if (!c) return EXPB200_OK;
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; r++)
+    if (c->mapped[r]) cudaIpcCloseMemHandle(c->mapped[r]);
+  if (c->local) cudaFree(c->local);
+  if (c->err_host) cudaFreeHost(c->err_host);
   Api *a = api();
-  if (!a) return EXPB200_ENCCL;
-  if (comm) a->destroy(comm);
+  if (a && c->nccl) a->destroy(c->nccl);
+  c->magic = 0;
+  delete c;
   return EXPB200_OK;
 }
 
 int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream)
 {
   return nccl_allreduce_sum_f64(comm, device_buf, n, (cudaStream_t)stream);
+}
+
+// Peer-memory all-reduce, step 1: allocate this rank's receive buffer and export it
+// (cudaIpcMemHandle_t, 64 bytes).  The host exchanges the handles of all ranks (any
+// transport: the tests use torch.distributed all_gather) and calls _peer_connect.
+int expb200_comm_peer_handle(void *comm, char handle[64])
+{
+  Comm *c = as_comm(comm);
+  REQUIRE(c && handle, "bad argument");
+  REQUIRE(c->world <= kPeerMaxWorld, "peer all-reduce supports up to %d ranks", kPeerMaxWorld);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard g(c->device);
+  if (!c->local) {
+    CU_TRY(cudaMalloc(&c->local, peer_bytes(c->world)));
+    CU_TRY(cudaMemset(c->local, 0, peer_bytes(c->world)));
+    CU_TRY(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
+    *c->err_host = 0;
+    CU_TRY(cudaHostGetDevicePointer(&c->err_dev, c->err_host, 0));
+  }
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, c->local));
+  memcpy(handle, &h, 64);
+  return EXPB200_OK;
+}
+
+// step 2: handles[nranks][64] in rank order.  Collective in effect: every rank must have
+// zeroed its buffer (done in _peer_handle) before any rank starts an all-reduce, which
+// the handle exchange itself guarantees.
+int expb200_comm_peer_connect(void *comm, const char *handles)
+{
+  Comm *c = as_comm(comm);
+  REQUIRE(c && handles && c->local, "call expb200_comm_peer_handle first");
+  DeviceGuard g(c->device);
+  for (int r = 0; r < c->world; r++) {
+    void *base = c->local;
+    if (r != c->rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + (size_t)r * 64, 64);
+      CU_TRY(cudaIpcOpenMemHandle(&c->mapped[r], h, cudaIpcMemLazyEnablePeerAccess));
+      base = c->mapped[r];
+    }
+    c->P.flags[r] = static_cast<unsigned long long *>(base);
+    c->P.data[r] = reinterpret_cast<double *>(static_cast<char *>(base) + peer_flag_bytes(c->world));
+  }
+  c->connected = true;
+  return EXPB200_OK;
 }
 
 } // extern "C"

@@ -129,7 +129,7 @@ class Sphere:
 
     def level_coefficients(self, which: str, mlevel: int):
         out = np.empty((self.nrow, self.nmax))
-        w = {"N": 0, "L": 1, "differ": 2}[which]
+        w = {"N": 0, "L": 1, "differ": 2, "use": 3, "accum": 4}[which]    # use: installed for the force
         check(_lib.lib().expb200_sphere_get_level_coefficients(self._h, w, mlevel, out.ctypes.data_as(c_dp)))
         return out
 

@@ -317,6 +317,14 @@ int expb200_comm_unique_id(char id[128]);                       /* ncclGetUnique
 int expb200_comm_create(int device, int nranks, int rank, const char id[128], void **comm);
 int expb200_comm_destroy(void *comm);
 int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream);
+/* Optional: all-reduces of up to 16384 doubles (every one on this path) done by one kernel
+ * over NVLink peer memory instead of ncclAllReduce: each rank stores its vector into every
+ * peer's receive buffer, then adds the world's vectors in rank order (bitwise identical on
+ * all ranks).  _peer_handle exports this rank's buffer (a cudaIpcMemHandle_t); the host
+ * gathers the handles of all ranks, in rank order, and passes them to _peer_connect.
+ * Ranks must be processes on one node.  Without these calls NCCL is used. */
+int expb200_comm_peer_handle(void *comm, char handle[64]);
+int expb200_comm_peer_connect(void *comm, const char *handles /* [nranks][64] */);
 
 /* ------------------------------------------------------------------------
  * Instrumentation (what bench.py reads): launch counters are always on; event

@@ -33,7 +33,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_per, nsteps, multistep, out):
+def _worker(rank, world, port, n_per, nsteps, multistep, out, peer):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -56,6 +56,8 @@ def _worker(rank, world, port, n_per, nsteps, multistep, out):
     dist.broadcast(idt, 0)
     comm = C.c_void_p()
     _lib.check(L.expb200_comm_create(rank, world, rank, bytes(idt.numpy().tobytes()), C.byref(comm)))
+    if peer:        # the small all-reduces by one kernel over NVLink peer memory instead of NCCL
+        _lib.connect_peers(comm, dist, world)
 
     tab = get_table("hernquist", 4, 10)
     pos, vel, mass = ics.hernquist_halo(n_per * world, lo=rank * n_per, hi=(rank + 1) * n_per, seed=9)
@@ -71,7 +73,7 @@ def _worker(rank, world, port, n_per, nsteps, multistep, out):
         c.zero_pot_acc()
         s.get_acceleration_and_potential(c)
         s.steps(c, 2.0e-3, nsteps, comm=comm)
-        coef = np.zeros((s.nrow, s.nmax))
+        coef = s.level_coefficients("use", 0)
     else:
         stp = SphereStepper(c, s, 0.02, multistep, comm=comm, dynfracV=0.02, dynfracA=0.06)
         stp.initialize()
@@ -114,15 +116,15 @@ def _single(n, nsteps, multistep):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("multistep", [0, 3])
-def test_two_gpus_match_one(tmp_path, multistep):
+@pytest.mark.parametrize("multistep,peer", [(0, False), (3, False), (0, True), (3, True)])
+def test_two_gpus_match_one(tmp_path, multistep, peer):
     if _ndev() < 2:
         pytest.skip("needs two CUDA devices")
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import acc_rel_err
     world, n_per, nsteps = 2, 40000, 3
-    mp.spawn(_worker, args=(world, _free_port(), n_per, nsteps, multistep, str(tmp_path)),
+    mp.spawn(_worker, args=(world, _free_port(), n_per, nsteps, multistep, str(tmp_path), peer),
              nprocs=world, join=True)
     r = [np.load(os.path.join(tmp_path, f"rank{k}.npz")) for k in range(world)]
     one, coef = _single(n_per * world, nsteps, multistep)
@@ -135,6 +137,8 @@ def test_two_gpus_match_one(tmp_path, multistep):
     # the level kernel is bit-exact for identical inputs; here the accelerations differ by the
     # summation order of the all-reduce (1e-15), so allow a borderline particle or two
     assert int((lev != one["level"]).sum()) <= 2
+    if peer:     # the peer all-reduce adds in rank order on every rank: bitwise the same result
+        assert r[0]["coef"].tobytes() == r[1]["coef"].tobytes()
     if multistep:
         assert r[0]["coef"].tobytes() == r[1]["coef"].tobytes()   # same on every rank
         d = r[0]["coef"] - coef
