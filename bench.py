@@ -228,6 +228,7 @@ def run_ours(args):
 
     dist = None
     comm = None
+    peer = False
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -245,7 +246,11 @@ def run_ours(args):
         # the 882-double coefficient all-reduce by one kernel over NVLink peer memory (rank-ordered,
         # bitwise identical on every rank) instead of ncclAllReduce; EXPB200_NO_PEER=1 keeps NCCL
         if not os.environ.get("EXPB200_NO_PEER"):
-            _lib.connect_peers(comm, dist, world)
+            try:
+                _lib.connect_peers(comm, dist, world)
+                peer = True
+            except Exception as e:          # e.g. no P2P between two devices: NCCL does it
+                print(f"[bench] peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
 
     def barrier():
         if dist is not None:
@@ -375,7 +380,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, world),
+        "config": dict(workload_config(args, world),
+                       allreduce=("none" if world == 1 else
+                                  "one kernel over NVLink peer memory, rank-ordered sum" if peer else "ncclAllReduce")),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.e2e_steps,
