@@ -80,7 +80,29 @@ def _prepare(mass, pos, center, rot, posvelrows):
     return m, p, ctr
 
 
-class SphericalSL:
+class _ComponentCache:
+    """One device-resident particle store per basis object, reused across createFromArray /
+    getFields / getAccel calls: a sweep over snapshots (BASELINE configs[4]) would otherwise pay a
+    dozen cudaMalloc/cudaFree pairs of O(n) per call, which costs more than the kernels."""
+
+    def _component(self, n):
+        n = max(int(n), 1)
+        c = getattr(self, "_comp", None)
+        if c is None or c.capacity < n:
+            if c is not None:
+                c.close()
+            c = Component(max(n, 1024), device=self.device)
+            self._comp = c
+        return c
+
+    def close(self):
+        c = getattr(self, "_comp", None)
+        if c is not None:
+            c.close()
+            self._comp = None
+
+
+class SphericalSL(_ComponentCache):
     """BasisClasses::SphericalSL with the SLGridSph tables given explicitly."""
 
     def __init__(self, table, *, scale=1.0, rmin=None, rmax=None, NO_L0=False, NO_L1=False,
@@ -103,14 +125,11 @@ class SphericalSL:
                         roundrobin=True, posvelrows=False):
         """BiorthBasis::createFromArray: coefficients of the particle set (mass[n], pos[n,3])."""
         m, p, ctr = _prepare(mass, pos, center, rot, posvelrows)
-        c = Component(max(len(p), 1), device=self.device)
-        try:
-            c.upload(p, None, m)
-            c.set_center(ctr)
-            self.expcoef = self._sph.determine_coefficients(c)
-            self.used = int(self._sph.used)
-        finally:
-            c.close()
+        c = self._component(len(p))
+        c.upload(p, None, m)
+        c.set_center(ctr)
+        self.expcoef = self._sph.determine_coefficients(c)
+        self.used = int(self._sph.used)
         self.coefctr = np.asarray(center, dtype=np.float64)
         self.coefret = self._load_coefs(time)
         return self.coefret
@@ -144,16 +163,13 @@ class SphericalSL:
 
     # ---- evaluation -------------------------------------------------------------------
     def _eval(self, sphere, coef, pts):
-        c = Component(max(len(pts), 1), device=self.device)
-        try:
-            c.upload(pts, None, np.ones(len(pts)))
-            c.set_center(self.coefctr)
-            sphere.set_coefficients(coef)
-            c.zero_pot_acc()
-            sphere.get_acceleration_and_potential(c)
-            out = c.download(pos=False, vel=False)
-        finally:
-            c.close()
+        c = self._component(len(pts))
+        c.upload(pts, None, np.ones(len(pts)))
+        c.set_center(self.coefctr)
+        sphere.set_coefficients(coef)
+        c.zero_pot_acc()
+        sphere.get_acceleration_and_potential(c)
+        out = c.download(pos=False, vel=False)
         return out["acc"], out["pot"]
 
     def getAccel(self, x, y=None, z=None):
@@ -194,7 +210,7 @@ class SphericalSL:
         return [float(v) for v in out[:, 0]] if scalar else out
 
 
-class Cylindrical:
+class Cylindrical(_ComponentCache):
     """BasisClasses::Cylindrical with the EmpCylSL grids given explicitly (exp_b200.cyltable)."""
 
     def __init__(self, table, *, rcylmax=20.0, acyl=None, device=0, **flags):
@@ -212,14 +228,11 @@ class Cylindrical:
     def createFromArray(self, mass, pos, time=0.0, center=(0.0, 0.0, 0.0), rot=None,
                         roundrobin=True, posvelrows=False):
         m, p, ctr = _prepare(mass, pos, center, rot, posvelrows)
-        c = Component(max(len(p), 1), device=self.device)
-        try:
-            c.upload(p, None, m)
-            c.set_center(ctr)
-            self.cos, self.sin = self._cyl.determine_coefficients(c)
-            self.used, self.cylmass = int(self._cyl.used), float(self._cyl.cylmass)
-        finally:
-            c.close()
+        c = self._component(len(p))
+        c.upload(p, None, m)
+        c.set_center(ctr)
+        self.cos, self.sin = self._cyl.determine_coefficients(c)
+        self.used, self.cylmass = int(self._cyl.used), float(self._cyl.cylmass)
         self.coefctr = np.asarray(center, dtype=np.float64)
         self.coefret = CylStruct(self.mmax, self.nmax, float(time), self.cos + 1j * self.sin,
                                  tuple(self.coefctr))          # Cylindrical::load_coefs :1864-1895
@@ -236,14 +249,11 @@ class Cylindrical:
 
     def getAccel(self, x, y=None, z=None):
         pts = _points(x, y, z)
-        c = Component(max(len(pts), 1), device=self.device)
-        try:
-            c.upload(pts, None, np.ones(len(pts)))
-            c.set_center(self.coefctr)
-            self._cyl.set_coefficients(self.cos, self.sin, self.cylmass)
-            c.zero_pot_acc()
-            self._cyl.get_acceleration_and_potential(c)
-            out = c.download(pos=False, vel=False)
-        finally:
-            c.close()
+        c = self._component(len(pts))
+        c.upload(pts, None, np.ones(len(pts)))
+        c.set_center(self.coefctr)
+        self._cyl.set_coefficients(self.cos, self.sin, self.cylmass)
+        c.zero_pot_acc()
+        self._cyl.get_acceleration_and_potential(c)
+        out = c.download(pos=False, vel=False)
         return out["acc"]
