@@ -46,7 +46,7 @@ def _hbm_peak():
 HBM_PEAK_GBS = _hbm_peak()
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # capture of this workload (profiles/r01_ncu_*): bytes per launch at 1e7 particles
-NCU_TRAFFIC = {"force": 1.645e9, "deposit": 7.42e8}   # profiles/r01e_ncu_full_summary.txt
+NCU_TRAFFIC = {"force": 1.645e9, "deposit": 7.42e8}   # profiles/r01f_ncu_full_summary.txt
 
 METRIC = "particle-steps/sec (coef+force+kick-drift) sphereSL"
 UNIT = "particle-steps/s"
