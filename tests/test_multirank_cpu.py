@@ -4,7 +4,11 @@
 (2) coefficients are additive over shards, so summing per-rank vectors with one
     all-reduce reproduces the single-rank result (the reference's MPI_Allreduce,
     src/SphericalBasis.cc:864-903, replaced on the GPU by one NCCL all-reduce);
-(3) forces computed per shard from the reduced coefficients equal the global ones.
+(3) forces computed per shard from the reduced coefficients equal the global ones;
+(4) the centring pass (Component::fix_positions): per-level {mass, m*pos, m*vel, m*acc} rows are
+    additive over shards, reduced the way the peer-memory kernel does it -- every rank gathers
+    all ranks' vectors and adds them in rank order, so the result is bitwise the same on
+    every rank -- and give the single-rank centre of mass.
 """
 import os
 import socket
@@ -48,8 +52,17 @@ def _worker(rank, world, port, n_per, out):
     u = torch.tensor([used])
     dist.all_reduce(u)
     O.sph_accel(g, P, S, t.numpy())
+    # (4) centring sums with levels; rank-ordered reduction (what peer_allreduce_kernel does)
+    multistep = 2
+    S.level[:] = (np.arange(rank * n_per, (rank + 1) * n_per) % (multistep + 1)).astype(np.uint32)
+    lev, _ = O.fix_positions(S, 0, multistep)
+    parts = [torch.zeros_like(torch.from_numpy(lev)) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(lev.copy()))
+    tot = np.zeros_like(lev)
+    for q in range(world):
+        tot += parts[q].numpy()
     np.savez(os.path.join(out, f"rank{rank}.npz"), pos=pos, coef=t.numpy(), used=u.numpy(),
-             acc=S.acc, pot=S.pot)
+             acc=S.acc, pot=S.pot, com_lev=tot)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,3 +93,12 @@ def test_two_ranks_gloo(tmp_path):
     acc = np.concatenate([r[0]["acc"], r[1]["acc"]])
     an = np.linalg.norm(S.acc, axis=1)
     assert (np.linalg.norm(acc - S.acc, axis=1) / an).max() < 1e-11              # (3)
+    # (4)
+    multistep = 2
+    S.level[:] = (np.arange(n_per * world) % (multistep + 1)).astype(np.uint32)
+    lev, out = O.fix_positions(S, 0, multistep)
+    assert r[0]["com_lev"].tobytes() == r[1]["com_lev"].tobytes()                # rank-ordered sum
+    scale = np.abs(lev).max() + 1e-300
+    assert np.abs(r[0]["com_lev"] - lev).max() <= 1e-13 * scale
+    tot = r[0]["com_lev"].sum(axis=0)
+    assert np.abs(tot[1:] / tot[0] - out[1:]).max() <= 1e-12 * max(1.0, np.abs(out[1:]).max())
