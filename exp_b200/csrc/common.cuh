@@ -181,6 +181,10 @@ struct expb200_component_s {
   // staging for (un)packing host AoS arrays
   double *stage = nullptr;              // 7*chunk doubles
   size_t stage_chunk = 0;
+  // pinned bounce buffers (2 x 7 x 256K doubles) for uploads from pageable host arrays, and the
+  // event that says buffer b's host->device copy has completed (allocated on first use)
+  double *hstage = nullptr;
+  cudaEvent_t hstage_free[2] = {nullptr, nullptr};
 
   // sort state: perm[cur] = particle slots ordered by key, keys[cur] sorted keys
   uint32_t *keys[2] = {nullptr, nullptr};

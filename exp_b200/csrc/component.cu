@@ -10,6 +10,9 @@
 #include "nccl_shim.h"
 
 #include <algorithm>
+#include <cstring>
+#include <thread>
+#include <tuple>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -58,6 +61,7 @@ bool stream_is_live(cudaStream_t st)
 namespace {
 
 constexpr size_t kStageChunk = 1u << 20;   // particles per staging chunk
+constexpr size_t kBounceChunk = 1u << 18;  // particles per pinned bounce buffer (14 MB)
 constexpr int kStageDoubles = 10;          // pos3 vel3 acc3 pot1 (download) / pos3 vel3 mass1 (upload)
 
 // ---------------------------------------------------------------------------
@@ -582,6 +586,8 @@ int expb200_component_destroy(expb200_component c)
   for (int k = 0; k < 2; k++) { cudaFree(c->keys[k]); cudaFree(c->perm[k]); }
   cudaFree(c->hist); cudaFree(c->rank); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats); cudaFree(c->com_part);
   cudaEventDestroy(c->copy_done);
+  if (c->hstage) cudaFreeHost(c->hstage);
+  for (int k = 0; k < 2; k++) if (c->hstage_free[k]) cudaEventDestroy(c->hstage_free[k]);
   stream_register(c->stream, false);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
@@ -609,6 +615,40 @@ int expb200_component_set_count(expb200_component c, size_t n)
 // Upload [first, first+count): H2D on the copy stream into one of two staging
 // buffers, pack on the compute stream; the two alternate so that the copy of
 // chunk k+1 overlaps the pack of chunk k.
+namespace {
+// true for ordinary (pageable) host memory: neither cudaHostAlloc'ed nor cudaHostRegister'ed
+bool is_pageable(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy split over a few host threads: one thread moves ~10 GB/s, the PCIe link 50
+void parallel_copy(const std::vector<std::tuple<double *, const double *, size_t>> &jobs)
+{
+  static const unsigned nthr = [] {
+    unsigned h = std::thread::hardware_concurrency();
+    return h >= 8 ? 8u : h >= 2 ? h : 1u;
+  }();
+  size_t total = 0;
+  for (auto &j : jobs) total += std::get<2>(j);
+  if (nthr == 1 || total < (1u << 16)) {
+    for (auto &j : jobs) memcpy(std::get<0>(j), std::get<1>(j), std::get<2>(j) * sizeof(double));
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nthr; t++)
+    th.emplace_back([&, t] {
+      for (auto &j : jobs) {
+        const size_t n = std::get<2>(j), lo = n * t / nthr, hi = n * (t + 1) / nthr;
+        if (hi > lo) memcpy(std::get<0>(j) + lo, std::get<1>(j) + lo, (hi - lo) * sizeof(double));
+      }
+    });
+  for (auto &x : th) x.join();
+}
+} // namespace
+
 int expb200_component_upload_range(expb200_component c, size_t first, size_t count,
                                    const double *pos, const double *vel, const double *mass)
 {
@@ -616,16 +656,42 @@ int expb200_component_upload_range(expb200_component c, size_t first, size_t cou
   REQUIRE(first + count <= c->cap, "range [%zu,%zu) exceeds capacity %zu", first, first + count, c->cap);
   DeviceGuard g(c->device);
   const size_t ch = c->stage_chunk;
-  int b = 0;
+  // Pageable host arrays (numpy arrays, the std::vectors of the host driver): a cudaMemcpy from
+  // them is staged by the driver at ~10 GB/s.  Bounce them through our own pinned buffers,
+  // filled by several host threads while the previous chunk is on the wire.
+  const bool bounce = count >= 4096 && (is_pageable(pos) || is_pageable(mass) || (vel && is_pageable(vel)));
+  const size_t hs = ch < kBounceChunk ? ch : kBounceChunk;      // particles per pinned buffer
+  if (bounce && !c->hstage) {
+    CU_TRY(cudaHostAlloc(&c->hstage, 2 * hs * 7 * sizeof(double), cudaHostAllocDefault));
+    for (int k = 0; k < 2; k++) CU_TRY(cudaEventCreateWithFlags(&c->hstage_free[k], cudaEventDisableTiming));
+  }
+  int b = 0, hb = 0;
   for (size_t off = 0; off < count; off += ch, b ^= 1) {
     size_t m = count - off < ch ? count - off : ch;
     double *s = c->stage + (size_t)b * ch * kStageDoubles;
     double *spos = s, *svel = s + 3 * ch, *smass = s + 6 * ch;
     // the pack kernel that last read this staging buffer must be done
     CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0));
-    CU_TRY(cudaMemcpyAsync(spos, pos + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
-    if (vel) CU_TRY(cudaMemcpyAsync(svel, vel + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
-    CU_TRY(cudaMemcpyAsync(smass, mass + off, m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    if (bounce) {
+      for (size_t so = 0; so < m; so += hs, hb ^= 1) {
+        const size_t sm = m - so < hs ? m - so : hs;
+        double *h = c->hstage + (size_t)hb * hs * 7;
+        CU_TRY(cudaEventSynchronize(c->hstage_free[hb]));     // its last copy has left the host
+        std::vector<std::tuple<double *, const double *, size_t>> jobs;
+        jobs.emplace_back(h, pos + 3 * (off + so), 3 * sm);
+        if (vel) jobs.emplace_back(h + 3 * hs, vel + 3 * (off + so), 3 * sm);
+        jobs.emplace_back(h + 6 * hs, mass + off + so, sm);
+        parallel_copy(jobs);
+        CU_TRY(cudaMemcpyAsync(spos + 3 * so, h, 3 * sm * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        if (vel) CU_TRY(cudaMemcpyAsync(svel + 3 * so, h + 3 * hs, 3 * sm * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        CU_TRY(cudaMemcpyAsync(smass + so, h + 6 * hs, sm * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        CU_TRY(cudaEventRecord(c->hstage_free[hb], c->copy_stream));
+      }
+    } else {
+      CU_TRY(cudaMemcpyAsync(spos, pos + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+      if (vel) CU_TRY(cudaMemcpyAsync(svel, vel + 3 * off, 3 * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+      CU_TRY(cudaMemcpyAsync(smass, mass + off, m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    }
     cudaEvent_t ev;
     CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU_TRY(cudaEventRecord(ev, c->copy_stream));
