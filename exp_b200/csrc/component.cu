@@ -649,6 +649,16 @@ void parallel_copy(const std::vector<std::tuple<double *, const double *, size_t
 }
 } // namespace
 
+namespace {
+int ensure_bounce(expb200_component_s *c, size_t hs)
+{
+  if (c->hstage) return EXPB200_OK;
+  CU_TRY(cudaHostAlloc(&c->hstage, 2 * hs * kStageDoubles * sizeof(double), cudaHostAllocDefault));
+  for (int k = 0; k < 2; k++) CU_TRY(cudaEventCreateWithFlags(&c->hstage_free[k], cudaEventDisableTiming));
+  return EXPB200_OK;
+}
+} // namespace
+
 int expb200_component_upload_range(expb200_component c, size_t first, size_t count,
                                    const double *pos, const double *vel, const double *mass)
 {
@@ -661,10 +671,7 @@ int expb200_component_upload_range(expb200_component c, size_t first, size_t cou
   // filled by several host threads while the previous chunk is on the wire.
   const bool bounce = count >= 4096 && (is_pageable(pos) || is_pageable(mass) || (vel && is_pageable(vel)));
   const size_t hs = ch < kBounceChunk ? ch : kBounceChunk;      // particles per pinned buffer
-  if (bounce && !c->hstage) {
-    CU_TRY(cudaHostAlloc(&c->hstage, 2 * hs * 7 * sizeof(double), cudaHostAllocDefault));
-    for (int k = 0; k < 2; k++) CU_TRY(cudaEventCreateWithFlags(&c->hstage_free[k], cudaEventDisableTiming));
-  }
+  if (bounce) { int rc = ensure_bounce(c, hs); if (rc) return rc; }
   int b = 0, hb = 0;
   for (size_t off = 0; off < count; off += ch, b ^= 1) {
     size_t m = count - off < ch ? count - off : ch;
@@ -675,7 +682,7 @@ int expb200_component_upload_range(expb200_component c, size_t first, size_t cou
     if (bounce) {
       for (size_t so = 0; so < m; so += hs, hb ^= 1) {
         const size_t sm = m - so < hs ? m - so : hs;
-        double *h = c->hstage + (size_t)hb * hs * 7;
+        double *h = c->hstage + (size_t)hb * hs * kStageDoubles;
         CU_TRY(cudaEventSynchronize(c->hstage_free[hb]));     // its last copy has left the host
         std::vector<std::tuple<double *, const double *, size_t>> jobs;
         jobs.emplace_back(h, pos + 3 * (off + so), 3 * sm);
@@ -775,6 +782,26 @@ int expb200_component_download_range(expb200_component c, size_t first, size_t c
     CU_TRY(cudaEventCreateWithFlags(&unpacked[k], cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
   }
+  // pageable destinations: bounce through the pinned buffers (see upload_range)
+  const bool bounce = count >= 4096 && ((pos && is_pageable(pos)) || (vel && is_pageable(vel)) ||
+                                        (acc && is_pageable(acc)) || (pot && is_pageable(pot)));
+  const size_t hs = ch < kBounceChunk ? ch : kBounceChunk;
+  if (bounce) { int rc = ensure_bounce(c, hs); if (rc) return rc; }
+  int hb = 0;
+  double *pend_h = nullptr;
+  size_t pend_off = 0, pend_n = 0;
+  cudaEvent_t pend_ev = nullptr;
+  auto drain = [&]() -> int {          // the pending sub-chunk: wait for its copy, hand it out
+    CU_TRY(cudaEventSynchronize(pend_ev));
+    std::vector<std::tuple<double *, const double *, size_t>> jobs;
+    if (pos) jobs.emplace_back(pos + 3 * pend_off, pend_h, 3 * pend_n);
+    if (vel) jobs.emplace_back(vel + 3 * pend_off, pend_h + 3 * hs, 3 * pend_n);
+    if (acc) jobs.emplace_back(acc + 3 * pend_off, pend_h + 6 * hs, 3 * pend_n);
+    if (pot) jobs.emplace_back(pot + pend_off, pend_h + 9 * hs, pend_n);
+    parallel_copy(jobs);
+    pend_n = 0;
+    return EXPB200_OK;
+  };
   // order after any upload staging still in flight
   CU_TRY(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
   size_t round = 0;
@@ -792,12 +819,29 @@ int expb200_component_download_range(expb200_component c, size_t first, size_t c
     CU_LAUNCH_CHECK();
     CU_TRY(cudaEventRecord(unpacked[b], c->stream));
     CU_TRY(cudaStreamWaitEvent(c->copy_stream, unpacked[b], 0));
+    if (bounce) {
+      // device staging -> pinned buffer (async); the previous sub-chunk is copied out to the
+      // caller's pageable arrays by the host threads meanwhile
+      for (size_t so = 0; so < m; so += hs, hb ^= 1) {
+        const size_t sm = m - so < hs ? m - so : hs;
+        double *h = c->hstage + (size_t)hb * hs * kStageDoubles;
+        if (pos) CU_TRY(cudaMemcpyAsync(h, spos + 3 * so, 3 * sm * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        if (vel) CU_TRY(cudaMemcpyAsync(h + 3 * hs, svel + 3 * so, 3 * sm * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        if (acc) CU_TRY(cudaMemcpyAsync(h + 6 * hs, sacc + 3 * so, 3 * sm * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        if (pot) CU_TRY(cudaMemcpyAsync(h + 9 * hs, spot + so, sm * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        CU_TRY(cudaEventRecord(c->hstage_free[hb], c->copy_stream));
+        if (pend_n) { int rc = drain(); if (rc) return rc; }
+        pend_h = h; pend_off = off + so; pend_n = sm; pend_ev = c->hstage_free[hb];
+      }
+    } else {
     if (pos) CU_TRY(cudaMemcpyAsync(pos + 3 * off, spos, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
     if (vel) CU_TRY(cudaMemcpyAsync(vel + 3 * off, svel, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
     if (acc) CU_TRY(cudaMemcpyAsync(acc + 3 * off, sacc, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
     if (pot) CU_TRY(cudaMemcpyAsync(pot + off, spot, m * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     CU_TRY(cudaEventRecord(copied[b], c->copy_stream));
   }
+  if (pend_n) { int rc = drain(); if (rc) return rc; }
   CU_TRY(cudaStreamSynchronize(c->copy_stream));
   // later uploads must not overwrite staging before these copies finished (they have)
   CU_TRY(cudaEventRecord(c->copy_done, c->stream));
