@@ -129,3 +129,46 @@ def exponential_disk(ntot: int, lo: int = 0, hi: int | None = None, seed: int = 
         return pos, vel
 
     return _assemble(gen, lo, hi, mass, ntot)
+
+
+def table_model_halo(r, rho, m, u, n: int, seed: int = 11):
+    """Equilibrium realisation of a tabulated spherical model (columns r, rho, M(<r), U(r) of a
+    reference-format SLGridSph.model file; the job of the reference's `gensph`,
+    utils/ICs): radii from the mass profile, isotropic velocities from the Eddington
+    distribution function f(E) of (rho, U).  Equal masses m_tot / n."""
+    r, rho, m, u = (np.asarray(a, dtype=np.float64) for a in (r, rho, m, u))
+    rng = np.random.Generator(np.random.Philox(key=[seed, 0]))
+    psi = -(u - u[-1])                       # relative potential, 0 at the truncation radius
+    # rho(psi): psi decreases with r; work on increasing psi
+    ps, rh = psi[::-1], rho[::-1]
+    ps, keep = np.unique(ps, return_index=True)
+    rh = rh[keep]
+    drho = np.gradient(rh, ps)
+    # G(e) = int_0^e rho'(psi) dpsi / sqrt(e - psi) = 2 int_0^sqrt(e) rho'(e - t^2) dt
+    eg = np.linspace(0.0, ps[-1], 2000)
+    tt = np.linspace(0.0, 1.0, 400)
+    G = np.empty_like(eg)
+    for k, e in enumerate(eg):
+        t = tt * math.sqrt(e)
+        G[k] = 2.0 * np.trapezoid(np.interp(e - t * t, ps, drho), t) if e > 0 else 0.0
+    f = np.maximum(np.gradient(G, eg), 0.0)           # up to the constant 1/(sqrt(8) pi^2)
+    # radii: inverse of M(r)
+    rr = np.interp(rng.uniform(m[0], m[-1], n), m, r)
+    pr = np.interp(rr, r, psi)
+    # speeds: pdf(v) ~ v^2 f(psi - v^2/2) on [0, sqrt(2 psi)], inverted on a per-particle grid
+    s = np.linspace(0.0, 1.0, 257)[None, :]
+    v = s * np.sqrt(2.0 * pr)[:, None]
+    pdf = v * v * np.interp(pr[:, None] - 0.5 * v * v, eg, f)
+    cdf = np.cumsum(0.5 * (pdf[:, 1:] + pdf[:, :-1]), axis=1)
+    cdf = np.concatenate([np.zeros((n, 1)), cdf], axis=1)
+    tot = cdf[:, -1:]
+    q = rng.uniform(0.0, 1.0, n)[:, None] * tot
+    idx = np.clip((cdf < q).sum(axis=1), 1, 256)
+    ar = np.arange(n)
+    c0, c1 = cdf[ar, idx - 1], cdf[ar, idx]
+    w = np.where(c1 > c0, (q[:, 0] - c0) / np.maximum(c1 - c0, 1e-300), 0.5)
+    speed = v[ar, idx - 1] + w * (v[ar, idx] - v[ar, idx - 1])
+    pos = rr[:, None] * _isotropic(rng, n)
+    vel = speed[:, None] * _isotropic(rng, n)
+    mass = np.full(n, m[-1] / n)
+    return pos, vel, mass

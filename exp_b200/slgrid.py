@@ -95,6 +95,12 @@ class TableModel:
         a = np.asarray(rows)
         self.r, self.rho, self.m, self.u = a.T
 
+    @classmethod
+    def from_arrays(cls, r, rho, m, u):
+        self = cls.__new__(cls)
+        self.r, self.rho, self.m, self.u = (np.asarray(a, dtype=np.float64) for a in (r, rho, m, u))
+        return self
+
     def pot(self, r):
         return np.interp(r, self.r, self.u)
 

@@ -8,12 +8,21 @@
  * --impl reference legs may load it; the product (exp_b200/, libexpb200.so)
  * never does.
  *
- * PARITY UNPINNED: the reference ships no golden vectors for this path
- *  and cannot be built here (needs Eigen3, MPI, HDF5,
- * gfortran).  Exception: oracle/_ref/libexpref_basis.so compiles the
- * reference's own src/Basis.cc (Legendre / trig recursions) against shim
- * headers and is used to pin orc_legendre_R / orc_dlegendre_R /
- * orc_sinecosine_R bit-for-bit (tests/test_oracle_ref.py).
+ * PARITY PINNED to the reference's own code: the reference cannot be built as a whole here
+ * (needs Eigen3, MPI, HDF5, gfortran), but its hot-path member functions compile on their
+ * own.  oracle/ref_extract.py cuts them from /root/reference where they lie (into the
+ * git-ignored oracle/_ref/gen/), oracle/ref_path_wrap.cc compiles them unmodified against
+ * shim declarations (oracle/ref_shim/pathshim.H) into oracle/_ref/libexpref_path.so, and
+ * tests/test_oracle_ref.py checks this restatement against them BIT FOR BIT: Basis
+ * recursions, SLGridSph maps/get_pot/get_force/get_dens, the factorial table,
+ * SphericalBasis::determine_coefficients_thread (+ pcavar/pcaeof) and
+ * determine_acceleration_and_potential_thread, EmpCylSL r_to_xi/z_to_y/get_pot/accumulate/
+ * accumulated_eval (the covar branch to 1e-14: Eigen expression order), incr_position/
+ * incr_velocity threads, adjust_multistep_level_thread.  The reference's own N-body test case
+ * (tests/Halo: SLGridSph.model, Lmax=2 nmax=10 numr=4000 multistep=4, 2T/VC check) runs from
+ * tests/golden/halo_fixture.npz (tests/test_halo_reference_case.py).  Not pinned (restated
+ * only): the Cylinder:: thread wrappers around EmpCylSL (orientation, erf blend), the
+ * multistep difference tables, fix_positions, and the pyEXP twins (oracle/pyexp_oracle.py).
  *
  * All arrays are plain row-major C arrays.  Coefficient layout is the
  * reference's: row index = l*l + {0 (m=0), 2m-1 (cos), 2m (sin)}, nmax

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  Never imported by exp_b200/.
-PARITY UNPINNED except for the Legendre/trig recursions (see exp_oracle.h).
+Pinned bit for bit to the reference's own member functions compiled in place
+(oracle/_ref/libexpref_path.so, tests/test_oracle_ref.py; see exp_oracle.h).
 """
 from __future__ import annotations
 
@@ -28,8 +29,14 @@ def build(force: bool = False) -> None:
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(("_oracle.cc", ".h"))]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
-    if force or stale or (os.path.isdir("/root/reference") and
-                          not os.path.exists(os.path.join(_HERE, "_ref", "libexpref_basis.so"))):
+    if os.path.isdir("/root/reference"):
+        # the reference's own code compiled in place (only in the build container)
+        refs = [os.path.join(_HERE, "_ref", f) for f in ("libexpref_basis.so", "libexpref_path.so")]
+        rsrc = [os.path.join(_HERE, f) for f in ("ref_path_wrap.cc", "ref_extract.py", "ref_basis_wrap.cc")]
+        rsrc += [os.path.join(_HERE, "ref_shim", f) for f in os.listdir(os.path.join(_HERE, "ref_shim"))]
+        stale = stale or any(not os.path.exists(r) for r in refs) or \
+            max(os.path.getmtime(s) for s in rsrc) > min(os.path.getmtime(r) for r in refs)
+    if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True, capture_output=True)
 
 

@@ -1,0 +1,110 @@
+"""GPU parity against the reference's OWN code: the CUDA library through the C ABI vs
+oracle/_ref/libexpref_path.so (SphericalBasis / SLGridSph / EmpCylSL member functions compiled
+from /root/reference where they lie; built in the build container, travels with the snapshot).
+
+Tolerances are BASELINE.json's: coefficients <= 1e-10 relative RMS, accelerations and potentials
+<= 1e-8 relative, level vector and dtreq bit-exact."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import acc_rel_err, get_table, rel_rms
+from exp_b200 import cyltable, ics
+from exp_b200.component import Component
+from exp_b200.cylinder import Cylinder
+from exp_b200.sphere import Sphere
+from oracle import oracle as O
+from oracle import ref_path as R
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not R.available(), reason="oracle/_ref/libexpref_path.so not built")]
+
+
+@pytest.mark.parametrize("kind,L,N,n", [("hernquist", 4, 10, 100000), ("nfw", 6, 18, 100000)])
+def test_sphere_vs_reference_code(kind, L, N, n):
+    """BASELINE configs[0] (1e5, lmax=4, nmax=10) and the shape of configs[1] (lmax=6, nmax=18)"""
+    tab = get_table(kind, L, N, rmax=50.0 if kind == "hernquist" else 20.0)
+    gen = ics.hernquist_halo if kind == "hernquist" else ics.nfw_halo
+    pos, vel, mass = gen(n, seed=17)
+    pos = pos + np.array([0.01, -0.02, 0.005])
+    pos[:5] *= 100.0
+    ref = R.RefSphere(tab)
+    rc = ref.coefficients(pos, mass, nthreads=4)
+    racc, rpot = ref.accel(pos, rc["coef"], nthreads=4)
+
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    s = Sphere(tab)
+    coef = s.determine_coefficients(c)
+    assert s.used == rc["used"]
+    assert rel_rms(coef, rc["coef"]) <= 1e-10
+    s.set_coefficients(rc["coef"])
+    c.zero_pot_acc()
+    s.get_acceleration_and_potential(c)
+    out = c.download()
+    assert acc_rel_err(out["acc"], racc).max() <= 1e-8
+    assert np.abs(out["pot"] - rpot).max() <= 1e-8 * np.abs(rpot).max()
+
+
+def test_cylinder_vs_reference_code():
+    tab = cyltable.synthetic_cyl_table(mmax=6, norder=18, numx=128, numy=64)
+    g = O.CylGridPy(tab)
+    consts = (g.c.Rtable, g.c.XMIN, g.c.dX, g.c.YMIN, g.c.dY)
+    n = 20000
+    pos, vel, mass = ics.exponential_disk(n, seed=44)
+    ref = R.RefCylinder(tab, consts)
+    rc = ref.accumulate(pos, mass)
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    cyl = Cylinder(tab, rcylmax=1e6)
+    cs, sn = cyl.determine_coefficients(c)
+    assert cyl.used == rc["used"]
+    assert rel_rms(cs, rc["cos"]) <= 1e-10
+    assert rel_rms(sn[1:], rc["sin"][1:]) <= 1e-10
+    # force inside the blend radius (ratio < 0.75): pure EmpCylSL::accumulated_eval
+    cyl.set_coefficients(rc["cos"], rc["sin"], 0.0)
+    c.zero_pot_acc()
+    cyl.get_acceleration_and_potential(c)
+    out = c.download()
+    rr = np.sqrt((pos ** 2).sum(axis=1))
+    idx = np.nonzero(rr < 0.7 * g.c.Rtable * tab.ascale)[0][:3000]
+    facc, fpot = np.zeros((len(idx), 3)), np.zeros(len(idx))
+    for k, i in enumerate(idx):
+        x, y, z = pos[i]
+        r = math.sqrt(x * x + y * y)
+        phi = math.atan2(y, x)
+        p0, p, fr, fz, fp = ref.accumulated_eval(rc["cos"], rc["sin"], r, z, phi)
+        # src/Cylinder.cc:1389-1391, 1400
+        facc[k] = (fr * x / r - fp * y / (r * r), fr * y / r + fp * x / (r * r), fz)
+        fpot[k] = p
+    assert acc_rel_err(out["acc"][idx], facc).max() <= 1e-8
+    assert np.abs(out["pot"][idx] - fpot).max() <= 1e-8 * np.abs(fpot).max()
+
+
+def test_levels_and_leapfrog_vs_reference_code():
+    rng = np.random.default_rng(5)
+    n = 200000
+    pos, vel, mass = ics.hernquist_halo(n, seed=9)
+    acc = rng.normal(size=(n, 3)) * np.exp(rng.uniform(-4, 4, n))[:, None]
+    pot = -np.exp(rng.uniform(-6, 1, n))
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    c.set_acc_pot(acc, pot)
+    c.incr_velocity(0.0123)
+    c.incr_position(0.0456)
+    out = c.download()
+    v_ref = R.incr_velocity(pos, vel, acc, 0.0123, nthreads=4)
+    p_ref = R.incr_position(pos, v_ref, 0.0456, nthreads=4)
+    # fused multiply-add on the device vs separate multiply and add in the reference build
+    assert np.abs(out["vel"] - v_ref).max() <= 1e-15 * max(1.0, np.abs(v_ref).max())
+    assert np.abs(out["pos"] - p_ref).max() <= 1e-15 * max(1.0, np.abs(p_ref).max())
+
+    c.upload(pos, vel, mass)
+    c.set_acc_pot(acc, pot)
+    c.adjust_multistep_level(dtime=0.01, multistep=6, reset_dtreq=True)
+    got = c.download(level=True, dtreq=True)
+    lev, dq, *_ = R.adjust_levels(vel, acc, pot, np.zeros(n), None, np.zeros(n, np.uint32),
+                                  np.zeros(n, np.float32), 0.01, 6, nthreads=4)
+    assert np.array_equal(got["level"], lev)
+    assert got["dtreq"].tobytes() == dq.tobytes()

@@ -1,0 +1,330 @@
+"""Pins the CPU restatement (oracle/exp_oracle.cc, cyl_oracle.cc) to the reference's OWN code:
+oracle/_ref/libexpref_path.so holds the reference's hot-path member functions, cut from
+/root/reference by oracle/ref_extract.py and compiled unmodified (oracle/ref_path_wrap.cc).
+
+Bit-exact (`tobytes()`) wherever the oracle keeps the reference's operation order; where a
+reference expression runs through Eigen expression templates (covariance outer products)
+the comparison is to 1e-14 of the largest entry.  Runs on CPU; the .so is built in the build
+container (where /root/reference exists) and travels with the repo snapshot."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from conftest import get_table
+from exp_b200 import cyltable, ics
+from oracle import oracle as O
+from oracle import ref_path as R
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libexpref_path.so not built")
+
+
+def _radii(tab, n=400, seed=0):
+    rng = np.random.default_rng(seed)
+    r = np.exp(rng.uniform(np.log(tab.rmin * 0.5), np.log(tab.rmax * 1.5), n))
+    return np.concatenate([r, [tab.rmin, tab.rmax, tab.rmin * 1e-3, tab.rmax * 10.0, 1.0]])
+
+
+@pytest.mark.parametrize("cfg", [("hernquist", 4, 10, 1), ("nfw", 6, 18, 1), ("hernquist", 2, 6, 2),
+                                 ("hernquist", 2, 6, 0)])
+def test_slgrid_tables_bit_exact(cfg):
+    """a5-a7: r_to_xi, d_xi_to_r, the grid constants, get_pot, get_force, get_dens
+    (exputil/SLGridMP2.cc:711-765, 872-989, 1362-1376), all three coordinate maps."""
+    kind, L, N, cmap = cfg
+    import copy
+    tab = copy.copy(get_table(kind, L, N, rmax=20.0 if kind == "nfw" else 50.0))
+    tab.cmap = cmap                       # the table values are just numbers for this comparison
+    g = O.Grid(tab)
+    ref = R.RefSphere(tab)
+    assert ref.consts() == (g.c.xmin, g.c.xmax, g.c.dxi)
+    L_ = O.lib()
+    for r in _radii(tab):
+        assert ref.r_to_xi(r) == L_.orc_r_to_xi(C.byref(g.c), float(r))
+        xi = ref.r_to_xi(r)
+        if cmap != 1 or -1.0 <= xi < 1.0:
+            assert ref.d_xi_to_r(xi) == L_.orc_d_xi_to_r(C.byref(g.c), xi)
+        assert ref.get_pot(r).tobytes() == g.get_pot(r).tobytes()
+        assert ref.get_force(r).tobytes() == g.get_force(r).tobytes()
+        d = np.zeros((L + 1, N))
+        L_.orc_slgrid_get_dens(C.byref(g.c), float(r), O._dp(d))
+        assert ref.get_dens(r).tobytes() == d.tobytes()
+
+
+def test_factorial_bit_exact():
+    """a4: the factorial(l,m) table of src/SphericalBasis.cc:328-335"""
+    for L in (2, 4, 6):
+        for l in range(L + 1):
+            for m in range(l + 1):
+                assert R.lib().ref_factorial(L, l, m) == O.lib().orc_factorial(l, m)
+
+
+def _halo(kind, n, seed, shift=(0.0, 0.0, 0.0)):
+    pos, vel, mass = (ics.hernquist_halo if kind == "hernquist" else ics.nfw_halo)(n, seed=seed)
+    return pos + np.asarray(shift), vel, mass
+
+
+@pytest.mark.parametrize("cfg", [("hernquist", 4, 10), ("nfw", 6, 18)])
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_sphere_coefficients_bit_exact(cfg, nthreads):
+    """a8/a9: SphericalBasis::determine_coefficients_thread + the thread sum
+    (src/SphericalBasis.cc:429-599, 855-858), with centre offset, rtrunc freeze and rmin/rmax cut."""
+    kind, L, N = cfg
+    tab = get_table(kind, L, N, rmax=20.0 if kind == "nfw" else 50.0)
+    pos, vel, mass = _halo(kind, 3000, 11, shift=(0.02, -0.01, 0.03))
+    center, rtrunc = (0.02, -0.01, 0.03), 15.0
+    g = O.Grid(tab)
+    S = O.ParticleSet(pos, vel, mass, center=center, rtrunc=rtrunc)
+    P = O.sph_params(scale=1.0, rmin=0.05, rmax=12.0)
+    lst = np.arange(0, 3000, 1, dtype=np.int32)[::-1].copy()      # a non-trivial levlist order
+    coef, used = O.sph_coefficients(g, P, S, lst=lst, adb=0.7, nthreads=nthreads)
+    ref = R.RefSphere(tab, scale=1.0, rmin=0.05, rmax=12.0)
+    out = ref.coefficients(pos, mass, lst=lst, adb=0.7, nthreads=nthreads, center=center, rtrunc=rtrunc)
+    assert used == out["used"] and 0 < used < 3000
+    assert coef.tobytes() == out["coef"].tobytes()
+
+
+def test_sphere_scale_and_m0_only():
+    tab = get_table("hernquist", 4, 10)
+    pos, vel, mass = _halo("hernquist", 1500, 5)
+    g = O.Grid(tab)
+    S = O.ParticleSet(pos, vel, mass)
+    P = O.sph_params(scale=1.7, rmin=tab.rmin, rmax=tab.rmax, M0_only=True)
+    coef, used = O.sph_coefficients(g, P, S)
+    out = R.RefSphere(tab, scale=1.7, M0_only=True).coefficients(pos, mass)
+    assert used == out["used"]
+    assert coef.tobytes() == out["coef"].tobytes()
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(NO_L0=True), dict(NO_L1=True), dict(EVEN_L=True),
+                                   dict(EVEN_M=True), dict(M0_only=True)])
+def test_sphere_accel_bit_exact(flags):
+    """a11: SphericalBasis::determine_acceleration_and_potential_thread (src/SphericalBasis.cc:
+    1476-1660) incl. get_pot_coefs_safe, Sphere::get_dpotl, the r > rmax continuation and the
+    NO_L0/NO_L1/EVEN_L/EVEN_M/M0_only switches."""
+    tab = get_table("hernquist", 4, 10)
+    pos, vel, mass = _halo("hernquist", 2500, 21, shift=(0.01, 0.0, -0.02))
+    pos[:40] *= 30.0                                        # beyond rmax
+    pos[40] = np.array([0.01, 0.0, 0.7 - 0.02])             # on the pole of the shifted frame
+    center = (0.01, 0.0, -0.02)
+    g = O.Grid(tab)
+    P = O.sph_params(scale=1.0, rmin=tab.rmin, rmax=10.0, **flags)
+    S = O.ParticleSet(pos, vel, mass, center=center, rtrunc=400.0)
+    coef, _ = O.sph_coefficients(g, O.sph_params(rmin=tab.rmin, rmax=10.0), S)
+    O.sph_accel(g, P, S, coef, nthreads=2)
+    ref = R.RefSphere(tab, scale=1.0, rmin=tab.rmin, rmax=10.0, **flags)
+    acc, pot = ref.accel(pos, coef, nthreads=2, center=center, rtrunc=400.0)
+    assert S.acc.tobytes() == acc.tobytes()
+    assert S.pot.tobytes() == pot.tobytes()
+    assert np.abs(acc).max() > 0
+
+
+def test_sphere_accel_external_component_uses_owner_centre():
+    """use_external: the other component's particles are taken Inertial and converted with the
+    OWNING component's centre (src/SphericalBasis.cc:1524-1540); only freeze() uses theirs."""
+    tab = get_table("hernquist", 4, 10)
+    pos, vel, mass = _halo("hernquist", 1200, 31)
+    g = O.Grid(tab)
+    P = O.sph_params(rmin=tab.rmin, rmax=tab.rmax)
+    S0 = O.ParticleSet(pos, vel, mass)
+    coef, _ = O.sph_coefficients(g, P, S0)
+    own, theirs = (0.05, 0.02, -0.03), (0.4, 0.0, 0.0)
+    ref = R.RefSphere(tab)
+    acc, pot = ref.accel(pos, coef, center=theirs, rtrunc=3.0, own_center=own)
+    # restatement: evaluate about the owner's centre, freeze about theirs
+    r2 = ((pos - np.asarray(theirs)) ** 2).sum(axis=1)
+    keep = np.nonzero(r2 <= 9.0)[0].astype(np.int32)
+    S = O.ParticleSet(pos, vel, mass, center=own)
+    O.sph_accel(g, P, S, coef, lst=keep)
+    assert S.acc.tobytes() == acc.tobytes() and S.pot.tobytes() == pot.tobytes()
+
+
+def test_sphere_covariance_pcavar():
+    """a10: the pcavar/pcaeof branches (src/SphericalBasis.cc:501-509, 525-545, 563-581)"""
+    tab = get_table("hernquist", 2, 6) if False else get_table("hernquist", 4, 10)
+    pos, vel, mass = _halo("hernquist", 800, 41)
+    g = O.Grid(tab)
+    S = O.ParticleSet(pos, vel, mass)
+    P = O.sph_params(rmin=tab.rmin, rmax=tab.rmax)
+    sampT = 7
+    o = O.sph_coefficients_cov(g, P, S, sampT, adb=0.9)
+    r = R.RefSphere(tab).coefficients(pos, mass, adb=0.9, sampT=sampT, pcaeof=True)
+    assert o["used"] == r["used"]
+    assert o["coef"].tobytes() == r["coef"].tobytes()
+    assert o["massT"].tobytes() == r["massT"].tobytes()
+    assert np.array_equal(o["countT"], r["countT"])
+    assert o["muse"] == r["muse"]
+    assert np.abs(r["coefM"].imag).max() == 0.0
+    sT = np.abs(r["coefT"]).max()
+    assert np.abs(o["coefT"] - r["coefT"]).max() <= 1e-15 * sT
+    sM = np.abs(r["coefM"]).max()
+    assert np.abs(o["coefM"] - r["coefM"].real).max() <= 1e-15 * sM
+    # pcaeof tvar = sum over bins of the m=0-style products wk wk / mass (no facL^2 for m>0)
+    assert r["tvar"] is not None and np.abs(r["tvar"]).max() > 0
+
+
+# ---- cylinder ---------------------------------------------------------------------------
+def _cyl(numx=32, numy=16, **kw):
+    tab = cyltable.synthetic_cyl_table(mmax=4, norder=6, numx=numx, numy=numy, **kw)
+    g = O.CylGridPy(tab)
+    consts = (g.c.Rtable, g.c.XMIN, g.c.dX, g.c.YMIN, g.c.dY)
+    return tab, g, consts
+
+
+@pytest.mark.parametrize("cmap", [(1, 1), (0, 0), (1, 2)])
+def test_cylinder_maps_and_get_pot_bit_exact(cmap):
+    """a14: EmpCylSL::r_to_xi / z_to_y / get_pot (exputil/EmpCylSL.cc:6446-6463, 7109-7117,
+    5557-5632)"""
+    tab, g, consts = _cyl(cmapr=cmap[0], cmapz=cmap[1])
+    ref = R.RefCylinder(tab, consts)
+    L = O.lib()
+    L.orc_cyl_r_to_xi.restype = C.c_double
+    L.orc_cyl_r_to_xi.argtypes = [C.POINTER(O.CylGrid), C.c_double]
+    L.orc_cyl_z_to_y.restype = C.c_double
+    L.orc_cyl_z_to_y.argtypes = [C.POINTER(O.CylGrid), C.c_double]
+    rng = np.random.default_rng(3)
+    M1, N = tab.mmax + 1, tab.norder
+    for _ in range(300):
+        r = float(np.exp(rng.uniform(np.log(1e-5), np.log(0.5))))
+        z = float(rng.normal() * 0.004) if rng.uniform() < 0.8 else float(rng.normal() * 0.5)
+        assert ref.r_to_xi(r) == L.orc_cyl_r_to_xi(C.byref(g.c), r)
+        assert ref.z_to_y(z) == L.orc_cyl_z_to_y(C.byref(g.c), z)
+        Vc, Vs = np.zeros((M1, N)), np.zeros((M1, N))
+        L.orc_cyl_get_pot(C.byref(g.c), r, z, O._dp(Vc), O._dp(Vs))
+        rc, rs = ref.get_pot(r, z)
+        assert Vc.tobytes() == rc.tobytes() and Vs.tobytes() == rs.tobytes()
+
+
+def test_cylinder_accumulate_bit_exact():
+    """a15/a16: EmpCylSL::accumulate (exputil/EmpCylSL.cc:4049-4146) under the gates of
+    Cylinder::determine_coefficients_thread (src/Cylinder.cc:823-890), incl. the cylmass1 quirk"""
+    tab, g, consts = _cyl()
+    pos, vel, mass = ics.exponential_disk(2000, seed=44)
+    pos[:25] *= 40.0                                     # off the table
+    P = O.cyl_params(rcylmax=1e6, acyl=0.01)
+    S = O.ParticleSet(pos, vel, mass)
+    cs, sn, used, cylmass = O.cyl_coefficients(g, P, S, adb=0.8)
+    ref = R.RefCylinder(tab, consts)
+    out = ref.accumulate(pos, mass * 0.8)
+    assert used >= out["used"] > 0
+    assert cs.tobytes() == out["cos"].tobytes()
+    assert sn.tobytes() == out["sin"].tobytes()
+    # cylmass1 is incremented inside the m loop (x (MMAX+1)), exputil/EmpCylSL.cc:4143
+    inside = np.sqrt((pos ** 2).sum(axis=1)) / tab.ascale <= g.c.Rtable
+    assert math.isclose(out["cylmass1"], (tab.mmax + 1) * (mass[inside] * 0.8).sum(), rel_tol=1e-12)
+
+
+def test_cylinder_covariance_covar():
+    """a15: the covar branch (exputil/EmpCylSL.cc:4123-4141); the reference evaluates it through
+    Eigen expressions, so agreement is to rounding"""
+    tab, g, consts = _cyl()
+    pos, vel, mass = ics.exponential_disk(600, seed=45)
+    P = O.cyl_params(rcylmax=1e6, acyl=0.01)
+    S = O.ParticleSet(pos, vel, mass)
+    sampT = 5
+    o = O.cyl_coefficients_cov(g, P, S, sampT)
+    r = R.RefCylinder(tab, consts).accumulate(pos, mass, sampT=sampT)
+    assert o["cos"].tobytes() == r["cos"].tobytes() and o["sin"].tobytes() == r["sin"].tobytes()
+    assert np.array_equal(o["numbT"], r["numbT"])
+    assert o["massT"].tobytes() == r["massT"].tobytes()
+    assert np.abs(o["VC"] - r["VC"]).max() <= 1e-14 * np.abs(r["VC"]).max()
+    assert np.abs(o["MV"] - r["MV"]).max() <= 1e-14 * np.abs(r["MV"]).max()
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(EVEN_M=True), dict(MMIN=1, MLIM=3), dict(NMIN=1, NLIM=4)])
+def test_cylinder_accumulated_eval_bit_exact(flags):
+    """a18: EmpCylSL::accumulated_eval (exputil/EmpCylSL.cc:5256-5410)"""
+    tab = cyltable.synthetic_cyl_table(mmax=4, norder=6, numx=32, numy=16)
+    g = O.CylGridPy(tab, **flags)
+    consts = (g.c.Rtable, g.c.XMIN, g.c.dX, g.c.YMIN, g.c.dY)
+    ref = R.RefCylinder(tab, consts, **flags)
+    rng = np.random.default_rng(9)
+    cos, sin = rng.normal(size=(5, 6)), rng.normal(size=(5, 6))
+    sin[0] = 0.0
+    L = O.lib()
+    L.orc_cyl_accumulated_eval.argtypes = [C.POINTER(O.CylGrid), O.c_dp, O.c_dp, C.c_double, C.c_double,
+                                           C.c_double] + [O.c_dp] * 5
+    for _ in range(300):
+        r = float(np.exp(rng.uniform(np.log(1e-5), np.log(0.3))))
+        z = float(rng.normal() * 0.004)
+        phi = float(rng.uniform(-np.pi, np.pi))
+        o = np.zeros(5)
+        L.orc_cyl_accumulated_eval(C.byref(g.c), O._dp(cos), O._dp(sin), r, z, phi,
+                                   *[o[k:].ctypes.data_as(O.c_dp) for k in range(5)])
+        assert tuple(o) == ref.accumulated_eval(cos, sin, r, z, phi)
+
+
+# ---- leapfrog and level assignment ----------------------------------------------------------
+@pytest.mark.parametrize("mlevel", [-1, 0, 2])
+def test_leapfrog_bit_exact(mlevel):
+    """a21: incr_position_thread / incr_velocity_thread (src/incpos.cc:15-70, src/incvel.cc:15-89)"""
+    rng = np.random.default_rng(2)
+    n = 5000
+    pos, vel, acc = rng.normal(size=(n, 3)), rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    level = rng.integers(0, 4, n).astype(np.uint32)
+    for dim in (3, 2):
+        S = O.ParticleSet(pos, vel, None, level=level)
+        S.acc[:] = acc
+        lst = None if mlevel < 0 else S.levlist(mlevel)
+        O.incr_velocity(S, 0.0123, lst=lst, dim=dim)
+        v_ref = R.incr_velocity(pos, vel, acc, 0.0123, level=level, nlev=4, mlevel=mlevel, dim=dim, nthreads=3)
+        assert S.vel.tobytes() == v_ref.tobytes()
+        O.incr_position(S, 0.0456, lst=lst, dim=dim)
+        p_ref = R.incr_position(pos, v_ref, 0.0456, level=level, nlev=4, mlevel=mlevel, dim=dim, nthreads=3)
+        assert S.pos.tobytes() == p_ref.tobytes()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(shiftlevl=1), dict(mfirst_mdrft=2), dict(dynfracS=0.5, with_scale=True),
+                                dict(noswitch=True), dict(dim=2)])
+def test_level_assignment_bit_exact(kw):
+    """a22: adjust_multistep_level_thread (src/multistep.cc:52-236): dtreq through float, the
+    floor(log(dtime/dtreq)/log 2) level incl. exact powers of two, shiftlevl, mfirst, offgrid counts"""
+    kw = dict(kw)
+    with_scale = kw.pop("with_scale", False)
+    rng = np.random.default_rng(7)
+    n = 20000
+    vel = rng.normal(size=(n, 3)) * np.exp(rng.uniform(-6, 2, n))[:, None]
+    acc = rng.normal(size=(n, 3)) * np.exp(rng.uniform(-6, 6, n))[:, None]
+    pot = -np.exp(rng.uniform(-8, 2, n))
+    potext = rng.normal(size=n) * 0.01
+    scale = np.exp(rng.uniform(-3, 1, n)).astype(np.float32) if with_scale else None
+    level = rng.integers(0, 5, n).astype(np.uint32)
+    dtime, multistep = 0.01, 4
+    # plant exact powers of two: dtv = dynfracV*sqrt(v2/(a2+eps)) is hard to hit, so make the float
+    # dtreq land on dtime/2^k through dtd (dynfracD small) for a few particles in a second pass
+    S = O.ParticleSet(np.zeros((n, 3)), vel, None, level=level, scale=scale)
+    S.acc[:] = acc; S.pot[:] = pot; S.potext[:] = potext
+    # the wrapper evaluates at mstep == 0 with DTreset on: NoSwitch components reset dtreq first
+    P = O.level_params(dtime=dtime, multistep=multistep, reset_dtreq=bool(kw.get("noswitch")),
+                       **{k: v for k, v in kw.items()})
+    nsw, which, offlo, offhi = O.adjust_levels(S, P)
+    lev, dq, nsw_r, lo_r, hi_r = R.adjust_levels(vel, acc, pot, potext, scale, level, np.zeros(n, np.float32),
+                                                 dtime, multistep, nthreads=3, **kw)
+    assert np.array_equal(S.level, lev)
+    assert S.dtreq.tobytes() == dq.tobytes()
+    assert (nsw, offlo, offhi) == (nsw_r, lo_r, hi_r)
+    assert len(np.unique(lev)) >= 3
+
+
+def test_level_assignment_powers_of_two():
+    """dtreq == dtime / 2^k exactly (and one float ulp either side): libm's floor(log(x)/log(2))"""
+    multistep, dtime = 8, 1.0
+    vals = []
+    for k in range(0, 9):
+        t = np.float32(dtime / 2 ** k)
+        vals += [t, np.nextafter(t, np.float32(0)), np.nextafter(t, np.float32(2))]
+    vals = np.array(vals, dtype=np.float64)
+    n = len(vals)
+    # dts = dynfracS * scale / |sqrt(v2) + eps| with v = 1 and dynfracS chosen so that dts = vals
+    vel = np.zeros((n, 3)); vel[:, 0] = 1.0
+    acc = np.zeros((n, 3))
+    pot = np.zeros(n); potext = np.zeros(n)
+    scale = (vals * (1.0 + 1e-10)).astype(np.float32)
+    level = np.zeros(n, dtype=np.uint32)
+    S = O.ParticleSet(np.zeros((n, 3)), vel, None, level=level, scale=scale)
+    P = O.level_params(dtime=dtime, multistep=multistep, dynfracV=1e30, dynfracD=1e30)
+    O.adjust_levels(S, P)
+    lev, dq, *_ = R.adjust_levels(vel, acc, pot, potext, scale, level, np.zeros(n, np.float32), dtime,
+                                  multistep, dynfracV=1e30, dynfracD=1e30)
+    assert np.array_equal(S.level, lev) and S.dtreq.tobytes() == dq.tobytes()
+    assert len(np.unique(lev)) >= 8
