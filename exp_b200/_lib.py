@@ -161,6 +161,8 @@ SIGNATURES = {
     "expb200_sphere_create": (C.c_int, [C.c_int, C.POINTER(SphereConfig), c_dp, c_dp, c_dp,
                                         C.POINTER(_H)]),
     "expb200_sphere_destroy": (C.c_int, [_H]),
+    "expb200_sphere_set_owner": (C.c_int, [_H, _H]),
+    "expb200_cylinder_set_owner": (C.c_int, [_H, _H]),
     "expb200_sphere_determine_coefficients": (C.c_int, [_H, _H, C.c_int, C.c_double, c_dp, c_u64p]),
     "expb200_sphere_coef_device": (C.c_int, [_H, C.POINTER(c_dp), C.POINTER(C.c_void_p)]),
     "expb200_sphere_set_coefficients": (C.c_int, [_H, c_dp]),
@@ -206,6 +208,7 @@ SIGNATURES = {
     "expb200_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "expb200_comm_destroy": (C.c_int, [C.c_void_p]),
     "expb200_allreduce_sum": (C.c_int, [C.c_void_p, c_dp, C.c_size_t, C.c_void_p]),
+    "expb200_comm_check": (C.c_int, [C.c_void_p]),
     "expb200_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
     "expb200_comm_peer_connect": (C.c_int, [C.c_void_p, C.c_char_p]),
 }

@@ -199,6 +199,10 @@ struct expb200_component_s {
   const void *sort_owner = nullptr;
   uint32_t keys_per_level = 1;
   uint64_t pos_ver = 1, lev_ver = 1, sort_pos_ver = 0, sort_lev_ver = 0;
+  // what else the cells of the current sort depend on: the expansion origin (the centre of the
+  // force's owning component, which need not be this one) and the owner's orientation version
+  double sort_origin[3] = {0, 0, 0};
+  uint64_t sort_aux_ver = 0;
 
   // multistep statistics scratch
   unsigned long long *stats = nullptr;  // device, 8 words

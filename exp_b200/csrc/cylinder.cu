@@ -590,6 +590,8 @@ struct expb200_cylinder_s {
   int device = 0;
   expb200_cylinder_config cfg;
   CylGeom geom;
+  const expb200_component_s *owner = nullptr;   // PotAccel::component (expb200_cylinder_set_owner)
+  uint64_t orient_ver = 1;          // bumped by set_orientation: the cells depend on it
   int nlev = 1;
   int nkpad = 0;
   size_t ncoef = 0;                 // 2*(mmax+1)*norder
@@ -621,7 +623,11 @@ namespace {
 CylGeom geom_for(const expb200_cylinder_s *s, const expb200_component_s *c)
 {
   CylGeom g = s->geom;
-  g.cx = c->center[0]; g.cy = c->center[1]; g.cz = c->center[2];
+  // origin: the centre of the component that owns this force (component->ConvertPos,
+  // src/Cylinder.cc:1343-1349); the cylinder's force pass has no freeze test, and the
+  // coefficient pass always runs on the owner itself
+  const expb200_component_s *o = s->owner ? s->owner : c;
+  g.cx = o->center[0]; g.cy = o->center[1]; g.cz = o->center[2];
   g.rtrunc2 = c->rtrunc * c->rtrunc;
   return g;
 }
@@ -630,8 +636,10 @@ int ensure_sorted(expb200_cylinder_s *s, expb200_component_s *c, int mlevel, dou
 {
   const uint32_t kpl = (uint32_t)s->geom.ncell + 2u;
   const uint32_t nkeys = (uint32_t)s->nlev * kpl;
+  CylGeom g = geom_for(s, c);
   const bool valid = c->sort_kind == 3 && c->sort_owner == s && c->sort_pos_ver == c->pos_ver &&
-                     c->sort_lev_ver == c->lev_ver;
+                     c->sort_lev_ver == c->lev_ver && c->sort_aux_ver == s->orient_ver &&
+                     c->sort_origin[0] == g.cx && c->sort_origin[1] == g.cy && c->sort_origin[2] == g.cz;
   if (valid && !want_mass) return EXPB200_OK;
   if (c->seg_cap < (size_t)nkeys + 2) {
     if (c->seg) cudaFree(c->seg);
@@ -639,7 +647,6 @@ int ensure_sorted(expb200_cylinder_s *s, expb200_component_s *c, int mlevel, dou
     CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
     c->seg_cap = (size_t)nkeys + 2;
   }
-  CylGeom g = geom_for(s, c);
   const unsigned nb = grid_for(c->n ? c->n : 1, 256);
   {
     ProfRegion pr(K_KEY, c->stream, 2);
@@ -666,6 +673,8 @@ int ensure_sorted(expb200_cylinder_s *s, expb200_component_s *c, int mlevel, dou
   c->keys_per_level = kpl;
   c->sort_pos_ver = c->pos_ver;
   c->sort_lev_ver = c->lev_ver;
+  c->sort_aux_ver = s->orient_ver;
+  c->sort_origin[0] = g.cx; c->sort_origin[1] = g.cy; c->sort_origin[2] = g.cz;
   return EXPB200_OK;
 }
 
@@ -783,6 +792,14 @@ int expb200_cylinder_set_orientation(expb200_cylinder s, const double *body, con
   } else {
     s->geom.rotate = 0;
   }
+  s->orient_ver++;          // cached (level, cell) sorts were made in the old frame
+  return EXPB200_OK;
+}
+
+int expb200_cylinder_set_owner(expb200_cylinder s, expb200_component owner)
+{
+  REQUIRE(s, "cylinder is NULL");
+  s->owner = owner;
   return EXPB200_OK;
 }
 

@@ -69,6 +69,13 @@ int fail(Api *a, int rc, const char *what)
 // identical on every rank and independent of arrival order, which ncclAllReduce does not
 // promise.  Buffers are double-buffered by the parity of the sequence number: a rank can
 // run at most one all-reduce ahead of the slowest (it needs that rank's data to finish).
+// That argument needs the calls of one communicator to execute in issue order on every
+// rank; callers pass different streams (one per component), so each call waits on the
+// event recorded after the previous one when the stream differs.  A flag that is not
+// exactly the expected sequence number, or a wait longer than the time-out
+// (EXPB200_PEER_TIMEOUT_S seconds, default 600, 0 = wait for ever like MPI), poisons the
+// vector with NaN instead of summing stale slots and raises the error flag, which
+// expb200_comm_check() and the next all-reduce report.
 // ---------------------------------------------------------------------------
 constexpr int kPeerMaxWorld = 16;
 constexpr size_t kPeerCap = 16384;            // doubles per rank slot
@@ -89,16 +96,28 @@ struct Comm {
   bool connected = false;
   unsigned long long seq = 0;
   int *err_host = nullptr, *err_dev = nullptr;   // mapped pinned: set by a kernel that timed out
+  cudaStream_t last_stream = nullptr;            // stream of the previous peer all-reduce
+  cudaEvent_t last_done = nullptr;               // recorded after it
+  unsigned long long timeout_ns = 600ull * 1000000000ull;
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 size_t peer_flag_bytes(int world) { return ((size_t)2 * world * sizeof(unsigned long long) + 255) / 256 * 256; }
 size_t peer_bytes(int world) { return peer_flag_bytes(world) + (size_t)2 * world * kPeerCap * sizeof(double); }
 
 __global__ void __launch_bounds__(256)
 peer_allreduce_kernel(PeerPtrs P, int world, int rank, double *__restrict__ buf, size_t n,
-                      unsigned long long seq, int *err)
+                      unsigned long long seq, unsigned long long timeout_ns, int *err)
 {
+  __shared__ int bad;
   const int par = (int)(seq & 1ull), tid = threadIdx.x;
+  if (tid == 0) bad = 0;
   // 1. my vector -> slot [par][rank] of every rank (P2P stores; the local one included)
   for (int r = 0; r < world; r++) {
     double *dst = P.data[r] + ((size_t)par * world + rank) * kPeerCap;
@@ -113,13 +132,19 @@ peer_allreduce_kernel(PeerPtrs P, int world, int rank, double *__restrict__ buf,
   // 2. wait until every rank's vector of this sequence number has landed here
   if (tid < world) {
     volatile unsigned long long *f = P.flags[rank] + (size_t)par * world + tid;
-    const long long t0 = clock64();
-    while (*f < seq) {
-      if (clock64() - t0 > 8000000000ll) { *err = 1; break; }      // ~4 s: a peer died
+    const unsigned long long t0 = global_ns();
+    unsigned long long v;
+    while ((v = *f) < seq) {
+      if (timeout_ns && global_ns() - t0 > timeout_ns) { *err = 1; bad = 1; break; }   // a peer died
     }
+    if (v > seq) { *err = 2; bad = 1; }      // calls of this communicator ran out of order
   }
   __syncthreads();
   __threadfence_system();
+  if (bad) {                                  // never sum stale slots: make the failure visible
+    for (size_t i = tid; i < n; i += blockDim.x) buf[i] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
   // 3. sum in rank order (bypassing L1: the data was written by other GPUs)
   const double *src = P.data[rank] + (size_t)par * world * kPeerCap;
   for (size_t i = tid; i < n; i += blockDim.x) {
@@ -142,11 +167,21 @@ int nccl_allreduce_sum_f64(void *comm, double *buf, size_t n, cudaStream_t strea
   Comm *c = as_comm(comm);
   if (!c) { set_error("not an expb200 communicator"); return EXPB200_EINVAL; }
   if (c->connected && n <= kPeerCap) {
-    if (*c->err_host) { set_error("peer all-reduce timed out waiting for another rank"); return EXPB200_ENCCL; }
+    if (*c->err_host) {
+      set_error(*c->err_host == 2 ? "peer all-reduce: sequence numbers out of order"
+                                  : "peer all-reduce timed out waiting for another rank");
+      return EXPB200_ENCCL;
+    }
     DeviceGuard g(c->device);       // the stream belongs to the communicator's device
+    // calls on one communicator must execute in issue order: join the previous call's stream
+    if (c->last_done && c->last_stream != stream) CU_TRY(cudaStreamWaitEvent(stream, c->last_done, 0));
     c->seq++;
-    peer_allreduce_kernel<<<1, 256, 0, stream>>>(c->P, c->world, c->rank, buf, n, c->seq, c->err_dev);
+    peer_allreduce_kernel<<<1, 256, 0, stream>>>(c->P, c->world, c->rank, buf, n, c->seq, c->timeout_ns,
+                                                 c->err_dev);
     CU_LAUNCH_CHECK();
+    if (!c->last_done) CU_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(c->last_done, stream));
+    c->last_stream = stream;
     return EXPB200_OK;
   }
   Api *a = api();
@@ -201,6 +236,7 @@ int expb200_comm_destroy(void *comm)
     if (c->mapped[r]) cudaIpcCloseMemHandle(c->mapped[r]);
   if (c->local) cudaFree(c->local);
   if (c->err_host) cudaFreeHost(c->err_host);
+  if (c->last_done) cudaEventDestroy(c->last_done);
   Api *a = api();
   if (a && c->nccl) a->destroy(c->nccl);
   c->magic = 0;
@@ -211,6 +247,21 @@ int expb200_comm_destroy(void *comm)
 int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream)
 {
   return nccl_allreduce_sum_f64(comm, device_buf, n, (cudaStream_t)stream);
+}
+
+// Error state of the peer all-reduces issued so far (call after a stream/device sync):
+// 0, or EXPB200_ENCCL when one timed out or saw an out-of-order sequence number (its result
+// vector was filled with NaN).
+int expb200_comm_check(void *comm)
+{
+  Comm *c = as_comm(comm);
+  REQUIRE(c, "not an expb200 communicator");
+  if (c->err_host && *c->err_host) {
+    set_error(*c->err_host == 2 ? "peer all-reduce: sequence numbers out of order"
+                                : "peer all-reduce timed out waiting for another rank");
+    return EXPB200_ENCCL;
+  }
+  return EXPB200_OK;
 }
 
 // Peer-memory all-reduce, step 1: allocate this rank's receive buffer and export it
@@ -229,6 +280,7 @@ int expb200_comm_peer_handle(void *comm, char handle[64])
     CU_TRY(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
     *c->err_host = 0;
     CU_TRY(cudaHostGetDevicePointer(&c->err_dev, c->err_host, 0));
+    if (const char *e = getenv("EXPB200_PEER_TIMEOUT_S")) c->timeout_ns = strtoull(e, nullptr, 10) * 1000000000ull;
   }
   cudaIpcMemHandle_t h;
   CU_TRY(cudaIpcGetMemHandle(&h, c->local));

@@ -109,6 +109,11 @@ struct SphGeom {
   double inv_rmap, inv_dxi, inv_scale, inv_rmax;
   double scale, rmin, rmax; // SphericalBasis scale and expansion radii
   double cx, cy, cz, rtrunc2;
+  // Force evaluated on ANOTHER component's particles (use_external): the expansion origin
+  // (cx,cy,cz) is the owning component's centre, Component::freeze uses the particles' own
+  // component's centre (fx,fy,fz) (src/SphericalBasis.cc:1519-1540).  ext = 0: both coincide.
+  double fx, fy, fz;
+  int ext;
 };
 
 constexpr int kSphPoly = 5;   // double2 entries per (cell, slot): c0 c1 c2 d0 d1, each (cos, sin)
@@ -331,7 +336,10 @@ HD bool sph_force_setup(const SphGeom &g, const rec4 &pm, SphForce &S)
 {
   S.x = pm.x - g.cx; S.y = pm.y - g.cy; S.z = pm.z - g.cz;
   double r2 = S.x * S.x + S.y * S.y + S.z * S.z;
-  if (r2 > g.rtrunc2) return false;
+  if (g.ext) {
+    const double a = pm.x - g.fx, b = pm.y - g.fy, c = pm.z - g.fz;
+    if (a * a + b * b + c * c > g.rtrunc2) return false;
+  } else if (r2 > g.rtrunc2) return false;
 
   double r = fast_sqrt(r2) + EXPB200_DSMALL;
   S.ir = fast_rcp(r);

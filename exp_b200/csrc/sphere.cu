@@ -719,6 +719,25 @@ __device__ __forceinline__ void cp_async_rec(rec4 *dst_smem, const rec4 *src)
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(smem_u32(dst_smem) + 16),
                  "l"(reinterpret_cast<const char *>(src) + 16) : "memory");
 }
+// The same copy with the two 16-byte halves issued in the order (h, h^1): with h = bit 2 of the
+// lane and records 32 bytes apart, the eight lanes of a quarter warp then touch eight different
+// 16-byte bank groups per instruction (conflict-free), where the plain order is 2-way conflicted.
+__device__ __forceinline__ void cp_async_rec_rot(rec4 *dst_smem, const rec4 *src, int h)
+{
+  const uint32_t d = smem_u32(dst_smem);
+  const char *s = reinterpret_cast<const char *>(src);
+  const uint32_t o0 = 16u * (uint32_t)h, o1 = 16u - o0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+               "cp.async.cg.shared.global [%2], [%3], 16;"
+               ::"r"(d + o0), "l"(s + o0), "r"(d + o1), "l"(s + o1) : "memory");
+}
+// shared-memory read of a 32-byte record with the same rotation
+__device__ __forceinline__ rec4 lds_rec_rot(const rec4 *p, int h)
+{
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  const double2 a = q[h], b = q[h ^ 1];
+  return h ? rec4{b.x, b.y, a.x, a.y} : rec4{a.x, a.y, b.x, b.y};
+}
 __device__ __forceinline__ void cp_async_u64(void *dst_smem, const void *src)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -795,7 +814,14 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
   __syncthreads();
 
   const rec4 *side = F.mode ? F.vel : F.accp;     // the record force_store combines the result with
-  rec4 *myv = &SH.vbuf[2 * tid];
+  // A warp owns 64 consecutive sorted particles of the tile; lane l evaluates particles l and
+  // l + 32 of them (they almost always share the radial cell), so that the lanes of a warp read
+  // consecutive 32-byte records: conflict-free shared-memory reads with the (h, h^1) rotation,
+  // and consecutive records in the global stores of the epilogue (the permutation is nearly
+  // the identity).
+  const int lane = tid & 31, rot = (lane >> 2) & 1;
+  const int pA = (tid & ~31) * 2 + lane, pB = pA + 32;
+  rec4 *myvA = &SH.vbuf[pA], *myvB = &SH.vbuf[pB];
   // The warps of a CTA stay in lockstep (one block barrier per tile): they run the same
   // long straight-line code on the four sub-partitions at the same time and share its
   // instruction fetches; letting them drift (per-stage "empty" barriers) measured slower.
@@ -814,18 +840,18 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
     const FPDesc d = desc[s];
     const Stage &S = SH.stage[s];
 
-    const size_t k0 = t * kFPTile + 2 * (size_t)tid;
-    const bool validA = k0 >= lo && k0 < n, validB = k0 + 1 >= lo && k0 + 1 < n;
+    const size_t kA = t * kFPTile + (size_t)pA, kB = kA + 32;
+    const bool validA = kA >= lo && kA < n, validB = kB >= lo && kB < n;
     uint32_t iA, iB;
     SphForce A, B;
     bool okA, okB;
     {
       const rec4 dummy = rec4{g.cx + 1.0, g.cy, g.cz, 0.0};
-      const rec4 pmA = validA ? S.ps[2 * tid] : dummy, pmB = validB ? S.ps[2 * tid + 1] : dummy;
-      const uint2 ii = *reinterpret_cast<const uint2 *>(&S.perm[2 * tid]);
-      iA = validA ? ii.x : 0; iB = validB ? ii.y : 0;
-      if (validA) cp_async_rec(myv, side + iA);
-      if (validB) cp_async_rec(myv + 1, side + iB);
+      const rec4 pmA = validA ? lds_rec_rot(&S.ps[pA], rot) : dummy;
+      const rec4 pmB = validB ? lds_rec_rot(&S.ps[pB], rot) : dummy;
+      iA = validA ? S.perm[pA] : 0; iB = validB ? S.perm[pB] : 0;
+      if (validA) cp_async_rec_rot(myvA, side + iA, rot);
+      if (validB) cp_async_rec_rot(myvB, side + iB, rot);
       okA = sph_force_setup<true>(g, pmA, A) && validA;
       okB = sph_force_setup<true>(g, pmB, B) && validB;
     }
@@ -854,8 +880,8 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
     // the position records are re-read from the stage rather than held in registers across
     // the evaluation
     cp_async_wait_all();
-    if (validA) force_store_side(g, F, iA, okA, oa, S.ps[2 * tid], myv[0]);
-    if (validB) force_store_side(g, F, iB, okB, ob, S.ps[2 * tid + 1], myv[1]);
+    if (validA) force_store_side(g, F, iA, okA, oa, lds_rec_rot(&S.ps[pA], rot), lds_rec_rot(myvA, rot));
+    if (validB) force_store_side(g, F, iB, okB, ob, lds_rec_rot(&S.ps[pB], rot), lds_rec_rot(myvB, rot));
     if (++s == NST) { s = 0; ph ^= 1; }
   }
 }
@@ -1238,6 +1264,7 @@ struct expb200_sphere_s {
   int device = 0;
   expb200_sphere_config cfg;
   SphGeom geom;              // centre fields filled per call from the component
+  const expb200_component_s *owner = nullptr;   // PotAccel::component (expb200_sphere_set_owner)
   int nlev = 1;
   size_t ncoef = 0;
 
@@ -1286,7 +1313,12 @@ int deposit_chunk(size_t n)
 SphGeom geom_for(const expb200_sphere_s *s, const expb200_component_s *c)
 {
   SphGeom g = s->geom;
-  g.cx = c->center[0]; g.cy = c->center[1]; g.cz = c->center[2];
+  // expansion origin: the centre of the component that OWNS this force (PotAccel::component);
+  // freeze: the centre and rtrunc of the component whose particles are evaluated (cC)
+  const expb200_component_s *o = s->owner ? s->owner : c;
+  g.cx = o->center[0]; g.cy = o->center[1]; g.cz = o->center[2];
+  g.fx = c->center[0]; g.fy = c->center[1]; g.fz = c->center[2];
+  g.ext = (g.cx != g.fx || g.cy != g.fy || g.cz != g.fz) ? 1 : 0;
   g.rtrunc2 = c->rtrunc * c->rtrunc;
   return g;
 }
@@ -1322,6 +1354,8 @@ void mark_sorted(expb200_sphere_s *s, expb200_component_s *c)
   c->keys_per_level = s->cfg.numr;
   c->sort_pos_ver = c->pos_ver;
   c->sort_lev_ver = c->lev_ver;
+  const expb200_component_s *o = s->owner ? s->owner : c;
+  for (int k = 0; k < 3; k++) c->sort_origin[k] = o->center[k];
 }
 
 int ensure_seg(expb200_component_s *c, uint32_t nkeys)
@@ -1339,12 +1373,13 @@ int ensure_seg(expb200_component_s *c, uint32_t nkeys)
 // nor levels changed.
 int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
 {
+  SphGeom g = geom_for(s, c);
   if (c->sort_kind == 2 && c->sort_owner == s && c->sort_pos_ver == c->pos_ver &&
-      c->sort_lev_ver == c->lev_ver)
+      c->sort_lev_ver == c->lev_ver && c->sort_origin[0] == g.cx && c->sort_origin[1] == g.cy &&
+      c->sort_origin[2] == g.cz)
     return EXPB200_OK;
   const uint32_t nkeys = (uint32_t)s->nlev * (uint32_t)s->cfg.numr;
   { int rc = ensure_seg(c, nkeys); if (rc) return rc; }
-  SphGeom g = geom_for(s, c);
   if (c->n) {
     { ProfRegion pr(K_KEY, c->stream);
     sph_key_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(g, c->posm, c->level, c->n,
@@ -1518,6 +1553,13 @@ int expb200_sphere_create(int device, const expb200_sphere_config *cfg, const do
     CU_TRY(cudaMemset(s->differ, 0, bytes));
   }
   *out = s;
+  return EXPB200_OK;
+}
+
+int expb200_sphere_set_owner(expb200_sphere s, expb200_component owner)
+{
+  REQUIRE(s, "sphere is NULL");
+  s->owner = owner;
   return EXPB200_OK;
 }
 

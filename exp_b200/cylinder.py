@@ -50,6 +50,11 @@ class Cylinder:
     def set_multistep_level(self, n):
         self.mlevel = int(n)
 
+    def set_owner(self, c):
+        """PotAccel::component: the component whose centre is the expansion origin when the
+        force is evaluated on another component's particles (use_external)."""
+        check(_lib.lib().expb200_cylinder_set_owner(self._h, c._h if c is not None else None))
+
     def set_orientation(self, body=None, orig=None):
         if body is None:
             check(_lib.lib().expb200_cylinder_set_orientation(self._h, None, None))

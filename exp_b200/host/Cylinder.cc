@@ -69,6 +69,11 @@ void Cylinder::get_acceleration_and_potential(Component *cC)
   EXPHOST_CHECK(expb200_cylinder_determine_acceleration(b200c, cC->b200, (int)mlevel));
 }
 
+void Cylinder::RegisterComponent()
+{
+  EXPHOST_CHECK(expb200_cylinder_set_owner(b200c, component ? component->b200 : nullptr));
+}
+
 void Cylinder::multistep_reset()
 {
   used = 0;

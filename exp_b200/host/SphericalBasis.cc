@@ -62,6 +62,11 @@ void SphericalBasis::get_acceleration_and_potential(Component *cC)
   EXPHOST_CHECK(expb200_sphere_determine_acceleration(b200s, cC->b200, (int)mlevel));
 }
 
+void SphericalBasis::RegisterComponent()
+{
+  EXPHOST_CHECK(expb200_sphere_set_owner(b200s, component ? component->b200 : nullptr));
+}
+
 void SphericalBasis::multistep_reset()
 {
   used = 0;

@@ -54,6 +54,11 @@ class Sphere:
     def set_multistep_level(self, n: int):
         self.mlevel = int(n)
 
+    def set_owner(self, c: Component | None):
+        """PotAccel::component: the component whose centre is the expansion origin when the
+        force is evaluated on another component's particles (use_external)."""
+        check(_lib.lib().expb200_sphere_set_owner(self._h, c._h if c is not None else None))
+
     def determine_coefficients(self, c: Component, adb: float = 1.0, to_host: bool = True):
         """Accumulate levlist[mlevel] of ``c``; returns expcoef0 (rows x nmax)."""
         used = C.c_uint64(0)

@@ -169,6 +169,14 @@ int expb200_sphere_create(int device, const expb200_sphere_config *cfg,
                           const double *ev, const double *ef, const double *p0,
                           expb200_sphere *out);
 int expb200_sphere_destroy(expb200_sphere s);
+/* The component this force belongs to (PotAccel::component, set by Component::configure,
+ * src/Component.cc:1070-1115).  When the force is evaluated on ANOTHER component's particles
+ * (SetExternal, src/ComponentContainer.cc:785-823) positions are taken about the OWNER's centre
+ * (cC->Pos(Inertial) then component->ConvertPos(Local|Centered), src/SphericalBasis.cc:1519-1540)
+ * while Component::freeze keeps using the particles' own centre and rtrunc.  NULL (default):
+ * the component passed to each call is its own origin.  The owner must outlive the force or be
+ * reset to NULL. */
+int expb200_sphere_set_owner(expb200_sphere s, expb200_component owner);
 
 /* ~ SphericalBasis::determine_coefficients_cuda(compute) + DtoH_coefs
  * (src/SphericalBasis.cc:832-843).  Accumulates levlist[mlevel] (all particles
@@ -261,6 +269,9 @@ int expb200_cylinder_create(int device, const expb200_cylinder_config *cfg,
                             const double *rforceS, const double *zforceC, const double *zforceS,
                             expb200_cylinder *out);
 int expb200_cylinder_destroy(expb200_cylinder s);
+/* as expb200_sphere_set_owner (src/Cylinder.cc:1343-1349); the cylinder's force pass has no
+ * freeze test */
+int expb200_cylinder_set_owner(expb200_cylinder s, expb200_component owner);
 /* orient->transformBody() / transformOrig() (row-major 3x3); NULL, NULL = none
  * (src/Cylinder.cc:846-847, 1352-1353, 1418-1419) */
 int expb200_cylinder_set_orientation(expb200_cylinder s, const double *body, const double *orig);
@@ -316,7 +327,13 @@ int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mle
 int expb200_comm_unique_id(char id[128]);                       /* ncclGetUniqueId (rank 0) */
 int expb200_comm_create(int device, int nranks, int rank, const char id[128], void **comm);
 int expb200_comm_destroy(void *comm);
+/* Calls on one communicator may use different streams (one per component): each call is
+ * ordered after the previous one.  ~ MPI_Allreduce(MPI_SUM, MPI_DOUBLE) in place. */
 int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream);
+/* Error state of the peer-memory all-reduces issued so far (after a sync): a rank that never
+ * arrived within EXPB200_PEER_TIMEOUT_S seconds (default 600; 0 = wait for ever, like MPI) or
+ * out-of-order sequence numbers fill the result with NaN and make this return EXPB200_ENCCL. */
+int expb200_comm_check(void *comm);
 /* Optional: all-reduces of up to 16384 doubles (every one on this path) done by one kernel
  * over NVLink peer memory instead of ncclAllReduce: each rank stores its vector into every
  * peer's receive buffer, then adds the world's vectors in rank order (bitwise identical on

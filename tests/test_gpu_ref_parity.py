@@ -108,3 +108,57 @@ def test_levels_and_leapfrog_vs_reference_code():
                                   np.zeros(n, np.float32), 0.01, 6, nthreads=4)
     assert np.array_equal(got["level"], lev)
     assert got["dtreq"].tobytes() == dq.tobytes()
+
+
+def test_external_component_uses_owner_centre():
+    """interaction forces (ComponentContainer::compute_potential, src/ComponentContainer.cc:785-823):
+    another component's particles are evaluated about the OWNER's centre; freeze uses theirs"""
+    tab = get_table("hernquist", 4, 10)
+    n = 30000
+    pos, vel, mass = ics.hernquist_halo(n, seed=23)
+    own, theirs = (0.05, 0.02, -0.03), (0.4, 0.0, 0.0)
+    ref = R.RefSphere(tab)
+    rc = ref.coefficients(pos, mass, center=own)
+    other = pos[:20000] * 0.8 + np.array([0.1, 0.0, 0.0])
+    racc, rpot = ref.accel(other, rc["coef"], center=theirs, rtrunc=3.0, own_center=own, nthreads=4)
+
+    cA, cB = Component(n), Component(len(other))
+    cA.upload(pos, vel, mass)
+    cA.set_center(own)
+    cB.upload(other, vel[:20000], mass[:20000])
+    cB.set_center(theirs, rtrunc=3.0)
+    s = Sphere(tab)
+    s.set_owner(cA)
+    coef = s.determine_coefficients(cA)
+    assert rel_rms(coef, rc["coef"]) <= 1e-10
+    s.set_coefficients(rc["coef"])
+    cB.zero_pot_acc()
+    s.get_acceleration_and_potential(cB)
+    out = cB.download()
+    frozen = ((other - np.asarray(theirs)) ** 2).sum(axis=1) > 9.0
+    assert frozen.any() and not frozen.all()
+    assert np.all(out["acc"][frozen] == 0.0) and np.all(racc[frozen] == 0.0)
+    assert acc_rel_err(out["acc"][~frozen], racc[~frozen]).max() <= 1e-8
+    assert np.abs(out["pot"] - rpot).max() <= 1e-8 * np.abs(rpot).max()
+
+    # cylinder: origin = owner's centre, no freeze test in the force pass (src/Cylinder.cc:1343-1349)
+    tabC = cyltable.synthetic_cyl_table(mmax=4, norder=6, numx=48, numy=24)
+    g = O.CylGridPy(tabC)
+    nd = 8000
+    pd, vd, md = ics.exponential_disk(nd, seed=8)
+    cs = np.random.default_rng(1).normal(size=(5, 6)); sn = np.random.default_rng(2).normal(size=(5, 6)); sn[0] = 0
+    S = O.ParticleSet(pd + np.array([0.003, -0.001, 0.0005]), vd, md, center=(0.003, -0.001, 0.0005))
+    O.cyl_accel(g, O.cyl_params(rcylmax=20.0, acyl=tabC.ascale), S, cs, sn, 0.7)
+    cD, cH = Component(nd), Component(nd)
+    cD.upload(pd, vd, md)
+    cD.set_center((0.003, -0.001, 0.0005))
+    cH.upload(S.pos, vd, md)
+    cH.set_center((0.9, 0.9, 0.9), rtrunc=1e-3)            # would freeze everything if it were used
+    cyl = Cylinder(tabC)
+    cyl.set_owner(cD)
+    cyl.set_coefficients(cs, sn, 0.7)
+    cH.zero_pot_acc()
+    cyl.get_acceleration_and_potential(cH)
+    out = cH.download()
+    assert acc_rel_err(out["acc"], S.acc).max() <= 1e-8
+    assert np.abs(out["pot"] - S.pot).max() <= 1e-8 * np.abs(S.pot).max()
