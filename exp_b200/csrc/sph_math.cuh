@@ -331,6 +331,13 @@ struct SphForce {
   bool ioff;
 };
 
+// Legendre derivative clamp (src/Basis.cc:81-86)
+HD double sph_clamp_x(double x)
+{
+  if (1.0 - fabs(x) < EXPB200_MINEPS) return x > 0 ? 1.0 - EXPB200_MINEPS : -(1.0 - EXPB200_MINEPS);
+  return x;
+}
+
 template <bool OFF>
 HD bool sph_force_setup(const SphGeom &g, const rec4 &pm, SphForce &S)
 {
@@ -363,17 +370,34 @@ HD bool sph_force_setup(const SphGeom &g, const rec4 &pm, SphForce &S)
   S.q = t - S.j;
   S.fac = sph_d_xi_to_r(g, xi) * g.inv_dxi;
 
-  // Legendre derivative clamp (src/Basis.cc:81-86)
-  double xd = S.costh;
-  if (1.0 - fabs(xd) < EXPB200_MINEPS) xd = xd > 0 ? 1.0 - EXPB200_MINEPS : -(1.0 - EXPB200_MINEPS);
-  S.xd = xd;
-  S.somx2i = fast_rcp(xd * xd - 1.0);
+  S.xd = sph_clamp_x(S.costh);
+  S.somx2i = fast_rcp(S.xd * S.xd - 1.0);
   return true;
 }
 
+// Cartesian projection of the four field sums of a particle (src/SphericalBasis.cc:1640-1653;
+// note: r is the clamped radius when r0 > rmax): sums = {potl, potr, pott, potp} as the (l,m)
+// loops leave them; o[0..3] += (ax, ay, az, pot).
+HD void sph_force_project(const SphForce &S, bool ioff, const double *sums, double *o)
+{
+  const double tt = sums[2] * S.somx2i, rr = ioff ? sums[1] : sums[1] * S.fac;
+  const double ir = S.ir, ir3 = ir * ir * ir;
+  o[0] += -(rr * S.x * ir - tt * S.x * S.z * ir3);
+  o[1] += -(rr * S.y * ir - tt * S.y * S.z * ir3);
+  o[2] += -(rr * S.z * ir + tt * S.R2 * ir3);
+  if (S.R2 > EXPB200_DSMALL) {
+    o[0] += sums[3] * S.y * S.iR2;
+    o[1] += -sums[3] * S.x * S.iR2;
+  }
+  o[3] += sums[0];
+}
+
+// The (l,m) loops of one particle: sums = {potl, potr, pott, potp} (potr without the
+// d xi/d r factor, pott without 1/(x^2-1)).  Reads only costh, xd, c1, s1, p, q (and ratio,
+// r0i, ioff with OFF) of S.
 template <int L, bool OFF, class LD>
-HD void sph_force_eval(const double *inv, const SphForce &S, const double2 *Tc, const double2 *Td,
-                       LD &&ld, double &ax, double &ay, double &az, double &pot)
+HD void sph_force_sums(const double *inv, const SphForce &S, const double2 *Tc, const double2 *Td,
+                       LD &&ld, double *sums)
 {
   const double p = S.p, q = S.q, xd = S.xd;
   const bool ioff = OFF && S.ioff;
@@ -433,19 +457,17 @@ HD void sph_force_eval(const double *inv, const SphForce &S, const double2 *Tc, 
     }
   });
 
-  pott *= S.somx2i;
-  if (!ioff) potr *= S.fac;
+  sums[0] = potl; sums[1] = potr; sums[2] = pott; sums[3] = potp;
+}
 
-  // src/SphericalBasis.cc:1645-1653 (note: r is the clamped radius when r0 > rmax)
-  const double ir = S.ir, ir3 = ir * ir * ir;
-  ax += -(potr * S.x * ir - pott * S.x * S.z * ir3);
-  ay += -(potr * S.y * ir - pott * S.y * S.z * ir3);
-  az += -(potr * S.z * ir + pott * S.R2 * ir3);
-  if (S.R2 > EXPB200_DSMALL) {
-    ax += potp * S.y * S.iR2;
-    ay += -potp * S.x * S.iR2;
-  }
-  pot += potl;
+template <int L, bool OFF, class LD>
+HD void sph_force_eval(const double *inv, const SphForce &S, const double2 *Tc, const double2 *Td,
+                       LD &&ld, double &ax, double &ay, double &az, double &pot)
+{
+  double sums[4], o[4] = {ax, ay, az, pot};
+  sph_force_sums<L, OFF>(inv, S, Tc, Td, ld, sums);
+  sph_force_project(S, OFF && S.ioff, sums, o);
+  ax = o[0]; ay = o[1]; az = o[2]; pot = o[3];
 }
 
 // Two particles that read the same two table rows (same cell and stencil centre) evaluated
@@ -453,8 +475,8 @@ HD void sph_force_eval(const double *inv, const SphForce &S, const double2 *Tc, 
 // file's input bandwidth, not the FP64 pipe, bounds the single-particle form (a table entry
 // is 16 B per lane per term).  r <= rmax for both (no continuation).
 template <int L, class LD>
-HD void sph_force_eval2(const double *inv, const SphForce &A, const SphForce &B, const double2 *Tc,
-                        const double2 *Td, LD &&ld, double *oa, double *ob)
+HD void sph_force_sums2(const double *inv, const SphForce &A, const SphForce &B, const double2 *Tc,
+                        const double2 *Td, LD &&ld, double *sa, double *sb)
 {
   double potl[2] = {0.0, 0.0}, potr[2] = {0.0, 0.0}, pott[2] = {0.0, 0.0}, potp[2] = {0.0, 0.0};
   double cm[2] = {1.0, 1.0}, sm[2] = {0.0, 0.0}, cm1[2] = {0.0, 0.0}, sm1[2] = {0.0, 0.0};
@@ -528,21 +550,18 @@ HD void sph_force_eval2(const double *inv, const SphForce &A, const SphForce &B,
     }
   }
 
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-    const SphForce &S = k ? B : A;
-    double *o = k ? ob : oa;
-    const double tt = pott[k] * S.somx2i, rr = potr[k] * S.fac;
-    const double ir = S.ir, ir3 = ir * ir * ir;
-    o[0] += -(rr * S.x * ir - tt * S.x * S.z * ir3);
-    o[1] += -(rr * S.y * ir - tt * S.y * S.z * ir3);
-    o[2] += -(rr * S.z * ir + tt * S.R2 * ir3);
-    if (S.R2 > EXPB200_DSMALL) {
-      o[0] += potp[k] * S.y * S.iR2;
-      o[1] += -potp[k] * S.x * S.iR2;
-    }
-    o[3] += potl[k];
-  }
+  sa[0] = potl[0]; sa[1] = potr[0]; sa[2] = pott[0]; sa[3] = potp[0];
+  sb[0] = potl[1]; sb[1] = potr[1]; sb[2] = pott[1]; sb[3] = potp[1];
+}
+
+template <int L, class LD>
+HD void sph_force_eval2(const double *inv, const SphForce &A, const SphForce &B, const double2 *Tc,
+                        const double2 *Td, LD &&ld, double *oa, double *ob)
+{
+  double sa[4], sb[4];
+  sph_force_sums2<L>(inv, A, B, Tc, Td, ld, sa, sb);
+  sph_force_project(A, false, sa, oa);
+  sph_force_project(B, false, sb, ob);
 }
 
 template <int L, bool OFF>

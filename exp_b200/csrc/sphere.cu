@@ -719,25 +719,6 @@ __device__ __forceinline__ void cp_async_rec(rec4 *dst_smem, const rec4 *src)
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(smem_u32(dst_smem) + 16),
                  "l"(reinterpret_cast<const char *>(src) + 16) : "memory");
 }
-// The same copy with the two 16-byte halves issued in the order (h, h^1): with h = bit 2 of the
-// lane and records 32 bytes apart, the eight lanes of a quarter warp then touch eight different
-// 16-byte bank groups per instruction (conflict-free), where the plain order is 2-way conflicted.
-__device__ __forceinline__ void cp_async_rec_rot(rec4 *dst_smem, const rec4 *src, int h)
-{
-  const uint32_t d = smem_u32(dst_smem);
-  const char *s = reinterpret_cast<const char *>(src);
-  const uint32_t o0 = 16u * (uint32_t)h, o1 = 16u - o0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-               "cp.async.cg.shared.global [%2], [%3], 16;"
-               ::"r"(d + o0), "l"(s + o0), "r"(d + o1), "l"(s + o1) : "memory");
-}
-// shared-memory read of a 32-byte record with the same rotation
-__device__ __forceinline__ rec4 lds_rec_rot(const rec4 *p, int h)
-{
-  const double2 *q = reinterpret_cast<const double2 *>(p);
-  const double2 a = q[h], b = q[h ^ 1];
-  return h ? rec4{b.x, b.y, a.x, a.y} : rec4{a.x, a.y, b.x, b.y};
-}
 __device__ __forceinline__ void cp_async_u64(void *dst_smem, const void *src)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -814,14 +795,7 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
   __syncthreads();
 
   const rec4 *side = F.mode ? F.vel : F.accp;     // the record force_store combines the result with
-  // A warp owns 64 consecutive sorted particles of the tile; lane l evaluates particles l and
-  // l + 32 of them (they almost always share the radial cell), so that the lanes of a warp read
-  // consecutive 32-byte records: conflict-free shared-memory reads with the (h, h^1) rotation,
-  // and consecutive records in the global stores of the epilogue (the permutation is nearly
-  // the identity).
-  const int lane = tid & 31, rot = (lane >> 2) & 1;
-  const int pA = (tid & ~31) * 2 + lane, pB = pA + 32;
-  rec4 *myvA = &SH.vbuf[pA], *myvB = &SH.vbuf[pB];
+  rec4 *myv = &SH.vbuf[2 * tid];
   // The warps of a CTA stay in lockstep (one block barrier per tile): they run the same
   // long straight-line code on the four sub-partitions at the same time and share its
   // instruction fetches; letting them drift (per-stage "empty" barriers) measured slower.
@@ -840,18 +814,18 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
     const FPDesc d = desc[s];
     const Stage &S = SH.stage[s];
 
-    const size_t kA = t * kFPTile + (size_t)pA, kB = kA + 32;
-    const bool validA = kA >= lo && kA < n, validB = kB >= lo && kB < n;
+    const size_t k0 = t * kFPTile + 2 * (size_t)tid;
+    const bool validA = k0 >= lo && k0 < n, validB = k0 + 1 >= lo && k0 + 1 < n;
     uint32_t iA, iB;
     SphForce A, B;
     bool okA, okB;
     {
       const rec4 dummy = rec4{g.cx + 1.0, g.cy, g.cz, 0.0};
-      const rec4 pmA = validA ? lds_rec_rot(&S.ps[pA], rot) : dummy;
-      const rec4 pmB = validB ? lds_rec_rot(&S.ps[pB], rot) : dummy;
-      iA = validA ? S.perm[pA] : 0; iB = validB ? S.perm[pB] : 0;
-      if (validA) cp_async_rec_rot(myvA, side + iA, rot);
-      if (validB) cp_async_rec_rot(myvB, side + iB, rot);
+      const rec4 pmA = validA ? S.ps[2 * tid] : dummy, pmB = validB ? S.ps[2 * tid + 1] : dummy;
+      const uint2 ii = *reinterpret_cast<const uint2 *>(&S.perm[2 * tid]);
+      iA = validA ? ii.x : 0; iB = validB ? ii.y : 0;
+      if (validA) cp_async_rec(myv, side + iA);
+      if (validB) cp_async_rec(myv + 1, side + iB);
       okA = sph_force_setup<true>(g, pmA, A) && validA;
       okB = sph_force_setup<true>(g, pmB, B) && validB;
     }
@@ -880,9 +854,250 @@ sph_force2p_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, For
     // the position records are re-read from the stage rather than held in registers across
     // the evaluation
     cp_async_wait_all();
-    if (validA) force_store_side(g, F, iA, okA, oa, lds_rec_rot(&S.ps[pA], rot), lds_rec_rot(myvA, rot));
-    if (validB) force_store_side(g, F, iB, okB, ob, lds_rec_rot(&S.ps[pB], rot), lds_rec_rot(myvB, rot));
+    if (validA) force_store_side(g, F, iA, okA, oa, S.ps[2 * tid], myv[0]);
+    if (validB) force_store_side(g, F, iB, okB, ob, S.ps[2 * tid + 1], myv[1]);
     if (++s == NST) { s = 0; ph ^= 1; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// force, warp-specialised (EXPB200_FORCE_VARIANT=3; kept as a measured alternative).
+//
+// What bounded sph_force2p_kernel (profiles/r01f_ncu_full_summary.txt): the dense (l,m)
+// evaluation runs at the FP64 pipe's rate but was only ~41 % of a warp's time; the geometric
+// set-up (sqrt / reciprocal chains), the epilogue (projection, kicks, drift, next key, global
+// gathers and stores) and the tile barrier are latency-bound, and at 168 registers only three
+// warps per scheduler were there to cover them.  Here the two kinds of work run in different
+// warps of one CTA:
+//   warps 0-3 ("evaluation", 168 registers each after setmaxnreg.inc) do nothing but the
+//     (l,m) loops, two particles per lane, from operands already waiting in shared memory;
+//   warps 4-7 ("helpers", 88 registers after setmaxnreg.dec) do the set-up of the NEXT tile,
+//     the epilogue of the PREVIOUS one, and issue the TMA copies.
+// Two such CTAs are resident per SM: every scheduler holds two evaluation warps that keep the
+// FP64 pipe busy back to back and two helper warps whose latencies nobody waits for.
+//
+// A CTA walks tiles of 256 sorted particles (tile i of the CTA = "window" i).  In window i:
+//   evaluation warp w : particles 64w..64w+63 of tile i   : prep[i&1] + rows[i&1] -> res[i&1]
+//   helper warp w     : epilogue of tile i-1 (res, keep, ps of i-1 -> global memory),
+//                       then set-up of tile i+1 (ps[(i+1)%3] -> prep[(i+1)&1], keep[(i+1)&1])
+//   helper thread 224 : TMA of the table rows of tile i+1 and of the particles of tile i+2
+// with one CTA barrier per window (the evaluation is the long pole; the helpers have slack),
+// so every buffer is written in one window and read in the next.  The arithmetic per particle
+// is that of sph_force_setup / sph_force_sums(2) / sph_force_project, i.e. of the other force
+// kernels.
+// ---------------------------------------------------------------------------
+constexpr int kWSTile = 256;
+constexpr int kWSPairs = kWSTile / 2;
+constexpr int kWSThreads = 256;
+constexpr int kWSSlots = 4;           // particle-record ring: tiles i-1 (epilogue), i, i+1 (set-up), i+2 (in flight)
+
+template <int L, int ROWS> struct WSShared {
+  static constexpr int ROW = (L + 1) * (L + 2) / 2 * kSphPoly;
+  double2 rows[2][ROWS * ROW];
+  rec4 ps[kWSSlots][kWSTile];
+  uint32_t perm[kWSSlots][kWSTile];
+  // set-up -> evaluation; .x / .y = first / second particle of a lane
+  double2 costh[2][kWSPairs], c1[2][kWSPairs], s1[2][kWSPairs], p[2][kWSPairs], q[2][kWSPairs];
+  int2 info[2][kWSPairs];                             // cell | (j != cell) << 16 | ok << 17 | ioff << 18
+  // evaluation -> epilogue
+  double2 sums[2][4][kWSPairs];
+  // set-up -> epilogue (ir: 1/r of the particle itself; beyond rmax the evaluation derives the
+  // continuation factors from it and the epilogue uses 1/rmax)
+  double2 ir[2][kWSPairs], iR2[2][kWSPairs], somx2i[2][kWSPairs], fac[2][kWSPairs];
+};
+
+__device__ __forceinline__ double &d2_at(double2 &v, int k) { return reinterpret_cast<double *>(&v)[k]; }
+__device__ __forceinline__ int &i2_at(int2 &v, int k) { return reinterpret_cast<int *>(&v)[k]; }
+
+template <int L, int ROWS, int REGE, int REGH>
+__global__ void __launch_bounds__(kWSThreads, 2)
+sph_force_ws_kernel(SphGeom g, const double2 *__restrict__ T, const rec4 *ps, ForceOut F,
+                    const uint32_t *__restrict__ perm, const int2 *__restrict__ tdesc,
+                    const uint32_t *__restrict__ seg, int keybase, size_t n)
+{
+  static_assert(REGE + REGH == 256 && REGE % 8 == 0, "the two roles share 2 x 128 registers per thread pair");
+  using SHT = WSShared<L, ROWS>;
+  constexpr int ROW = SHT::ROW;
+  extern __shared__ __align__(128) unsigned char ws_smem[];
+  SHT &SH = *reinterpret_cast<SHT *>(ws_smem);
+  __shared__ __align__(8) uint64_t rows_full[2], ps_full[kWSSlots];
+  __shared__ FPDesc desc[2];
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const bool is_eval = wid < 4;
+  const int pi = (wid & 3) * 32 + lane;             // the lane's particle pair within a tile
+  const bool issuer = tid == kWSThreads - 32;
+
+  const size_t lo = seg[keybase];
+  const size_t t_end = (n + kWSTile - 1) / kWSTile;
+  const size_t t0 = lo / kWSTile + blockIdx.x;
+  const size_t stride = gridDim.x;
+  const int ntiles = t0 < t_end ? (int)((t_end - t0 + stride - 1) / stride) : 0;
+
+  if (tid == 0) {
+    for (int k = 0; k < 2; k++) mbar_init(&rows_full[k], 1);
+    for (int k = 0; k < kWSSlots; k++) mbar_init(&ps_full[k], 1);
+  }
+  __syncthreads();
+  if (ntiles == 0) return;
+
+  auto issue_rows = [&](int i) {
+    const int s = i & 1;
+    const int2 nd = __ldg(tdesc + t0 + (size_t)i * stride);
+    desc[s].rlo = nd.x;
+    desc[s].nrows = nd.y;
+    const uint32_t bytes = (uint32_t)nd.y * ROW * (uint32_t)sizeof(double2);
+    mbar_expect(&rows_full[s], bytes);
+    if (nd.y) tma_bulk_copy(SH.rows[s], T + (size_t)nd.x * ROW, bytes, &rows_full[s]);
+  };
+  auto issue_ps = [&](int i) {
+    const int s = i % kWSSlots;
+    const size_t k0 = (t0 + (size_t)i * stride) * kWSTile;
+    mbar_expect(&ps_full[s], kWSTile * (uint32_t)(sizeof(rec4) + sizeof(uint32_t)));
+    tma_bulk_copy(SH.ps[s], ps + k0, kWSTile * (uint32_t)sizeof(rec4), &ps_full[s]);
+    tma_bulk_copy(SH.perm[s], perm + k0, kWSTile * (uint32_t)sizeof(uint32_t), &ps_full[s]);
+  };
+
+  // ---- helper: set-up of tile i -------------------------------------------------------------
+  auto setup_one = [&](int b, int s, size_t gk, int k) {
+    const bool valid = gk >= lo && gk < n;
+    const rec4 pm = valid ? SH.ps[s][2 * pi + k] : rec4{g.cx + 1.0, g.cy, g.cz, 0.0};
+    SphForce S;
+    const bool ok = sph_force_setup<true>(g, pm, S) && valid;
+    d2_at(SH.costh[b][pi], k) = S.costh;
+    d2_at(SH.c1[b][pi], k) = S.c1;
+    d2_at(SH.s1[b][pi], k) = S.s1;
+    d2_at(SH.p[b][pi], k) = S.p;
+    d2_at(SH.q[b][pi], k) = S.q;
+    i2_at(SH.info[b][pi], k) = ok ? (S.cell | ((S.j != S.cell) << 16) | (1 << 17) | ((int)S.ioff << 18)) : 0;
+    // beyond rmax S.ir is 1/rmax and r0i = (1/r)/scale: keep 1/r itself
+    d2_at(SH.ir[b][pi], k) = S.ioff ? S.r0i * g.scale : S.ir;
+    d2_at(SH.iR2[b][pi], k) = S.iR2;
+    d2_at(SH.somx2i[b][pi], k) = S.somx2i;
+    d2_at(SH.fac[b][pi], k) = S.fac;
+  };
+  auto setup = [&](int i) {
+    const int b = i & 1, s = i % kWSSlots;
+    mbar_wait(&ps_full[s], (i / kWSSlots) & 1);
+    const size_t k0 = (t0 + (size_t)i * stride) * kWSTile + 2 * (size_t)pi;
+    setup_one(b, s, k0, 0);
+    setup_one(b, s, k0 + 1, 1);
+  };
+
+  // ---- helper: epilogue of tile i -----------------------------------------------------------
+  // The records the result is combined with (velocity, or acc/pot in mode 0) are gathered most
+  // of a window ahead (prefetch_side(i) right after the epilogue of tile i-1, used by
+  // epilogue(i) in the next window), so that no helper waits on a global load.
+  const rec4 *side = F.mode ? F.vel : F.accp;
+  rec4 sideA = rec4{0.0, 0.0, 0.0, 0.0}, sideB = sideA;
+  auto prefetch_side = [&](int i) {
+    const int s = i % kWSSlots;
+    const size_t k0 = (t0 + (size_t)i * stride) * kWSTile + 2 * (size_t)pi;
+    const uint2 ii = *reinterpret_cast<const uint2 *>(&SH.perm[s][2 * pi]);
+    if (k0 >= lo && k0 < n) sideA = ld_rec_rw(side + ii.x);
+    if (k0 + 1 >= lo && k0 + 1 < n) sideB = ld_rec_rw(side + ii.y);
+  };
+  auto epilogue_one = [&](int b, int s, size_t gk, int k, uint32_t idx, const rec4 &v) {
+    if (!(gk >= lo && gk < n)) return;
+    const int inf = i2_at(SH.info[b][pi], k);
+    const bool ok = (inf >> 17) & 1, ioff = (inf >> 18) & 1;
+    const rec4 pm = SH.ps[s][2 * pi + k];
+    double o[4] = {0.0, 0.0, 0.0, 0.0};
+    if (ok) {
+      SphForce S;
+      S.x = pm.x - g.cx; S.y = pm.y - g.cy; S.z = pm.z - g.cz;
+      S.R2 = S.x * S.x + S.y * S.y;
+      S.ir = ioff ? g.inv_rmax : d2_at(SH.ir[b][pi], k);
+      S.iR2 = d2_at(SH.iR2[b][pi], k);
+      S.somx2i = d2_at(SH.somx2i[b][pi], k);
+      S.fac = d2_at(SH.fac[b][pi], k);
+      const double sm[4] = {d2_at(SH.sums[b][0][pi], k), d2_at(SH.sums[b][1][pi], k),
+                            d2_at(SH.sums[b][2][pi], k), d2_at(SH.sums[b][3][pi], k)};
+      sph_force_project(S, ioff, sm, o);
+    }
+    force_store_side(g, F, idx, ok, o, pm, v);
+  };
+  auto epilogue = [&](int i) {
+    const int b = i & 1, s = i % kWSSlots;
+    const size_t k0 = (t0 + (size_t)i * stride) * kWSTile + 2 * (size_t)pi;
+    const uint2 ii = *reinterpret_cast<const uint2 *>(&SH.perm[s][2 * pi]);
+    epilogue_one(b, s, k0, 0, ii.x, sideA);
+    epilogue_one(b, s, k0 + 1, 1, ii.y, sideB);
+  };
+
+  // ---- evaluation of tile i -------------------------------------------------------------------
+  auto evaluate = [&](int i) {
+    const int b = i & 1;
+    mbar_wait(&rows_full[b], (i >> 1) & 1);
+    const FPDesc d = desc[b];
+    const double2 *rows = SH.rows[b];
+    const int2 inf = SH.info[b][pi];
+    const bool okA = (inf.x >> 17) & 1, okB = (inf.y >> 17) & 1;
+    SphForce A, B;
+    {
+      const double2 ct = SH.costh[b][pi], c1 = SH.c1[b][pi], s1 = SH.s1[b][pi], pp = SH.p[b][pi], qq = SH.q[b][pi];
+      A.costh = ct.x; B.costh = ct.y;
+      A.xd = sph_clamp_x(ct.x); B.xd = sph_clamp_x(ct.y);
+      A.c1 = c1.x; B.c1 = c1.y; A.s1 = s1.x; B.s1 = s1.y;
+      A.p = pp.x; B.p = pp.y; A.q = qq.x; B.q = qq.y;
+    }
+    A.cell = inf.x & 0xffff; A.j = A.cell + ((inf.x >> 16) & 1); A.ioff = (inf.x >> 18) & 1;
+    B.cell = inf.y & 0xffff; B.j = B.cell + ((inf.y >> 16) & 1); B.ioff = (inf.y >> 18) & 1;
+    A.ratio = B.ratio = 1.0; A.r0i = B.r0i = 0.0;
+    const int rlo = d.rlo, rhi = d.rlo + d.nrows - 1;
+    const bool inA = A.cell >= rlo && A.j <= rhi, inB = B.cell >= rlo && B.j <= rhi;
+    double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool pair = okA && okB && A.cell == B.cell && A.j == B.j && !A.ioff && !B.ioff;
+    if (pair && inA) {
+      sph_force_sums2<L>(c_inv, A, B, rows + (A.cell - rlo) * ROW, rows + (A.j - rlo) * ROW,
+                         [](const double2 *a) { return *a; }, sa, sb);
+    } else if (pair) {
+      sph_force_sums2<L>(c_inv, A, B, T + (size_t)A.cell * ROW, T + (size_t)A.j * ROW,
+                         [](const double2 *a) { return __ldg(a); }, sa, sb);
+    } else {
+      // rare: the pair straddles a cell boundary, or a particle beyond rmax (generic loads);
+      // the continuation factors as sph_force_setup forms them
+      if (A.ioff) { const double ir0 = SH.ir[b][pi].x; A.ratio = g.rmax * ir0; A.r0i = ir0 * g.inv_scale; }
+      if (B.ioff) { const double ir0 = SH.ir[b][pi].y; B.ratio = g.rmax * ir0; B.r0i = ir0 * g.inv_scale; }
+      auto ld = [](const double2 *a) { return *a; };
+      const double2 *bA = inA ? rows - (ptrdiff_t)rlo * ROW : T;
+      const double2 *bB = inB ? rows - (ptrdiff_t)rlo * ROW : T;
+      if (okA) sph_force_sums<L, true>(c_inv, A, bA + (size_t)A.cell * ROW, bA + (size_t)A.j * ROW, ld, sa);
+      if (okB) sph_force_sums<L, true>(c_inv, B, bB + (size_t)B.cell * ROW, bB + (size_t)B.j * ROW, ld, sb);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) SH.sums[b][k][pi] = make_double2(sa[k], sb[k]);
+  };
+
+  // The two roles never share code after this point, so that ptxas allocates registers for
+  // each branch within its own setmaxnreg budget.  Both execute 1 + (ntiles + 1) CTA barriers.
+  if (is_eval) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGE));
+    asm volatile("bar.sync 0;" ::: "memory");               // prep of tile 0 is there
+    for (int i = 0; i <= ntiles; i++) {
+      if (i < ntiles) evaluate(i);
+      asm volatile("bar.sync 0;" ::: "memory");
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGH));
+    if (issuer) {
+      issue_rows(0);
+      issue_ps(0);
+      if (ntiles > 1) issue_ps(1);
+    }
+    setup(0);
+    prefetch_side(0);
+    asm volatile("bar.sync 0;" ::: "memory");
+    for (int i = 0; i <= ntiles; i++) {
+      if (issuer) {
+        if (i + 1 < ntiles) issue_rows(i + 1);      // rows slot (i+1)&1 was drained in window i-1
+        if (i + 2 < ntiles) issue_ps(i + 2);        // ps slot (i+2)%4 == (i-2)%4: its epilogue ran in window i-1
+      }
+      if (i >= 1) epilogue(i - 1);
+      if (i < ntiles) prefetch_side(i);             // for epilogue(i) in the next window
+      if (i + 1 < ntiles) setup(i + 1);
+      asm volatile("bar.sync 0;" ::: "memory");
+    }
   }
 }
 
@@ -1203,15 +1418,51 @@ template <int L> struct Launch {
     CU_LAUNCH_CHECK();
     return EXPB200_OK;
   }
+  template <int ROWS, int REGE>
+  static int force_ws(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
+                      const ForceOut &F, const uint32_t *perm, const uint32_t *skeys,
+                      const uint32_t *seg, int keybase, size_t n, int2 *tdesc)
+  {
+    auto kern = sph_force_ws_kernel<L, ROWS, REGE, 256 - REGE>;
+    constexpr size_t sm = sizeof(WSShared<L, ROWS>);
+    static int ctas[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &occ = ctas[dev & 63];
+    if (!occ) {
+      CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      int nb = 0, nsm = 0;
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWSThreads, sm));
+      CU_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      occ = (nb > 0 ? nb : 1) * nsm;
+    }
+    const size_t ntiles = div_up(n, (size_t)kWSTile);
+    const unsigned grid = (unsigned)(ntiles < (size_t)occ ? ntiles : (size_t)occ);
+    sph_tile_desc_kernel<<<div_up(ntiles, 256), 256, 0, st>>>(skeys, seg, keybase, n, kWSTile, g.numr, ROWS, tdesc);
+    kern<<<grid, kWSThreads, sm, st>>>(g, T, ps, F, perm, tdesc, seg, keybase, n);
+    CU_LAUNCH_CHECK();
+    return EXPB200_OK;
+  }
   static int force(cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps, const ForceOut &F,
                    const uint32_t *perm, const uint32_t *skeys, const uint32_t *seg, int keybase, size_t n,
                    int2 *tdesc)
   {
-    // 2: persistent pipelined kernel (default), 1: one-shot two-particle kernel, 0: one particle per lane
+    // 2: persistent pipelined kernel (default), 3: warp-specialised persistent kernel (measured
+    // 0.70 ms against 0.69 ms at 1e7 particles: not faster),
+    // 1: one-shot two-particle kernel, 0: one particle per lane
     static const int variant = getenv("EXPB200_FORCE_VARIANT") ? atoi(getenv("EXPB200_FORCE_VARIANT")) : 2;
     if constexpr (L <= 8) {
-      // the pipelined kernel reads the sorted keys while (mode 2) writing the next step's keys:
+      // the pipelined kernels read the sorted keys while (mode 2) writing the next step's keys:
       // they must be different buffers
+      if (variant >= 3 && skeys && tdesc && !(F.mode == 2 && skeys == F.keys)) {
+        static const int split = getenv("EXPB200_WS_REGS") ? atoi(getenv("EXPB200_WS_REGS")) : 0;
+        if (split == 1) return force_ws<4, 160>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        if (split == 2) return force_ws<4, 152>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        if (split == 3) return force_ws<4, 144>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        if (split == 4) return force_ws<4, 136>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        if (split == 5) return force_ws<4, 128>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+        return force_ws<4, 168>(st, g, T, ps, F, perm, skeys, seg, keybase, n, tdesc);
+      }
       if (variant >= 2 && skeys && tdesc && !(F.mode == 2 && skeys == F.keys)) {
         // CTAs of two warps (tiles of 128 particles), 6 per SM, 4 table rows per stage, two stages:
         // the fastest of the shapes measured at 1e7 particles (128x3, 192x2, 384x1 were slower)
@@ -1822,11 +2073,20 @@ int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int n
     CU_TRY(cudaMemcpyAsync(s->coef_use, s->coef, s->ncoef * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     if ((rc = build_field(s, c->stream))) return rc;
     const bool last = step == nsteps - 1;
-    ForceOut F{c->accp, c->vel, c->posm, c->keys[0], 0.5 * dt, dt, last ? 1 : 2};
-    ProfRegion pr(K_FORCE, c->stream, 2);   // tile pre-pass + force
-    rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->keys[c->cur],
-                      c->seg, 0, c->n, s->tdesc);
-    if (rc) return rc;
+    // the force kernel reads the sorted keys (tile descriptors) and, when another step follows,
+    // writes the next step's keys: after a two-pass sort the sorted keys sit in keys[0], so the
+    // new ones go through the sort's scratch array (the same kernel runs either way, which keeps
+    // step() x k and steps(k) bit-identical)
+    const bool alias = !last && c->keys[c->cur] == c->keys[0];
+    ForceOut F{c->accp, c->vel, c->posm, alias ? c->rank : c->keys[0], 0.5 * dt, dt, last ? 1 : 2};
+    {
+      ProfRegion pr(K_FORCE, c->stream, 2);   // tile pre-pass + force
+      rc = launch_force(s->cfg.lmax, c->stream, gm, s->T, c->psort, F, c->perm[c->cur], c->keys[c->cur],
+                        c->seg, 0, c->n, s->tdesc);
+      if (rc) return rc;
+    }
+    if (alias)
+      CU_TRY(cudaMemcpyAsync(c->keys[0], c->rank, c->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   }
   return EXPB200_OK;
 }
