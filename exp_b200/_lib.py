@@ -176,6 +176,7 @@ SIGNATURES = {
     "expb200_sphere_set_level_coefficients": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_sphere_covariance": (C.c_int, [_H, _H, C.c_int, C.c_double, C.c_int, C.c_uint64, c_up, c_dp,
                                             c_dp, c_dp]),
+    "expb200_sphere_covariance_eof": (C.c_int, [_H, _H, C.c_int, C.c_double, c_dp]),
     "expb200_sphere_step": (C.c_int, [_H, _H, C.c_double, C.c_double, C.c_void_p]),
     "expb200_sphere_steps": (C.c_int, [_H, _H, C.c_double, C.c_int, C.c_double, C.c_void_p]),
     "expb200_cylinder_create": (C.c_int, [C.c_int, C.POINTER(CylinderConfig), c_dp, c_dp, c_dp, c_dp,
@@ -198,6 +199,8 @@ SIGNATURES = {
     "expb200_cylinder_get_mass": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_cylinder_covariance": (C.c_int, [_H, _H, C.c_int, C.c_double, C.c_int, C.c_uint64, c_up, c_dp,
                                               c_dp, c_dp]),
+    "expb200_cylinder_covariance_pca": (C.c_int, [_H, _H, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int,
+                                                  c_up, c_dp, c_dp, c_dp]),
     "expb200_profile_enable": (C.c_int, [C.c_int]),
     "expb200_profile_reset": (C.c_int, []),
     "expb200_profile_kernels": (C.c_int, []),
@@ -209,6 +212,7 @@ SIGNATURES = {
     "expb200_comm_destroy": (C.c_int, [C.c_void_p]),
     "expb200_allreduce_sum": (C.c_int, [C.c_void_p, c_dp, C.c_size_t, C.c_void_p]),
     "expb200_comm_check": (C.c_int, [C.c_void_p]),
+    "expb200_allreduce_sum_host": (C.c_int, [C.c_void_p, c_dp, C.c_size_t]),
     "expb200_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
     "expb200_comm_peer_connect": (C.c_int, [C.c_void_p, C.c_char_p]),
 }

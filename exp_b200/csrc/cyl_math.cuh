@@ -44,6 +44,9 @@ struct CylGeom {
   double cx, cy, cz, rtrunc2;
   int rotate;
   double body[9], orig[9];   // orient->transformBody()/transformOrig(), row-major
+  // covariance pass: 0 = covar (complex vec vec^H), 1 = PCAVAR (moduli with the azimuthal
+  // factors), 2 = PCAEOF (moduli of the table values), exputil/EmpCylSL.cc:4089-4141
+  int cov_mode;
 };
 
 // EmpCylSL::r_to_xi (exputil/EmpCylSL.cc:6446-6463)

@@ -481,8 +481,15 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
           const double vc = z00.x * wj[0] + z10.x * wj[1] + z01.x * wj[2] + z11.x * wj[3];
           const double vs = z00.y * wj[0] + z10.y * wj[1] + z01.y * wj[2] + z11.y * wj[3];
           const double cm = trg[(j * M1 + mg0 + ml) * 2], sm = trg[(j * M1 + mg0 + ml) * 2 + 1];
-          a = vc * cm + vs * sm;
-          b = vc * sm - vs * cm;
+          if (g.cov_mode == 0) {
+            a = vc * cm + vs * sm;
+            b = vc * sm - vs * cm;
+          } else if (g.cov_mode == 1) {       // sqrt(mass) * |(Vc cos, Vs sin)|: vc, vs carry -4 pi sqrt(mass)
+            const double hc = vc * cm, hs = vs * sm;
+            a = sqrt(hc * hc + hs * hs) * (0.25 / M_PI);
+          } else {                            // sqrt(mass) * |norm| * |(Vc, Vs)|
+            a = sqrt(vc * vc + vs * vs);
+          }
           vcr += sqm[j] * a;
           vci += sqm[j] * b;
         }
@@ -728,7 +735,7 @@ int expb200_cylinder_create(int device, const expb200_cylinder_config *cfg,
   g.ascale = cfg->ascale; g.hscale = cfg->hscale;
   // EmpCylSL::setup_table (exputil/EmpCylSL.cc:2130-2137)
   g.rtable = M_SQRT1_2 * cfg->rmax;
-  g.cx = g.cy = g.cz = 0.0; g.rtrunc2 = 1.0e300; g.rotate = 0;
+  g.cx = g.cy = g.cz = 0.0; g.rtrunc2 = 1.0e300; g.rotate = 0; g.cov_mode = 0;
   g.xmin = cyl_r_to_xi(g, cfg->rmin * cfg->ascale);
   double xmax = cyl_r_to_xi(g, g.rtable * cfg->ascale);
   g.dx = (xmax - g.xmin) / cfg->numx;
@@ -1059,9 +1066,9 @@ int expb200_cylinder_get_level_coefficients(expb200_cylinder s, int which, int m
 }
 
 // ~ the covariance branch of EmpCylSL::accumulate for levlist[mlevel] (see the kernels above)
-int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mlevel, double adb,
-                                int sampT, uint64_t indx_base, unsigned *numbT, double *massT,
-                                double *VC, double *MV)
+static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int mlevel, double adb,
+                                    int sampT, uint64_t indx_base, unsigned *numbT, double *massT,
+                                    double *VC, double *MV, int mode)
 {
   REQUIRE(s && c, "NULL argument");
   REQUIRE(s->device == c->device, "device mismatch");
@@ -1081,6 +1088,7 @@ int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mle
   if (c->n == 0) return EXPB200_OK;
 
   CylGeom g = geom_for(s, c);
+  g.cov_mode = mode;
   g.rotate = s->geom.rotate;
   ProfRegion pr(K_COV, st, 0);
   if (!s->Zt) {
@@ -1169,6 +1177,34 @@ int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mle
   COV_TRY(cudaStreamSynchronize(st));
 #undef COV_TRY
   cleanup();
+  return EXPB200_OK;
+}
+
+int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mlevel, double adb,
+                                int sampT, uint64_t indx_base, unsigned *numbT, double *massT,
+                                double *VC, double *MV)
+{
+  return cylinder_covariance_impl(s, c, mlevel, adb, sampT, indx_base, numbT, massT, VC, MV, 0);
+}
+
+// ~ the PCAVAR / PCAEOF branches of EmpCylSL::accumulate (exputil/EmpCylSL.cc:4089-4119):
+//   which = 1 (PCAVAR): covV[T][m][n] += mass modu1,  covM[T][m](n,o) += mass modu1 modu2,
+//                       modu = |(Vc cos m phi, Vs sin m phi)|
+//   which = 2 (PCAEOF): tvar[m](n,o) += mass modu1 modu2, modu = |norm| |(Vc, Vs)| (pass sampT = 1
+//                       and read covM; covV is then sum mass modu)
+// Real outputs covV [sampT][(mmax+1)][norder], covM [sampT][(mmax+1)][norder][norder].
+int expb200_cylinder_covariance_pca(expb200_cylinder s, expb200_component c, int mlevel, double adb,
+                                    int sampT, uint64_t indx_base, int which, unsigned *numbT,
+                                    double *massT, double *covV, double *covM)
+{
+  REQUIRE(s && (which == 1 || which == 2), "which=%d (1: PCAVAR, 2: PCAEOF)", which);
+  const size_t MN = (size_t)(s->cfg.mmax + 1) * s->cfg.norder, N = s->cfg.norder;
+  std::vector<double> VC(covV ? (size_t)sampT * MN * 2 : 0), MV(covM ? (size_t)sampT * MN * N * 2 : 0);
+  int rc = cylinder_covariance_impl(s, c, mlevel, adb, sampT, indx_base, numbT, massT,
+                                    covV ? VC.data() : nullptr, covM ? MV.data() : nullptr, which);
+  if (rc) return rc;
+  if (covV) for (size_t k = 0; k < (size_t)sampT * MN; k++) covV[k] = VC[2 * k];
+  if (covM) for (size_t k = 0; k < (size_t)sampT * MN * N; k++) covM[k] = MV[2 * k];
   return EXPB200_OK;
 }
 

@@ -96,9 +96,12 @@ struct Comm {
   bool connected = false;
   unsigned long long seq = 0;
   int *err_host = nullptr, *err_dev = nullptr;   // mapped pinned: set by a kernel that timed out
-  cudaStream_t last_stream = nullptr;            // stream of the previous peer all-reduce
+  cudaStream_t last_stream = nullptr;            // stream of the previous all-reduce
   cudaEvent_t last_done = nullptr;               // recorded after it
   unsigned long long timeout_ns = 600ull * 1000000000ull;
+  cudaStream_t host_stream = nullptr;            // expb200_allreduce_sum_host staging
+  double *host_stage = nullptr;
+  size_t host_stage_cap = 0;
 };
 
 __device__ __forceinline__ unsigned long long global_ns()
@@ -166,28 +169,29 @@ int nccl_allreduce_sum_f64(void *comm, double *buf, size_t n, cudaStream_t strea
 {
   Comm *c = as_comm(comm);
   if (!c) { set_error("not an expb200 communicator"); return EXPB200_EINVAL; }
+  DeviceGuard g(c->device);         // the stream belongs to the communicator's device
+  // collectives on one communicator must execute in issue order on every rank (the peer
+  // kernel's double buffering and NCCL both rely on it): join the previous call's stream
+  if (c->last_done && c->last_stream != stream) CU_TRY(cudaStreamWaitEvent(stream, c->last_done, 0));
   if (c->connected && n <= kPeerCap) {
     if (*c->err_host) {
       set_error(*c->err_host == 2 ? "peer all-reduce: sequence numbers out of order"
                                   : "peer all-reduce timed out waiting for another rank");
       return EXPB200_ENCCL;
     }
-    DeviceGuard g(c->device);       // the stream belongs to the communicator's device
-    // calls on one communicator must execute in issue order: join the previous call's stream
-    if (c->last_done && c->last_stream != stream) CU_TRY(cudaStreamWaitEvent(stream, c->last_done, 0));
     c->seq++;
     peer_allreduce_kernel<<<1, 256, 0, stream>>>(c->P, c->world, c->rank, buf, n, c->seq, c->timeout_ns,
                                                  c->err_dev);
     CU_LAUNCH_CHECK();
-    if (!c->last_done) CU_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
-    CU_TRY(cudaEventRecord(c->last_done, stream));
-    c->last_stream = stream;
-    return EXPB200_OK;
+  } else {
+    Api *a = api();
+    if (!a) return EXPB200_ENCCL;
+    int rc = a->allreduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, stream);
+    if (rc) return fail(a, rc, "ncclAllReduce");
   }
-  Api *a = api();
-  if (!a) return EXPB200_ENCCL;
-  int rc = a->allreduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, stream);
-  if (rc) return fail(a, rc, "ncclAllReduce");
+  if (!c->last_done) CU_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(c->last_done, stream));
+  c->last_stream = stream;
   return EXPB200_OK;
 }
 
@@ -196,6 +200,8 @@ int nccl_allreduce_sum_f64(void *comm, double *buf, size_t n, cudaStream_t strea
 using namespace expb200;
 
 extern "C" {
+
+int expb200_comm_check(void *comm);
 
 int expb200_comm_unique_id(char id[128])
 {
@@ -237,6 +243,8 @@ int expb200_comm_destroy(void *comm)
   if (c->local) cudaFree(c->local);
   if (c->err_host) cudaFreeHost(c->err_host);
   if (c->last_done) cudaEventDestroy(c->last_done);
+  if (c->host_stage) cudaFree(c->host_stage);
+  if (c->host_stream) cudaStreamDestroy(c->host_stream);
   Api *a = api();
   if (a && c->nccl) a->destroy(c->nccl);
   c->magic = 0;
@@ -247,6 +255,30 @@ int expb200_comm_destroy(void *comm)
 int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream)
 {
   return nccl_allreduce_sum_f64(comm, device_buf, n, (cudaStream_t)stream);
+}
+
+// In-place sum over ranks of a HOST vector (the reference's MPI_Allreduce of the covariance
+// arrays, src/AxisymmetricBasis.cc:1224-1254, exputil/EmpCylSL.cc:4272-4275, 4567-4571):
+// staged through a device buffer of the communicator, blocking.
+int expb200_allreduce_sum_host(void *comm, double *host_buf, size_t n)
+{
+  Comm *c = as_comm(comm);
+  REQUIRE(c && (host_buf || n == 0), "bad argument");
+  if (n == 0) return EXPB200_OK;
+  DeviceGuard g(c->device);
+  if (!c->host_stream) CU_TRY(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
+  if (c->host_stage_cap < n) {
+    if (c->host_stage) cudaFree(c->host_stage);
+    c->host_stage = nullptr; c->host_stage_cap = 0;
+    CU_TRY(cudaMalloc(&c->host_stage, n * sizeof(double)));
+    c->host_stage_cap = n;
+  }
+  CU_TRY(cudaMemcpyAsync(c->host_stage, host_buf, n * sizeof(double), cudaMemcpyHostToDevice, c->host_stream));
+  int rc = nccl_allreduce_sum_f64(comm, c->host_stage, n, c->host_stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(host_buf, c->host_stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->host_stream));
+  CU_TRY(cudaStreamSynchronize(c->host_stream));
+  return expb200_comm_check(comm);
 }
 
 // Error state of the peer all-reduces issued so far (call after a stream/device sync):

@@ -34,7 +34,7 @@ inline SphGeom make_sph_geom(const expb200_sphere_config &cfg)
   g.scale = cfg.scale; g.rmin = cfg.rmin; g.rmax = cfg.rmax;
   g.inv_rmap = 1.0 / g.rmap; g.inv_dxi = 1.0 / g.dxi; g.inv_scale = 1.0 / g.scale; g.inv_rmax = 1.0 / g.rmax;
   g.cx = g.cy = g.cz = 0.0; g.rtrunc2 = 1.0e300;
-  g.fx = g.fy = g.fz = 0.0; g.ext = 0;
+  g.fx = g.fy = g.fz = 0.0; g.ext = 0; g.cov_unit_m = 0;
   return g;
 }
 

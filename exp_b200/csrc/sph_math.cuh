@@ -114,6 +114,9 @@ struct SphGeom {
   // component's centre (fx,fy,fz) (src/SphericalBasis.cc:1519-1540).  ext = 0: both coincide.
   double fx, fy, fz;
   int ext;
+  // covariance pass: 1 = the pcaeof variant (tvar, src/SphericalBasis.cc:536-545, 573-581), whose
+  // m > 0 products carry no angular factor
+  int cov_unit_m;
 };
 
 constexpr int kSphPoly = 5;   // double2 entries per (cell, slot): c0 c1 c2 d0 d1, each (cos, sin)

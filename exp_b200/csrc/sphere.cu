@@ -1189,7 +1189,7 @@ sph_cov_deposit_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__r
       const bool mine = cell == c;
       const double aa = mine ? waa : 0.0, ab = mine ? wab : 0.0, bb = mine ? wbb : 0.0;
       sph_for_each_plm<L, 0, L>(d.costh, c_inv, [](int) {}, [&](int l, int m, double plm, double) {
-        const double f = c_K[l * (kMaxL + 1) + m] * plm;
+        const double f = (g.cov_unit_m && m) ? 1.0 : c_K[l * (kMaxL + 1) + m] * plm;
         const double f2 = f * f;
         const int q = 3 * sph_slot(L, l, m);
         A[q] = fma(aa, f2, A[q]);
@@ -2102,9 +2102,9 @@ int expb200_sphere_step(expb200_sphere s, expb200_component c, double dt, double
 // matrices of the bin's particles.  Host outputs (any may be NULL):
 //   countT[sampT], massT[sampT], coefT[sampT][ldim][nmax][2], coefM[sampT][ldim][nmax][nmax]
 // with ldim = (lmax+1)(lmax+2)/2, index l(l+1)/2 + m (the reference's iC).
-int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel, double adb, int sampT,
-                              uint64_t indx_base, unsigned *countT, double *massT, double *coefT,
-                              double *coefM)
+static int sphere_covariance_impl(expb200_sphere s, expb200_component c, int mlevel, double adb, int sampT,
+                                  uint64_t indx_base, unsigned *countT, double *massT, double *coefT,
+                                  double *coefM, int unit_m)
 {
   REQUIRE(s && c, "NULL argument");
   REQUIRE(s->device == c->device, "device mismatch");
@@ -2116,7 +2116,8 @@ int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel,
   cudaStream_t st = c->stream;
   { cudaStream_t ws = s->work_stream(); if (ws != st) CU_TRY(cudaStreamSynchronize(ws)); }
   s->last_stream = st;
-  const SphGeom gm = geom_for(s, c);
+  SphGeom gm = geom_for(s, c);
+  gm.cov_unit_m = unit_m;
   const int R = gm.numr, N = gm.nmax, ldim = gm.nslot;
   const uint32_t nkeys = (uint32_t)sampT * R + 1;
   int rc = ensure_seg(c, nkeys);
@@ -2218,6 +2219,23 @@ int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel,
 #undef COV_TRY
   cleanup();
   return EXPB200_OK;
+}
+
+int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel, double adb, int sampT,
+                              uint64_t indx_base, unsigned *countT, double *massT, double *coefT,
+                              double *coefM)
+{
+  return sphere_covariance_impl(s, c, mlevel, adb, sampT, indx_base, countT, massT, coefT, coefM, 0);
+}
+
+// ~ the `compute && pcaeof` branch (src/SphericalBasis.cc:536-545, 573-581):
+// tvar[lm](n,o) = sum_p wk[n] wk[o] / mass with wk = potd(l,n) facL mass fac0 for m = 0 and
+// wk = potd(l,n) mass fac0 (no angular factor) for m > 0, over levlist[mlevel];
+// tvar [ldim][nmax][nmax] is overwritten.  Same pipeline as the pcavar matrices with one bin.
+int expb200_sphere_covariance_eof(expb200_sphere s, expb200_component c, int mlevel, double adb, double *tvar)
+{
+  REQUIRE(tvar, "tvar is NULL");
+  return sphere_covariance_impl(s, c, mlevel, adb, 1, 0, nullptr, nullptr, nullptr, tvar, 1);
 }
 
 } // extern "C"

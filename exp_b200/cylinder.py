@@ -93,6 +93,19 @@ class Cylinder:
         return dict(numbT=numbT, massT=massT, VC=VC[..., 0] + 1j * VC[..., 1],
                     MV=MV[..., 0] + 1j * MV[..., 1])
 
+    def covariance_pca(self, c: Component, sampT: int, which: str, adb: float = 1.0, indx_base: int = 0):
+        """The PCAVAR ('pcavar') / PCAEOF ('pcaeof') accumulations of EmpCylSL::accumulate
+        (exputil/EmpCylSL.cc:4089-4119): covV [T][m][n], covM [T][m][n][n] (real)."""
+        M1, N = self.mmax + 1, self.norder
+        numbT = np.zeros(sampT, dtype=np.uint32)
+        massT = np.zeros(sampT)
+        covV, covM = np.zeros((sampT, M1, N)), np.zeros((sampT, M1, N, N))
+        check(_lib.lib().expb200_cylinder_covariance_pca(
+            self._h, c._h, self.mlevel, float(adb), int(sampT), int(indx_base),
+            {"pcavar": 1, "pcaeof": 2}[which], numbT.ctypes.data_as(_lib.c_up), massT.ctypes.data_as(c_dp),
+            covV.ctypes.data_as(c_dp), covM.ctypes.data_as(c_dp)))
+        return dict(numbT=numbT, massT=massT, covV=covV, covM=covM)
+
     def set_coefficients(self, cos=None, sin=None, cylmass=-1.0):
         if cos is None:
             check(_lib.lib().expb200_cylinder_set_coefficients(self._h, None, None, float(cylmass)))

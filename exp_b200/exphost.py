@@ -51,6 +51,13 @@ def host():
         H.exphost_set_sphere.argtypes = [C.c_int, C.POINTER(SphereDesc)]
         H.exphost_set_cylinder.argtypes = [C.c_int, C.POINTER(CylinderDesc)]
         H.exphost_add_interaction.argtypes = [C.c_int, C.c_int]
+        H.exphost_component_global.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
+        H.exphost_sphere_pca_options.argtypes = [C.c_int] * 9 + [C.c_double] * 4
+        H.exphost_sphere_get_covariance.argtypes = [C.c_int, C.POINTER(C.c_int), c_dp, _lib.c_up, c_dp, c_dp,
+                                                    c_dp, c_dp, c_dp, c_dp, c_dp]
+        H.exphost_cylinder_cov_options.argtypes = [C.c_int] * 7
+        H.exphost_cylinder_get_covariance.argtypes = [C.c_int, C.POINTER(C.c_int), _lib.c_up] + [c_dp] * 6
+        H.exphost_pca_hall.argtypes = [C.c_int] * 6 + [C.c_double] * 4 + [c_dp] * 9
         H.exphost_do_steps.argtypes = [C.c_int]
         H.exphost_do_steps_timed.argtypes = [C.c_int, c_dp]
         H.exphost_get_particles.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, _lib.c_up, _lib.c_fp]
@@ -124,6 +131,69 @@ class Simulation:
         _check(self.H.exphost_set_cylinder(idx, C.byref(d)))
         self.kinds[idx] = ("cylinder", tab.mmax + 1, tab.norder)
 
+    def component_global(self, idx, indx_base, nbodies_tot):
+        """sharded runs: this rank holds global particles [indx_base, indx_base + n)"""
+        _check(self.H.exphost_component_global(idx, int(indx_base), int(nbodies_tot)))
+
+    TK = {"Hall": 0, "VarianceCut": 1, "CumulativeCut": 2, "VarianceWeighted": 3, "None": 4}
+
+    def sphere_pca_options(self, idx, npca=2 ** 31 - 1, npca0=2 ** 31 - 1, nint=0, pcavar=False,
+                           pcaeof=False, samplesz=1, subsamp=False, tk_type="None", hexp=1.0, snr=1.0,
+                           tksmooth=3.0, tkcum=0.95):
+        """the covariance / PCA keys of the sphereSL force (src/AxisymmetricBasis.cc:64-92)"""
+        _check(self.H.exphost_sphere_pca_options(idx, npca, npca0, nint, int(pcavar), int(pcaeof),
+                                                 samplesz, int(subsamp), self.TK[tk_type], hexp, snr,
+                                                 tksmooth, tkcum))
+
+    def sphere_covariance(self, idx):
+        """massT, countT, expcoefT, expcoefM, tvar and the Hall factors after the last compute step"""
+        _, nrow, nmax = self.kinds[idx]
+        L = int(round(np.sqrt(nrow))) - 1
+        ldim = (L + 1) * (L + 2) // 2
+        sT, mu = C.c_int(0), C.c_double(0.0)
+        _check(self.H.exphost_sphere_get_covariance(idx, C.byref(sT), None, None, None, None, None, None,
+                                                    None, None, C.byref(mu)))
+        T = sT.value
+        if T == 0:
+            return None
+        out = dict(sampT=T, muse=mu.value, massT=np.zeros(T), countT=np.zeros(T, dtype=np.uint32),
+                   coefT=np.zeros((T, ldim, nmax, 2)), coefM=np.zeros((T, ldim, nmax, nmax)),
+                   tvar=np.zeros((ldim, nmax, nmax)), b_Hall=np.zeros((ldim, nmax)),
+                   s_Hall=np.ones((ldim, nmax)), weight=np.ones((ldim, nmax)))
+        _check(self.H.exphost_sphere_get_covariance(
+            idx, C.byref(sT), _p(out["massT"]), out["countT"].ctypes.data_as(_lib.c_up), _p(out["coefT"]),
+            _p(out["coefM"]), _p(out["tvar"]), _p(out["b_Hall"]), _p(out["s_Hall"]), _p(out["weight"]),
+            C.byref(mu)))
+        out["coefT"] = out["coefT"][..., 0] + 1j * out["coefT"][..., 1]
+        return out
+
+    def cylinder_cov_options(self, idx, nint=0, npca=2 ** 30, npca0=2 ** 30, pcavar=False, pcaeof=False,
+                             samplesz=1):
+        _check(self.H.exphost_cylinder_cov_options(idx, nint, npca, npca0, int(pcavar), int(pcaeof), samplesz))
+
+    def cylinder_covariance(self, idx, covar=True, pcavar=False, pcaeof=False):
+        _, M1, N = self.kinds[idx]
+        sT = C.c_int(0)
+        _check(self.H.exphost_cylinder_get_covariance(idx, C.byref(sT), None, None, None, None, None, None, None))
+        T = sT.value
+        if T == 0:
+            return None
+        out = dict(sampT=T, numbT=np.zeros(T, dtype=np.uint32), massT=np.zeros(T))
+        if covar:
+            out["VC"], out["MV"] = np.zeros((T, M1, N, 2)), np.zeros((T, M1, N, N, 2))
+        if pcavar:
+            out["covV"], out["covM"] = np.zeros((T, M1, N)), np.zeros((T, M1, N, N))
+        if pcaeof:
+            out["tvar"] = np.zeros((M1, N, N))
+        g = lambda k: _p(out[k]) if k in out else None
+        _check(self.H.exphost_cylinder_get_covariance(idx, C.byref(sT), out["numbT"].ctypes.data_as(_lib.c_up),
+                                                      _p(out["massT"]), g("VC"), g("MV"), g("covV"), g("covM"),
+                                                      g("tvar")))
+        if covar:
+            out["VC"] = out["VC"][..., 0] + 1j * out["VC"][..., 1]
+            out["MV"] = out["MV"][..., 0] + 1j * out["MV"][..., 1]
+        return out
+
     def add_interaction(self, frm, on):
         _check(self.H.exphost_add_interaction(frm, on))
 
@@ -191,3 +261,24 @@ class Simulation:
         pc, vc = np.zeros(self.multistep + 1), np.zeros(self.multistep + 1)
         _check(self.H.exphost_state(C.byref(t), C.byref(k), _p(pc), _p(vc)))
         return dict(tnow=t.value, this_step=k.value, pos_check=pc, vel_check=vc)
+
+
+def pca_hall(Lmax, nmax, massT, coefT, coefM, used, subsamp=False, tk_type="None", hexp=1.0, snr=1.0,
+             tksmooth=3.0, tkcum=0.95, expcoef=None):
+    """AxisymmetricBasis::pca_hall_3d + smoothing (src/AxisymmetricBasis.cc:198-660) on given subsample
+    arrays; host-only.  coefT complex [T][ldim][nmax], coefM real [T][ldim][nmax][nmax]."""
+    H = host()
+    T = len(massT)
+    ldim = (Lmax + 1) * (Lmax + 2) // 2
+    cT = np.ascontiguousarray(np.stack([np.real(coefT), np.imag(coefT)], axis=-1), dtype=np.float64)
+    cM = np.ascontiguousarray(coefM, dtype=np.float64)
+    mT = np.ascontiguousarray(massT, dtype=np.float64)
+    out = dict(b_Hall=np.zeros((ldim, nmax)), s_Hall=np.zeros((ldim, nmax)), weight=np.zeros((ldim, nmax)),
+               evalJK=np.zeros((ldim, nmax)), evec=np.zeros((ldim, nmax, nmax)))
+    ex = None if expcoef is None else np.ascontiguousarray(expcoef, dtype=np.float64).copy()
+    _check(H.exphost_pca_hall(Lmax, nmax, T, int(used), int(subsamp), Simulation.TK[tk_type], hexp, snr,
+                              tksmooth, tkcum, _p(mT), _p(cT), _p(cM), _p(out["b_Hall"]), _p(out["s_Hall"]),
+                              _p(out["weight"]), _p(out["evalJK"]), _p(out["evec"]),
+                              None if ex is None else _p(ex)))
+    out["expcoef"] = ex
+    return out

@@ -1,6 +1,8 @@
 // Cylinder.cc -- see Cylinder.H
 #include "Cylinder.H"
 
+#include <cmath>
+
 #include "global.H"
 
 namespace exphost {
@@ -32,10 +34,21 @@ void Cylinder::determine_coefficients(Component *c)
 {
   if (!self_consistent && !firstime_coef && !initializing) return;
 
+  // subsample / PCA gating (src/Cylinder.cc:1004-1025)
+  compute = false;
+  covar = false;
+  if (nint) {
+    if (mstep == 0 && this_step % nint == 0) { compute = true; covar = true; }
+  }
+  if (pcavar || pcaeof) {
+    if (this_step >= npca0) compute = (mstep == 0) && !((this_step - npca0) % npca);
+  }
+
   uint64_t use1 = 0;
   double mass1 = 0.0;
   EXPHOST_CHECK(expb200_cylinder_determine_coefficients(b200c, c->b200, (int)mlevel, c->Adiabatic(),
                                                         nullptr, nullptr, &use1, &mass1));
+  if (compute) accumulate_covariance(c);
   // EmpCylSL::make_coefficients' two MPI_Allreduce calls and the cylmass one
   // (exputil/EmpCylSL.cc:4192-4214, src/Cylinder.cc:1093-1095) -> one device all-reduce of
   // [cos | sin | mass]
@@ -54,6 +67,64 @@ void Cylinder::determine_coefficients(Component *c)
     EXPHOST_CHECK(expb200_cylinder_multistep_commit(b200c, (int)mlevel));
   }
   firstime_coef = false;
+}
+
+// The compute branch of EmpCylSL::accumulate for this level's particles, added to the per-bin
+// arrays (zeroed at mlevel == 0), and at the last level their reduction over ranks
+// (EmpCylSL::make_coefficients / make_covar).
+void Cylinder::accumulate_covariance(Component *c)
+{
+  const size_t M1 = mmax + 1, N = ncylorder;
+  if (sampT == 0) {
+    sampT = defSampT ? defSampT : (unsigned)std::floor(std::sqrt((double)c->CurTotal()));
+    if (sampT < 1) sampT = 1;
+  }
+  const size_t T = sampT;
+  if (mlevel == 0) {
+    numbT.assign(T, 0); massT.assign(T, 0.0);
+    if (covar) { VC.assign(T * M1 * N * 2, 0.0); MV.assign(T * M1 * N * N * 2, 0.0); }
+    if (pcavar) { covV.assign(T * M1 * N, 0.0); covM.assign(T * M1 * N * N, 0.0); }
+    if (pcaeof) tvar.assign(M1 * N * N, 0.0);
+  }
+  std::vector<unsigned> nb(T);
+  std::vector<double> ms(T);
+  bool counted = false;
+  auto add_counts = [&]() {
+    if (counted) return;
+    for (size_t k = 0; k < T; k++) { numbT[k] += nb[k]; massT[k] += ms[k]; }
+    counted = true;
+  };
+  if (covar) {
+    std::vector<double> v(VC.size()), m(MV.size());
+    EXPHOST_CHECK(expb200_cylinder_covariance(b200c, c->b200, (int)mlevel, c->Adiabatic(), (int)T, c->indx_base,
+                                              nb.data(), ms.data(), v.data(), m.data()));
+    for (size_t k = 0; k < v.size(); k++) VC[k] += v[k];
+    for (size_t k = 0; k < m.size(); k++) MV[k] += m[k];
+    add_counts();
+  }
+  if (pcavar) {
+    std::vector<double> v(covV.size()), m(covM.size());
+    EXPHOST_CHECK(expb200_cylinder_covariance_pca(b200c, c->b200, (int)mlevel, c->Adiabatic(), (int)T,
+                                                  c->indx_base, 1, nb.data(), ms.data(), v.data(), m.data()));
+    for (size_t k = 0; k < v.size(); k++) covV[k] += v[k];
+    for (size_t k = 0; k < m.size(); k++) covM[k] += m[k];
+    add_counts();
+  }
+  if (pcaeof) {
+    std::vector<double> m(tvar.size());
+    EXPHOST_CHECK(expb200_cylinder_covariance_pca(b200c, c->b200, (int)mlevel, c->Adiabatic(), 1, 0, 2,
+                                                  nullptr, nullptr, nullptr, m.data()));
+    for (size_t k = 0; k < m.size(); k++) tvar[k] += m[k];
+  }
+  if (mlevel == multistep && nccl_comm) {
+    auto red = [&](std::vector<double> &a) {
+      if (!a.empty()) EXPHOST_CHECK(expb200_allreduce_sum_host(nccl_comm, a.data(), a.size()));
+    };
+    std::vector<double> cnt(numbT.begin(), numbT.end());
+    red(cnt);
+    for (size_t k = 0; k < cnt.size(); k++) numbT[k] = (unsigned)std::llround(cnt[k]);
+    red(massT); red(VC); red(MV); red(covV); red(covM); red(tvar);
+  }
 }
 
 void Cylinder::compute_multistep_coefficients()

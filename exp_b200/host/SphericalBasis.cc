@@ -1,6 +1,8 @@
 // SphericalBasis.cc -- see SphericalBasis.H
 #include "SphericalBasis.H"
 
+#include <limits>
+
 #include "global.H"
 
 namespace exphost {
@@ -18,6 +20,8 @@ SphericalBasis::SphericalBasis(const SLGridSphTables &t, int device, double scal
   expb200_sphere_config cfg = {t.lmax, t.nmax, t.numr, t.cmap, t.rmin, t.rmax, t.rmap, scale, rmin, rmax,
                                NO_L0, NO_L1, EVEN_L, EVEN_M, M0_only, (int)multistep};
   EXPHOST_CHECK(expb200_sphere_create(device, &cfg, t.ev, t.ef, t.p0, &b200s));
+  pca.Lmax = Lmax;
+  pca.nmax = nmax;
 }
 
 SphericalBasis::~SphericalBasis()
@@ -30,9 +34,33 @@ void SphericalBasis::determine_coefficients(Component *c)
   // src/SphericalBasis.cc:694: a fixed (not self-consistent) basis is computed once
   if (!self_consistent && !firstime_coef && !initializing) return;
 
+  // covariance gating (src/SphericalBasis.cc:696-781)
+  pca.update_compute(mstep, this_step);
+  if (pca.compute) {
+    pca.allocate(c->CurTotal());
+    if (mlevel == 0) pca.zero_accumulation();
+  }
+
   uint64_t use1 = 0;
   EXPHOST_CHECK(expb200_sphere_determine_coefficients(b200s, c->b200, (int)mlevel, c->Adiabatic(),
                                                       nullptr, &use1));
+  if (pca.compute) {
+    // the `compute` branch of determine_coefficients_thread (:501-509, 525-545, 563-581) for
+    // this level's particles; bins by the particle's global index
+    const int T = (int)pca.sampT, L = pca.ldim(), N = nmax;
+    if (pca.pcavar) {
+      std::vector<unsigned> cnt(T);
+      std::vector<double> mass(T), cT((size_t)T * L * N * 2), cM((size_t)T * L * N * N);
+      EXPHOST_CHECK(expb200_sphere_covariance(b200s, c->b200, (int)mlevel, c->Adiabatic(), T, c->indx_base,
+                                              cnt.data(), mass.data(), cT.data(), cM.data()));
+      pca.add_level(cnt.data(), mass.data(), cT.data(), cM.data());
+    }
+    if (pca.pcaeof) {
+      std::vector<double> tv((size_t)L * N * N);
+      EXPHOST_CHECK(expb200_sphere_covariance_eof(b200s, c->b200, (int)mlevel, c->Adiabatic(), tv.data()));
+      pca.add_tvar(tv.data());
+    }
+  }
   // the reference's (Lmax+1)^2 host MPI_Allreduce calls (:864-903) -> one device all-reduce
   if (nccl_comm) {
     double *d = nullptr; void *st = nullptr;
@@ -46,6 +74,23 @@ void SphericalBasis::determine_coefficients(Component *c)
     EXPHOST_CHECK(expb200_sphere_set_coefficients(b200s, nullptr));
   }
   if (multistep == 0 || tnow == resetT) used += (int)use1;          // :905-907
+
+  // last level (:909-931): gather the subsample arrays over ranks, then PCA / Hall smoothing of
+  // the installed coefficients
+  if (mlevel == multistep) {
+    if (pca.compute) pca.gather(nccl_comm);
+    if (pca.npca0 < std::numeric_limits<int>::max()) {
+      int used_all = pca.used_cov;
+      if (nccl_comm) { double u = used_all; EXPHOST_CHECK(expb200_allreduce_sum_host(nccl_comm, &u, 1)); used_all = (int)u; }
+      pca.pca_hall(pca.compute, used_all, nullptr);
+      if (pca.pcavar && pca.tk_type != AxisymmetricBasis::None && !pca.evec.empty()) {
+        if (multistep) compute_multistep_coefficients();
+        std::vector<double> ex = get_coefs();
+        pca.smooth(ex.data());
+        EXPHOST_CHECK(expb200_sphere_set_coefficients(b200s, ex.data()));
+      }
+    }
+  }
   firstime_coef = false;
 }
 
@@ -57,6 +102,8 @@ void SphericalBasis::compute_multistep_coefficients()
 void SphericalBasis::get_acceleration_and_potential(Component *cC)
 {
   if (!use_external) {
+    // (as in the reference, a multistep run re-forms expcoef from the level tables here, which
+    // discards a PCA-smoothed table installed by determine_coefficients: src/SphericalBasis.cc:1690-1695)
     if (multistep && (self_consistent || initializing)) compute_multistep_coefficients();
   }
   EXPHOST_CHECK(expb200_sphere_determine_acceleration(b200s, cC->b200, (int)mlevel));

@@ -125,6 +125,109 @@ int exphost_set_cylinder(int index, const exphost_cylinder_desc *d)
   });
 }
 
+int exphost_component_global(int index, uint64_t indx_base, uint64_t nbodies_tot)
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    c->indx_base = indx_base;
+    c->nbodies_tot = nbodies_tot;
+  });
+}
+
+int exphost_sphere_pca_options(int index, int npca, int npca0, int nint, int pcavar, int pcaeof,
+                               int samplesz, int subsamp, int tk_type, double hexp, double snr,
+                               double tksmooth, double tkcum)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<SphericalBasis *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not sphereSL", __FILE__, __LINE__);
+    AxisymmetricBasis &p = s->pca;
+    p.npca = npca; p.npca0 = npca0; p.nint = nint;
+    p.pcavar = pcavar || nint > 0;                    // src/AxisymmetricBasis.cc:86-89
+    p.pcaeof = pcaeof;
+    p.defSampT = (unsigned)samplesz;
+    p.subsamp = subsamp;
+    p.tk_type = (AxisymmetricBasis::TKType)tk_type;
+    p.hexp = hexp; p.snr = snr; p.tksmooth = tksmooth; p.tkcum = tkcum;
+  });
+}
+
+int exphost_sphere_get_covariance(int index, int *sampT, double *massT, unsigned *countT, double *coefT,
+                                  double *coefM, double *tvar, double *b_Hall, double *s_Hall,
+                                  double *weight, double *muse)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<SphericalBasis *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not sphereSL", __FILE__, __LINE__);
+    const AxisymmetricBasis &p = s->pca;
+    if (sampT) *sampT = p.massT.empty() ? 0 : (int)p.sampT;
+    if (muse) *muse = p.muse;
+    if (massT) std::copy(p.massT.begin(), p.massT.end(), massT);
+    if (countT) std::copy(p.countT.begin(), p.countT.end(), countT);
+    if (coefT) memcpy(coefT, p.expcoefT.data(), p.expcoefT.size() * sizeof(std::complex<double>));
+    if (coefM) std::copy(p.expcoefM.begin(), p.expcoefM.end(), coefM);
+    if (tvar) std::copy(p.tvar.begin(), p.tvar.end(), tvar);
+    if (b_Hall) std::copy(p.b_Hall.begin(), p.b_Hall.end(), b_Hall);
+    if (s_Hall) std::copy(p.s_Hall.begin(), p.s_Hall.end(), s_Hall);
+    if (weight) std::copy(p.weight.begin(), p.weight.end(), weight);
+  });
+}
+
+int exphost_cylinder_cov_options(int index, int nint, int npca, int npca0, int pcavar, int pcaeof, int samplesz)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<Cylinder *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not cylinder", __FILE__, __LINE__);
+    s->nint = nint; s->npca = npca; s->npca0 = npca0; s->pcavar = pcavar; s->pcaeof = pcaeof;
+    s->defSampT = (unsigned)samplesz;
+  });
+}
+
+int exphost_cylinder_get_covariance(int index, int *sampT, unsigned *numbT, double *massT, double *VC,
+                                    double *MV, double *covV, double *covM, double *tvar)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<Cylinder *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not cylinder", __FILE__, __LINE__);
+    if (sampT) *sampT = s->massT.empty() ? 0 : (int)s->sampT;
+    if (numbT) std::copy(s->numbT.begin(), s->numbT.end(), numbT);
+    if (massT) std::copy(s->massT.begin(), s->massT.end(), massT);
+    if (VC) std::copy(s->VC.begin(), s->VC.end(), VC);
+    if (MV) std::copy(s->MV.begin(), s->MV.end(), MV);
+    if (covV) std::copy(s->covV.begin(), s->covV.end(), covV);
+    if (covM) std::copy(s->covM.begin(), s->covM.end(), covM);
+    if (tvar) std::copy(s->tvar.begin(), s->tvar.end(), tvar);
+  });
+}
+
+int exphost_pca_hall(int Lmax, int nmax, int sampT, int used, int subsamp, int tk_type, double hexp,
+                     double snr, double tksmooth, double tkcum, const double *massT, const double *coefT,
+                     const double *coefM, double *b_Hall, double *s_Hall, double *weight, double *evalJK,
+                     double *evec, double *expcoef)
+{
+  return guarded([&] {
+    AxisymmetricBasis p;
+    p.Lmax = Lmax; p.nmax = nmax; p.pcavar = true; p.subsamp = subsamp;
+    p.tk_type = (AxisymmetricBasis::TKType)tk_type;
+    p.hexp = hexp; p.snr = snr; p.tksmooth = tksmooth; p.tkcum = tkcum;
+    p.defSampT = (unsigned)sampT;
+    p.allocate(0);
+    const size_t L = (size_t)p.ldim();
+    double mu = 0.0;
+    for (int T = 0; T < sampT; T++) { p.massT[T] = massT[T]; mu += massT[T]; }
+    p.muse = mu;
+    for (size_t k = 0; k < (size_t)sampT * L * nmax; k++) p.expcoefT[k] = std::complex<double>(coefT[2 * k], coefT[2 * k + 1]);
+    if (coefM) std::copy(coefM, coefM + (size_t)sampT * L * nmax * nmax, p.expcoefM.begin());
+    p.pca_hall(true, used, nullptr);
+    if (b_Hall) std::copy(p.b_Hall.begin(), p.b_Hall.end(), b_Hall);
+    if (s_Hall) std::copy(p.s_Hall.begin(), p.s_Hall.end(), s_Hall);
+    if (weight) std::copy(p.weight.begin(), p.weight.end(), weight);
+    if (evalJK) std::copy(p.evalJK.begin(), p.evalJK.end(), evalJK);
+    if (evec) std::copy(p.evec.begin(), p.evec.end(), evec);
+    if (expcoef) p.smooth(expcoef);
+  });
+}
+
 int exphost_add_interaction(int from, int on)
 {
   return guarded([&] { g_comp->add_interaction(component_at(from), component_at(on)); });

@@ -41,6 +41,36 @@ int exphost_component_options(int index, const double center[3], double rtrunc, 
                               int freezeLev, int dtreset);
 int exphost_set_sphere(int index, const exphost_sphere_desc *d);
 int exphost_set_cylinder(int index, const exphost_cylinder_desc *d);
+/* sharded runs: this rank's particles are global [indx_base, indx_base + n) of nbodies_tot */
+int exphost_component_global(int index, uint64_t indx_base, uint64_t nbodies_tot);
+/* covariance / PCA options of the sphereSL force (src/AxisymmetricBasis.cc:64-92): npca, npca0,
+ * nint (nint > 0 implies pcavar), pcavar, pcaeof, samplesz (0: floor(sqrt(N))), subsamp,
+ * tk_type (0 Hall, 1 VarianceCut, 2 CumulativeCut, 3 VarianceWeighted, 4 None), hexp, snr,
+ * tksmooth, tkcum */
+int exphost_sphere_pca_options(int index, int npca, int npca0, int nint, int pcavar, int pcaeof,
+                               int samplesz, int subsamp, int tk_type, double hexp, double snr,
+                               double tksmooth, double tkcum);
+/* the gathered subsample arrays after the last compute step: sampT, then massT[sampT],
+ * countT[sampT], coefT[sampT][ldim][nmax][2], coefM[sampT][ldim][nmax][nmax], tvar[ldim][nmax][nmax],
+ * b_Hall / s_Hall / weight [ldim][nmax] (any pointer may be NULL) */
+int exphost_sphere_get_covariance(int index, int *sampT, double *massT, unsigned *countT, double *coefT,
+                                  double *coefM, double *tvar, double *b_Hall, double *s_Hall,
+                                  double *weight, double *muse);
+/* the same switches for the cylinder force (src/Cylinder.cc:1004-1025): nint turns the `covar`
+ * accumulation on, pcavar / pcaeof the PCAVAR / PCAEOF ones; results after the last compute step
+ * (any pointer may be NULL): numbT, massT [sampT]; VC [sampT][mmax+1][norder][2],
+ * MV [sampT][mmax+1][norder][norder][2]; covV, covM (real); tvar [mmax+1][norder][norder] */
+int exphost_cylinder_cov_options(int index, int nint, int npca, int npca0, int pcavar, int pcaeof, int samplesz);
+int exphost_cylinder_get_covariance(int index, int *sampT, unsigned *numbT, double *massT, double *VC,
+                                    double *MV, double *covV, double *covM, double *tvar);
+/* Stateless AxisymmetricBasis::pca_hall_3d + the smoothing pass (src/AxisymmetricBasis.cc:198-660)
+ * on given subsample arrays (no GPU needed): in massT[sampT], coefT[sampT][ldim][nmax][2],
+ * coefM[sampT][ldim][nmax][nmax]; out b_Hall, s_Hall, weight, evalJK [ldim][nmax], evec
+ * [ldim][nmax][nmax]; expcoef[(Lmax+1)^2][nmax] smoothed in place (may be NULL). */
+int exphost_pca_hall(int Lmax, int nmax, int sampT, int used, int subsamp, int tk_type, double hexp,
+                     double snr, double tksmooth, double tkcum, const double *massT, const double *coefT,
+                     const double *coefM, double *b_Hall, double *s_Hall, double *weight, double *evalJK,
+                     double *evec, double *expcoef);
 int exphost_add_interaction(int from, int on);
 int exphost_begin_run(void);
 int exphost_do_steps(int nsteps);

@@ -84,6 +84,15 @@ class Sphere:
             coefM.ctypes.data_as(c_dp)))
         return dict(countT=countT, massT=massT, coefT=coefT[..., 0] + 1j * coefT[..., 1], coefM=coefM)
 
+    def covariance_eof(self, c: Component, adb: float = 1.0):
+        """The pcaeof accumulation tvar[ldim][nmax][nmax] of levlist[mlevel]
+        (src/SphericalBasis.cc:536-545, 573-581)."""
+        ldim = (self.lmax + 1) * (self.lmax + 2) // 2
+        tvar = np.zeros((ldim, self.nmax, self.nmax))
+        check(_lib.lib().expb200_sphere_covariance_eof(self._h, c._h, self.mlevel, float(adb),
+                                                       tvar.ctypes.data_as(c_dp)))
+        return tvar
+
     def set_coefficients(self, coef=None):
         """HtoD_coefs: install the coefficients the force evaluation uses (None: the
         vector accumulated on the device)."""

@@ -233,6 +233,12 @@ int expb200_sphere_covariance(expb200_sphere s, expb200_component c, int mlevel,
                               int sampT, uint64_t indx_base, unsigned *countT, double *massT,
                               double *coefT, double *coefM);
 
+/* The pcaeof accumulation (`compute && pcaeof`, src/SphericalBasis.cc:536-545, 573-581) for
+ * levlist[mlevel]: tvar[ldim][nmax][nmax] (overwritten) = sum_p wk[n] wk[o] / mass, where the m > 0
+ * products carry no angular factor. */
+int expb200_sphere_covariance_eof(expb200_sphere s, expb200_component c, int mlevel, double adb,
+                                  double *tvar);
+
 /* One fused single-level KDK step for a self-gravitating component, the
  * sequence of do_step (src/step.cc:272-322) with the arithmetic of the
  * separate calls: kick(dt/2) drift(dt) coefficients force kick(dt/2).
@@ -319,6 +325,15 @@ int expb200_cylinder_covariance(expb200_cylinder s, expb200_component c, int mle
                                 int sampT, uint64_t indx_base, unsigned *numbT, double *massT,
                                 double *VC, double *MV);
 
+/* The PCAVAR / PCAEOF variants of the same branch (exputil/EmpCylSL.cc:4089-4119; results as
+ * EmpCylSL::set_covV/set_covM/set_tvar take them): which = 1 (PCAVAR): covV[T][m][n] += mass modu,
+ * covM[T][m](n,o) += mass modu_n modu_o with modu = |(Vc cos m phi, Vs sin m phi)|; which = 2
+ * (PCAEOF): tvar[m](n,o) += mass modu_n modu_o with modu = 4 pi |(Vc, Vs)| (use sampT = 1 and read
+ * covM).  Real outputs covV[sampT][(mmax+1)][norder], covM[sampT][(mmax+1)][norder][norder]. */
+int expb200_cylinder_covariance_pca(expb200_cylinder s, expb200_component c, int mlevel, double adb,
+                                    int sampT, uint64_t indx_base, int which, unsigned *numbT,
+                                    double *massT, double *covV, double *covM);
+
 /* ------------------------------------------------------------------------
  * Multi-GPU: one process (MPI rank) per GPU; NCCL is loaded with dlopen.
  * Replaces the host MPI_Allreduce of the coefficient vector
@@ -330,6 +345,10 @@ int expb200_comm_destroy(void *comm);
 /* Calls on one communicator may use different streams (one per component): each call is
  * ordered after the previous one.  ~ MPI_Allreduce(MPI_SUM, MPI_DOUBLE) in place. */
 int expb200_allreduce_sum(void *comm, double *device_buf, size_t n, void *stream);
+/* The same for a host vector (staged through a device buffer, blocking): the reference's
+ * MPI_Allreduce of the covariance arrays (src/AxisymmetricBasis.cc:1224-1254,
+ * exputil/EmpCylSL.cc:4272-4275, 4323-4327, 4567-4571). */
+int expb200_allreduce_sum_host(void *comm, double *host_buf, size_t n);
 /* Error state of the peer-memory all-reduces issued so far (after a sync): a rank that never
  * arrived within EXPB200_PEER_TIMEOUT_S seconds (default 600; 0 = wait for ever, like MPI) or
  * out-of-order sequence numbers fill the result with NaN and make this return EXPB200_ENCCL. */

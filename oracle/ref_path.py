@@ -79,6 +79,8 @@ def lib():
         L.ref_cyl_accumulate.restype = C.c_long
         L.ref_cyl_accumulate.argtypes = [C.c_void_p, C.c_long, c_dp, c_dp, c_dp, c_dp, c_ulp, c_dp,
                                          c_dp, c_dp, C.c_int, c_up, c_dp, c_dp, c_dp]
+        L.ref_cyl_accumulate_pca.argtypes = [C.c_void_p, C.c_long, c_dp, c_dp, c_dp, c_dp, c_ulp, C.c_int,
+                                             C.c_int, c_dp, c_dp]
         L.ref_cyl_accumulated_eval.argtypes = [C.c_void_p, c_dp, c_dp, C.c_double, C.c_double,
                                                C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.ref_incr_position.argtypes = [C.c_long, c_dp, c_dp, c_up, C.c_int, C.c_double, C.c_int,
@@ -241,6 +243,21 @@ class RefCylinder:
                                         seq.ctypes.data_as(c_ulp), _dp(cs), _dp(sn), _dp(cm), 0,
                                         None, None, None, None)
         return dict(cos=cs, sin=sn, used=used, cylmass1=cm[0])
+
+    def accumulate_pca(self, pos, mass, which, sampT=1, seq=None):
+        """the PCAVAR ('pcavar') / PCAEOF ('pcaeof') branches of EmpCylSL::accumulate: covV, covM
+        (for 'pcaeof': covM[0] = tvar)"""
+        pos, mass = _f64(pos), _f64(mass)
+        n = len(pos)
+        r = np.sqrt(pos[:, 0] * pos[:, 0] + pos[:, 1] * pos[:, 1])
+        z = pos[:, 2].copy()
+        phi = np.array([math.atan2(y, x) for x, y in zip(pos[:, 0], pos[:, 1])])
+        seq = np.arange(n, dtype=np.uint64) if seq is None else np.ascontiguousarray(seq, dtype=np.uint64)
+        M1, N = self.mmax + 1, self.norder
+        covV, covM = np.zeros((sampT, M1, N)), np.zeros((sampT, M1, N, N))
+        lib().ref_cyl_accumulate_pca(self.h, n, _dp(r), _dp(z), _dp(phi), _dp(mass), seq.ctypes.data_as(c_ulp),
+                                     sampT, {"pcavar": 1, "pcaeof": 2}[which], _dp(covV), _dp(covM))
+        return covV, covM
 
     def accumulated_eval(self, cos, sin, r, z, phi):
         cos, sin = _f64(cos), _f64(sin)

@@ -397,6 +397,44 @@ long ref_cyl_accumulate(void *hh, long np, const double *r, const double *z, con
   return (long)e.howmany1[0][0];
 }
 
+/* the PCAVAR (which = 1) / PCAEOF (which = 2) branches of EmpCylSL::accumulate:
+ * covV[sampT][MMAX+1][NORDER], covM[sampT][MMAX+1][NORDER][NORDER] (PCAVAR) or
+ * tvar[MMAX+1][NORDER][NORDER] written to covM with sampT = 1 (PCAEOF) */
+void ref_cyl_accumulate_pca(void *hh, long np, const double *r, const double *z, const double *phi,
+                            const double *mass, const unsigned long *seq, int sampT, int which,
+                            double *covV, double *covM)
+{
+  EmpCylSL &e = static_cast<CylHandle *>(hh)->e;
+  const int M = e.MMAX, N = e.NORDER;
+  e.coefs_made.assign(1, false);
+  e.howmany1.assign(1, std::vector<unsigned>(1, 0));
+  e.vc.assign(1, Eigen::MatrixXd());
+  e.vs.assign(1, Eigen::MatrixXd());
+  e.cylmass1.assign(1, 0.0);
+  e.cosN.assign(1, std::make_shared<EmpCylSL::VectorD2>(1, std::vector<Eigen::VectorXd>(M + 1, Eigen::VectorXd(N))));
+  e.sinN.assign(1, std::make_shared<EmpCylSL::VectorD2>(1, std::vector<Eigen::VectorXd>(M + 1, Eigen::VectorXd(N))));
+  e.covar = false;
+  e.PCAVAR = which == 1;
+  e.PCAEOF = which == 2;
+  e.sampT = sampT;
+  e.numbT1.assign(1, std::vector<unsigned>(sampT, 0));
+  e.massT1.assign(1, std::vector<double>(sampT, 0.0));
+  e.covV.assign(1, std::vector<std::vector<Eigen::VectorXd>>(sampT, std::vector<Eigen::VectorXd>(M + 1, Eigen::VectorXd(N))));
+  e.covM.assign(1, std::vector<std::vector<Eigen::MatrixXd>>(sampT, std::vector<Eigen::MatrixXd>(M + 1, Eigen::MatrixXd(N, N))));
+  e.tvar.assign(1, std::vector<Eigen::MatrixXd>(M + 1, Eigen::MatrixXd(N, N)));
+  for (long i = 0; i < np; i++) e.accumulate(r[i], z[i], phi[i], mass[i], seq ? seq[i] : (unsigned long)i, 0, 0, true);
+  e.PCAVAR = e.PCAEOF = false;
+  for (int T = 0; T < sampT; T++)
+    for (int m = 0; m <= M; m++)
+      for (int a = 0; a < N; a++) {
+        if (covV) covV[((size_t)T * (M + 1) + m) * N + a] = which == 1 ? e.covV[0][T][m][a] : 0.0;
+        if (covM)
+          for (int b = 0; b < N; b++)
+            covM[(((size_t)T * (M + 1) + m) * N + a) * N + b] =
+                which == 1 ? e.covM[0][T][m](a, b) : (T == 0 ? e.tvar[0][m](a, b) : 0.0);
+      }
+}
+
 void ref_cyl_accumulated_eval(void *hh, const double *accum_cos, const double *accum_sin, double r,
                               double z, double phi, double *p0, double *p, double *fr, double *fz, double *fp)
 {

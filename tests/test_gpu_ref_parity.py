@@ -162,3 +162,40 @@ def test_external_component_uses_owner_centre():
     out = cH.download()
     assert acc_rel_err(out["acc"], S.acc).max() <= 1e-8
     assert np.abs(out["pot"] - S.pot).max() <= 1e-8 * np.abs(S.pot).max()
+
+
+def test_sphere_pcaeof_tvar_vs_reference_code():
+    """a10: the pcaeof branch tvar (src/SphericalBasis.cc:536-545, 573-581)"""
+    tab = get_table("hernquist", 4, 10)
+    n = 20000
+    pos, vel, mass = ics.hernquist_halo(n, seed=41)
+    pos = pos + np.array([0.01, -0.02, 0.005])
+    r = R.RefSphere(tab).coefficients(pos, mass, adb=0.9, sampT=3, pcaeof=True)
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    s = Sphere(tab)
+    tvar = s.covariance_eof(c, adb=0.9)
+    assert np.abs(tvar - r["tvar"]).max() <= 1e-10 * np.abs(r["tvar"]).max()
+    cov = s.covariance(c, 3, adb=0.9)
+    assert np.abs(cov["coefM"] - r["coefM"].real).max() <= 1e-10 * np.abs(r["coefM"]).max()
+    assert np.abs(cov["coefT"] - r["coefT"]).max() <= 1e-10 * np.abs(r["coefT"]).max()
+    assert np.array_equal(cov["countT"], r["countT"])
+
+
+@pytest.mark.parametrize("which", ["pcavar", "pcaeof"])
+def test_cylinder_pca_variants_vs_reference_code(which):
+    """a15: the PCAVAR / PCAEOF branches of EmpCylSL::accumulate (exputil/EmpCylSL.cc:4089-4119)"""
+    tab = cyltable.synthetic_cyl_table(mmax=4, norder=6, numx=48, numy=24)
+    g = O.CylGridPy(tab)
+    consts = (g.c.Rtable, g.c.XMIN, g.c.dX, g.c.YMIN, g.c.dY)
+    n = 6000
+    pos, vel, mass = ics.exponential_disk(n, seed=46)
+    sampT = 4 if which == "pcavar" else 1
+    rV, rM = R.RefCylinder(tab, consts).accumulate_pca(pos, mass, which, sampT=sampT)
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    cyl = Cylinder(tab, rcylmax=1e6)
+    out = cyl.covariance_pca(c, sampT, which)
+    assert np.abs(out["covM"] - rM).max() <= 1e-10 * np.abs(rM).max()
+    if which == "pcavar":
+        assert np.abs(out["covV"] - rV).max() <= 1e-10 * np.abs(rV).max()
