@@ -89,3 +89,13 @@ def synthetic_cyl_table(mmax=6, norder=18, numx=64, numy=32, ascale=0.01, hscale
                 out["rforce" + tag][m, n] = -(f(R + hR, Z, m, n, phase) - f(np.maximum(R - hR, 0.0), Z, m, n, phase)) / (2 * hR)
                 out["zforce" + tag][m, n] = -(f(R, Z + hZ, m, n, phase) - f(R, Z - hZ, m, n, phase)) / (2 * hZ)
     return CylTable(mmax, norder, numx, numy, cmapr, cmapz, ascale, hscale, rmin, rmax, **out)
+
+
+def table_from_cache(path: str) -> CylTable:
+    """The six EmpCylSL grids from a reference cache file (EmpCylSL::ReadH5Cache,
+    exputil/EmpCylSL.cc:7486-7680), read with exp_b200.h5lite."""
+    from . import h5lite
+    c = h5lite.read_cylinder_cache(path)
+    return CylTable(int(c["mmax"]), int(c["nmax"]), int(c["numx"]), int(c["numy"]), int(c["cmapr"]),
+                    int(c["cmapz"]), float(c["ascl"]), float(c["hscl"]), float(c["rmin"]), float(c["rmax"]),
+                    c["potC"], c["potS"], c["rforceC"], c["rforceS"], c["zforceC"], c["zforceS"])

@@ -267,3 +267,18 @@ def ortho_check(tab: SLGridSphTable, l: int) -> np.ndarray:
     wts[0] = wts[-1] = 0.5 * tab.dxi
     jac = tab.r ** 2 / d_xi_to_r(tab.xi, tab.cmap, tab.rmap) * wts
     return -(pot * jac[None, :]) @ den.T
+
+
+def table_from_cache(path: str, model) -> SLGridSphTable:
+    """The table image from a reference SLGridSph HDF5 cache (SLGridSph::ReadH5Cache,
+    exputil/SLGridMP2.cc:490-617) plus the model for p0 / d0 (SLGridSph::init_table, :1355-1382:
+    p0 = sphpot(r), d0 = sphdens(r) on the xi grid).  Read with exp_b200.h5lite (no HDF5 library)."""
+    from . import h5lite
+    c = h5lite.read_slgrid_cache(path)
+    lmax, nmax, numr, cmap = int(c["lmax"]), int(c["nmax"]), int(c["numr"]), int(c["cmap"])
+    rmin, rmax, rmap = float(c["rmin"]), float(c["rmax"]), float(c["rmapping"])
+    xmin, xmax = r_to_xi(rmin, cmap, rmap), r_to_xi(rmax, cmap, rmap)
+    xi = xmin + (xmax - xmin) / (numr - 1) * np.arange(numr)
+    r = xi_to_r(xi, cmap, rmap)
+    return SLGridSphTable(lmax, nmax, numr, cmap, rmin, rmax, rmap, c["ev"], c["ef"], model.pot(r),
+                          4.0 * math.pi * model.dens(r), xi, r)
