@@ -207,6 +207,7 @@ SIGNATURES = {
     "expb200_profile_name": (C.c_char_p, [C.c_int]),
     "expb200_profile_read": (C.c_int, [C.POINTER(C.c_ulonglong), c_dp, C.POINTER(C.c_ulonglong)]),
     "expb200_fp64_peak": (C.c_int, [C.c_int, c_dp, c_dp]),
+    "expb200_dmma_peak": (C.c_int, [C.c_int, C.c_int, c_dp]),
     "expb200_comm_unique_id": (C.c_int, [C.c_char_p]),
     "expb200_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "expb200_comm_destroy": (C.c_int, [C.c_void_p]),

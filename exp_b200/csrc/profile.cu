@@ -143,3 +143,83 @@ extern "C" int expb200_fp64_peak(int device, double *tflops, double *sm_mhz_hint
   if (sm_mhz_hint) *sm_mhz_hint = best * 1.0e12 / (2.0 * 64.0 * kSMsB200) / 1.0e6;   // if 64 DFMA/clk/SM
   return EXPB200_OK;
 }
+
+// ---------------------------------------------------------------------------
+// FP64 tensor-core (DMMA) peak by instruction shape: the roofline denominator of the covariance
+// kernels and the evidence for which mma.sync f64 shape to use on sm_100a.
+//   shape 0: m8n8k4 (the sm_80 shape), 1: m16n8k4, 2: m16n8k8, 3: m16n8k16
+// ---------------------------------------------------------------------------
+namespace expb200 {
+namespace {
+template <int SHAPE>
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double a0, double b0)
+{
+  double c[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { c[k][0] = c[k][1] = c[k][2] = c[k][3] = threadIdx.x * 1e-9 + k; }
+  double a[8], b[4];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = a0 + k * 1e-3;
+#pragma unroll
+  for (int k = 0; k < 4; k++) b[k] = b0 + k * 1e-3;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {       // four independent accumulator tiles
+      if (SHAPE == 0)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a[0]), "d"(b[0]));
+      else if (SHAPE == 1)
+        asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+d"(c[k][0]), "+d"(c[k][1]), "+d"(c[k][2]), "+d"(c[k][3]) : "d"(a[0]), "d"(a[1]), "d"(b[0]));
+      else if (SHAPE == 2)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+d"(c[k][0]), "+d"(c[k][1]), "+d"(c[k][2]), "+d"(c[k][3])
+                     : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+      else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+                     "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                     : "+d"(c[k][0]), "+d"(c[k][1]), "+d"(c[k][2]), "+d"(c[k][3])
+                     : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                       "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s += c[k][0] + c[k][1] + c[k][2] + c[k][3];
+  if (s == 123.456) out[0] = s;
+}
+} // namespace
+} // namespace expb200
+
+extern "C" int expb200_dmma_peak(int device, int shape, double *tflops)
+{
+  REQUIRE(tflops && shape >= 0 && shape <= 3, "bad argument");
+  DeviceGuard g(device);
+  double *d = nullptr;
+  CU_TRY(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t a, b;
+  CU_TRY(cudaEventCreate(&a));
+  CU_TRY(cudaEventCreate(&b));
+  const int blocks = kSMsB200 * 8, threads = 256, iters = 2048;
+  static const double fma_per_instr[4] = {8.0 * 8 * 4, 16.0 * 8 * 4, 16.0 * 8 * 8, 16.0 * 8 * 16};
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU_TRY(cudaEventRecord(a, 0));
+    switch (shape) {
+      case 0: dmma_peak_kernel<0><<<blocks, threads>>>(d, iters, 1.0, 1e-9); break;
+      case 1: dmma_peak_kernel<1><<<blocks, threads>>>(d, iters, 1.0, 1e-9); break;
+      case 2: dmma_peak_kernel<2><<<blocks, threads>>>(d, iters, 1.0, 1e-9); break;
+      default: dmma_peak_kernel<3><<<blocks, threads>>>(d, iters, 1.0, 1e-9); break;
+    }
+    CU_TRY(cudaEventRecord(b, 0));
+    CU_TRY(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, a, b));
+    const double flops = 2.0 * fma_per_instr[shape] * 4.0 * iters * (double)blocks * (threads / 32);
+    const double tf = flops / (ms * 1.0e-3) / 1.0e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  *tflops = best;
+  return EXPB200_OK;
+}

@@ -374,6 +374,9 @@ const char *expb200_profile_name(int id);
 int expb200_profile_read(unsigned long long *launches, double *ms, unsigned long long *timed);
 /* Dependency-free DFMA microbenchmark: the FP64 roofline denominator. */
 int expb200_fp64_peak(int device, double *tflops, double *sm_mhz_hint);
+/* FP64 tensor-core (mma.sync f64) microbenchmark by shape (0: m8n8k4, 1: m16n8k4, 2: m16n8k8,
+ * 3: m16n8k16): the roofline denominator of the covariance kernels. */
+int expb200_dmma_peak(int device, int shape, double *tflops);
 
 #ifdef __cplusplus
 }
