@@ -288,10 +288,24 @@ class Ranks:
 
 # ---- CPU reference arm -----------------------------------------------------------
 def cpu_step_rate(tab, pos, vel, mass, cores, steps, warmup):
-    """The oracle (line-faithful C++ restatement of the reference CPU path, pinned bit for bit to
-    the reference's own member functions: tests/test_oracle_ref.py) running the same step on
-    `cores` host threads with the reference's thread structure: contiguous slices, per-thread
-    partials, ordered sum."""
+    """-> (rate, seconds per step, kind).  kind "reference": the reference's OWN member functions
+    (incr_velocity/incr_position threads, SphericalBasis coefficient and force threads, SLGridSph
+    interpolation, Basis recursions) compiled from /root/reference where they lie
+    (oracle/_ref/libexpref_path.so, built in the build container and shipped with the snapshot) and
+    driven in do_step's order on `cores` host threads with the reference's fork/join structure.
+    kind "port" (only when that library is absent): the line-faithful restatement in
+    oracle/exp_oracle.cc, which tests/test_oracle_ref.py pins to it bit for bit."""
+    from oracle import ref_path as RP
+    if RP.available():
+        st = RP.RefSphereStepper(tab, pos, vel, mass, nthreads=cores)
+        st.force()
+        for _ in range(warmup):
+            st.step(DT)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            st.step(DT)
+        dt = time.perf_counter() - t0
+        return len(pos) * steps / dt, dt / steps, "reference"
     from oracle import oracle as O
     g = O.Grid(tab)
     P = O.sph_params(rmin=tab.rmin, rmax=tab.rmax)
@@ -314,7 +328,12 @@ def cpu_step_rate(tab, pos, vel, mass, cores, steps, warmup):
     for _ in range(steps):
         one()
     dt = time.perf_counter() - t0
-    return len(pos) * steps / dt, dt / steps
+    return len(pos) * steps / dt, dt / steps, "port"
+
+
+CPU_KIND_NOTE = {"reference": "the reference's own SphericalBasis/SLGridSph/Basis/leapfrog thread functions compiled in "
+                              "place (oracle/_ref/libexpref_path.so) over a flat particle store",
+                 "port": "oracle/exp_oracle.cc (restatement pinned bit for bit to the reference's functions)"}
 
 
 def workload_config(args, world, n_local):
@@ -346,9 +365,9 @@ def run_reference(args):
     tab = make_table()
     n = min(args.cpu_sample, ntot)
     pos, vel, mass = make_particles(ntot, 0, n)
-    rate, sec = cpu_step_rate(tab, pos, vel, mass, cores, args.steps, max(args.warmup, 1))
+    rate, sec, kind = cpu_step_rate(tab, pos, vel, mass, cores, args.steps, max(args.warmup, 1))
     sample = (f"{n} particles of the NFW workload per step (the first {n} of the {ntot}-body stream; the "
-              f"rate is per particle and extrapolates linearly), {cores} threads")
+              f"rate is per particle and extrapolates linearly), {cores} threads; {CPU_KIND_NOTE[kind]}")
     cfg = workload_config(args, world, slice_of(ntot, 0, world)[1])
     cfg["reference_sample_particles_per_step"] = n      # what this arm actually timed
     cfg["extrapolated"] = n != ntot
@@ -357,7 +376,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak" if args.particles_per_gpu else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -522,12 +541,11 @@ def run_sphere(args):
         cores = os.cpu_count() or 1
         m = min(args.cpu_sample, n)
         ksteps = args.cpu_steps
-        rate, sec = cpu_step_rate(tab, np.array(hpos[:m]), np.array(hvel[:m]), np.array(hmass[:m]),
-                                  cores, ksteps, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        rate, sec, kind = cpu_step_rate(tab, np.array(hpos[:m]), np.array(hvel[:m]), np.array(hmass[:m]),
+                                        cores, ksteps, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"first {m} particles of the workload, {ksteps} timed steps after 1 warm-up "
-                         f"({sec * ksteps:.1f} s of CPU work), {cores} host threads (oracle/exp_oracle.cc, "
-                         f"pinned to the reference's own member functions)"}
+                         f"({sec * ksteps:.1f} s of CPU work), {cores} host threads; {CPU_KIND_NOTE[kind]}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -68,6 +68,11 @@ def lib():
         L.ref_sph_accel.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip, C.c_long,
                                     c_dp, c_dp, C.c_double, c_ip, C.c_long, c_dp, C.c_int, c_dp,
                                     c_dp, c_dp]
+        L.ref_sph_load.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip, C.c_long, c_dp, c_dp,
+                                   c_dp, C.c_int]
+        L.ref_sph_step.restype = C.c_long
+        L.ref_sph_step.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.ref_sph_read.argtypes = [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.ref_cyl_create.restype = C.c_void_p
         L.ref_cyl_create.argtypes = [C.c_int] * 6 + [C.c_double] * 7 + [c_ip] + [c_dp] * 6
         L.ref_cyl_destroy.argtypes = [C.c_void_p]
@@ -191,6 +196,32 @@ class RefSphere:
                             float(rtrunc), lst.ctypes.data_as(c_ip), len(lst), _dp(coef), nthreads,
                             _dp(own), _dp(acc), _dp(pot))
         return acc, pot
+
+
+class RefSphereStepper:
+    """The reference's own thread functions (incr_velocity/incr_position threads, coefficient and force
+    threads of SphericalBasis) driven in do_step's single-level order on `nthreads` host threads: the
+    CPU baseline bench.py times (kind "reference")."""
+
+    def __init__(self, tab, pos, vel, mass, nthreads=1, scale=1.0):
+        self.ref = RefSphere(tab, scale=scale)
+        self.n = len(pos)
+        pos, vel, mass = _f64(pos), _f64(vel), _f64(mass)
+        lib().ref_sph_load(self.ref.h, self.ref.scale, self.ref.rmin, self.ref.rmax, self.ref.flags, self.n,
+                           _dp(pos), _dp(vel), _dp(mass), int(nthreads))
+
+    def force(self):
+        """coefficients + force on the current positions (no kicks), returns the number used"""
+        return lib().ref_sph_step(self.ref.h, 0.0, 0)
+
+    def step(self, dt):
+        return lib().ref_sph_step(self.ref.h, float(dt), 1)
+
+    def read(self):
+        out = dict(pos=np.zeros((self.n, 3)), vel=np.zeros((self.n, 3)), acc=np.zeros((self.n, 3)), pot=np.zeros(self.n),
+                   coef=np.zeros(((self.ref.lmax + 1) ** 2, self.ref.nmax)))
+        lib().ref_sph_read(self.ref.h, _dp(out["pos"]), _dp(out["vel"]), _dp(out["acc"]), _dp(out["pot"]), _dp(out["coef"]))
+        return out
 
 
 class RefCylinder:

@@ -299,6 +299,93 @@ void ref_sph_accel(void *hh, double scale, double rmin, double rmax, const int *
   }
 }
 
+/* ---- one KDK step with the reference's own thread functions on `nthreads` host threads ------
+ * (the CPU baseline of bench.py): do_step's single-level sequence (src/step.cc:272-322):
+ * incr_velocity(dt/2), incr_position(dt), determine_coefficients (threads + thread sum),
+ * zero acc/pot, determine_acceleration_and_potential (threads), incr_velocity(dt/2), forked and
+ * joined per phase like exp_thread_fork (src/PotAccel.cc:97-130).  The particle store is the flat
+ * Component of ref_shim/pathshim.H (an index instead of the reference's hash map). */
+void ref_sph_load(void *hh, double scale, double rmin, double rmax, const int *flags, long n,
+                  const double *pos, const double *vel, const double *mass, int nthreads)
+{
+  SphHandle *h = static_cast<SphHandle *>(hh);
+  sph_config(h, scale, rmin, rmax, flags, nthreads);
+  fill_component(h->comp, n, pos, vel, nullptr, nullptr, nullptr, mass, nullptr, nullptr, nullptr, nullptr, 1e20);
+  std::vector<int> all(n);
+  for (long i = 0; i < n; i++) all[i] = (int)i;
+  h->comp.levlist.assign(1, all);
+  h->comp.pmap.clear();
+  for (long i = 0; i < n; i++) h->comp.pmap[(unsigned long)i] = &h->comp.store[i];
+  h->sph.mlevel = 0;
+  h->sph.compute = false;
+  multistep = 0;
+}
+
+} // extern "C"
+#include <thread>
+namespace {
+template <class F> void fork_join(int nthreads, F &&f)
+{
+  std::vector<std::thread> th;
+  for (int id = 1; id < nthreads; id++) th.emplace_back([&, id] { f(id); });
+  f(0);
+  for (auto &t : th) t.join();
+}
+} // namespace
+extern "C" {
+
+long ref_sph_step(void *hh, double dt, int with_kicks)
+{
+  SphHandle *h = static_cast<SphHandle *>(hh);
+  Sphere &s = h->sph;
+  const int nth = nthrds;
+  ComponentContainer cc;
+  cc.components.push_back(&h->comp);
+  comp = &cc;
+  if (with_kicks) {
+    fork_join(nth, [&](int id) { thrd_pass_posvel a{0.5 * dt, -1, id}; incr_velocity_thread(&a); });
+    fork_join(nth, [&](int id) { thrd_pass_posvel a{dt, -1, id}; incr_position_thread(&a); });
+  }
+  const int N = s.nmax, nrow = (s.Lmax + 1) * (s.Lmax + 1);
+  for (auto &v : s.expcoef0) for (auto &p : v) p->setZero();
+  std::fill(s.use.begin(), s.use.end(), 0);
+  fork_join(nth, [&](int id) { int arg = id; s.determine_coefficients_thread(&arg); });
+  long use1 = 0;
+  for (int i = 0; i < nth; i++) use1 += s.use[i];
+  for (int i = 1; i < nth; i++)
+    for (int l = 0; l < nrow; l++)
+      for (int k = 0; k < N; k++) (*s.expcoef0[0][l])[k] += (*s.expcoef0[i][l])[k];
+  for (int l = 0; l < nrow; l++)
+    for (int k = 0; k < N; k++) (*s.expcoef[l])[k] = (*s.expcoef0[0][l])[k];
+  for (auto &p : h->comp.store) { p.acc[0] = p.acc[1] = p.acc[2] = 0.0; p.pot = 0.0; }
+  s.use_external = 0;
+  fork_join(nth, [&](int id) { int arg = id; s.determine_acceleration_and_potential_thread(&arg); });
+  if (with_kicks)
+    fork_join(nth, [&](int id) { thrd_pass_posvel a{0.5 * dt, -1, id}; incr_velocity_thread(&a); });
+  comp = nullptr;
+  return use1;
+}
+
+void ref_sph_read(void *hh, double *pos, double *vel, double *acc, double *pot, double *coef)
+{
+  SphHandle *h = static_cast<SphHandle *>(hh);
+  const long n = (long)h->comp.store.size();
+  for (long i = 0; i < n; i++) {
+    const Particle &p = h->comp.store[i];
+    for (int k = 0; k < 3; k++) {
+      if (pos) pos[3 * i + k] = p.pos[k];
+      if (vel) vel[3 * i + k] = p.vel[k];
+      if (acc) acc[3 * i + k] = p.acc[k];
+    }
+    if (pot) pot[i] = p.pot;
+  }
+  if (coef) {
+    const int N = h->sph.nmax, nrow = (h->sph.Lmax + 1) * (h->sph.Lmax + 1);
+    for (int l = 0; l < nrow; l++)
+      for (int k = 0; k < N; k++) coef[(size_t)l * N + k] = (*h->sph.expcoef[l])[k];
+  }
+}
+
 /* ---- EmpCylSL ------------------------------------------------------------------------------ */
 struct CylHandle { EmpCylSL e; };
 

@@ -328,3 +328,29 @@ def test_level_assignment_powers_of_two():
                                   multistep, dynfracV=1e30, dynfracD=1e30)
     assert np.array_equal(S.level, lev) and S.dtreq.tobytes() == dq.tobytes()
     assert len(np.unique(lev)) >= 8
+
+
+def test_full_step_bit_exact():
+    """do_step's single-level sequence driven with the reference's own thread functions
+    (RefSphereStepper, the CPU baseline bench.py times) == the same sequence with the oracle"""
+    tab = get_table("nfw", 6, 18, rmax=20.0)
+    pos, vel, mass = _halo("nfw", 20000, 77)
+    st = R.RefSphereStepper(tab, pos, vel, mass, nthreads=3)
+    g = O.Grid(tab)
+    P = O.sph_params(rmin=tab.rmin, rmax=tab.rmax)
+    S = O.ParticleSet(pos, vel, mass)
+    st.force()
+    coef, _ = O.sph_coefficients(g, P, S, nthreads=3)
+    O.sph_accel(g, P, S, coef, nthreads=3)
+    for _ in range(2):
+        st.step(1e-3)
+        O.incr_velocity(S, 0.5e-3)
+        O.incr_position(S, 1e-3)
+        coef, _ = O.sph_coefficients(g, P, S, nthreads=3)
+        S.acc[:] = 0.0
+        S.pot[:] = 0.0
+        O.sph_accel(g, P, S, coef, nthreads=3)
+        O.incr_velocity(S, 0.5e-3)
+    o = st.read()
+    for k, v in (("pos", S.pos), ("vel", S.vel), ("acc", S.acc), ("pot", S.pot), ("coef", coef)):
+        assert o[k].tobytes() == v.tobytes(), k
