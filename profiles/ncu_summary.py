@@ -52,5 +52,40 @@ def main(path):
         print()
 
 
+def traffic(path, n, out_json, tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sphere step's kernel families
+    -> profiles/ncu_traffic.json (read by bench.py for roofline.traffic)"""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    fam = {"force": "sph_force", "deposit": "sph_deposit_reg", "sort": "sort_apply"}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        for key, pat in fam.items():
+            if pat in name:
+                b = sum(float(r[col[m]].replace(",", "")) * scale[units[col[m]]]
+                        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                acc.setdefault((key, name.split("(")[0][-60:]), []).append(b)
+    tab = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    for (key, name), v in acc.items():
+        # the deposit is several sweeps per step: report the sum over the distinct sweeps of one step
+        tab.setdefault(key, [])
+    for key in fam:
+        per = [sum(v) / len(v) for (k, _), v in acc.items() if k == key]
+        if per:
+            tab[key] = [e for e in tab.get(key, []) if e["n"] != n] + [
+                {"n": n, "dram_bytes_per_launch": sum(per), "launch_kinds": len(per), "source": tag}]
+    json.dump(tab, open(out_json, "w"), indent=1)
+    print(json.dumps(tab, indent=1))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) >= 6 and sys.argv[2] == "--traffic":
+        traffic(sys.argv[1], int(float(sys.argv[3])), sys.argv[4], sys.argv[5])
+    else:
+        main(sys.argv[1])

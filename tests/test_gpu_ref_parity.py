@@ -199,3 +199,108 @@ def test_cylinder_pca_variants_vs_reference_code(which):
     assert np.abs(out["covM"] - rM).max() <= 1e-10 * np.abs(rM).max()
     if which == "pcavar":
         assert np.abs(out["covV"] - rV).max() <= 1e-10 * np.abs(rV).max()
+
+
+@pytest.mark.parametrize("cmap", [0, 2])
+def test_sphere_other_coordinate_maps_vs_reference_code(cmap):
+    """cmap = 0 (xi = r) and 2 (xi = log r) of SLGridSph::r_to_xi / d_xi_to_r
+    (exputil/SLGridMP2.cc:711-765); the table values are those of the cmap = 1 solve re-read on the
+    other grid, which is all the interpolation cares about"""
+    import copy
+    tab = copy.copy(get_table("hernquist", 4, 10))
+    tab.cmap = cmap
+    n = 30000
+    pos, vel, mass = ics.hernquist_halo(n, seed=19)
+    pos = pos + np.array([0.01, -0.02, 0.005])
+    ref = R.RefSphere(tab)
+    rc = ref.coefficients(pos, mass, nthreads=4)
+    racc, rpot = ref.accel(pos, rc["coef"], nthreads=4)
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    s = Sphere(tab)
+    coef = s.determine_coefficients(c)
+    assert s.used == rc["used"]
+    assert rel_rms(coef, rc["coef"]) <= 1e-10
+    s.set_coefficients(rc["coef"])
+    c.zero_pot_acc()
+    s.get_acceleration_and_potential(c)
+    out = c.download()
+    assert acc_rel_err(out["acc"], racc).max() <= 1e-8
+    assert np.abs(out["pot"] - rpot).max() <= 1e-8 * np.abs(rpot).max()
+
+
+def test_level_powers_of_two_vs_reference_code():
+    """dtreq == dtime / 2^k exactly and one float ulp either side, up to 2^20: the device's
+    floor(log(dtime/dtreq)/log 2) must equal libm's, also where log(x)/log(2) rounds up to k for
+    x just below 2^k"""
+    multistep, dtime = 20, 1.0
+    vals = []
+    for k in range(0, 21):
+        t = np.float32(dtime / 2 ** k)
+        vals += [t, np.nextafter(t, np.float32(0)), np.nextafter(t, np.float32(2))]
+    # doubles whose quotient dtime/dtreq sits within a few ulp below 2^k cannot arise from a float
+    # dtreq with dtime = 1; use a dtime that makes the quotient inexact
+    vals = np.array(vals, dtype=np.float64)
+    for dt_scale in (1.0, 3.0, 0.7):
+        n = len(vals)
+        vel = np.zeros((n, 3)); vel[:, 0] = 1.0
+        acc = np.zeros((n, 3)); pot = np.zeros(n)
+        scale = (vals * dt_scale * (1.0 + 1e-10)).astype(np.float32)
+        c = Component(n)
+        c.upload(np.zeros((n, 3)), vel, np.ones(n), scale=scale)
+        c.set_acc_pot(acc, pot)
+        c.adjust_multistep_level(dtime=dtime * dt_scale, multistep=multistep, dynfracV=1e30, dynfracD=1e30,
+                                 reset_dtreq=True)
+        got = c.download(level=True, dtreq=True)
+        lev, dq, *_ = R.adjust_levels(vel, acc, pot, np.zeros(n), scale, np.zeros(n, np.uint32),
+                                      np.zeros(n, np.float32), dtime * dt_scale, multistep, dynfracV=1e30,
+                                      dynfracD=1e30)
+        assert np.array_equal(got["level"], lev), (dt_scale, np.nonzero(got["level"] != lev)[0][:5])
+        assert got["dtreq"].tobytes() == dq.tobytes()
+
+
+def test_leapfrog_dim2_vs_reference_code():
+    """Component::dim = 2: only x and y advance (src/incpos.cc:63-66, src/incvel.cc:68-69)"""
+    rng = np.random.default_rng(12)
+    n = 50000
+    pos, vel, acc = rng.normal(size=(n, 3)), rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    c = Component(n)
+    c.upload(pos, vel, np.ones(n))
+    c.set_acc_pot(acc, np.zeros(n))
+    P = dict(dtime=0.01, multistep=3, dim=2, reset_dtreq=True)
+    c.adjust_multistep_level(**P)
+    got = c.download(level=True, dtreq=True)
+    lev, dq, *_ = R.adjust_levels(vel, acc, np.zeros(n), np.zeros(n), None, np.zeros(n, np.uint32),
+                                  np.zeros(n, np.float32), 0.01, 3, dim=2, nthreads=2)
+    assert np.array_equal(got["level"], lev) and got["dtreq"].tobytes() == dq.tobytes()
+
+
+def test_cylinder_default_grid_vs_reference_code():
+    """BASELINE configs[2]'s table shape (NUMX = 256, NUMY = 128: 257 x 129 nodes, mmax = 6,
+    norder = 18) against EmpCylSL::accumulate / accumulated_eval of the reference"""
+    tab = cyltable.synthetic_cyl_table(mmax=6, norder=18, numx=256, numy=128)
+    g = O.CylGridPy(tab)
+    consts = (g.c.Rtable, g.c.XMIN, g.c.dX, g.c.YMIN, g.c.dY)
+    n = 20000
+    pos, vel, mass = ics.exponential_disk(n, seed=47)
+    ref = R.RefCylinder(tab, consts)
+    rc = ref.accumulate(pos, mass)
+    c = Component(n)
+    c.upload(pos, vel, mass)
+    cyl = Cylinder(tab, rcylmax=1e6)
+    cs, sn = cyl.determine_coefficients(c)
+    assert cyl.used == rc["used"]
+    assert rel_rms(cs, rc["cos"]) <= 1e-10 and rel_rms(sn[1:], rc["sin"][1:]) <= 1e-10
+    cyl.set_coefficients(rc["cos"], rc["sin"], 0.0)
+    c.zero_pot_acc()
+    cyl.get_acceleration_and_potential(c)
+    out = c.download()
+    rr = np.sqrt((pos ** 2).sum(axis=1))
+    idx = np.nonzero(rr < 0.7 * g.c.Rtable * tab.ascale)[0][:1500]
+    facc = np.zeros((len(idx), 3))
+    for k, i in enumerate(idx):
+        x, y, z = pos[i]
+        r = math.sqrt(x * x + y * y)
+        p0, p, fr, fz, fp = ref.accumulated_eval(rc["cos"], rc["sin"], r, z, math.atan2(y, x))
+        facc[k] = (fr * x / r - fp * y / (r * r), fr * y / r + fp * x / (r * r), fz)
+    assert acc_rel_err(out["acc"][idx], facc).max() <= 1e-8
