@@ -296,9 +296,10 @@ __global__ void cyl_interp_kernel(const double *__restrict__ cL, const double *_
 // both are non-decreasing along the sorted order -- and a second kernel adds a bin's
 // partials in chunk order: no atomics, bit-reproducible.
 // ===========================================================================
-constexpr int kCovP = 16;             // particles per tile
-constexpr int kCovLD = 20;            // leading dimension of a panel row (doubles): 2-way = minimal
+constexpr int kCovP = 32;             // particles per tile (one producer-warp pass: lane = particle)
+constexpr int kCovLD = 36;            // leading dimension of a panel row (doubles): 2-way = minimal
                                       // bank conflicts for the 64-bit fragment loads
+constexpr int kCovThreads = 288;      // 8 panel/DMMA warps + 1 geometry warp
 constexpr int kCovMG = 8;             // harmonics per CTA (one per warp)
 constexpr int kCovSplit = 4;          // particle interleave of the panel evaluation (max)
 
@@ -356,8 +357,14 @@ __global__ void cyl_cov_bounds_kernel(const uint32_t *__restrict__ skeys, size_t
   bstart[T] = (uint32_t)lo;
 }
 
+// The three phases of a tile -- geometry of its particles (one lane per particle: gather of the
+// position record, coordinate maps, cell, corner weights, azimuthal factors), the panel u[m][n][j]
+// (8 KB of table gathers per particle, L2), and the rank-k update (DMMA) -- overlap: warp 8 is a
+// producer that prepares the geometry of tile t+1 in the other half of a double buffer while
+// warps 0-7 evaluate the panel of tile t and multiply it (round 2: with the phases in sequence the
+// kernel sat at the CTA barrier, FP64 pipe 8 % active, profiles/r02h_cyl_ncu_full_summary.txt).
 template <int NT>
-__global__ void __launch_bounds__(256, NT <= 5 ? 2 : 1)
+__global__ void __maxnreg__(NT <= 5 ? 112 : 224)       // 2 x 288 or 1 x 288 threads per SM
 cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict__ posm,
                const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skeys,
                const uint32_t *__restrict__ bstart, int sampT, int CH, double adb, int nsplit,
@@ -369,20 +376,72 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
   const int nml = M1 - mg0 < kCovMG ? M1 - mg0 : kCovMG;       // harmonics of this CTA
   const int items = nml * N;
   double *U = cov_smem;                                        // [kCovMG][R2][kCovLD]
-  double *wgt = U + (size_t)kCovMG * R2 * kCovLD;              // [kCovP][4]
-  double *trg = wgt + kCovP * 4;                               // [kCovP][M1][2]
-  double *sqm = trg + (size_t)kCovP * M1 * 2;                  // [kCovP]
-  double *pms = sqm + kCovP;                                   // [kCovP]
-  int *nbs = reinterpret_cast<int *>(pms + kCovP);             // [kCovP]
-  int *info = nbs + kCovP;                                     // cnt, T
+  double *geo = U + (size_t)kCovMG * R2 * kCovLD;              // two geometry buffers
+  const size_t geo_doubles = (size_t)kCovP * 4 + (size_t)kCovP * M1 * 2 + 2 * kCovP + kCovP / 2 + 2;
+  auto WGT = [&](int b) { return geo + b * geo_doubles; };                        // [kCovP][4]
+  auto TRG = [&](int b) { return WGT(b) + kCovP * 4; };                           // [kCovP][M1][2]
+  auto SQM = [&](int b) { return TRG(b) + (size_t)kCovP * M1 * 2; };              // [kCovP]
+  auto PMS = [&](int b) { return SQM(b) + kCovP; };                               // [kCovP]
+  auto NBS = [&](int b) { return reinterpret_cast<int *>(PMS(b) + kCovP); };      // [kCovP]
+  auto INFO = [&](int b) { return NBS(b) + kCovP; };                              // cnt, T
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool producer = w == 8;
   const int gq = lane >> 2, t = lane & 3;
   const size_t nused = bstart[sampT];
   const size_t chunk = blockIdx.x;
   const size_t beg = chunk * (size_t)CH;
   if (beg >= nused) return;
   const size_t end = beg + CH < nused ? beg + CH : nused;
+
+  // ---- producer: geometry of the tile that starts at sorted position k0, into buffer b
+  auto geometry = [&](size_t k0, int b) -> int {
+    if (k0 >= end) { if (lane == 0) { INFO(b)[0] = 0; INFO(b)[1] = -1; } return 0; }
+    const size_t k = k0 + lane;
+    const bool valid = k < end;
+    const uint32_t key = valid ? skeys[k] : 0xffffffffu;
+    const int Tj = (int)(key / (uint32_t)g.ncell);
+    const int T0 = __shfl_sync(0xffffffffu, Tj, 0);
+    const unsigned mask = __ballot_sync(0xffffffffu, valid && Tj == T0);
+    const int cnt = mask == 0xffffffffu ? 32 : __ffs(~mask) - 1;        // leading run of the same bin
+    if (lane == 0) { INFO(b)[0] = cnt; INFO(b)[1] = T0; }
+    if (lane < cnt) {
+      const rec4 pm = ld_rec(&posm[perm[k]]);
+      double x, y, z, r;
+      cyl_classify(g, pm, x, y, z, r, 0);
+      double zz = z;
+      if (zz / g.ascale > g.rtable) zz = g.rtable * g.ascale;       // EmpCylSL::get_pot clamp
+      if (zz / g.ascale < -g.rtable) zz = -g.rtable * g.ascale;
+      const CylCell c = cyl_locate(g, r, zz);
+      const double mass = pm.w * adb;
+      const double sq = sqrt(mass), sw = -4.0 * M_PI * sq;
+      double *wgt = WGT(b);
+      wgt[lane * 4 + 0] = sw * c.c00; wgt[lane * 4 + 1] = sw * c.c10;
+      wgt[lane * 4 + 2] = sw * c.c01; wgt[lane * 4 + 3] = sw * c.c11;
+      NBS(b)[lane] = c.ix * (g.numy + 1) + c.iy;
+      SQM(b)[lane] = sq;
+      PMS(b)[lane] = mass;
+      double *trg = TRG(b);
+      cyl_trig(g.mmax, x, y, r, [&](int m, double cm, double sm) {
+        trg[(lane * M1 + m) * 2] = cm;
+        trg[(lane * M1 + m) * 2 + 1] = sm;
+      });
+    }
+    return cnt;
+  };
+
+  if (producer) {
+    // one tile ahead of the consumers; both sides pass one CTA barrier per tile (+ the first)
+    size_t k0 = beg;
+    int cnt = geometry(k0, 0);
+    __syncthreads();
+    for (int tile = 0; cnt > 0; tile++) {
+      k0 += cnt;
+      cnt = geometry(k0, (tile + 1) & 1);
+      __syncthreads();
+    }
+    return;
+  }
 
   // panel evaluation: thread -> (split, local m, n)
   const int split = tid / items, it = tid % items;
@@ -426,40 +485,13 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
     }
   };
 
-  for (size_t k0 = beg; k0 < end;) {
-    // ---- per-particle geometry of the tile (warp 0, lane = particle)
-    if (w == 0) {
-      const size_t k = k0 + lane;
-      const bool valid = lane < kCovP && k < end;
-      const uint32_t key = valid ? skeys[k] : 0xffffffffu;
-      const int Tj = (int)(key / (uint32_t)g.ncell);
-      const int T0 = __shfl_sync(0xffffffffu, Tj, 0);
-      const unsigned mask = __ballot_sync(0xffffffffu, valid && Tj == T0);
-      const int cnt = __ffs(~mask) - 1;                    // leading run of the same bin
-      if (lane == 0) { info[0] = cnt; info[1] = T0; }
-      if (lane < cnt) {
-        const rec4 pm = ld_rec(&posm[perm[k]]);
-        double x, y, z, r;
-        cyl_classify(g, pm, x, y, z, r, 0);
-        double zz = z;
-        if (zz / g.ascale > g.rtable) zz = g.rtable * g.ascale;       // EmpCylSL::get_pot clamp
-        if (zz / g.ascale < -g.rtable) zz = -g.rtable * g.ascale;
-        const CylCell c = cyl_locate(g, r, zz);
-        const double mass = pm.w * adb;
-        const double sq = sqrt(mass), sw = -4.0 * M_PI * sq;
-        wgt[lane * 4 + 0] = sw * c.c00; wgt[lane * 4 + 1] = sw * c.c10;
-        wgt[lane * 4 + 2] = sw * c.c01; wgt[lane * 4 + 3] = sw * c.c11;
-        nbs[lane] = c.ix * (g.numy + 1) + c.iy;
-        sqm[lane] = sq;
-        pms[lane] = mass;
-        cyl_trig(g.mmax, x, y, r, [&](int m, double cm, double sm) {
-          trg[(lane * M1 + m) * 2] = cm;
-          trg[(lane * M1 + m) * 2 + 1] = sm;
-        });
-      }
-    }
-    __syncthreads();
-    const int cnt = info[0], T0 = info[1];
+  __syncthreads();                            // geometry of tile 0 is there
+  for (int tile = 0;; tile++) {
+    const int b = tile & 1;
+    const int cnt = INFO(b)[0], T0 = INFO(b)[1];
+    if (cnt == 0) break;
+    const double *wgt = WGT(b), *trg = TRG(b), *sqm = SQM(b), *pms = PMS(b);
+    const int *nbs = NBS(b);
     if (T0 != curT) {
       if (curT >= 0) flush(curT);
       curT = T0;
@@ -472,7 +504,7 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
     if (evalr) {
       double *ua = U + ((size_t)ml * R2 + nn) * kCovLD, *ub = ua + (size_t)N * kCovLD;
       for (int j = split; j < kpad; j += nsplit) {
-        double a = 0.0, b = 0.0;
+        double a = 0.0, b2 = 0.0;
         if (j < cnt) {
           const double2 *z = Zt + (size_t)nbs[j] * MN + mn;
           const double2 z00 = __ldg(z), z01 = __ldg(z + MN);
@@ -483,7 +515,7 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
           const double cm = trg[(j * M1 + mg0 + ml) * 2], sm = trg[(j * M1 + mg0 + ml) * 2 + 1];
           if (g.cov_mode == 0) {
             a = vc * cm + vs * sm;
-            b = vc * sm - vs * cm;
+            b2 = vc * sm - vs * cm;
           } else if (g.cov_mode == 1) {       // sqrt(mass) * |(Vc cos, Vs sin)|: vc, vs carry -4 pi sqrt(mass)
             const double hc = vc * cm, hs = vs * sm;
             a = sqrt(hc * hc + hs * hs) * (0.25 / M_PI);
@@ -491,13 +523,13 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
             a = sqrt(vc * vc + vs * vs);
           }
           vcr += sqm[j] * a;
-          vci += sqm[j] * b;
+          vci += sqm[j] * b2;
         }
         ua[j] = a;
-        ub[j] = b;
+        ub[j] = b2;
       }
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");        // the eight consumer warps: panel complete
     // ---- rank-k update on the tensor cores: warp w owns harmonic mg0 + w
     if (w < nml) {
       const double *Um = U + (size_t)w * R2 * kCovLD;
@@ -511,12 +543,10 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
 #pragma unroll
         for (int a = 0; a < NT; a++)
 #pragma unroll
-          for (int b = a; b < NT; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], af[b]);
+          for (int b3 = a; b3 < NT; b3++) dmma_m8n8k4(acc[a][b3][0], acc[a][b3][1], af[a], af[b3]);
       }
     }
-    k0 += cnt;
-    // the next tile's geometry is written by warp 0 only after it finished its own update;
-    // the barrier after it orders the panel rewrite against every warp's update
+    __syncthreads();      // panel consumed, geometry buffer b free, the next tile's geometry ready
   }
   if (curT >= 0) flush(curT);
 }
@@ -574,8 +604,8 @@ int launch_cyl_cov(cudaStream_t st, dim3 grid, size_t smem, const CylGeom &g, co
                    int sampT, int CH, double adb, int nsplit, double *PC, double *PV, double *PM)
 {
   CU_TRY(cudaFuncSetAttribute(cyl_cov_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cyl_cov_kernel<NT><<<grid, 256, smem, st>>>(g, Zt, posm, perm, skeys, bstart, sampT, CH, adb, nsplit,
-                                              PC, PV, PM);
+  cyl_cov_kernel<NT><<<grid, kCovThreads, smem, st>>>(g, Zt, posm, perm, skeys, bstart, sampT, CH, adb, nsplit,
+                                                      PC, PV, PM);
   CU_LAUNCH_CHECK();
   return EXPB200_OK;
 }
@@ -1155,8 +1185,8 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
   COV_TRY(cov_alloc((void **)&dMass, (size_t)sampT * sizeof(double), 6));
   COV_TRY(cov_alloc((void **)&dCount, (size_t)sampT * sizeof(unsigned), 7));
 
-  const size_t smem = ((size_t)kCovMG * R2 * kCovLD + kCovP * 4 + (size_t)kCovP * M1 * 2 + 2 * kCovP) * sizeof(double) +
-                      (kCovP + 4) * sizeof(int);
+  const size_t smem = ((size_t)kCovMG * R2 * kCovLD +
+                       2 * ((size_t)kCovP * 4 + (size_t)kCovP * M1 * 2 + 2 * kCovP + kCovP / 2 + 2)) * sizeof(double);
   const dim3 grid(nchunks, mgroups);
   const int NT = (R2 + 7) / 8;
 #define COV_LAUNCH(K) rc = launch_cyl_cov<K>(st, grid, smem, g, s->Zt, c->posm, c->perm[c->cur], c->keys[c->cur], \

@@ -90,6 +90,7 @@ class Simulation:
         self.device, self.multistep = device, multistep
         self._keep = []
         self.kinds = []
+        self.meta = []
         _check(self.H.exphost_reset())
         _check(self.H.exphost_set_params(dtime, multistep, dynfracS, dynfracD, dynfracV, dynfracA,
                                          dynfracP, shiftlevl))
@@ -105,6 +106,7 @@ class Simulation:
         _check(self.H.exphost_component_options(idx.value, None if ctr is None else _p(ctr), rtrunc,
                                                 int(noswitch), int(freezeLev), int(dtreset)))
         self.kinds.append(None)
+        self.meta.append(dict(name=name, center=np.zeros(3) if ctr is None else ctr.copy()))
         return idx.value
 
     def set_sphere(self, idx, tab, scale=1.0, rmin=-1.0, rmax=-1.0, NO_L0=False, NO_L1=False,
@@ -116,6 +118,7 @@ class Simulation:
                        int(EVEN_L), int(EVEN_M), int(M0_only), int(self_consistent))
         _check(self.H.exphost_set_sphere(idx, C.byref(d)))
         self.kinds[idx] = ("sphere", (tab.lmax + 1) ** 2, tab.nmax)
+        self.meta[idx].update(geometry="sphere", forceID="SphereSL", lmax=tab.lmax, nmax=tab.nmax, scale=scale)
 
     def set_cylinder(self, idx, tab, rcylmax=20.0, acyl=-1.0, EVEN_M=False, MMIN=0, MLIM=2 ** 30,
                      NMIN=0, NLIM=2 ** 30, self_consistent=True, body=None, orig=None):
@@ -130,6 +133,8 @@ class Simulation:
                          None if rot[0] is None else _p(rot[0]), None if rot[1] is None else _p(rot[1]))
         _check(self.H.exphost_set_cylinder(idx, C.byref(d)))
         self.kinds[idx] = ("cylinder", tab.mmax + 1, tab.norder)
+        self.meta[idx].update(geometry="cylinder", forceID="Cylinder", mmax=tab.mmax, nmax=tab.norder,
+                              rotation=body)
 
     def component_global(self, idx, indx_base, nbodies_tot):
         """sharded runs: this rank holds global particles [indx_base, indx_base + n)"""
@@ -248,6 +253,25 @@ class Simulation:
         if n2 < 0:
             _check(int(n2))
         return buf.raw[:n2]
+
+    def coef_struct(self, idx):
+        """the force's SphStruct / CylStruct array: complex ((lmax+1)(lmax+2)/2 | mmax+1, nmax), cosine
+        coefficient in the real part, sine in the imaginary part"""
+        m = self.meta[idx]
+        rows = (m["lmax"] + 1) * (m["lmax"] + 2) // 2 if m["geometry"] == "sphere" else m["mmax"] + 1
+        return np.frombuffer(self.dump_coefs(idx, kind=2), dtype=np.complex128).reshape(rows, m["nmax"]).copy()
+
+    def dump_coefs_h5(self, idx, path, config=""):
+        """SphericalBasis::dump_coefs_h5 / Cylinder::dump_coefs_h5 (reference src/SphericalBasis.cc:
+        1909-1975, src/Cylinder.cc:1625-1689): create the HDF5 coefficient file or append the current
+        coefficients to it as one more snapshot, in the layout CoefClasses::{Sph,Cyl}Coefs write
+        through HighFive (exp_b200/h5lite.py: dump_coefs_h5)."""
+        from . import h5lite
+        m = self.meta[idx]
+        kw = dict(lmax=m["lmax"], scale=m["scale"]) if m["geometry"] == "sphere" else dict(mmax=m["mmax"])
+        return h5lite.dump_coefs_h5(path, m["geometry"], m["name"], m["forceID"], self.state()["tnow"],
+                                    self.coef_struct(idx), config=config, center=m["center"],
+                                    rotation=m.get("rotation"), **kw)
 
     def com(self, idx):
         """[mtot, com[3], cov[3], coa[3]] of component idx after its last fix_positions, and the

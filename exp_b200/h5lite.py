@@ -30,6 +30,7 @@ import zlib
 import numpy as np
 
 SIG = b"\x89HDF\r\n\x1a\n"
+COMPLEX = np.dtype([("r", "<f8"), ("i", "<f8")])       # HighFive's on-disk std::complex<double>
 UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
@@ -271,8 +272,33 @@ class File(Group):
             if (b0 & 0x0F) == 1:
                 return ("vlen-str",), 8 + used
             return ("vlen", base), 8 + used
-        if cls == 6:                                                   # compound: skip over the members
-            raise H5Error("compound datatypes are not supported")
+        if cls == 6:                                                   # compound -> numpy structured dtype
+            nmemb = b0 | (b1 << 8)
+            q = p + 8
+            names, formats, offsets = [], [], []
+            for _ in range(nmemb):
+                end = self.buf.index(b"\0", q)
+                names.append(self.buf[q:end].decode("utf-8"))
+                nlen = end - q + 1
+                q += (nlen + 7) // 8 * 8 if ver < 3 else nlen
+                if ver == 3:
+                    ob = 1 if size < 256 else 2 if size < 65536 else 4
+                    offsets.append(self._uint(q, ob)); q += ob
+                else:
+                    offsets.append(self._uint(q, 4)); q += 4
+                    if ver == 1:
+                        if self.buf[q]:
+                            raise H5Error("compound members with array dimensions are not supported")
+                        q += 28                                        # dimensionality, permutation, sizes
+                mt, used = self._datatype(q)
+                q += used
+                if isinstance(mt, np.dtype):
+                    formats.append(mt)
+                elif mt[0] == "S":
+                    formats.append(np.dtype(f"S{mt[1]}"))
+                else:
+                    raise H5Error(f"compound member of type {mt} not supported")
+            return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": size}), q - p
         raise H5Error(f"datatype class {cls} not supported")
 
     def _layout(self, p):
@@ -330,7 +356,9 @@ class File(Group):
         count = int(np.prod(shape)) if shape else 1
         if isinstance(dtype, np.dtype):
             a = np.frombuffer(self.buf, dtype=dtype, count=count, offset=raw_at).astype(dtype.newbyteorder("="))
-            return a.reshape(shape) if shape else a[0].item()
+            if shape:
+                return a.reshape(shape)
+            return a[0] if dtype.names else a[0].item()
         if dtype[0] == "S":
             n = dtype[1]
             vals = [self.buf[raw_at + k * n:raw_at + (k + 1) * n].split(b"\0")[0].decode("utf-8") for k in range(count)]
@@ -456,10 +484,15 @@ class Writer:
         return g
 
     def dataset(self, parent, name, array):
-        a = np.ascontiguousarray(array)
-        if a.dtype.kind not in "fiu":
-            raise H5Error("datasets must be numeric")
-        parent["children"][name] = {"kind": "dataset", "data": a, "attrs": {}}
+        a = np.asarray(array)
+        a = np.ascontiguousarray(a).reshape(a.shape)            # ascontiguousarray makes 0-d arrays 1-d
+        if a.dtype.kind == "c":                                 # HighFive's std::complex<double>: {r, i}
+            a = a.astype(np.complex128).view(COMPLEX).reshape(a.shape)
+        if a.dtype.kind not in "fiuV":
+            raise H5Error("datasets must be numeric or compound")
+        node = {"kind": "dataset", "data": a, "attrs": {}}
+        parent["children"][name] = node
+        return node
 
     # ---- serialisation ----------------------------------------------------------------------
     def write(self, path):
@@ -493,6 +526,16 @@ class Writer:
     @staticmethod
     def _dtype_msg(dt):
         dt = np.dtype(dt)
+        if dt.kind == "V" and dt.names:                      # compound, version 1 (libhdf5's default)
+            body = b""
+            for nm in dt.names:
+                mt, off = dt.fields[nm][0], dt.fields[nm][1]
+                b = nm.encode() + b"\0"
+                body += b + b"\0" * (-len(b) % 8) + struct.pack("<I", off) + b"\0" * 28 + Writer._dtype_msg(mt)
+            n = len(dt.names)
+            return struct.pack("<BBBBI", 0x16, n & 0xFF, n >> 8, 0, dt.itemsize) + body
+        if dt.kind == "S":                                   # fixed-length, null-terminated, ASCII
+            return struct.pack("<BBBBI", 0x13, 0x00, 0, 0, dt.itemsize)
         if dt.kind == "f":
             if dt.itemsize == 8:
                 props = struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
@@ -570,8 +613,6 @@ class Writer:
         for name in sorted(node["children"], key=lambda s: s.encode()):
             caddr, cbt, cheap = self._emit(node["children"][name])
             entries.append((name, caddr, cbt, cheap))
-        if len(entries) > 2 * self.LEAF_K:
-            raise H5Error(f"group with {len(entries)} entries: more than one symbol node is not implemented")
         heap = bytearray(b"\0" * 8)                      # offset 0: the empty string
         offs = []
         for name, *_ in entries:
@@ -582,19 +623,40 @@ class Writer:
         heap += struct.pack("<QQ", 1, 32) + b"\0" * 16   # one free block at the end
         heap_data = self._alloc(bytes(heap))
         heap_addr = self._alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free, heap_data))
-        snod = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(entries)))
-        for (name, caddr, cbt, cheap), off in zip(entries, offs):
-            if cbt is not None:
-                snod += struct.pack("<QQII", off, caddr, 1, 0) + struct.pack("<QQ", cbt, cheap)
-            else:
-                snod += struct.pack("<QQII", off, caddr, 0, 0) + b"\0" * 16
-        snod += b"\0" * (8 + 2 * self.LEAF_K * 40 - len(snod))
-        snod_addr = self._alloc(bytes(snod))
-        bt = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, 0, 1 if entries else 0, UNDEF, UNDEF))
-        if entries:
-            bt += struct.pack("<QQQ", 0, snod_addr, offs[-1])
-        bt += b"\0" * (24 + (2 * self.INT_K + 1) * 8 + 2 * self.INT_K * 8 - len(bt))
-        bt_addr = self._alloc(bytes(bt))
+        # symbol nodes of up to 2*LEAF_K entries under a B-tree (version 1, node type 0) whose nodes
+        # hold up to 2*INT_K children; key i of a node = heap offset of the largest name in child i-1
+        # (key 0 = the empty string)
+        nodes = []                                       # (address, heap offset of the largest name below)
+        for k0 in range(0, len(entries), 2 * self.LEAF_K):
+            part = list(zip(entries, offs))[k0:k0 + 2 * self.LEAF_K]
+            snod = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(part)))
+            for (name, caddr, cbt, cheap), off in part:
+                if cbt is not None:
+                    snod += struct.pack("<QQII", off, caddr, 1, 0) + struct.pack("<QQ", cbt, cheap)
+                else:
+                    snod += struct.pack("<QQII", off, caddr, 0, 0) + b"\0" * 16
+            snod += b"\0" * (8 + 2 * self.LEAF_K * 40 - len(snod))
+            nodes.append((self._alloc(bytes(snod)), part[-1][1]))
+        level = 0
+        node_size = 24 + (2 * self.INT_K + 1) * 8 + 2 * self.INT_K * 8
+        while True:
+            parents = []
+            for k0 in range(0, max(len(nodes), 1), 2 * self.INT_K):
+                part = nodes[k0:k0 + 2 * self.INT_K]
+                bt = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, level, len(part), UNDEF, UNDEF))
+                bt += struct.pack("<Q", 0)
+                for addr, last in part:
+                    bt += struct.pack("<QQ", addr, last)
+                bt += b"\0" * (node_size - len(bt))
+                parents.append([self._alloc(bytes(bt)), part[-1][1] if part else 0])
+            for a, b in zip(parents, parents[1:]):       # sibling links of this level
+                struct.pack_into("<Q", self.out, a[0] + 16, b[0])
+                struct.pack_into("<Q", self.out, b[0] + 8, a[0])
+            nodes = [tuple(x) for x in parents]
+            level += 1
+            if len(nodes) == 1:
+                break
+        bt_addr = nodes[0][0]
         msgs = [(0x11, struct.pack("<QQ", bt_addr, heap_addr), [])] + self._attr_msgs(node["attrs"])
         return self._header(msgs), bt_addr, heap_addr
 
@@ -697,3 +759,136 @@ def write_cylinder_cache(path, tab, model="Exponential", version="1.0", cmass=0.
                     w.dataset(g, k, getattr(tab, k)[m, n])
                 w.dataset(g, "densS", zero if dens is None else dens[1][m, n])
     w.write(path)
+
+
+# =============================================================================================
+# The reference's coefficient files (CoefClasses::SphCoefs / CylCoefs through HighFive)
+# =============================================================================================
+UNIT = np.dtype([("name", "S16"), ("unit", "S16"), ("value", "<f4")])    # expui/Coefficients.H:36-55
+DEFAULT_UNITS = (("length", "none", 1.0), ("mass", "none", 1.0), ("time", "none", 1.0))
+
+
+def _units_array(units):
+    u = np.zeros(len(units), dtype=UNIT)
+    for k, (n, t, v) in enumerate(units):
+        u[k] = (n.encode()[:15], t.encode()[:15], v)
+    return u
+
+
+def _tree_of(node, name="/"):
+    """reader object -> Writer node (the whole file in memory; coefficient files are small)"""
+    if isinstance(node, Dataset):
+        return {"kind": "dataset", "data": np.asarray(node.read()), "attrs": dict(node.attrs)}
+    out = {"kind": "group", "children": {}, "attrs": dict(node.attrs)}
+    for k in node.keys():
+        out["children"][k] = _tree_of(node[k], k)
+    return out
+
+
+def _add_snapshot(w, snaps, count, time, center, rotation, coefs):
+    """one stanza of {Sph,Cyl}Coefs::WriteH5Times (expui/Coefficients.cc:907-940, 1375-1402): group
+    "%08d" with attributes Time, Center[3], Rotation[3][3] and the complex dataset "coefficients"
+    (rows, nmax), row-major on disk, each element the compound {r, i}"""
+    s = w.group(snaps, f"{count:08d}")
+    s["attrs"]["Time"] = float(time)
+    s["attrs"]["Center"] = np.asarray(center, dtype=np.float64).reshape(3)
+    s["attrs"]["Rotation"] = np.asarray(rotation, dtype=np.float64).reshape(3, 3)
+    w.dataset(s, "coefficients", np.asarray(coefs, dtype=np.complex128))
+    return count + 1
+
+
+def dump_coefs_h5(path, geometry, name, forceID, time, coefs, *, lmax=None, mmax=None, scale=1.0, config="",
+                  center=(0.0, 0.0, 0.0), rotation=None, units=DEFAULT_UNITS):
+    """SphericalBasis::dump_coefs_h5 / Cylinder::dump_coefs_h5 (reference src/SphericalBasis.cc:
+    1909-1975, src/Cylinder.cc:1625-1689): create the coefficient file on the first call
+    (Coefs::WriteH5Coefs, expui/Coefficients.cc:3100-3163: root attributes CoefficientOutputVersion,
+    geometry, name, config + the basis parameters of WriteH5Params -- lmax, nmax, scale, forceID for
+    a sphere (:841-852), mmax, nmax, forceID for a cylinder (:1323-1332) --, the compound dataset
+    "Units", the scalar dataset "count", the group "snapshots"), and append one snapshot to it
+    afterwards (Coefs::ExtendH5Coefs, :3165-3205, after the same parameter check as CheckH5Params).
+    coefs: complex (rows, nmax), cosine in the real and sine in the imaginary part."""
+    import os
+    coefs = np.asarray(coefs, dtype=np.complex128)
+    rows, nmax = coefs.shape
+    rot = np.eye(3) if rotation is None else rotation
+    if geometry == "sphere":
+        if lmax is None or rows != (lmax + 1) * (lmax + 2) // 2:
+            raise H5Error("sphere coefficients must be ((lmax+1)(lmax+2)/2, nmax)")
+        params = {"lmax": int(lmax), "nmax": int(nmax), "scale": float(scale), "forceID": forceID}
+    elif geometry == "cylinder":
+        if mmax is None or rows != mmax + 1:
+            raise H5Error("cylinder coefficients must be (mmax+1, nmax)")
+        params = {"mmax": int(mmax), "nmax": int(nmax), "forceID": forceID}
+    else:
+        raise H5Error(f"geometry {geometry!r} is outside the force loop's scope")
+    w = Writer()
+    if os.path.exists(path):
+        w.root = _tree_of(File(path))
+        a = w.root["attrs"]
+        for k, v in params.items():                  # {Sph,Cyl}Coefs::CheckH5Params
+            old = a.get(k)
+            bad = abs(old - v) > 1.0e-8 * max(abs(old), abs(v)) if k == "scale" else old != v
+            if old is None or bad:
+                raise H5Error(f"dump_coefs_h5: {k} mismatch {v!r} != {old!r}, not extending {path}")
+        count = int(w.root["children"]["count"]["data"])
+        count = _add_snapshot(w, w.root["children"]["snapshots"], count, time, center, rot, coefs)
+    else:
+        a = w.root["attrs"]
+        a["CoefficientOutputVersion"], a["geometry"], a["name"], a["config"] = "1.0", geometry, name, config
+        a.update(params)
+        w.dataset(w.root, "Units", _units_array(units))
+        snaps = w.group(w.root, "snapshots")
+        count = _add_snapshot(w, snaps, 0, time, center, rot, coefs)
+    w.dataset(w.root, "count", np.uint32(count))
+    tmp = path + ".tmp"
+    w.write(tmp)
+    os.replace(tmp, path)
+    return count
+
+
+def read_coefs_h5(path, stride=1, tmin=-np.inf, tmax=np.inf):
+    """the H5 constructors of CoefClasses::SphCoefs / CylCoefs (expui/Coefficients.cc:225-332,
+    1080-1180): -> dict(geometry, name, forceID, config, units, lmax|mmax, nmax, [scale,] times[T],
+    centers[T][3], rotations[T][3][3], coefs[T][rows][nmax] complex).  Files without the
+    CoefficientOutputVersion attribute hold the legacy (column-major) storage order and are
+    re-ordered the way the reference does (:300-310)."""
+    f = File(path)
+    a = dict(f.attrs)
+    geometry = a.get("geometry")
+    if geometry not in ("sphere", "cylinder"):
+        raise H5Error(f"coefficient file of geometry {geometry!r} not supported")
+    legacy = "CoefficientOutputVersion" not in a
+    out = {k: a.get(k) for k in ("geometry", "name", "forceID", "config")}
+    nmax = int(a["nmax"])
+    if geometry == "sphere":
+        out["lmax"], out["scale"] = int(a["lmax"]), float(a["scale"])
+        rows = (out["lmax"] + 1) * (out["lmax"] + 2) // 2
+    else:
+        out["mmax"] = int(a["mmax"])
+        rows = out["mmax"] + 1
+    out["nmax"] = nmax
+    out["units"] = [(u["name"].decode(), u["unit"].decode(), float(u["value"])) for u in f["Units"].read()] \
+        if "Units" in f else []
+    count = int(f["count"].read())
+    snaps = f["snapshots"]
+    times, ctrs, rots, cfs = [], [], [], []
+    for n in range(0, count, stride):
+        s = snaps[f"{n:08d}"]
+        t = float(s.attrs["Time"])
+        if t < tmin or t > tmax:
+            continue
+        d = np.asarray(s["coefficients"].read())
+        c = d["r"] + 1j * d["i"] if d.dtype.names else d
+        if c.shape != (rows, nmax):
+            continue                                  # the reference skips stanzas of the wrong shape
+        if legacy:
+            c = c.reshape(-1).reshape((rows, nmax), order="F")
+        times.append(t)
+        ctrs.append(np.asarray(s.attrs.get("Center", np.zeros(3)), dtype=float).reshape(-1)[:3])
+        rots.append(np.asarray(s.attrs.get("Rotation", np.eye(3)), dtype=float).reshape(3, 3))
+        cfs.append(c)
+    out["times"] = np.array(times)
+    out["centers"] = np.array(ctrs).reshape(-1, 3)
+    out["rotations"] = np.array(rots).reshape(-1, 3, 3)
+    out["coefs"] = np.array(cfs).reshape(-1, rows, nmax)
+    return out

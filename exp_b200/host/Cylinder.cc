@@ -11,7 +11,7 @@ Cylinder::Cylinder(const EmpCylSLTables &t, int device, double rcylmax_, double 
                    int MMIN, int MLIM, int NMIN, int NLIM)
   : mmax(t.mmax), ncylorder(t.norder), rcylmax(rcylmax_), EVEN_M(even_m)
 {
-  id = "cylinder";
+  id = "Cylinder";             // src/Cylinder.cc:99
   acyl = acyl_ < 0.0 ? t.ascale : acyl_;
   expb200_cylinder_config cfg = {t.mmax, t.norder, t.numx, t.numy, t.cmapr, t.cmapz, t.ascale, t.hscale,
                                  t.rmin, t.rmax, rcylmax, acyl, EVEN_M, MMIN, MLIM, NMIN, NLIM,

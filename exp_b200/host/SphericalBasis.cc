@@ -13,7 +13,7 @@ SphericalBasis::SphericalBasis(const SLGridSphTables &t, int device, double scal
   : Lmax(t.lmax), nmax(t.nmax), scale(scale_), NO_L0(no_l0), NO_L1(no_l1), EVEN_L(even_l),
     EVEN_M(even_m), M0_only(m0_only)
 {
-  id = "sphereSL";
+  id = "SphereSL";             // src/Sphere.cc:31
   // rmin/rmax default to the table's range, as the Sphere constructor does (src/Sphere.cc:65-66)
   rmin = rmin_ < 0.0 ? t.rmin : rmin_;
   rmax = rmax_ < 0.0 ? t.rmax : rmax_;

@@ -45,6 +45,7 @@ int exphost_reset(void)
     g_comp = new ComponentContainer();
     comp = g_comp;
     level_report.clear();
+    pos_check.clear(); vel_check.clear();
     reset_globals();
   });
 }
@@ -384,9 +385,11 @@ int exphost_state(double *tnow_, int *this_step_, double *pc, double *vc)
 {
   if (tnow_) *tnow_ = tnow;
   if (this_step_) *this_step_ = this_step;
-  for (size_t i = 0; i < pos_check.size(); i++) {
-    if (pc) pc[i] = pos_check[i];
-    if (vc) vc[i] = vel_check[i];
+  // pc, vc hold multistep + 1 entries (the caller sizes them from the multistep it configured);
+  // the CHK_STEP sums exist only for multistep > 0 (step.cc)
+  for (size_t i = 0; i <= multistep; i++) {
+    if (pc) pc[i] = i < pos_check.size() ? pos_check[i] : 0.0;
+    if (vc) vc[i] = i < vel_check.size() ? vel_check[i] : 0.0;
   }
   return 0;
 }

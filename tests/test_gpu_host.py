@@ -57,10 +57,10 @@ def _check_coef_output(sim, h, d, tnow):
     buf = sim.dump_coefs(h, 0)
     magic, node, off = CF.parse_header(buf)
     assert magic == 0xc0a57a2
-    assert node["id"] == "sphereSL" and node["nmax"] == nmax and node["lmax"] == lmax and node["normed"] is True
+    assert node["id"] == "SphereSL" and node["nmax"] == nmax and node["lmax"] == lmax and node["normed"] is True
     assert node["time"] == tnow and node["scale"] == 1.0
     assert np.array_equal(np.frombuffer(buf[off:]), CF.sphere_payload(ex, lmax, nmax))
-    assert sim.dump_coefs(h, 1) == CF.sphere_old_stream(ex, "sphereSL", tnow, 1.0, lmax, nmax)
+    assert sim.dump_coefs(h, 1) == CF.sphere_old_stream(ex, "SphereSL", tnow, 1.0, lmax, nmax)
     cof = np.frombuffer(sim.dump_coefs(h, 2), dtype=np.complex128).reshape(-1, nmax)
     assert np.array_equal(cof, CF.sphere_struct(ex, lmax, nmax))
     cs, sn, _ = sim.cylinder_coefs(d)
@@ -71,6 +71,21 @@ def _check_coef_output(sim, h, d, tnow):
     assert np.array_equal(np.frombuffer(buf[off:]), CF.cylinder_payload(cs, sn))
     cof = np.frombuffer(sim.dump_coefs(d, 2), dtype=np.complex128).reshape(cs.shape)
     assert np.array_equal(cof.real, cs) and np.array_equal(cof.imag[1:], sn[1:]) and not cof.imag[0].any()
+    # dump_coefs_h5: first call creates the file, the second appends a snapshot
+    import os
+    import tempfile
+    from exp_b200 import h5lite
+    with tempfile.TemporaryDirectory() as td:
+        for idx, geom, fid in ((h, "sphere", "SphereSL"), (d, "cylinder", "Cylinder")):
+            path = os.path.join(td, f"coefs.{geom}.h5")
+            assert sim.dump_coefs_h5(idx, path, config="id: test\n") == 1
+            assert sim.dump_coefs_h5(idx, path) == 2
+            r = h5lite.read_coefs_h5(path)
+            assert (r["geometry"], r["forceID"], r["config"]) == (geom, fid, "id: test\n")
+            assert r["name"] == ("halo" if geom == "sphere" else "disk")
+            assert np.array_equal(r["times"], [tnow, tnow]) and r["coefs"].shape[0] == 2
+            assert np.array_equal(r["coefs"][1], sim.coef_struct(idx))
+            assert np.array_equal(r["rotations"][0], np.eye(3))
 
 
 @pytest.mark.parametrize("multistep", [0, 2])

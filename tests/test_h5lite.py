@@ -126,3 +126,78 @@ def test_chunked_deflate_dataset_is_read():
     out[0:len(sb)] = sb
     f = h5lite.File(bytes(out))
     assert np.array_equal(f["x"].read(), a)
+
+
+# ---- coefficient files (CoefClasses::SphCoefs / CylCoefs layout) --------------------------------
+def test_coefficient_file_create_extend_read(tmp_path):
+    """dump_coefs_h5: first call = Coefs::WriteH5Coefs, later calls = ExtendH5Coefs (reference
+    expui/Coefficients.cc:3100-3205); the snapshot group grows past one symbol node and past one
+    B-tree node (32 and 1024 entries)"""
+    rng = np.random.default_rng(5)
+    p = str(tmp_path / "outcoef.halo.h5")
+    lmax, nmax = 4, 7
+    rows = (lmax + 1) * (lmax + 2) // 2
+    want = []
+    for k in range(40):
+        c = rng.normal(size=(rows, nmax)) + 1j * rng.normal(size=(rows, nmax))
+        want.append(c)
+        n = h5lite.dump_coefs_h5(p, "sphere", "dark halo", "SphereSL", 0.01 * k, c, lmax=lmax, scale=0.05,
+                                 config="id: SphereSL\nparameters: {Lmax: 4}\n", center=(0.1 * k, 0.0, -1.0))
+        assert n == k + 1
+    f = h5lite.File(p)
+    assert f.attrs["CoefficientOutputVersion"] == "1.0" and f.attrs["geometry"] == "sphere"
+    assert f.attrs["name"] == "dark halo" and f.attrs["forceID"] == "SphereSL"
+    assert f.attrs["lmax"] == lmax and f.attrs["nmax"] == nmax and f.attrs["scale"] == 0.05
+    assert int(f["count"].read()) == 40 and f["count"].shape == ()
+    u = f["Units"].read()
+    assert u.dtype.names == ("name", "unit", "value") and u.dtype.itemsize == 36
+    assert [x.decode() for x in u["name"]] == ["length", "mass", "time"]
+    d = f["snapshots/00000039/coefficients"]
+    assert d.shape == (rows, nmax) and d.dtype.names == ("r", "i") and d.dtype.itemsize == 16
+    r = h5lite.read_coefs_h5(p)
+    assert np.array_equal(r["coefs"], np.array(want))
+    assert np.allclose(r["times"], 0.01 * np.arange(40)) and np.array_equal(r["centers"][3], [0.1 * 3, 0.0, -1.0])
+    r2 = h5lite.read_coefs_h5(p, stride=4, tmin=0.1)
+    assert np.array_equal(r2["coefs"], np.array(want)[12::4])
+    # CheckH5Params: a different basis does not extend the file
+    with pytest.raises(h5lite.H5Error):
+        h5lite.dump_coefs_h5(p, "sphere", "dark halo", "SphereSL", 1.0, want[0], lmax=lmax, scale=0.06)
+    with pytest.raises(h5lite.H5Error):
+        h5lite.dump_coefs_h5(p, "sphere", "dark halo", "SphereSL", 1.0, want[0][:, :5].copy(), lmax=lmax, scale=0.05)
+
+
+def test_coefficient_file_many_snapshots_and_cylinder(tmp_path):
+    p = str(tmp_path / "outcoef.disk.h5")
+    w = h5lite.Writer()
+    a = w.root["attrs"]
+    a["CoefficientOutputVersion"], a["geometry"], a["name"], a["config"] = "1.0", "cylinder", "disk", ""
+    a["mmax"], a["nmax"], a["forceID"] = 3, 5, "Cylinder"
+    snaps = w.group(w.root, "snapshots")
+    rng = np.random.default_rng(6)
+    want = rng.normal(size=(1100, 4, 5)) + 1j * rng.normal(size=(1100, 4, 5))
+    cnt = 0
+    for c in want:
+        cnt = h5lite._add_snapshot(w, snaps, cnt, 0.5 * cnt, np.zeros(3), np.eye(3), c)
+    w.dataset(w.root, "count", np.uint32(cnt))
+    w.write(p)
+    r = h5lite.read_coefs_h5(p)
+    assert r["mmax"] == 3 and r["coefs"].shape == (1100, 4, 5) and np.array_equal(r["coefs"], want)
+    assert h5lite.dump_coefs_h5(p, "cylinder", "disk", "Cylinder", 999.0, want[0], mmax=3) == 1101
+    assert h5lite.read_coefs_h5(p, tmin=900.0)["times"].tolist() == [999.0]
+
+
+def test_coefficient_file_legacy_order(tmp_path):
+    """files without CoefficientOutputVersion hold the transposed legacy order (reference
+    expui/Coefficients.cc:248-251, 300-310)"""
+    p = str(tmp_path / "legacy.h5")
+    c = np.arange(12.0).reshape(3, 4) + 0j
+    w = h5lite.Writer()
+    a = w.root["attrs"]
+    a["geometry"], a["name"], a["config"], a["mmax"], a["nmax"], a["forceID"] = "cylinder", "d", "", 2, 4, "Cylinder"
+    s = w.group(w.group(w.root, "snapshots"), "00000000")
+    s["attrs"]["Time"] = 0.0
+    w.dataset(s, "coefficients", c)
+    w.dataset(w.root, "count", np.uint32(1))
+    w.write(p)
+    got = h5lite.read_coefs_h5(p)["coefs"][0]
+    assert np.array_equal(got, c.reshape(-1).reshape((3, 4), order="F"))
