@@ -296,11 +296,12 @@ __global__ void cyl_interp_kernel(const double *__restrict__ cL, const double *_
 // both are non-decreasing along the sorted order -- and a second kernel adds a bin's
 // partials in chunk order: no atomics, bit-reproducible.
 // ===========================================================================
-constexpr int kCovP = 32;             // particles per tile (one producer-warp pass: lane = particle)
-constexpr int kCovLD = 36;            // leading dimension of a panel row (doubles): 2-way = minimal
-                                      // bank conflicts for the 64-bit fragment loads
-constexpr int kCovThreads = 288;      // 8 panel/DMMA warps + 1 geometry warp
-constexpr int kCovMG = 8;             // harmonics per CTA (one per warp)
+constexpr int kCovLDpad = 4;          // leading dimension of a panel row = tile + 4 doubles: the 64-bit
+                                      // fragment loads of a half warp then fall into 16 distinct banks
+constexpr int kCovMG = 7;             // harmonics per CTA: one DMMA warp each (warps 0-6)
+constexpr int kCovPanel = 512;        // panel threads (warps 8-23); warp 7 stages the geometry
+constexpr int kCovThreads = 768;
+constexpr int kCovTile = 32;          // particles per tile
 constexpr int kCovSplit = 4;          // particle interleave of the panel evaluation (max)
 
 __global__ void __launch_bounds__(256)
@@ -357,36 +358,74 @@ __global__ void cyl_cov_bounds_kernel(const uint32_t *__restrict__ skeys, size_t
   bstart[T] = (uint32_t)lo;
 }
 
-// The three phases of a tile -- geometry of its particles (one lane per particle: gather of the
-// position record, coordinate maps, cell, corner weights, azimuthal factors), the panel u[m][n][j]
-// (8 KB of table gathers per particle, L2), and the rank-k update (DMMA) -- overlap: warp 8 is a
-// producer that prepares the geometry of tile t+1 in the other half of a double buffer while
-// warps 0-7 evaluate the panel of tile t and multiply it (round 2: with the phases in sequence the
-// kernel sat at the CTA barrier, FP64 pipe 8 % active, profiles/r02h_cyl_ncu_full_summary.txt).
-template <int NT>
-__global__ void __maxnreg__(NT <= 5 ? 112 : 224)       // 2 x 288 or 1 x 288 threads per SM
-cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict__ posm,
-               const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skeys,
-               const uint32_t *__restrict__ bstart, int sampT, int CH, double adb, int nsplit,
-               double *__restrict__ PC, double *__restrict__ PV, double *__restrict__ PM)
+// Geometry of the used particles in sorted order, one thread per particle (gather of the position
+// record, coordinate maps, cell, corner weights, azimuthal factors): GW[k][4] corner weights times
+// -4 pi sqrt(mass), GT[k][M1][2] (cos, sin) m phi, GS[k] sqrt(mass), GM[k] mass, GN[k] node index.
+__global__ void __launch_bounds__(256)
+cyl_cov_geom_kernel(CylGeom g, const rec4 *__restrict__ posm, const uint32_t *__restrict__ perm,
+                    size_t nused, double adb, double *__restrict__ GW, double *__restrict__ GT,
+                    double *__restrict__ GS, double *__restrict__ GM, int *__restrict__ GN)
+{
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nused) return;
+  const int M1 = g.mmax + 1;
+  const rec4 pm = ld_rec(&posm[perm[k]]);
+  double x, y, z, r;
+  cyl_classify(g, pm, x, y, z, r, 0);
+  double zz = z;
+  if (zz / g.ascale > g.rtable) zz = g.rtable * g.ascale;       // EmpCylSL::get_pot clamp
+  if (zz / g.ascale < -g.rtable) zz = -g.rtable * g.ascale;
+  const CylCell c = cyl_locate(g, r, zz);
+  const double mass = pm.w * adb;
+  const double sq = sqrt(mass), sw = -4.0 * M_PI * sq;
+  double4 wv;
+  wv.x = sw * c.c00; wv.y = sw * c.c10; wv.z = sw * c.c01; wv.w = sw * c.c11;
+  reinterpret_cast<double4 *>(GW)[k] = wv;
+  GN[k] = c.ix * (g.numy + 1) + c.iy;
+  GS[k] = sq;
+  GM[k] = mass;
+  double2 *trg = reinterpret_cast<double2 *>(GT) + k * M1;
+  cyl_trig(g.mmax, x, y, r, [&](int m, double cm, double sm) {
+    double2 v; v.x = cm; v.y = sm;
+    trg[m] = v;
+  });
+}
+
+// The three stages of a tile of 32 sorted particles -- staging of its geometry records in shared
+// memory, the panel u[m][n][j] (8 KB of table gathers per particle, L1/L2), and the rank-k update
+// (DMMA) -- run as a software pipeline over the tiles of the chunk with one CTA barrier per step: in
+// step i warp 7 copies the geometry of tile i, warps 8-23 evaluate the panel of tile i-1 into one
+// half of a double-buffered U, and warps 0-6 (one harmonic each) multiply the panel of tile i-2 from
+// the other half.  The DMMA warps hold the accumulators (2 NT^2 doubles) and take REGD registers
+// each (setmaxnreg), the sixteen panel warps REGP: the panel stage is bound by instruction issue,
+// not by memory (round 2, 1e7 particles, sampT = 100, profiles/r02p_*: all stages in sequence in
+// the same 8 warps 16.0 ms; geometry in a producer warp 13.2 ms; this pipeline with 4 panel warps
+// 12.6 ms, the panel stage alone 11.2 ms at 0.25 instructions per cycle and scheduler).
+template <int NT, int REGD, int REGP>
+__global__ void __launch_bounds__(kCovThreads, 1)
+cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const double *__restrict__ GW,
+               const double *__restrict__ GT, const double *__restrict__ GS, const double *__restrict__ GM,
+               const int *__restrict__ GN, const uint32_t *__restrict__ bstart, int sampT, int CH, int nsplit,
+               int MG, double *__restrict__ PC, double *__restrict__ PV, double *__restrict__ PM)
 {
   extern __shared__ double cov_smem[];
+  constexpr int P = kCovTile, LD = P + kCovLDpad;
   const int N = g.norder, R2 = 2 * N, M1 = g.mmax + 1, MN = M1 * N;
-  const int mg0 = blockIdx.y * kCovMG;
-  const int nml = M1 - mg0 < kCovMG ? M1 - mg0 : kCovMG;       // harmonics of this CTA
-  const int items = nml * N;
-  double *U = cov_smem;                                        // [kCovMG][R2][kCovLD]
-  double *geo = U + (size_t)kCovMG * R2 * kCovLD;              // two geometry buffers
-  const size_t geo_doubles = (size_t)kCovP * 4 + (size_t)kCovP * M1 * 2 + 2 * kCovP + kCovP / 2 + 2;
-  auto WGT = [&](int b) { return geo + b * geo_doubles; };                        // [kCovP][4]
-  auto TRG = [&](int b) { return WGT(b) + kCovP * 4; };                           // [kCovP][M1][2]
-  auto SQM = [&](int b) { return TRG(b) + (size_t)kCovP * M1 * 2; };              // [kCovP]
-  auto PMS = [&](int b) { return SQM(b) + kCovP; };                               // [kCovP]
-  auto NBS = [&](int b) { return reinterpret_cast<int *>(PMS(b) + kCovP); };      // [kCovP]
-  auto INFO = [&](int b) { return NBS(b) + kCovP; };                              // cnt, T
+  const int mg0 = blockIdx.y * MG;                             // MG <= kCovMG harmonics per CTA
+  const int nml = M1 - mg0 < MG ? M1 - mg0 : MG;               // harmonics of this CTA
+  const int items = nml * N;                                   // <= kCovPanel
+  const size_t u_doubles = (size_t)MG * R2 * LD;
+  double *geo = cov_smem + 2 * u_doubles;                      // after the two panels
+  const size_t geo_doubles = (size_t)P * 4 + (size_t)P * M1 * 2 + 2 * P + P / 2;
+  auto UB = [&](int b) { return cov_smem + b * u_doubles; };                      // [MG][R2][LD]
+  auto WGT = [&](int b) { return geo + b * geo_doubles; };                        // [P][4]
+  auto TRG = [&](int b) { return WGT(b) + P * 4; };                               // [P][M1][2]
+  auto SQM = [&](int b) { return TRG(b) + (size_t)P * M1 * 2; };                  // [P]
+  auto PMS = [&](int b) { return SQM(b) + P; };                                   // [P]
+  auto NBS = [&](int b) { return reinterpret_cast<int *>(PMS(b) + P); };          // [P]
+  int *info = reinterpret_cast<int *>(geo + 2 * geo_doubles);                     // [4][2]: cnt, T of tile i & 3
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const bool producer = w == 8;
   const int gq = lane >> 2, t = lane & 3;
   const size_t nused = bstart[sampT];
   const size_t chunk = blockIdx.x;
@@ -394,159 +433,174 @@ cyl_cov_kernel(CylGeom g, const double2 *__restrict__ Zt, const rec4 *__restrict
   if (beg >= nused) return;
   const size_t end = beg + CH < nused ? beg + CH : nused;
 
-  // ---- producer: geometry of the tile that starts at sorted position k0, into buffer b
-  auto geometry = [&](size_t k0, int b) -> int {
-    if (k0 >= end) { if (lane == 0) { INFO(b)[0] = 0; INFO(b)[1] = -1; } return 0; }
-    const size_t k = k0 + lane;
-    const bool valid = k < end;
-    const uint32_t key = valid ? skeys[k] : 0xffffffffu;
-    const int Tj = (int)(key / (uint32_t)g.ncell);
-    const int T0 = __shfl_sync(0xffffffffu, Tj, 0);
-    const unsigned mask = __ballot_sync(0xffffffffu, valid && Tj == T0);
-    const int cnt = mask == 0xffffffffu ? 32 : __ffs(~mask) - 1;        // leading run of the same bin
-    if (lane == 0) { INFO(b)[0] = cnt; INFO(b)[1] = T0; }
-    if (lane < cnt) {
-      const rec4 pm = ld_rec(&posm[perm[k]]);
-      double x, y, z, r;
-      cyl_classify(g, pm, x, y, z, r, 0);
-      double zz = z;
-      if (zz / g.ascale > g.rtable) zz = g.rtable * g.ascale;       // EmpCylSL::get_pot clamp
-      if (zz / g.ascale < -g.rtable) zz = -g.rtable * g.ascale;
-      const CylCell c = cyl_locate(g, r, zz);
-      const double mass = pm.w * adb;
-      const double sq = sqrt(mass), sw = -4.0 * M_PI * sq;
-      double *wgt = WGT(b);
-      wgt[lane * 4 + 0] = sw * c.c00; wgt[lane * 4 + 1] = sw * c.c10;
-      wgt[lane * 4 + 2] = sw * c.c01; wgt[lane * 4 + 3] = sw * c.c11;
-      NBS(b)[lane] = c.ix * (g.numy + 1) + c.iy;
-      SQM(b)[lane] = sq;
-      PMS(b)[lane] = mass;
-      double *trg = TRG(b);
-      cyl_trig(g.mmax, x, y, r, [&](int m, double cm, double sm) {
-        trg[(lane * M1 + m) * 2] = cm;
-        trg[(lane * M1 + m) * 2 + 1] = sm;
-      });
-    }
-    return cnt;
-  };
-
-  if (producer) {
-    // one tile ahead of the consumers; both sides pass one CTA barrier per tile (+ the first)
-    size_t k0 = beg;
-    int cnt = geometry(k0, 0);
-    __syncthreads();
-    for (int tile = 0; cnt > 0; tile++) {
-      k0 += cnt;
-      cnt = geometry(k0, (tile + 1) & 1);
+  if (w >= 8) {
+    // ---- stage 2: panel u[m][n][j], u[m][N+n][j] of tile i-1 (zero beyond cnt); thread -> (split, m, n)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGP));
+    const int pt = tid - 256;
+    const int split = pt / items, it = pt % items;
+    const bool evalr = split < nsplit;
+    const int ml = it / N, nn = it % N;
+    const int mn = (mg0 + ml) * N + nn;
+    double vcr = 0.0, vci = 0.0;            // this thread's share of VC[T][m][n]
+    double bmass = 0.0, bcount = 0.0;       // thread 0: massT / numbT of the current bin
+    int curT = -1;
+    auto flush = [&](int T) {
+      const size_t slot = chunk + (size_t)T;
+      if (evalr) {
+        double *V = PV + ((slot * kCovSplit + split) * MN + mn) * 2;
+        V[0] = vcr; V[1] = vci;
+        vcr = vci = 0.0;
+      }
+      if (pt == 0 && mg0 == 0) {
+        PM[slot * 2] = bmass; PM[slot * 2 + 1] = bcount;
+        bmass = bcount = 0.0;
+      }
+    };
+    for (int i = 0;; i++) {
+      const int cnt = i >= 1 ? info[((i - 1) & 3) * 2] : 0;
+      if (cnt > 0) {
+        const int b = (i - 1) & 1, T0 = info[((i - 1) & 3) * 2 + 1];
+        const double *wgt = WGT(b), *trg = TRG(b), *sqm = SQM(b), *pms = PMS(b);
+        const int *nbs = NBS(b);
+        if (T0 != curT) {
+          if (curT >= 0) flush(curT);
+          curT = T0;
+        }
+        if (pt == 0)
+          for (int j = 0; j < cnt; j++) { bmass += pms[j]; bcount += 1.0; }
+        const int kpad = (cnt + 3) & ~3;
+        if (evalr) {
+          double *ua = UB(b) + ((size_t)ml * R2 + nn) * LD, *ub = ua + (size_t)N * LD;
+          for (int j = split; j < kpad; j += nsplit) {
+            double a = 0.0, b2 = 0.0;
+            if (j < cnt) {
+              const double2 *z = Zt + (size_t)nbs[j] * MN + mn;
+              const double2 z00 = __ldg(z), z01 = __ldg(z + MN);
+              const double2 z10 = __ldg(z + (size_t)(g.numy + 1) * MN), z11 = __ldg(z + (size_t)(g.numy + 2) * MN);
+              const double *wj = wgt + j * 4;
+              const double vc = z00.x * wj[0] + z10.x * wj[1] + z01.x * wj[2] + z11.x * wj[3];
+              const double vs = z00.y * wj[0] + z10.y * wj[1] + z01.y * wj[2] + z11.y * wj[3];
+              const double cm = trg[(j * M1 + mg0 + ml) * 2], sm = trg[(j * M1 + mg0 + ml) * 2 + 1];
+              if (g.cov_mode == 0) {
+                a = vc * cm + vs * sm;
+                b2 = vc * sm - vs * cm;
+              } else if (g.cov_mode == 1) {   // sqrt(mass) * |(Vc cos, Vs sin)|: vc, vs carry -4 pi sqrt(mass)
+                const double hc = vc * cm, hs = vs * sm;
+                a = sqrt(hc * hc + hs * hs) * (0.25 / M_PI);
+              } else {                        // sqrt(mass) * |norm| * |(Vc, Vs)|
+                a = sqrt(vc * vc + vs * vs);
+              }
+              vcr += sqm[j] * a;
+              vci += sqm[j] * b2;
+            }
+            ua[j] = a;
+            ub[j] = b2;
+          }
+        }
+      }
       __syncthreads();
+      if (i >= 2 && info[((i - 2) & 3) * 2] == 0) break;
+    }
+    if (curT >= 0) flush(curT);
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGD));
+  if (w == 7) {
+    // ---- stage 1: the geometry records of the tile that starts at sorted position k0 -> shared
+    // memory (cnt = 0 past the end of the chunk); tiles do not straddle a partition boundary
+    size_t k0 = beg;
+    int T = 0;
+    size_t tend = bstart[1];
+    for (int i = 0;; i++) {
+      const int b = i & 1;
+      int cnt = 0;
+      if (k0 < end) {
+        while (k0 >= tend) { T++; tend = bstart[T + 1]; }
+        const size_t lim = tend < end ? tend : end;
+        cnt = lim - k0 < (size_t)P ? (int)(lim - k0) : P;
+        const double2 *gw = reinterpret_cast<const double2 *>(GW) + k0 * 2;
+        const double2 *gt = reinterpret_cast<const double2 *>(GT) + k0 * M1;
+        double2 *sw = reinterpret_cast<double2 *>(WGT(b)), *st = reinterpret_cast<double2 *>(TRG(b));
+        const int nw = cnt * 2, nt = cnt * M1;
+        double2 r0, r1, q[4];
+        r0.x = r0.y = r1.x = r1.y = 0.0;
+        if (lane < nw) r0 = __ldg(gw + lane);
+        if (lane + 32 < nw) r1 = __ldg(gw + lane + 32);
+        double sq = 0.0, ms = 0.0;
+        int nb = 0;
+        if (lane < cnt) { sq = __ldg(GS + k0 + lane); ms = __ldg(GM + k0 + lane); nb = __ldg(GN + k0 + lane); }
+        for (int e0 = 0; e0 < nt; e0 += 128) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (e0 + 32 * u + lane < nt) q[u] = __ldg(gt + e0 + 32 * u + lane);
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (e0 + 32 * u + lane < nt) st[e0 + 32 * u + lane] = q[u];
+        }
+        if (lane < nw) sw[lane] = r0;
+        if (lane + 32 < nw) sw[lane + 32] = r1;
+        if (lane < cnt) { SQM(b)[lane] = sq; PMS(b)[lane] = ms; NBS(b)[lane] = nb; }
+        k0 += cnt;
+      }
+      if (lane == 0) { info[(i & 3) * 2] = cnt; info[(i & 3) * 2 + 1] = T; }
+      __syncthreads();
+      if (i >= 2 && info[((i - 2) & 3) * 2] == 0) break;
     }
     return;
   }
 
-  // panel evaluation: thread -> (split, local m, n)
-  const int split = tid / items, it = tid % items;
-  const bool evalr = split < nsplit;
-  const int ml = it / N, nn = it % N;
-  const int mn = (mg0 + ml) * N + nn;
-
+  // ---- stage 3: rank-k update of tile i-2 on the tensor cores: warp w owns harmonic mg0 + w
   double acc[NT][NT][2];
 #pragma unroll
   for (int a = 0; a < NT; a++)
 #pragma unroll
     for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-  double vcr = 0.0, vci = 0.0;            // this thread's share of VC[T][m][n]
-  double bmass = 0.0, bcount = 0.0;       // thread 0: massT / numbT of the current bin
   int curT = -1;
-
   auto flush = [&](int T) {
     const size_t slot = chunk + (size_t)T;
     if (w < nml) {
-      double *P = PC + ((slot * M1 + (mg0 + w)) * R2) * R2;
+      double *Pm = PC + ((slot * M1 + (mg0 + w)) * R2) * R2;
 #pragma unroll
       for (int a = 0; a < NT; a++)
 #pragma unroll
         for (int b = a; b < NT; b++) {         // U U^T is symmetric: tiles on and above the diagonal
           const int row = 8 * a + gq, col = 8 * b + 2 * t;
           if (row < R2 && col < R2) {          // R2 is even: col + 1 < R2 as well
-            P[(size_t)row * R2 + col] = acc[a][b][0];
-            P[(size_t)row * R2 + col + 1] = acc[a][b][1];
+            Pm[(size_t)row * R2 + col] = acc[a][b][0];
+            Pm[(size_t)row * R2 + col + 1] = acc[a][b][1];
           }
           acc[a][b][0] = acc[a][b][1] = 0.0;
         }
     }
-    if (evalr) {
-      double *V = PV + ((slot * kCovSplit + split) * MN + mn) * 2;
-      V[0] = vcr; V[1] = vci;
-      vcr = vci = 0.0;
-    }
-    if (tid == 0 && mg0 == 0) {
-      PM[slot * 2] = bmass; PM[slot * 2 + 1] = bcount;
-      bmass = bcount = 0.0;
-    }
   };
-
-  __syncthreads();                            // geometry of tile 0 is there
-  for (int tile = 0;; tile++) {
-    const int b = tile & 1;
-    const int cnt = INFO(b)[0], T0 = INFO(b)[1];
-    if (cnt == 0) break;
-    const double *wgt = WGT(b), *trg = TRG(b), *sqm = SQM(b), *pms = PMS(b);
-    const int *nbs = NBS(b);
-    if (T0 != curT) {
-      if (curT >= 0) flush(curT);
-      curT = T0;
-    }
-    if (tid == 0) {
-      for (int j = 0; j < cnt; j++) { bmass += pms[j]; bcount += 1.0; }
-    }
-    // ---- panel: u[m][n][j], u[m][N+n][j] for the tile's particles (zero beyond cnt)
-    const int kpad = (cnt + 3) & ~3;
-    if (evalr) {
-      double *ua = U + ((size_t)ml * R2 + nn) * kCovLD, *ub = ua + (size_t)N * kCovLD;
-      for (int j = split; j < kpad; j += nsplit) {
-        double a = 0.0, b2 = 0.0;
-        if (j < cnt) {
-          const double2 *z = Zt + (size_t)nbs[j] * MN + mn;
-          const double2 z00 = __ldg(z), z01 = __ldg(z + MN);
-          const double2 z10 = __ldg(z + (size_t)(g.numy + 1) * MN), z11 = __ldg(z + (size_t)(g.numy + 2) * MN);
-          const double *wj = wgt + j * 4;
-          const double vc = z00.x * wj[0] + z10.x * wj[1] + z01.x * wj[2] + z11.x * wj[3];
-          const double vs = z00.y * wj[0] + z10.y * wj[1] + z01.y * wj[2] + z11.y * wj[3];
-          const double cm = trg[(j * M1 + mg0 + ml) * 2], sm = trg[(j * M1 + mg0 + ml) * 2 + 1];
-          if (g.cov_mode == 0) {
-            a = vc * cm + vs * sm;
-            b2 = vc * sm - vs * cm;
-          } else if (g.cov_mode == 1) {       // sqrt(mass) * |(Vc cos, Vs sin)|: vc, vs carry -4 pi sqrt(mass)
-            const double hc = vc * cm, hs = vs * sm;
-            a = sqrt(hc * hc + hs * hs) * (0.25 / M_PI);
-          } else {                            // sqrt(mass) * |norm| * |(Vc, Vs)|
-            a = sqrt(vc * vc + vs * vs);
+  for (int i = 0;; i++) {
+    const int cnt = i >= 2 ? info[((i - 2) & 3) * 2] : 0;
+    if (cnt > 0) {
+      const int T0 = info[((i - 2) & 3) * 2 + 1];
+      if (T0 != curT) {
+        if (curT >= 0) flush(curT);
+        curT = T0;
+      }
+      if (w < nml) {
+        const int kpad = (cnt + 3) & ~3;
+        const double *Um = UB(i & 1) + (size_t)w * R2 * LD;
+        for (int kk = 0; kk < kpad; kk += 4) {
+          double af[NT];
+#pragma unroll
+          for (int r = 0; r < NT; r++) {
+            const int row = 8 * r + gq;
+            af[r] = row < R2 ? Um[(size_t)row * LD + kk + t] : 0.0;
           }
-          vcr += sqm[j] * a;
-          vci += sqm[j] * b2;
+#pragma unroll
+          for (int a = 0; a < NT; a++)
+#pragma unroll
+            for (int b3 = a; b3 < NT; b3++) dmma_m8n8k4(acc[a][b3][0], acc[a][b3][1], af[a], af[b3]);
         }
-        ua[j] = a;
-        ub[j] = b2;
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");        // the eight consumer warps: panel complete
-    // ---- rank-k update on the tensor cores: warp w owns harmonic mg0 + w
-    if (w < nml) {
-      const double *Um = U + (size_t)w * R2 * kCovLD;
-      for (int kk = 0; kk < kpad; kk += 4) {
-        double af[NT];
-#pragma unroll
-        for (int r = 0; r < NT; r++) {
-          const int row = 8 * r + gq;
-          af[r] = row < R2 ? Um[(size_t)row * kCovLD + kk + t] : 0.0;
-        }
-#pragma unroll
-        for (int a = 0; a < NT; a++)
-#pragma unroll
-          for (int b3 = a; b3 < NT; b3++) dmma_m8n8k4(acc[a][b3][0], acc[a][b3][1], af[a], af[b3]);
-      }
-    }
-    __syncthreads();      // panel consumed, geometry buffer b free, the next tile's geometry ready
+    __syncthreads();
+    if (i >= 2 && info[((i - 2) & 3) * 2] == 0) break;
   }
   if (curT >= 0) flush(curT);
 }
@@ -600,12 +654,19 @@ cyl_cov_combine_kernel(CylGeom g, const uint32_t *__restrict__ bstart, int CH, i
 
 template <int NT>
 int launch_cyl_cov(cudaStream_t st, dim3 grid, size_t smem, const CylGeom &g, const double2 *Zt,
-                   const rec4 *posm, const uint32_t *perm, const uint32_t *skeys, const uint32_t *bstart,
-                   int sampT, int CH, double adb, int nsplit, double *PC, double *PV, double *PM)
+                   const double *GW, const double *GT, const double *GS, const double *GM, const int *GN,
+                   const uint32_t *bstart, int sampT, int CH, int nsplit, int MG, double *PC, double *PV,
+                   double *PM)
 {
-  CU_TRY(cudaFuncSetAttribute(cyl_cov_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cyl_cov_kernel<NT><<<grid, kCovThreads, smem, st>>>(g, Zt, posm, perm, skeys, bstart, sampT, CH, adb, nsplit,
-                                                      PC, PV, PM);
+  // registers: 768 threads start with 80 each; the two DMMA warpgroups (accumulators: 2 NT^2
+  // doubles) grow to REGD out of what the four panel warpgroups release by shrinking to REGP
+  // (setmaxnreg.inc waits for the CTA's own pool: 256 REGD + 512 REGP <= 768 x 80)
+  constexpr int REGD = NT <= 5 ? 128 : NT <= 6 ? 144 : 160;
+  constexpr int REGP = NT <= 5 ? 56 : NT <= 6 ? 48 : 40;
+  static_assert(256 * REGD + 512 * REGP <= 768 * 80, "register budget");
+  auto kern = cyl_cov_kernel<NT, REGD, REGP>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kCovThreads, smem, st>>>(g, Zt, GW, GT, GS, GM, GN, bstart, sampT, CH, nsplit, MG, PC, PV, PM);
   CU_LAUNCH_CHECK();
   return EXPB200_OK;
 }
@@ -643,8 +704,8 @@ struct expb200_cylinder_s {
   size_t part_slots = 0;
   double *block_mass = nullptr;
   double2 *Zt = nullptr;            // covariance: node-major complex pot table [nnode][(mmax+1)*norder]
-  void *cov_buf[8] = {};       // cached scratch of the covariance call
-  size_t cov_cap[8] = {};
+  void *cov_buf[13] = {};      // cached scratch of the covariance call
+  size_t cov_cap[13] = {};
   bool field_valid = false, have_accum = false;
   cudaStream_t last_stream = nullptr, own_stream = nullptr;
   cudaStream_t work_stream()
@@ -814,7 +875,7 @@ int expb200_cylinder_destroy(expb200_cylinder s)
   cudaFree(s->coef); cudaFree(s->coef_use); cudaFree(s->coefN); cudaFree(s->coefL);
   cudaFree(s->differ); cudaFree(s->tmp);
   cudaFree(s->G); cudaFree(s->F); cudaFree(s->PA); cudaFree(s->block_mass); cudaFree(s->Zt);
-  for (int q = 0; q < 8; q++) cudaFree(s->cov_buf[q]);
+  for (int q = 0; q < 13; q++) cudaFree(s->cov_buf[q]);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
   return EXPB200_OK;
@@ -1172,9 +1233,13 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
   int CH = (int)(chq < 256 ? 256 : chq > 4096 ? 4096 : chq);
   const unsigned nchunks = div_up(nused, CH);
   const size_t slots = (size_t)nchunks + sampT + 1;
-  const int mgroups = (M1 + kCovMG - 1) / kCovMG;
-  const int items = (M1 < kCovMG ? M1 : kCovMG) * N;
-  int nsplit = 256 / items;
+  // harmonics per CTA: one DMMA warp each, and one panel thread per (m, n) of the group
+  int MG = kCovPanel / N;
+  if (MG > kCovMG) MG = kCovMG;
+  if (MG > M1) MG = M1;
+  const int mgroups = (M1 + MG - 1) / MG;
+  const int items = MG * N;
+  int nsplit = kCovPanel / items;
   if (nsplit > kCovSplit) nsplit = kCovSplit;
   COV_TRY(cov_alloc((void **)&PC, slots * M1 * R2 * R2 * sizeof(double), 1));
   COV_TRY(cov_alloc((void **)&PV, slots * kCovSplit * MN * 2 * sizeof(double), 2));
@@ -1185,12 +1250,23 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
   COV_TRY(cov_alloc((void **)&dMass, (size_t)sampT * sizeof(double), 6));
   COV_TRY(cov_alloc((void **)&dCount, (size_t)sampT * sizeof(unsigned), 7));
 
-  const size_t smem = ((size_t)kCovMG * R2 * kCovLD +
-                       2 * ((size_t)kCovP * 4 + (size_t)kCovP * M1 * 2 + 2 * kCovP + kCovP / 2 + 2)) * sizeof(double);
+  // geometry records of the used particles, in sorted order (164 B per particle at mmax = 6)
+  double *GW = nullptr, *GT = nullptr, *GS = nullptr, *GM = nullptr;
+  int *GN = nullptr;
+  COV_TRY(cov_alloc((void **)&GW, (size_t)nused * 4 * sizeof(double), 8));
+  COV_TRY(cov_alloc((void **)&GT, (size_t)nused * M1 * 2 * sizeof(double), 9));
+  COV_TRY(cov_alloc((void **)&GS, (size_t)nused * sizeof(double), 10));
+  COV_TRY(cov_alloc((void **)&GM, (size_t)nused * sizeof(double), 11));
+  COV_TRY(cov_alloc((void **)&GN, (size_t)nused * sizeof(int), 12));
+  cyl_cov_geom_kernel<<<div_up(nused, 256), 256, 0, st>>>(g, c->posm, c->perm[c->cur], nused, adb, GW, GT, GS, GM, GN);
+  COV_TRY(cudaGetLastError());
+  constexpr int P = kCovTile;
+  const size_t smem = (2 * (size_t)MG * R2 * (P + kCovLDpad) +
+                       2 * ((size_t)P * 4 + (size_t)P * M1 * 2 + 2 * P + P / 2)) * sizeof(double) + 8 * sizeof(int);
   const dim3 grid(nchunks, mgroups);
   const int NT = (R2 + 7) / 8;
-#define COV_LAUNCH(K) rc = launch_cyl_cov<K>(st, grid, smem, g, s->Zt, c->posm, c->perm[c->cur], c->keys[c->cur], \
-                                             bstart, sampT, CH, adb, nsplit, PC, PV, PM)
+#define COV_LAUNCH(K) rc = launch_cyl_cov<K>(st, grid, smem, g, s->Zt, GW, GT, GS, GM, GN, bstart, sampT, CH, nsplit, \
+                                             MG, PC, PV, PM)
   switch (NT) {
     case 1: COV_LAUNCH(1); break;  case 2: COV_LAUNCH(2); break;  case 3: COV_LAUNCH(3); break;
     case 4: COV_LAUNCH(4); break;  case 5: COV_LAUNCH(5); break;  case 6: COV_LAUNCH(6); break;

@@ -12,8 +12,8 @@ import sys
 from collections import defaultdict
 
 
-def main(path, top=40):
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+def main(path, top=40, view="cuda,sass"):
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", view],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = None
@@ -35,7 +35,9 @@ def main(path, top=40):
         except ValueError:
             continue
         key = r[si].strip()[:110]
-        if not key:
+        if view == "sass":
+            key = r[0] + " " + key          # one row per instruction: keep the address
+        elif not key:
             continue            # the SASS rows of the mixed view repeat the same samples
         agg[key][0] += s
         agg[key][1] += e
@@ -52,4 +54,4 @@ def main(path, top=40):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40, sys.argv[3] if len(sys.argv) > 3 else "cuda,sass")
