@@ -307,6 +307,9 @@ def run_diskhalo(args, B):
             "config": dict(_diskhalo_config(args, R.world, ntot, nd, nh), allreduce=R.allreduce_desc(),
                            level_populations=lv),
             "particle_substeps_per_sec": sub * steps / (ms * 1e-3),
+            "binning": {name: dict(zip(("whole_component_sorts", "active_tail_sorts", "tail_items", "whole_items"),
+                                       (int(x) for x in sim.sort_counters(i))))
+                        for name, i in (("disk", d), ("halo", h))},
             "clocks": clk, "e2e": None, "gpu_launches": sum(v[0] for v in prof.values()),
             "roofline": {"bound": "fp64", "kernel": "whole master step (see kernel_ms_per_step)", "achieved": None,
                          "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,

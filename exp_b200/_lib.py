@@ -154,6 +154,7 @@ SIGNATURES = {
     "expb200_component_event_record": (C.c_int, [_H, C.c_int]),
     "expb200_component_event_elapsed": (C.c_int, [_H, C.c_int, C.c_int, c_dp]),
     "expb200_component_level_counts": (C.c_int, [_H, C.c_int, c_u64p]),
+    "expb200_component_sort_counters": (C.c_int, [_H, c_u64p]),
     "expb200_component_fix_positions": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_dp, C.c_void_p]),
     "expb200_incr_position": (C.c_int, [_H, C.c_double, C.c_int]),
     "expb200_incr_velocity": (C.c_int, [_H, C.c_double, C.c_int]),

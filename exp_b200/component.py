@@ -135,6 +135,13 @@ class Component:
                                                         out.ctypes.data_as(_lib.c_u64p)))
         return out
 
+    def sort_counters(self):
+        """[whole-component sorts, tail-of-active-levels sorts, particles moved by the tail sorts,
+        particles moved by the whole-component sorts] since creation"""
+        out = np.zeros(4, dtype=np.uint64)
+        check(_lib.lib().expb200_component_sort_counters(self._h, out.ctypes.data_as(_lib.c_u64p)))
+        return out
+
     def fix_positions(self, mlevel, multistep, lev_sums=None, dim=3, nccl_comm=None):
         """Component::fix_positions (src/Component.cc:3354-3590) on the device: refreshes the rows
         M >= mlevel of lev_sums[M] = [com_mas, com_lev[3], cov_lev[3], coa_lev[3]] and returns

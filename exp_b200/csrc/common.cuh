@@ -143,8 +143,13 @@ struct expb200_component_s;
 namespace expb200 {
 // Physically re-orders the particle store into the order of the component's current sort
 // (perm[cur]); afterwards the permutation is the identity and psort == posm.
+// lev_start[L] = seg[L * kpl] for L in (from, nlev] -> host (synchronises the component's stream);
+// the level partition of perm[cur] is then known exactly.
+int component_read_bounds(expb200_component_s *c, uint32_t kpl, int nlev, int from);
 int component_reorder(expb200_component_s *c);
 constexpr int kReorderEvery = 64;      // sorts between physical re-orderings
+constexpr int kReorderEveryMulti = 16; // the same with multistep levels (tail sorts count): the level-filtered
+                                       // passes (kick, drift, zero) stream best over a level-major store
 }
 
 // ---- the device-resident particle store ------------------------------------
@@ -203,6 +208,19 @@ struct expb200_component_s {
   // force's owning component, which need not be this one) and the owner's orientation version
   double sort_origin[3] = {0, 0, 0};
   uint64_t sort_aux_ver = 0;
+  // Level partition of perm[cur] (multistep): positions [lev_start[L], lev_start[L+1]) hold the
+  // particles of level L.  Only the levels that are active on a sub-step move and change level
+  // (src/multistep.cc:194, src/step.cc:210-262), so a sub-step re-bins the suffix of its active
+  // levels and leaves the rest of the permutation alone (sphere.cu / cylinder.cu: refresh).
+  bool part_ok = false;                 // perm[cur] is partitioned by level
+  int part_nlev = 0;
+  int bound_ok_upto = 0;                // lev_start[L] is exact for L <= bound_ok_upto
+  int sort_from = 0;                    // the cell order of the current sort holds for levels >= sort_from
+  uint32_t lev_start[40] = {};          // host copy of the boundaries
+  uint32_t *bounds_dev = nullptr;       // 40 words
+  uint64_t sort_counters[4] = {0, 0, 0, 0};   // full sorts, tail sorts, items of each (diagnostics)
+  uint32_t *sw_perm = nullptr;          // permutation scratch of the level-switch update
+  size_t sw_cap = 0;
 
   // multistep statistics scratch
   unsigned long long *stats = nullptr;  // device, 8 words

@@ -432,6 +432,28 @@ level_count_kernel(const unsigned *__restrict__ level, size_t n, int nlev,
 
 // Applies the current sort permutation to the particle store (see common.cuh).  The
 // 4-byte arrays go through the sort's rank scratch, whose buffer they then swap with.
+__global__ void bounds_gather_kernel(const uint32_t *__restrict__ seg, uint32_t kpl, int nlev,
+                                     uint32_t *__restrict__ out)
+{
+  const int L = threadIdx.x;
+  if (L <= nlev) out[L] = seg[(size_t)L * kpl];
+}
+
+int component_read_bounds(expb200_component_s *c, uint32_t kpl, int nlev, int from)
+{
+  if (nlev + 1 > 40) { set_error("component_read_bounds: %d levels", nlev); return EXPB200_EINVAL; }
+  uint32_t tmp[40];
+  bounds_gather_kernel<<<1, 64, 0, c->stream>>>(c->seg, kpl, nlev, c->bounds_dev);
+  CU_LAUNCH_CHECK();
+  CU_TRY(cudaMemcpyAsync(tmp, c->bounds_dev, (size_t)(nlev + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  for (int L = from + 1; L <= nlev; L++) c->lev_start[L] = tmp[L];
+  c->part_ok = true;
+  c->part_nlev = nlev;
+  c->bound_ok_upto = nlev;
+  return EXPB200_OK;
+}
+
 int component_reorder(expb200_component_s *c)
 {
   const size_t n = c->n;
@@ -565,6 +587,7 @@ int expb200_component_create(int device, size_t capacity, expb200_component *out
   c->stage_chunk = capacity < kStageChunk ? capacity : kStageChunk;
   CU_TRY(cudaMalloc(&c->stage, 2 * c->stage_chunk * kStageDoubles * sizeof(double)));
   CU_TRY(cudaMalloc(&c->stats, 8 * sizeof(unsigned long long)));
+  CU_TRY(cudaMalloc(&c->bounds_dev, 40 * sizeof(uint32_t)));
   CU_TRY(cudaMemsetAsync(c->accp, 0, capacity * sizeof(rec4), c->stream));
   CU_TRY(cudaMemsetAsync(c->level, 0, capacity * sizeof(unsigned), c->stream));
   CU_TRY(cudaMemsetAsync(c->prev_level, 0, capacity * sizeof(unsigned), c->stream));
@@ -584,7 +607,7 @@ int expb200_component_destroy(expb200_component c)
   cudaFree(c->spare); cudaFree(c->slot_of); cudaFree(c->where);
   cudaFree(c->level); cudaFree(c->prev_level); cudaFree(c->dtreq); cudaFree(c->scale);
   for (int k = 0; k < 2; k++) { cudaFree(c->keys[k]); cudaFree(c->perm[k]); }
-  cudaFree(c->hist); cudaFree(c->rank); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats); cudaFree(c->com_part);
+  cudaFree(c->hist); cudaFree(c->rank); cudaFree(c->seg); cudaFree(c->stage); cudaFree(c->stats); cudaFree(c->com_part); cudaFree(c->bounds_dev); cudaFree(c->sw_perm);
   cudaEventDestroy(c->copy_done);
   if (c->hstage) cudaFreeHost(c->hstage);
   for (int k = 0; k < 2; k++) if (c->hstage_free[k]) cudaEventDestroy(c->hstage_free[k]);
@@ -605,7 +628,7 @@ int expb200_component_set_count(expb200_component c, size_t n)
     c->identity_order = true;
     c->never_reordered = true;
     c->sorts_since_reorder = 0;
-    c->sort_kind = 0;
+    c->sort_kind = 0; c->part_ok = false;
   }
   c->n = n;
   c->pos_ver++; c->lev_ver++;
@@ -728,7 +751,7 @@ int expb200_component_upload(expb200_component c, size_t n, const double *pos, c
   c->identity_order = true;
   c->never_reordered = true;
   c->sorts_since_reorder = 0;
-  c->sort_kind = 0;
+  c->sort_kind = 0; c->part_ok = false;
   if (n == 0) { c->pos_ver++; c->lev_ver++; return EXPB200_OK; }
   int rc = expb200_component_upload_range(c, 0, n, pos, vel, mass);
   if (rc) return rc;
@@ -948,7 +971,13 @@ int expb200_adjust_multistep_level(expb200_component c, const expb200_level_para
   unsigned long long out[8];
   CU_TRY(cudaMemcpyAsync(out, c->stats, sizeof out, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
-  if (out[1]) c->lev_ver++;
+  if (out[1]) {
+    c->lev_ver++;
+    // only particles of level >= minlev were examined and none went below mfirst[mdrft]: the
+    // level boundaries of the sorted permutation up to the lower of the two still hold
+    const int lo = A.minlev < A.mfirst ? A.minlev : A.mfirst;
+    if (lo < c->bound_ok_upto) c->bound_ok_upto = lo < 0 ? 0 : lo;
+  }
   if (stats) {
     stats->examined = out[0]; stats->switched = out[1]; stats->offlo = out[2]; stats->offhi = out[3];
     double mn, mx;
@@ -971,6 +1000,7 @@ int expb200_component_set_levels(expb200_component c, const unsigned *level)
   CU_TRY(cudaMemcpyAsync(c->prev_level, c->level, c->n * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   c->lev_ver++;
+  c->part_ok = false;
   return EXPB200_OK;
 }
 
@@ -1064,6 +1094,13 @@ int expb200_component_fix_positions(expb200_component c, int mlevel, int multist
   CU_TRY(cudaStreamSynchronize(c->stream));
   for (int mm = mlevel; mm < nlev; mm++)
     for (int r = 0; r < kComVals; r++) sums[mm * kComVals + r] = h[mm * kComVals + r];
+  return EXPB200_OK;
+}
+
+int expb200_component_sort_counters(expb200_component c, uint64_t counters[4])
+{
+  REQUIRE(c && counters, "NULL argument");
+  for (int k = 0; k < 4; k++) counters[k] = c->sort_counters[k];
   return EXPB200_OK;
 }
 

@@ -56,6 +56,37 @@ cyl_key_kernel(CylGeom g, const rec4 *__restrict__ posm, const unsigned *__restr
   }
 }
 
+// the same for the tail of the sorted permutation (levels >= m), keys relative to level m
+__global__ void __launch_bounds__(256)
+cyl_key_sub_kernel(CylGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                   const uint32_t *__restrict__ slots, size_t nsub, int m, int maxlev, int mlevel,
+                   uint32_t *__restrict__ keys, double *__restrict__ block_mass)
+{
+  __shared__ double sh[8];
+  double msum = 0.0;
+  const uint32_t kpl = (uint32_t)g.ncell + 2u;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nsub;
+       k += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t i = slots[k];
+    rec4 pm = ld_rec(&posm[i]);
+    uint32_t ck = cyl_cell_key(g, pm);
+    uint32_t lev = level[i];
+    if (lev > (uint32_t)maxlev) lev = maxlev;
+    if (lev < (uint32_t)m) lev = m;            // cannot happen while the partition holds
+    keys[k] = (lev - (uint32_t)m) * kpl + ck;
+    if ((int)lev == mlevel && ck <= (uint32_t)g.ncell) msum += pm.w;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) msum += __shfl_down_sync(0xffffffffu, msum, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = msum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; k++) t += sh[k];
+    block_mass[blockIdx.x] = t;
+  }
+}
+
 __global__ void cyl_mass_kernel(const double *__restrict__ block_mass, int nblocks, double adb,
                                 double *__restrict__ out)
 {
@@ -84,6 +115,22 @@ cyl_switch_key_kernel(CylGeom g, const rec4 *__restrict__ posm, const unsigned *
       key = lev * kpl + cyl_cell_key(g, ld_rec(&posm[i]), 1);
     }
     keys[i] = key;
+  }
+}
+
+// The same keys for a compacted list of switching particles (list[k] = store index): no sentinel.
+__global__ void __launch_bounds__(256)
+cyl_switch_key_list_kernel(CylGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                           const unsigned *__restrict__ prev, const uint32_t *__restrict__ list, size_t nsw,
+                           int use_prev, int nlev, uint32_t *__restrict__ keys)
+{
+  const uint32_t kpl = (uint32_t)g.ncell + 2u;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nsw;
+       k += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t i = list[k];
+    uint32_t lev = use_prev ? prev[i] : level[i];
+    if (lev >= (uint32_t)nlev) lev = nlev - 1;
+    keys[k] = lev * kpl + cyl_cell_key(g, ld_rec(&posm[i]), 1);
   }
 }
 
@@ -735,15 +782,56 @@ int ensure_sorted(expb200_cylinder_s *s, expb200_component_s *c, int mlevel, dou
   const uint32_t kpl = (uint32_t)s->geom.ncell + 2u;
   const uint32_t nkeys = (uint32_t)s->nlev * kpl;
   CylGeom g = geom_for(s, c);
+  if (s->nlev == 1) mlevel = 0;
   const bool valid = c->sort_kind == 3 && c->sort_owner == s && c->sort_pos_ver == c->pos_ver &&
                      c->sort_lev_ver == c->lev_ver && c->sort_aux_ver == s->orient_ver &&
-                     c->sort_origin[0] == g.cx && c->sort_origin[1] == g.cy && c->sort_origin[2] == g.cz;
+                     c->sort_origin[0] == g.cx && c->sort_origin[1] == g.cy && c->sort_origin[2] == g.cz &&
+                     c->sort_from <= mlevel;
   if (valid && !want_mass) return EXPB200_OK;
   if (c->seg_cap < (size_t)nkeys + 2) {
     if (c->seg) cudaFree(c->seg);
     c->seg = nullptr;
     CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
     c->seg_cap = (size_t)nkeys + 2;
+  }
+  // multistep: re-bin only the tail of the levels that can have moved (see sphere.cu: ensure_sorted)
+  int m = 0;
+  if (!valid && s->nlev > 1 && c->n && c->part_ok && c->part_nlev == s->nlev)
+    m = mlevel < c->bound_ok_upto ? mlevel : c->bound_ok_upto;
+  if (m > 0) {
+    const size_t off = c->lev_start[m], nsub = c->n - off;
+    const uint32_t nks = (uint32_t)(s->nlev - m) * kpl;
+    uint32_t *seg_sub = c->seg + (size_t)m * kpl;
+    const unsigned nbs = grid_for(nsub ? nsub : 1, 256);
+    const int W = suffix_key_buffer(c->cur, nks);
+    {
+      ProfRegion pr(K_KEY, c->stream, 2);
+      cyl_key_sub_kernel<<<nbs, 256, 0, c->stream>>>(g, c->posm, c->level, c->perm[c->cur] + off, nsub, m,
+                                                     s->nlev - 1, mlevel, c->keys[W] + off, s->block_mass);
+      cyl_mass_kernel<<<1, 32, 0, c->stream>>>(s->block_mass, nbs, adb, s->coef + s->ncoef);
+      CU_LAUNCH_CHECK();
+    }
+    int rc;
+    if (nsub) {
+      ProfRegion pr(K_SORT, c->stream, radix_sort_launches(nsub, nks, true) + 2);
+      rc = radix_sort_suffix(c->stream, c->keys, c->perm, c->cur, c->hist, c->rank, off, c->n, nks, seg_sub,
+                             SortPayload(), (uint32_t)m * kpl);
+    } else {
+      rc = segment_offsets(c->stream, c->keys[c->cur], 0, seg_sub, nks, (uint32_t)off);
+    }
+    if (rc) return rc;
+    if ((rc = component_read_bounds(c, kpl, s->nlev, m))) return rc;
+    c->sort_kind = 3;
+    c->sort_owner = s;
+    c->keys_per_level = kpl;
+    c->sort_pos_ver = c->pos_ver;
+    c->sort_lev_ver = c->lev_ver;
+    c->sort_aux_ver = s->orient_ver;
+    c->sort_origin[0] = g.cx; c->sort_origin[1] = g.cy; c->sort_origin[2] = g.cz;
+    c->sort_from = m;
+    c->sort_counters[1]++; c->sort_counters[2] += nsub;
+    c->sorts_since_reorder++;
+    return EXPB200_OK;
   }
   const unsigned nb = grid_for(c->n ? c->n : 1, 256);
   {
@@ -773,6 +861,9 @@ int ensure_sorted(expb200_cylinder_s *s, expb200_component_s *c, int mlevel, dou
   c->sort_lev_ver = c->lev_ver;
   c->sort_aux_ver = s->orient_ver;
   c->sort_origin[0] = g.cx; c->sort_origin[1] = g.cy; c->sort_origin[2] = g.cz;
+  c->sort_from = 0;
+  c->sort_counters[0]++; c->sort_counters[3] += c->n;
+  if (s->nlev > 1 && c->n) return component_read_bounds(c, kpl, s->nlev, -1);
   return EXPB200_OK;
 }
 
@@ -1081,8 +1172,16 @@ int expb200_cylinder_multistep_update(expb200_cylinder s, expb200_component c, d
       CU_TRY(cudaMalloc(&c->seg, ((size_t)nkeys + 2) * sizeof(uint32_t)));
       c->seg_cap = (size_t)nkeys + 2;
     }
-    const int CH = cyl_chunk(c->n);
-    const size_t slots = (c->n + CH - 1) / CH + (size_t)g.ncell + 1;
+    // compact the switching particles first (see expb200_sphere_multistep_update)
+    size_t nsw = 0;
+    uint32_t *list = c->rank + c->n / 2;
+    { int rc = compact_differing(st, c->level, c->prev_level, c->n, c->hist, c->keys[1], &nsw); if (rc) return rc; }
+    const bool compact = nsw > 0 && 2 * nsw <= c->n;
+    if (compact)
+      CU_TRY(cudaMemcpyAsync(list, c->keys[1], nsw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    const size_t nn = compact ? nsw : c->n;
+    const int CH = cyl_chunk(nn);
+    const size_t slots = (nn + CH - 1) / CH + (size_t)g.ncell + 1;
     if (slots > s->part_slots) {
       if (s->PA) cudaFree(s->PA);
       s->PA = nullptr; s->part_slots = 0;
@@ -1091,19 +1190,40 @@ int expb200_cylinder_multistep_update(expb200_cylinder s, expb200_component c, d
     }
     const int stride = (g.nk + 4) | 1;
     const size_t sm = (size_t)kCylDepositWarps * (32 * stride + 16) * sizeof(double);
-    const unsigned nchunks = div_up(c->n, CH);
-    for (int side = 0; side < 2; side++) {          // 0: "to" (+), 1: "from" (-)
-      cyl_switch_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(g, c->posm, c->level, c->prev_level, c->n,
-                                                                 side, s->nlev, c->keys[0]);
-      CU_LAUNCH_CHECK();
-      int cur = 0;
-      int rc = radix_sort_pairs(st, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur, c->seg);
-      if (rc) return rc;
-      c->cur = cur;
+    const unsigned nchunks = div_up(nn, CH);
+    if (compact && c->sw_cap < nsw) {
+      if (c->sw_perm) cudaFree(c->sw_perm);
+      c->sw_perm = nullptr; c->sw_cap = 0;
+      CU_TRY(cudaMalloc(&c->sw_perm, nsw * sizeof(uint32_t)));
+      c->sw_cap = nsw;
+    }
+    // the compact path leaves perm[cur] (the level partition of the component's own sort) alone
+    uint32_t *kl[2] = {c->keys[0], c->keys[1]};
+    uint32_t *pl2[2] = {c->sw_perm, c->perm[c->cur ^ 1]};
+    for (int side = 0; side < 2 && nsw > 0; side++) {          // 0: "to" (+), 1: "from" (-)
+      const uint32_t *sperm = nullptr;
+      if (compact) {
+        cyl_switch_key_list_kernel<<<grid_for(nsw, 256), 256, 0, st>>>(g, c->posm, c->level, c->prev_level, list,
+                                                                       nsw, side, s->nlev, kl[0]);
+        CU_LAUNCH_CHECK();
+        int cur = 0;
+        int rc = radix_sort_pairs(st, kl, pl2, c->hist, c->rank, nsw, nkeys, &cur, c->seg, SortPayload(), list);
+        if (rc) return rc;
+        sperm = pl2[cur];
+      } else {
+        cyl_switch_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(g, c->posm, c->level, c->prev_level, c->n,
+                                                                   side, s->nlev, c->keys[0]);
+        CU_LAUNCH_CHECK();
+        int cur = 0;
+        int rc = radix_sort_pairs(st, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur, c->seg);
+        if (rc) return rc;
+        c->cur = cur;
+        sperm = c->perm[cur];
+      }
       for (int M = 0; M < s->nlev; M++) {
         const int keybase = M * (int)kpl;
         cyl_deposit_kernel<<<div_up(nchunks, kCylDepositWarps), kCylDepositWarps * 32, sm, st>>>(
-            g, c->posm, c->perm[cur], c->seg, keybase, CH, adb, stride, 1, s->PA);
+            g, c->posm, sperm, c->seg, keybase, CH, adb, stride, 1, s->PA);
         cyl_combine_kernel<<<div_up(g.nnode, 128), 128, 0, st>>>(g, c->seg, keybase, CH, s->PA, s->G);
         // rows get_pot does not fill (m > MLIM, odd m with EVEN_M) stay zero, as in the
         // coefficient pass (src/CylEXP.cc:170-186 loops mm = 0..MMAX over what get_pot filled)
@@ -1114,7 +1234,11 @@ int expb200_cylinder_multistep_update(expb200_cylinder s, expb200_component c, d
         CU_LAUNCH_CHECK();
       }
     }
-    c->sort_kind = 0;          // the component's regular sort was overwritten
+    if (nsw > 0) {
+      // keys and cell offsets were overwritten; the level partition survives the compact path
+      c->sort_pos_ver = 0;
+      if (!compact) { c->sort_kind = 0; c->part_ok = false; }
+    }
   }
   if (finish) return expb200_cylinder_multistep_update_finish(s);
   return EXPB200_OK;
@@ -1199,7 +1323,7 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
   int rc = radix_sort_pairs(st, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur);
   if (rc) return rc;
   c->cur = cur;
-  c->sort_kind = 0;
+  c->sort_kind = 0; c->part_ok = false;
 
   uint32_t *bstart = nullptr;
   double *PC = nullptr, *PV = nullptr, *PM = nullptr, *dMV = nullptr, *dVC = nullptr, *dMass = nullptr;

@@ -233,7 +233,7 @@ sort_apply_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
 
 // seg[k] = number of sorted keys < k  (first position of key k), k in [0, nkeys]
 __global__ void seg_offsets_kernel(const uint32_t *__restrict__ sorted, size_t n,
-                                   uint32_t *__restrict__ seg, uint32_t nkeys)
+                                   uint32_t *__restrict__ seg, uint32_t nkeys, uint32_t base)
 {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > nkeys) return;
@@ -242,7 +242,97 @@ __global__ void seg_offsets_kernel(const uint32_t *__restrict__ sorted, size_t n
     size_t mid = (lo + hi) >> 1;
     if (sorted[mid] < k) lo = mid + 1; else hi = mid;
   }
-  seg[k] = (uint32_t)lo;
+  seg[k] = base + (uint32_t)lo;
+}
+
+// ---- compaction of the indices where two arrays differ (the level switches of a substep) ----
+constexpr int kCompactChunk = 4096;      // items per CTA: 256 threads x 16 consecutive items
+
+__global__ void __launch_bounds__(256)
+compact_count_kernel(const unsigned *__restrict__ a, const unsigned *__restrict__ b, size_t n,
+                     uint32_t *__restrict__ counts)
+{
+  const size_t base = (size_t)blockIdx.x * kCompactChunk;
+  unsigned cnt = 0;
+  for (int k = threadIdx.x; k < kCompactChunk; k += 256) {
+    const size_t i = base + k;
+    if (i < n && a[i] != b[i]) cnt++;
+  }
+  __shared__ unsigned ws[8];
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; w++) t += ws[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of counts[0..nb) into bases[0..nb], bases[nb] = total (one CTA)
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, unsigned nb)
+{
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (unsigned b0 = 0; b0 < nb; b0 += 1024) {
+    const unsigned i = b0 + threadIdx.x;
+    const uint32_t v = i < nb ? counts[i] : 0u;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += u;
+    }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t y = ws[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(0xffffffffu, y, o);
+        if (lane >= o) y += u;
+      }
+      ws[lane] = y;
+    }
+    __syncthreads();
+    const uint32_t incl = x + (w ? ws[w - 1] : 0u) + carry;
+    if (i < nb) bases[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bases[nb] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+compact_write_kernel(const unsigned *__restrict__ a, const unsigned *__restrict__ b, size_t n,
+                     const uint32_t *__restrict__ bases, uint32_t *__restrict__ list)
+{
+  // thread t owns the 16 consecutive items [base + 16 t, base + 16 t + 16): ranks in index order
+  const size_t base = (size_t)blockIdx.x * kCompactChunk + (size_t)threadIdx.x * 16;
+  unsigned flags = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const size_t i = base + k;
+    if (i < n && a[i] != b[i]) flags |= 1u << k;
+  }
+  const unsigned cnt = __popc(flags);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned x = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned u = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += u;
+  }
+  __shared__ unsigned ws[8];
+  if (lane == 31) ws[w] = x;
+  __syncthreads();
+  unsigned off = bases[blockIdx.x] + x - cnt;
+  for (int ww = 0; ww < w; ww++) off += ws[ww];
+#pragma unroll
+  for (int k = 0; k < 16; k++)
+    if (flags & (1u << k)) list[off++] = (uint32_t)(base + k);
 }
 
 struct Plan { int npass, bits; unsigned nctas, gs; };
@@ -275,7 +365,7 @@ int radix_sort_launches(size_t n, uint32_t nkeys, bool want_seg)
 
 int radix_sort_pairs(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], uint32_t *hist,
                      uint32_t *rank, size_t n, uint32_t nkeys, int *out_cur, uint32_t *seg,
-                     SortPayload payload)
+                     SortPayload payload, const uint32_t *perm_init)
 {
   // keys[0] holds the unsorted keys; values start as the identity.
   const Plan p = plan_for(n, nkeys);
@@ -303,7 +393,7 @@ int radix_sort_pairs(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], uint
                                            (uint32_t)n);
     sort_rank_kernel<<<p.nctas, kSortThreads, smem, st>>>(keys[cur], rank, n, shift, mask, hist, gtot,
                                                           dbase, p.gs);
-    const uint32_t *pin = q == 0 ? nullptr : perm[cur];
+    const uint32_t *pin = q == 0 ? perm_init : perm[cur];
     if (last && payload.src)
       sort_apply_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(keys[cur], pin, rank, keys[cur ^ 1],
                                                                 perm[cur ^ 1], (uint32_t)n, payload.src,
@@ -319,10 +409,66 @@ int radix_sort_pairs(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], uint
   return EXPB200_OK;
 }
 
-int segment_offsets(cudaStream_t st, const uint32_t *sorted, size_t n, uint32_t *seg, uint32_t nkeys)
+int compact_differing(cudaStream_t st, const unsigned *a, const unsigned *b, size_t n, uint32_t *scratch,
+                      uint32_t *list, size_t *count_host)
 {
-  seg_offsets_kernel<<<div_up((size_t)nkeys + 1, 256), 256, 0, st>>>(sorted, n, seg, nkeys);
+  *count_host = 0;
+  if (n == 0) return EXPB200_OK;
+  const unsigned nb = div_up(n, kCompactChunk);
+  uint32_t *counts = scratch, *bases = scratch + nb;
+  compact_count_kernel<<<nb, 256, 0, st>>>(a, b, n, counts);
+  compact_scan_kernel<<<1, 1024, 0, st>>>(counts, bases, nb);
   CU_LAUNCH_CHECK();
+  uint32_t total = 0;
+  CU_TRY(cudaMemcpyAsync(&total, bases + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *count_host = total;
+  if (total == 0) return EXPB200_OK;
+  compact_write_kernel<<<nb, 256, 0, st>>>(a, b, n, bases, list);
+  CU_LAUNCH_CHECK();
+  return EXPB200_OK;
+}
+
+int segment_offsets(cudaStream_t st, const uint32_t *sorted, size_t n, uint32_t *seg, uint32_t nkeys,
+                    uint32_t base)
+{
+  seg_offsets_kernel<<<div_up((size_t)nkeys + 1, 256), 256, 0, st>>>(sorted, n, seg, nkeys, base);
+  CU_LAUNCH_CHECK();
+  return EXPB200_OK;
+}
+
+__global__ void add_u32_kernel(uint32_t *__restrict__ a, size_t n, uint32_t add)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    a[i] += add;
+}
+
+int radix_sort_passes(uint32_t nkeys) { return plan_for(1, nkeys).npass; }
+
+// the result of p passes started in buffer W lands in W ^ (p & 1): start where it ends in cur
+int suffix_key_buffer(int cur, uint32_t nkeys_sub) { return cur ^ (radix_sort_passes(nkeys_sub) & 1); }
+
+int radix_sort_suffix(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], int cur, uint32_t *hist,
+                      uint32_t *rank, size_t off, size_t n, uint32_t nkeys_sub, uint32_t *seg_sub,
+                      SortPayload payload, uint32_t key_base)
+{
+  const size_t nsub = n - off;
+  const int W = suffix_key_buffer(cur, nkeys_sub);
+  uint32_t *kl[2] = {keys[W] + off, keys[W ^ 1] + off};
+  uint32_t *pl[2] = {perm[W] + off, perm[W ^ 1] + off};
+  if (W != cur)        // odd number of passes: the first pass writes perm[cur], so it reads a copy
+    CU_TRY(cudaMemcpyAsync(pl[0], perm[cur] + off, nsub * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  if (payload.dst) payload.dst += off;
+  int out = 0;
+  int rc = radix_sort_pairs(st, kl, pl, hist, rank, nsub, nkeys_sub, &out, nullptr, payload, pl[0]);
+  if (rc) return rc;
+  if ((W ^ out) != cur) { set_error("radix_sort_suffix: result in the wrong buffer"); return EXPB200_ESTATE; }
+  rc = segment_offsets(st, keys[cur] + off, nsub, seg_sub, nkeys_sub, (uint32_t)off);
+  if (rc) return rc;
+  if (key_base) {        // the sorted keys as the consumers index them (absolute)
+    add_u32_kernel<<<grid_for(nsub, 256), 256, 0, st>>>(keys[cur] + off, nsub, key_base);
+    CU_LAUNCH_CHECK();
+  }
   return EXPB200_OK;
 }
 

@@ -67,6 +67,22 @@ sph_key_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restr
   }
 }
 
+// keys of the tail of the sorted permutation (levels >= m), relative to level m: see ensure_sorted
+__global__ void __launch_bounds__(256)
+sph_key_sub_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                   const uint32_t *__restrict__ slots, size_t nsub, int m, int maxlev,
+                   uint32_t *__restrict__ keys)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nsub;
+       k += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t i = slots[k];
+    uint32_t lev = level[i];
+    if (lev > (uint32_t)maxlev) lev = maxlev;
+    if (lev < (uint32_t)m) lev = m;            // cannot happen while the partition holds
+    keys[k] = (lev - (uint32_t)m) * (uint32_t)g.numr + sph_cell_of(g, ld_rec(&posm[i]));
+  }
+}
+
 // Single-level step: first half kick, drift and the radial key of the new position in one
 // pass over the particle records (src/step.cc:272-290; arithmetic of src/incvel.cc:68-69,
 // src/incpos.cc:63-66).
@@ -105,6 +121,21 @@ sph_switch_key_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *
       key = lev * (uint32_t)g.numr + sph_cell_of(g, ld_rec(&posm[i]), 1);
     }
     keys[i] = key;
+  }
+}
+
+// The same keys for a compacted list of switching particles (list[k] = store index): no sentinel.
+__global__ void __launch_bounds__(256)
+sph_switch_key_list_kernel(SphGeom g, const rec4 *__restrict__ posm, const unsigned *__restrict__ level,
+                           const unsigned *__restrict__ prev, const uint32_t *__restrict__ list, size_t nsw,
+                           int use_prev, int nlev, uint32_t *__restrict__ keys)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nsw;
+       k += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t i = list[k];
+    uint32_t lev = use_prev ? prev[i] : level[i];
+    if (lev >= (uint32_t)nlev) lev = nlev - 1;
+    keys[k] = lev * (uint32_t)g.numr + sph_cell_of(g, ld_rec(&posm[i]), 1);
   }
 }
 
@@ -1580,7 +1611,6 @@ SphGeom geom_for(const expb200_sphere_s *s, const expb200_component_s *c)
 // 32-byte DRAM transaction) or every kReorderEvery sorts (particles drift across cells).
 int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool allow_reorder)
 {
-  (void)s;
   int cur = 0;
   {
     ProfRegion pr(K_SORT, c->stream, radix_sort_launches(c->n, nkeys, true));
@@ -1593,7 +1623,7 @@ int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool
   c->cur = cur;
   c->psort = c->posm_sorted;
   c->sorts_since_reorder++;
-  if (allow_reorder && (c->never_reordered || c->sorts_since_reorder >= kReorderEvery))
+  if (allow_reorder && (c->never_reordered || c->sorts_since_reorder >= (s->nlev > 1 ? kReorderEveryMulti : kReorderEvery)))
     return component_reorder(c);
   return EXPB200_OK;
 }
@@ -1605,6 +1635,7 @@ void mark_sorted(expb200_sphere_s *s, expb200_component_s *c)
   c->keys_per_level = s->cfg.numr;
   c->sort_pos_ver = c->pos_ver;
   c->sort_lev_ver = c->lev_ver;
+  c->sort_from = 0;
   const expb200_component_s *o = s->owner ? s->owner : c;
   for (int k = 0; k < 3; k++) c->sort_origin[k] = o->center[k];
 }
@@ -1620,17 +1651,56 @@ int ensure_seg(expb200_component_s *c, uint32_t nkeys)
   return EXPB200_OK;
 }
 
-// (level, radial cell) sort of component c for sphere s, reused while neither positions
-// nor levels changed.
-int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
+// (level, radial cell) sort of component c for sphere s with the cell order current for the levels
+// >= mlevel, reused while neither positions nor levels changed.  Multistep: when the level partition
+// of the permutation is known (a full sort established it and only levels >= some lo have changed
+// level since), only the tail of the levels >= min(mlevel, lo) is re-binned -- on a sub-step only
+// the active levels have moved (src/step.cc:210-262) -- instead of the whole component.
+int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c, int mlevel = 0)
 {
   SphGeom g = geom_for(s, c);
+  if (s->nlev == 1) mlevel = 0;
   if (c->sort_kind == 2 && c->sort_owner == s && c->sort_pos_ver == c->pos_ver &&
       c->sort_lev_ver == c->lev_ver && c->sort_origin[0] == g.cx && c->sort_origin[1] == g.cy &&
-      c->sort_origin[2] == g.cz)
+      c->sort_origin[2] == g.cz && c->sort_from <= mlevel)
     return EXPB200_OK;
-  const uint32_t nkeys = (uint32_t)s->nlev * (uint32_t)s->cfg.numr;
+  const uint32_t numr = (uint32_t)s->cfg.numr;
+  const uint32_t nkeys = (uint32_t)s->nlev * numr;
   { int rc = ensure_seg(c, nkeys); if (rc) return rc; }
+  int m = 0;
+  if (s->nlev > 1 && c->n && c->part_ok && c->part_nlev == s->nlev)
+    m = mlevel < c->bound_ok_upto ? mlevel : c->bound_ok_upto;
+  if (m > 0) {
+    const size_t off = c->lev_start[m], nsub = c->n - off;
+    const uint32_t nks = (uint32_t)(s->nlev - m) * numr;
+    uint32_t *seg_sub = c->seg + (size_t)m * numr;
+    if (nsub) {
+      const int W = suffix_key_buffer(c->cur, nks);
+      { ProfRegion pr(K_KEY, c->stream);
+        sph_key_sub_kernel<<<grid_for(nsub, 256), 256, 0, c->stream>>>(g, c->posm, c->level, c->perm[c->cur] + off,
+                                                                       nsub, m, s->nlev - 1, c->keys[W] + off);
+      }
+      CU_LAUNCH_CHECK();
+      ProfRegion pr(K_SORT, c->stream, radix_sort_launches(nsub, nks, true) + 2);
+      SortPayload pl;
+      pl.src = c->posm;
+      pl.dst = c->posm_sorted;
+      int rc = radix_sort_suffix(c->stream, c->keys, c->perm, c->cur, c->hist, c->rank, off, c->n, nks, seg_sub, pl,
+                                 (uint32_t)m * numr);
+      if (rc) return rc;
+      c->psort = c->posm_sorted;         // [0, off) of the stream is stale: levels < m are not read
+    } else {
+      int rc = segment_offsets(c->stream, c->keys[c->cur], 0, seg_sub, nks, (uint32_t)off);
+      if (rc) return rc;
+    }
+    int rc = component_read_bounds(c, numr, s->nlev, m);
+    if (rc) return rc;
+    mark_sorted(s, c);
+    c->sort_from = m;
+    c->sort_counters[1]++; c->sort_counters[2] += nsub;
+    c->sorts_since_reorder++;
+    return EXPB200_OK;
+  }
   if (c->n) {
     { ProfRegion pr(K_KEY, c->stream);
     sph_key_kernel<<<grid_for(c->n, 256), 256, 0, c->stream>>>(g, c->posm, c->level, c->n,
@@ -1639,6 +1709,8 @@ int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c)
     CU_LAUNCH_CHECK();
     int rc = sort_keyed(s, c, nkeys, true);
     if (rc) return rc;
+    c->sort_counters[0]++; c->sort_counters[3] += c->n;
+    if (s->nlev > 1 && (rc = component_read_bounds(c, numr, s->nlev, -1))) return rc;
   } else {
     CU_TRY(cudaMemsetAsync(c->seg, 0, ((size_t)nkeys + 1) * sizeof(uint32_t), c->stream));
   }
@@ -1713,7 +1785,7 @@ int accumulate_sorted(expb200_sphere_s *s, expb200_component_s *c, int mlevel, d
 int accumulate(expb200_sphere_s *s, expb200_component_s *c, int mlevel, double adb)
 {
   { cudaStream_t ws = s->work_stream(); if (ws != c->stream) CU_TRY(cudaStreamSynchronize(ws)); }
-  int rc = ensure_sorted(s, c);
+  int rc = ensure_sorted(s, c, mlevel);
   if (rc) return rc;
   return accumulate_sorted(s, c, mlevel, adb);
 }
@@ -1884,7 +1956,7 @@ int expb200_sphere_determine_acceleration(expb200_sphere s, expb200_component c,
   REQUIRE(mlevel >= 0 && mlevel < s->nlev, "mlevel=%d outside [0,%d]", mlevel, s->nlev - 1);
   DeviceGuard g(s->device);
   if (c->n == 0) return EXPB200_OK;
-  int rc = ensure_sorted(s, c);
+  int rc = ensure_sorted(s, c, mlevel);
   if (rc) return rc;
   { cudaStream_t ws = s->work_stream(); if (ws != c->stream) CU_TRY(cudaStreamSynchronize(ws)); }
   if (!s->field_valid) {
@@ -1991,17 +2063,55 @@ int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, doubl
     const uint32_t nkeys = (uint32_t)s->nlev * (uint32_t)s->cfg.numr + 1;
     int rc = ensure_seg(c, nkeys);
     if (rc) return rc;
-    const int CH = deposit_chunk(c->n);
-    if ((rc = ensure_partials(s, c->n, CH))) return rc;
-    for (int side = 0; side < 2; side++) {          // 0: "to" (+), 1: "from" (-)
-      sph_switch_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(gm, c->posm, c->level, c->prev_level,
-                                                                 c->n, side, s->nlev, c->keys[0]);
-      CU_LAUNCH_CHECK();
-      if ((rc = sort_keyed(s, c, nkeys, false))) return rc;
+    // the switching particles are few: compact their store indices (ascending, deterministic) and
+    // bin only those -- two full (level, cell) sorts of the component per substep otherwise
+    // (round 2: half of the disk+halo step's sort time, profiles/r02q_bench_diskhalo.json)
+    size_t nsw = 0;
+    uint32_t *list = c->rank + c->n / 2;             // the sort of nsw <= n/2 items uses rank[0, nsw)
+    rc = compact_differing(st, c->level, c->prev_level, c->n, c->hist, c->keys[1], &nsw);
+    if (rc) return rc;
+    const bool compact = nsw > 0 && 2 * nsw <= c->n;
+    if (compact)
+      CU_TRY(cudaMemcpyAsync(list, c->keys[1], nsw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    const size_t nn = compact ? nsw : c->n;          // items binned per side
+    const int CH = deposit_chunk(nn);
+    if ((rc = ensure_partials(s, nn, CH))) return rc;
+    if (compact && c->sw_cap < nsw) {
+      if (c->sw_perm) cudaFree(c->sw_perm);
+      c->sw_perm = nullptr; c->sw_cap = 0;
+      CU_TRY(cudaMalloc(&c->sw_perm, nsw * sizeof(uint32_t)));
+      c->sw_cap = nsw;
+    }
+    // the compact path leaves perm[cur] (the level partition of the component's own sort) alone:
+    // its permutation buffers are the scratch one and the spare half
+    uint32_t *kl[2] = {c->keys[0], c->keys[1]};
+    uint32_t *pl2[2] = {c->sw_perm, c->perm[c->cur ^ 1]};
+    for (int side = 0; side < 2 && nsw > 0; side++) {          // 0: "to" (+), 1: "from" (-)
+      const uint32_t *skeys = nullptr;
+      if (compact) {
+        sph_switch_key_list_kernel<<<grid_for(nsw, 256), 256, 0, st>>>(gm, c->posm, c->level, c->prev_level, list,
+                                                                       nsw, side, s->nlev, kl[0]);
+        CU_LAUNCH_CHECK();
+        ProfRegion pr(K_SORT, st, radix_sort_launches(nsw, nkeys, true));
+        SortPayload pl;
+        pl.src = c->posm;
+        pl.dst = c->posm_sorted;
+        int cur = 0;
+        rc = radix_sort_pairs(st, kl, pl2, c->hist, c->rank, nsw, nkeys, &cur, c->seg, pl, list);
+        if (rc) return rc;
+        skeys = kl[cur];
+        c->psort = c->posm_sorted;
+      } else {
+        sph_switch_key_kernel<<<grid_for(c->n, 256), 256, 0, st>>>(gm, c->posm, c->level, c->prev_level,
+                                                                   c->n, side, s->nlev, c->keys[0]);
+        CU_LAUNCH_CHECK();
+        if ((rc = sort_keyed(s, c, nkeys, false))) return rc;
+        skeys = c->keys[c->cur];
+      }
       for (int M = 0; M < s->nlev; M++) {
         const int keybase = M * s->cfg.numr;
-        unsigned nchunks = div_up(c->n, CH);
-        rc = launch_deposit(s->cfg.lmax, st, nchunks, gm, s->p0, c->psort, c->keys[c->cur],
+        unsigned nchunks = div_up(nn, CH);
+        rc = launch_deposit(s->cfg.lmax, st, nchunks, gm, s->p0, c->psort, skeys,
                             c->seg, keybase, CH, adb, s->PA, s->PB);
         if (rc) return rc;
         sph_combine_kernel<<<gm.numr, 64, 0, st>>>(gm, c->seg, keybase, CH, 0, s->PA, s->PB, s->G);
@@ -2011,7 +2121,12 @@ int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, doubl
         CU_LAUNCH_CHECK();
       }
     }
-    c->sort_kind = 0;          // the component's regular sort was overwritten
+    if (nsw > 0) {
+      // keys, cell offsets and the sorted position stream were overwritten: the cell order has
+      // to be rebuilt before its next use; the level partition survives the compact path
+      c->sort_pos_ver = 0;
+      if (!compact) { c->sort_kind = 0; c->part_ok = false; }
+    }
   }
   if (finish) return expb200_sphere_multistep_update_finish(s);
   return EXPB200_OK;
@@ -2135,7 +2250,7 @@ static int sphere_covariance_impl(expb200_sphere s, expb200_component c, int mle
                                                           c->keys[0]);
   CU_LAUNCH_CHECK();
   if ((rc = sort_keyed(s, c, nkeys, false))) return rc;
-  c->sort_kind = 0;                       // the component's regular sort was overwritten
+  c->sort_kind = 0; c->part_ok = false;                       // the component's regular sort was overwritten
 
   // bin boundaries on the host: seg[T*R] (first particle of bin T) and seg[T*R + R - 1]
   std::vector<uint32_t> hseg((size_t)nkeys + 1);

@@ -64,6 +64,8 @@ def host():
         H.exphost_get_sphere_coefs.argtypes = [C.c_int, C.c_int, C.c_int, c_dp]
         H.exphost_get_cylinder_coefs.argtypes = [C.c_int, c_dp, c_dp, c_dp]
         H.exphost_level_report.argtypes = [C.c_int] + [_lib.c_u64p] * 5
+        H.exphost_sort_counters.argtypes = [C.c_int, _lib.c_u64p]
+        H.exphost_sort_counters.restype = C.c_int
         H.exphost_state.argtypes = [c_dp, C.POINTER(C.c_int), c_dp, c_dp]
         H.exphost_get_com.argtypes = [C.c_int, c_dp, c_dp]
         H.exphost_dump_coefs.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_long]
@@ -241,6 +243,13 @@ class Simulation:
                                            counts.ctypes.data_as(_lib.c_u64p)))
         return dict(examined=v[0].value, switched=v[1].value, offlo=v[2].value, offhi=v[3].value,
                     counts=counts)
+
+    def sort_counters(self, idx):
+        """device binning diagnostics of component idx: [whole-component sorts, tail sorts of the active
+        levels, particles moved by the tail sorts, particles moved by the whole-component sorts]"""
+        out = np.zeros(4, dtype=np.uint64)
+        _check(self.H.exphost_sort_counters(idx, out.ctypes.data_as(_lib.c_u64p)))
+        return out
 
     def dump_coefs(self, idx, kind=0):
         """bytes of the force's dump_coefs stream (kind 0: NewCoefs, 1: old style) or of its

@@ -316,6 +316,14 @@ int exphost_level_report(int index, uint64_t *examined, uint64_t *switched, uint
   });
 }
 
+int exphost_sort_counters(int index, uint64_t counters[4])
+{
+  return guarded([&] {
+    Component *c = component_at(index);
+    EXPHOST_CHECK(expb200_component_sort_counters(c->b200, counters));
+  });
+}
+
 int exphost_multistep_tables(int ms, int *mintvl_, int *mfirst_, int *dL, int *dN)
 {
   return guarded([&] {

@@ -82,6 +82,8 @@ int exphost_get_sphere_coefs(int index, int which, int M, double *coef);
 int exphost_get_cylinder_coefs(int index, double *cosv, double *sinv, double *cylmass);
 int exphost_level_report(int index, uint64_t *examined, uint64_t *switched, uint64_t *offlo,
                          uint64_t *offhi, uint64_t *counts /* [multistep+1] */);
+/* device binning diagnostics of a component (expb200_component_sort_counters) */
+int exphost_sort_counters(int index, uint64_t counters[4]);
 /* initialize_multistep tables for `multistep` levels (no GPU needed): mintvl[multistep+1],
  * mfirst[Mstep+1], dstepL/dstepN[(multistep+1)][Mstep] */
 int exphost_multistep_tables(int multistep, int *mintvl, int *mfirst, int *dstepL, int *dstepN);

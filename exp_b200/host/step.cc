@@ -22,15 +22,20 @@ void do_step(int n)
     for (mstep = 0; mstep < Mstep; mstep++) {
       mdrft = mstep;
 
-      // coefficients of the levels that move on this sub-step
+      // The levels that move on this sub-step: first half kick and drift, then their coefficients
+      // at the drifted positions.  The reference interleaves the three per level
+      // (src/step.cc:215-237); level M's kick, drift and coefficients touch level-M particles only,
+      // so doing all the moves first gives the same numbers and lets the device bin the moved
+      // levels once per sub-step instead of once per level (csrc/sphere.cu: ensure_sorted).
       for (unsigned M = (unsigned)mfirst[mstep]; M <= multistep; M++) {
         const double DT = dt * mintvl[M];
         incr_velocity(0.5 * DT, (int)M);               // first half kick
         vel_check[M] += 0.5 * DT;
         incr_position(DT, (int)M);                     // drift
         pos_check[M] += DT;
-        comp->compute_expansion(M);                    // coefficients at the drifted position
       }
+      for (unsigned M = (unsigned)mfirst[mstep]; M <= multistep; M++)
+        comp->compute_expansion(M);                    // coefficients at the drifted position
 
       tnow += dt;
 

@@ -136,6 +136,10 @@ int expb200_adjust_multistep_level(expb200_component c, const expb200_level_para
 /* Populations per level: counts[multistep+1].  ~ CudaGetLevelRange
  * (src/cudaComponent.cu:490-526). */
 int expb200_component_level_counts(expb200_component c, int multistep, uint64_t *counts);
+/* Diagnostics of the device-side binning (no reference counterpart): counters[0] = (level, cell)
+ * sorts of the whole component, [1] = sorts of the tail of the active levels only, [2] = particles
+ * those tail sorts moved, [3] = particles the whole-component sorts moved. */
+int expb200_component_sort_counters(expb200_component c, uint64_t counters[4]);
 
 /* Centre-of-mass sums per multistep level of the non-frozen particles with
  * level >= mlevel:  sums[M*10 + {0: mass, 1..3: mass*pos, 4..6: mass*vel,

@@ -138,6 +138,12 @@ def test_disk_halo_interactions(multistep):
     if multistep:
         lv = np.concatenate([ref.S[rh].level, ref.S[rd].level])
         assert len(np.unique(lv)) >= 2
+        # sub-steps re-bin only the tail of their active levels (csrc: ensure_sorted): after the
+        # whole-component sorts of sub-step 0 the later sub-steps take the tail path
+        for idx in (h, d):
+            full, tail, tail_items, full_items = (int(x) for x in sim.sort_counters(idx))
+            assert tail > 0 and full > 0
+            assert tail_items < tail * (full_items // full)
     assert rel_rms(sim.sphere_coefs(h), ref.F[rh].use[0]) <= 1e-10
     _check_coef_output(sim, h, d, nsteps * dtime)
     cs, sn, cm = sim.cylinder_coefs(d)
