@@ -158,6 +158,7 @@ SIGNATURES = {
     "expb200_component_fix_positions": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_dp, C.c_void_p]),
     "expb200_incr_position": (C.c_int, [_H, C.c_double, C.c_int]),
     "expb200_incr_velocity": (C.c_int, [_H, C.c_double, C.c_int]),
+    "expb200_move_levels": (C.c_int, [_H, c_dp, c_dp, C.c_int, C.c_int]),
     "expb200_adjust_multistep_level": (C.c_int, [_H, C.POINTER(LevelParams), C.POINTER(LevelStats)]),
     "expb200_sphere_create": (C.c_int, [C.c_int, C.POINTER(SphereConfig), c_dp, c_dp, c_dp,
                                         C.POINTER(_H)]),

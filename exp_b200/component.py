@@ -109,6 +109,15 @@ class Component:
     def incr_velocity(self, dt, mlevel=-1):
         check(_lib.lib().expb200_incr_velocity(self._h, float(dt), mlevel))
 
+    def move_levels(self, dt_kick, dt_drift, mlevel_lo=0):
+        """the per-level kicks and drifts of one sub-step in one pass (expb200_move_levels): level M >=
+        mlevel_lo gets vel += acc dt_kick[M], then pos += vel dt_drift[M]; either table may be None"""
+        k = None if dt_kick is None else _f64(dt_kick)
+        d = None if dt_drift is None else _f64(dt_drift)
+        nlev = len(k if k is not None else d)
+        check(_lib.lib().expb200_move_levels(self._h, None if k is None else _dp(k),
+                                             None if d is None else _dp(d), nlev, mlevel_lo))
+
     def adjust_multistep_level(self, dtime, multistep, mfirst_mdrft=0, minlev=0, dynfracS=1.0,
                                dynfracD=1.0e32, dynfracV=0.01, dynfracA=0.03, dynfracP=0.05,
                                shiftlevl=0, noswitch=False, reset_dtreq=False, apply=True, dim=3):

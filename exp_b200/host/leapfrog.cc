@@ -9,6 +9,12 @@ void incr_position(double dt, int mlevel)
   for (auto c : comp->components) EXPHOST_CHECK(expb200_incr_position(c->b200, dt, mlevel));
 }
 
+void move_levels(const double *dt_kick, const double *dt_drift, int mlevel_lo)
+{
+  for (auto c : comp->components)
+    EXPHOST_CHECK(expb200_move_levels(c->b200, dt_kick, dt_drift, (int)multistep + 1, mlevel_lo));
+}
+
 void incr_velocity(double dt, int mlevel)
 {
   for (auto c : comp->components) EXPHOST_CHECK(expb200_incr_velocity(c->b200, dt, mlevel));

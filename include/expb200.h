@@ -106,6 +106,12 @@ int expb200_component_zero_pot_acc(expb200_component c, int minlev);
  * arithmetic of src/incpos.cc:63-66, src/incvel.cc:68-69. */
 int expb200_incr_position(expb200_component c, double dt, int mlevel);
 int expb200_incr_velocity(expb200_component c, double dt, int mlevel);
+/* The per-level kicks and drifts of one sub-step (the loops of src/step.cc:215-237, 253-262 over
+ * incr_velocity / incr_position) in one pass: a particle of level M in [mlevel_lo, nlev) gets
+ * vel += acc * dt_kick[M] (dt_kick != NULL), then pos += vel * dt_drift[M] (dt_drift != NULL).
+ * Same arithmetic per particle as the two calls above; only the active levels are visited. */
+int expb200_move_levels(expb200_component c, const double *dt_kick, const double *dt_drift, int nlev,
+                        int mlevel_lo);
 
 /* Multistep level assignment.  ~ cuda_compute_levels (src/cudaMultistep.cu),
  * arithmetic of adjust_multistep_level_thread (src/multistep.cc:52-236),

@@ -83,6 +83,44 @@ def test_per_level_coefficients_and_force():
     assert np.all(out["acc"][lev < 2] == 0.0)
 
 
+@pytest.mark.gpu
+def test_move_levels_equals_per_level_calls():
+    """expb200_move_levels = the per-level incr_velocity / incr_position loop of a sub-step (reference
+    src/step.cc:215-237, 253-262), bit for bit, with and without a known level partition"""
+    tab = get_table("hernquist", 4, 10)
+    n = 50000
+    pos, vel, mass = _state(n, seed=35)
+    rng = np.random.default_rng(3)
+    lev = rng.integers(0, 5, n).astype(np.uint32)
+    acc = rng.normal(size=(n, 3))
+    dtk = np.array([0.0, 0.0, 0.004, 0.002, 0.001])
+    dtd = 2.0 * dtk
+    out = []
+    for fused in (False, True, True):
+        c = Component(n)
+        c.upload(pos, vel, mass, level=lev)
+        c.set_acc_pot(acc, np.zeros(n))
+        if len(out) == 2:           # a sorted component: the active tail of the permutation is walked
+            s = Sphere(tab, multistep=4)
+            s.set_multistep_level(0)
+            s.determine_coefficients(c)
+            c.set_acc_pot(acc, np.zeros(n))
+        if fused:
+            c.move_levels(dtk, dtd, 2)
+            c.move_levels(dtk, None, 3)
+        else:
+            for M in (2, 3, 4):
+                c.incr_velocity(dtk[M], M)
+                c.incr_position(dtd[M], M)
+            for M in (3, 4):
+                c.incr_velocity(dtk[M], M)
+        out.append(c.download())
+    for k in ("pos", "vel"):
+        assert np.array_equal(out[0][k], out[1][k]) and np.array_equal(out[0][k], out[2][k])
+    assert np.array_equal(out[0]["pos"][lev < 2], pos[lev < 2])
+    assert not np.array_equal(out[0]["pos"][lev >= 2], pos[lev >= 2])
+
+
 def test_multistep_interpolation_and_update():
     tab = get_table("hernquist", 2, 8, numr=400)
     n = 20000
