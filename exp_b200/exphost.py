@@ -58,6 +58,10 @@ def host():
         H.exphost_cylinder_cov_options.argtypes = [C.c_int] * 7
         H.exphost_cylinder_get_covariance.argtypes = [C.c_int, C.POINTER(C.c_int), _lib.c_up] + [c_dp] * 6
         H.exphost_pca_hall.argtypes = [C.c_int] * 6 + [C.c_double] * 4 + [c_dp] * 9
+        H.exphost_cylinder_pca_options.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+        H.exphost_cylinder_get_pca.argtypes = [C.c_int, C.POINTER(C.c_int)] + [c_dp] * 6
+        H.exphost_cyl_pca_hall.argtypes = ([C.c_int] * 4 + [C.c_double, C.c_int, C.c_double, C.c_double, _lib.c_up]
+                                           + [c_dp] * 9)
         H.exphost_do_steps.argtypes = [C.c_int]
         H.exphost_do_steps_timed.argtypes = [C.c_int, c_dp]
         H.exphost_get_particles.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, _lib.c_up, _lib.c_fp]
@@ -178,6 +182,24 @@ class Simulation:
                              samplesz=1):
         _check(self.H.exphost_cylinder_cov_options(idx, nint, npca, npca0, int(pcavar), int(pcaeof), samplesz))
 
+    CYL_TK = {"Hall": 0, "Truncate": 1, "None": 2}
+
+    def cylinder_pca_options(self, idx, tk_type="None", snr=1.0, hexp=1.0, subsamp=False):
+        """Hall smoothing switches of the cylinder force (src/Cylinder.cc:231-241, 469)"""
+        _check(self.H.exphost_cylinder_pca_options(idx, self.CYL_TK[tk_type], snr, hexp, int(subsamp)))
+
+    def cylinder_pca(self, idx):
+        """the last EmpCylSL::pca_hall analysis: meanJK, evalJK, ratio [m][n], evecJK [m][n][n], and the
+        coefficients the last smoothing started from (raw_cos, raw_sin; zero-size if none was applied)"""
+        _, M1, N = self.kinds[idx]
+        out = dict(meanJK=np.zeros((M1, N)), evalJK=np.zeros((M1, N)), ratio=np.zeros((M1, N)),
+                   evecJK=np.zeros((M1, N, N)), raw_cos=np.zeros((M1, N)), raw_sin=np.zeros((M1, N)))
+        ok = C.c_int(0)
+        _check(self.H.exphost_cylinder_get_pca(idx, C.byref(ok), _p(out["meanJK"]), _p(out["evalJK"]),
+                                               _p(out["ratio"]), _p(out["evecJK"]), _p(out["raw_cos"]),
+                                               _p(out["raw_sin"])))
+        return out if ok.value else None
+
     def cylinder_covariance(self, idx, covar=True, pcavar=False, pcaeof=False):
         _, M1, N = self.kinds[idx]
         sT = C.c_int(0)
@@ -294,6 +316,26 @@ class Simulation:
         pc, vc = np.zeros(self.multistep + 1), np.zeros(self.multistep + 1)
         _check(self.H.exphost_state(C.byref(t), C.byref(k), _p(pc), _p(vc)))
         return dict(tnow=t.value, this_step=k.value, pos_check=pc, vel_check=vc)
+
+
+def cyl_pca_hall(mmax, norder, numbT, massT, covV, covM, nbodstot, subsamp=False, tk_type="None", snr=1.0,
+                 hexp=1.0, cosv=None, sinv=None):
+    """EmpCylSL::pca_hall (PCAVAR part) + set_trimmed (exputil/EmpCylSL.cc:4577-4970, 5141-5207) on given
+    partition arrays; host-only.  covV [T][mmax+1][norder], covM [T][mmax+1][norder][norder]."""
+    H = host()
+    T, M1, N = len(massT), mmax + 1, norder
+    nb = np.ascontiguousarray(numbT, dtype=np.uint32)
+    mT, cV, cM = (np.ascontiguousarray(a, dtype=np.float64) for a in (massT, covV, covM))
+    out = dict(meanJK=np.zeros((M1, N)), evalJK=np.zeros((M1, N)), ratio=np.zeros((M1, N)),
+               evecJK=np.zeros((M1, N, N)))
+    cs = None if cosv is None else np.ascontiguousarray(cosv, dtype=np.float64).copy()
+    sn = None if sinv is None else np.ascontiguousarray(sinv, dtype=np.float64).copy()
+    _check(H.exphost_cyl_pca_hall(mmax, norder, T, int(subsamp), float(nbodstot), Simulation.CYL_TK[tk_type],
+                                  snr, hexp, nb.ctypes.data_as(_lib.c_up), _p(mT), _p(cV), _p(cM),
+                                  _p(out["meanJK"]), _p(out["evalJK"]), _p(out["ratio"]), _p(out["evecJK"]),
+                                  None if cs is None else _p(cs), None if sn is None else _p(sn)))
+    out["cos"], out["sin"] = cs, sn
+    return out
 
 
 def pca_hall(Lmax, nmax, massT, coefT, coefM, used, subsamp=False, tk_type="None", hexp=1.0, snr=1.0,

@@ -1,5 +1,10 @@
 // Cylinder.cc -- see Cylinder.H
 #include "Cylinder.H"
+#include "AxisymmetricBasis.H"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
 
 #include <cmath>
 
@@ -66,6 +71,21 @@ void Cylinder::determine_coefficients(Component *c)
   } else {
     EXPHOST_CHECK(expb200_cylinder_multistep_commit(b200c, (int)mlevel));
   }
+  // Hall smoothing (src/Cylinder.cc:1115-1134): the analysis at the last level of a compute step,
+  // then the installed coefficients are smoothed in the decorrelated basis
+  if (npca0 < (1 << 30) && mlevel == multistep && compute && pcavar) {
+    // (EmpCylSL::pca_hall then cleans the partition storage, :4941-4957; here the arrays are
+    // re-zeroed at the next compute step's level 0 and stay readable until then)
+    pca_hall(mmax, ncylorder, sampT, subsamp, (double)c->CurTotal(), numbT, massT, covV, covM, pb);
+  }
+  if (pcavar && used && npca0 < (1 << 30) && pb.valid && tk_type != None &&
+      (multistep == 0 || !self_consistent)) {
+    std::vector<double> cosv, sinv;
+    get_coefs(cosv, sinv);
+    raw_cos = cosv; raw_sin = sinv;
+    set_trimmed(pb, tk_type, snr, hexp, cosv, sinv);
+    EXPHOST_CHECK(expb200_cylinder_set_coefficients(b200c, cosv.data(), sinv.data(), cylmass));
+  }
   firstime_coef = false;
 }
 
@@ -124,6 +144,90 @@ void Cylinder::accumulate_covariance(Component *c)
     red(cnt);
     for (size_t k = 0; k < cnt.size(); k++) numbT[k] = (unsigned)std::llround(cnt[k]);
     red(massT); red(VC); red(MV); red(covV); red(covM); red(tvar);
+  }
+}
+
+// EmpCylSL::pca_hall, PCAVAR branch (exputil/EmpCylSL.cc:4617-4631, 4684-4742, 4845-4884)
+bool Cylinder::pca_hall(int mmax, int norder, unsigned sampT, bool subsamp, double nbodstot,
+                        const std::vector<unsigned> &numbT, const std::vector<double> &massT,
+                        const std::vector<double> &covV, const std::vector<double> &covM, PCA &pb)
+{
+  const size_t M1 = mmax + 1, N = norder;
+  pb = PCA();
+  pb.mmax = mmax; pb.norder = norder;
+  for (auto v : numbT) pb.Tnumb += v;
+  for (auto v : massT) pb.Tmass += v;
+  if (pb.Tmass <= 0.0) return false;                               // no data
+  pb.meanJK.assign(M1 * N, 0.0); pb.evalJK.assign(M1 * N, 0.0); pb.ratio.assign(M1 * N, 0.0);
+  pb.covrJK.assign(M1 * N * N, 0.0); pb.evecJK.assign(M1 * N * N, 0.0);
+  std::vector<double> sym(N * N), eval, evec;
+  for (size_t mm = 0; mm < M1; mm++) {
+    double *mean = &pb.meanJK[mm * N], *cov = &pb.covrJK[mm * N * N];
+    for (unsigned T = 0; T < sampT; T++) {                         // data partitions
+      if (massT[T] <= 0.0) continue;                               // skip empty partition
+      const double *v = &covV[((size_t)T * M1 + mm) * N];
+      const double *m = &covM[((size_t)T * M1 + mm) * N * N];
+      for (size_t nn = 0; nn < N; nn++) {
+        mean[nn] += v[nn] / massT[T] / sampT;
+        for (size_t oo = 0; oo < N; oo++)
+          cov[nn * N + oo] += subsamp ? v[nn] / massT[T] * v[oo] / massT[T] / sampT
+                                      : m[nn * N + oo] / massT[T] / sampT;
+      }
+    }
+    for (size_t nn = 0; nn < N; nn++)
+      for (size_t oo = 0; oo < N; oo++) cov[nn * N + oo] -= mean[nn] * mean[oo];
+    // the reference solves the (symmetric) matrix with Eigen::EigenSolver, whose eigenvalue order
+    // is implementation-defined; here: symmetric Jacobi, eigenvalues descending
+    for (size_t nn = 0; nn < N; nn++)
+      for (size_t oo = 0; oo < N; oo++) sym[nn * N + oo] = 0.5 * (cov[nn * N + oo] + cov[oo * N + nn]);
+    jacobi_eigen((int)N, sym, eval, evec);
+    const size_t nfid = std::min<size_t>(4, N) - 1;                 // sign convention (:4735-4739)
+    for (size_t j = 0; j < N; j++)
+      if (evec[nfid * N + j] < 0.0)
+        for (size_t k = 0; k < N; k++) evec[k * N + j] = -evec[k * N + j];
+    std::copy(eval.begin(), eval.end(), &pb.evalJK[mm * N]);
+    std::copy(evec.begin(), evec.end(), &pb.evecJK[mm * N * N]);
+    for (size_t nn = 0; nn < N; nn++) {
+      double dd = 0.0;                                             // projected mean
+      for (size_t k = 0; k < N; k++) dd += evec[k * N + nn] * mean[k];
+      double var = std::max(eval[nn], std::numeric_limits<double>::min());
+      if (subsamp) var *= nbodstot / (double)sampT;                // CLT estimate of the N-particle variance
+      pb.ratio[mm * N + nn] = var / (dd * dd) / nbodstot;
+    }
+  }
+  pb.valid = true;
+  return true;
+}
+
+// EmpCylSL::set_trimmed (exputil/EmpCylSL.cc:5141-5207) without the `rem` branch
+void Cylinder::set_trimmed(const PCA &pb, TKType tk, double snr, double hexp, std::vector<double> &cosv,
+                           std::vector<double> &sinv)
+{
+  if (!pb.valid || tk == None) return;
+  const size_t M1 = pb.mmax + 1, N = pb.norder;
+  std::vector<double> smth(N), dd(N), wrk(N);
+  for (size_t mm = 0; mm < M1; mm++) {
+    const double *evec = &pb.evecJK[mm * N * N];
+    for (size_t i = 0; i < N; i++) {
+      const double b = pb.ratio[mm * N + i];
+      if (tk == Hall) smth[i] = 1.0 / (1.0 + std::pow(snr * b, hexp));
+      else            smth[i] = 1.0 / b > snr ? 1.0 : 0.0;
+    }
+    auto apply = [&](double *c) {
+      for (size_t nn = 0; nn < N; nn++) {                          // project to the decorrelated basis
+        double t = 0.0;
+        for (size_t k = 0; k < N; k++) t += evec[k * N + nn] * c[k];
+        wrk[nn] = t * smth[nn];                                    // smooth
+      }
+      for (size_t k = 0; k < N; k++) {                             // deproject
+        double t = 0.0;
+        for (size_t nn = 0; nn < N; nn++) t += evec[k * N + nn] * wrk[nn];
+        dd[k] = t;
+      }
+      std::copy(dd.begin(), dd.end(), c);
+    };
+    apply(&cosv[mm * N]);
+    if (mm) apply(&sinv[mm * N]);
   }
 }
 

@@ -201,6 +201,61 @@ int exphost_cylinder_get_covariance(int index, int *sampT, unsigned *numbT, doub
   });
 }
 
+int exphost_cylinder_pca_options(int index, int tk_type, double snr, double hexp, int subsamp)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<Cylinder *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not cylinder", __FILE__, __LINE__);
+    if (tk_type < 0 || tk_type > 2) throw GenericError("tk_type: 0 Hall, 1 Truncate, 2 None", __FILE__, __LINE__);
+    s->tk_type = (Cylinder::TKType)tk_type; s->snr = snr; s->hexp = hexp; s->subsamp = subsamp != 0;
+  });
+}
+
+static void copy_pca(const Cylinder::PCA &pb, double *meanJK, double *evalJK, double *ratio, double *evecJK)
+{
+  if (meanJK) std::copy(pb.meanJK.begin(), pb.meanJK.end(), meanJK);
+  if (evalJK) std::copy(pb.evalJK.begin(), pb.evalJK.end(), evalJK);
+  if (ratio) std::copy(pb.ratio.begin(), pb.ratio.end(), ratio);
+  if (evecJK) std::copy(pb.evecJK.begin(), pb.evecJK.end(), evecJK);
+}
+
+int exphost_cylinder_get_pca(int index, int *valid, double *meanJK, double *evalJK, double *ratio, double *evecJK,
+                             double *raw_cos, double *raw_sin)
+{
+  return guarded([&] {
+    auto *s = dynamic_cast<Cylinder *>(component_at(index)->force.get());
+    if (!s) throw GenericError("component force is not cylinder", __FILE__, __LINE__);
+    if (valid) *valid = s->pb.valid ? 1 : 0;
+    if (s->pb.valid) copy_pca(s->pb, meanJK, evalJK, ratio, evecJK);
+    if (raw_cos) std::copy(s->raw_cos.begin(), s->raw_cos.end(), raw_cos);
+    if (raw_sin) std::copy(s->raw_sin.begin(), s->raw_sin.end(), raw_sin);
+  });
+}
+
+int exphost_cyl_pca_hall(int mmax, int norder, int sampT, int subsamp, double nbodstot, int tk_type, double snr,
+                         double hexp, const unsigned *numbT, const double *massT, const double *covV,
+                         const double *covM, double *meanJK, double *evalJK, double *ratio, double *evecJK,
+                         double *cosv, double *sinv)
+{
+  return guarded([&] {
+    if (mmax < 0 || norder < 1 || sampT < 1 || tk_type < 0 || tk_type > 2)
+      throw GenericError("exphost_cyl_pca_hall: bad argument", __FILE__, __LINE__);
+    const size_t M1 = mmax + 1, N = norder, T = sampT;
+    std::vector<unsigned> nb(numbT, numbT + T);
+    std::vector<double> ms(massT, massT + T), v(covV, covV + T * M1 * N), m(covM, covM + T * M1 * N * N);
+    Cylinder::PCA pb;
+    if (!Cylinder::pca_hall(mmax, norder, (unsigned)sampT, subsamp != 0, nbodstot, nb, ms, v, m, pb))
+      throw GenericError("exphost_cyl_pca_hall: no mass in the partitions", __FILE__, __LINE__);
+    copy_pca(pb, meanJK, evalJK, ratio, evecJK);
+    if (cosv && sinv) {
+      std::vector<double> c(cosv, cosv + M1 * N), s(sinv, sinv + M1 * N);
+      Cylinder::set_trimmed(pb, (Cylinder::TKType)tk_type, snr, hexp, c, s);
+      std::copy(c.begin(), c.end(), cosv);
+      std::copy(s.begin(), s.end(), sinv);
+    }
+  });
+}
+
 int exphost_pca_hall(int Lmax, int nmax, int sampT, int used, int subsamp, int tk_type, double hexp,
                      double snr, double tksmooth, double tkcum, const double *massT, const double *coefT,
                      const double *coefM, double *b_Hall, double *s_Hall, double *weight, double *evalJK,

@@ -63,6 +63,21 @@ int exphost_sphere_get_covariance(int index, int *sampT, double *massT, unsigned
 int exphost_cylinder_cov_options(int index, int nint, int npca, int npca0, int pcavar, int pcaeof, int samplesz);
 int exphost_cylinder_get_covariance(int index, int *sampT, unsigned *numbT, double *massT, double *VC,
                                     double *MV, double *covV, double *covM, double *tvar);
+/* Hall smoothing of the cylinder force (src/Cylinder.cc:231-241, 1115-1134): tk_type 0 Hall,
+ * 1 Truncate, 2 None; results of the last analysis (any pointer may be NULL): meanJK, evalJK, ratio
+ * [mmax+1][norder], evecJK [mmax+1][norder][norder] (eigenvectors = columns); returns 1 in *valid
+ * when an analysis exists */
+int exphost_cylinder_pca_options(int index, int tk_type, double snr, double hexp, int subsamp);
+int exphost_cylinder_get_pca(int index, int *valid, double *meanJK, double *evalJK, double *ratio, double *evecJK,
+                             double *raw_cos, double *raw_sin /* [mmax+1][norder]: before the last smoothing */);
+/* Stateless EmpCylSL::pca_hall (PCAVAR part) + set_trimmed (exputil/EmpCylSL.cc:4577-4970, 5141-5207)
+ * on given partition arrays (no GPU needed): in numbT, massT [sampT], covV [sampT][mmax+1][norder],
+ * covM [sampT][mmax+1][norder][norder]; out as exphost_cylinder_get_pca; cosv, sinv
+ * [mmax+1][norder] smoothed in place (may be NULL) */
+int exphost_cyl_pca_hall(int mmax, int norder, int sampT, int subsamp, double nbodstot, int tk_type, double snr,
+                         double hexp, const unsigned *numbT, const double *massT, const double *covV,
+                         const double *covM, double *meanJK, double *evalJK, double *ratio, double *evecJK,
+                         double *cosv, double *sinv);
 /* Stateless AxisymmetricBasis::pca_hall_3d + the smoothing pass (src/AxisymmetricBasis.cc:198-660)
  * on given subsample arrays (no GPU needed): in massT[sampT], coefT[sampT][ldim][nmax][2],
  * coefM[sampT][ldim][nmax][nmax]; out b_Hall, s_Hall, weight, evalJK [ldim][nmax], evec

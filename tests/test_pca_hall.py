@@ -143,6 +143,119 @@ def test_host_driver_covariance_wiring():
     assert np.abs(cov2["coefM"] - o["coefM"]).max() <= 1e-10 * np.abs(o["coefM"]).max()
 
 
+def _cyl_pca_numpy(numbT, massT, covV, covM, nbodstot, subsamp):
+    """EmpCylSL::pca_hall, PCAVAR branch (reference exputil/EmpCylSL.cc:4684-4742, 4845-4884) with numpy"""
+    T, M1, N = covV.shape
+    out = dict(meanJK=np.zeros((M1, N)), evalJK=np.zeros((M1, N)), ratio=np.zeros((M1, N)), evecJK=np.zeros((M1, N, N)))
+    for m in range(M1):
+        mean, cov = np.zeros(N), np.zeros((N, N))
+        for t in range(T):
+            if massT[t] <= 0:
+                continue
+            v = covV[t, m] / massT[t]
+            mean += v / T
+            cov += (np.outer(v, v) if subsamp else covM[t, m] / massT[t]) / T
+        cov -= np.outer(mean, mean)
+        w, V = np.linalg.eigh(0.5 * (cov + cov.T))
+        w, V = w[::-1], V[:, ::-1]
+        nfid = min(4, N) - 1
+        V = V * np.where(V[nfid] < 0, -1.0, 1.0)
+        dd = V.T @ mean
+        var = np.maximum(w, np.finfo(float).tiny) * (nbodstot / T if subsamp else 1.0)
+        out["meanJK"][m], out["evalJK"][m], out["evecJK"][m] = mean, w, V
+        out["ratio"][m] = var / dd ** 2 / nbodstot
+    return out
+
+
+def _cyl_trim_numpy(p, tk, snr, hexp, cosv, sinv):
+    cosv, sinv = cosv.copy(), sinv.copy()
+    for m in range(cosv.shape[0]):
+        b, V = p["ratio"][m], p["evecJK"][m]
+        smth = 1.0 / (1.0 + (snr * b) ** hexp) if tk == "Hall" else np.where(1.0 / b > snr, 1.0, 0.0)
+        cosv[m] = V @ ((V.T @ cosv[m]) * smth)
+        if m:
+            sinv[m] = V @ ((V.T @ sinv[m]) * smth)
+    return cosv, sinv
+
+
+@pytest.mark.parametrize("subsamp", [False, True])
+def test_cylinder_pca_hall_matches_numpy(subsamp):
+    """host mirror of EmpCylSL::pca_hall + set_trimmed against a numpy restatement (no GPU)"""
+    from exp_b200.exphost import cyl_pca_hall
+    rng = np.random.default_rng(11)
+    T, M1, N, ntot = 9, 4, 6, 40000
+    massT = rng.uniform(0.8, 1.2, T) / T
+    massT[3] = 0.0                                         # an empty partition is skipped
+    numbT = np.where(massT > 0, ntot // T, 0).astype(np.uint32)
+    base = rng.normal(size=(M1, N)) * np.array([1.0, 0.5, 0.2, 0.1, 0.05, 0.02])
+    covV = (base[None] + 0.05 * rng.normal(size=(T, M1, N))) * massT[:, None, None]
+    A = rng.normal(size=(T, M1, N, N))
+    covM = (np.einsum("tmi,tmj->tmij", covV, covV) / np.where(massT > 0, massT, 1.0)[:, None, None, None] ** 2
+            + 0.01 * A @ np.swapaxes(A, -1, -2)) * massT[:, None, None, None]
+    cosv, sinv = rng.normal(size=(M1, N)), rng.normal(size=(M1, N))
+    sinv[0] = 0.0
+    want = _cyl_pca_numpy(numbT, massT, covV, covM, ntot, subsamp)
+    for tk in ("Hall", "Truncate", "None"):
+        got = cyl_pca_hall(M1 - 1, N, numbT, massT, covV, covM, ntot, subsamp=subsamp, tk_type=tk, snr=2.0,
+                           hexp=1.5, cosv=cosv, sinv=sinv)
+        for k in ("meanJK", "evalJK", "ratio"):
+            assert np.abs(got[k] - want[k]).max() <= 1e-9 * np.abs(want[k]).max(), k
+        # eigenvectors up to the degenerate / tiny-eigenvalue directions: compare the projectors
+        for m in range(M1):
+            P1 = got["evecJK"][m] @ np.diag(want["evalJK"][m]) @ got["evecJK"][m].T
+            P2 = want["evecJK"][m] @ np.diag(want["evalJK"][m]) @ want["evecJK"][m].T
+            assert np.abs(P1 - P2).max() <= 1e-9 * np.abs(P2).max()
+        if tk == "None":
+            assert np.array_equal(got["cos"], cosv) and np.array_equal(got["sin"], sinv)
+        else:
+            wc, ws = _cyl_trim_numpy(got, tk, 2.0, 1.5, cosv, sinv)
+            assert np.abs(got["cos"] - wc).max() <= 1e-12 * np.abs(wc).max()
+            assert np.abs(got["sin"] - ws).max() <= 1e-12 * np.abs(ws).max()
+            assert np.array_equal(got["sin"][0], sinv[0])
+
+
+@pytest.mark.gpu
+def test_host_driver_cylinder_hall_smoothing():
+    """pcavar + tk_type = Hall through the host driver: the force uses the coefficients smoothed with the
+    analysis of that call's partitions (src/Cylinder.cc:1115-1134).  With multistep = 0 the reference
+    applies it on the start-up call only: `used` grows only while tnow == resetT (:1091-1099, 1786-1795)
+    and do_step advances tnow before the expansion (src/step.cc:274), so later calls see used == 0."""
+    from exp_b200 import cyltable
+    from exp_b200.exphost import Simulation, cyl_pca_hall
+    tab = cyltable.synthetic_cyl_table(mmax=3, norder=6, numx=48, numy=24)
+    n = 20000
+    pos, vel, mass = ics.exponential_disk(n, seed=9)
+    sim = Simulation(0.002, 0)
+    d = sim.add_component("disk", pos, vel, mass)
+    sim.set_cylinder(d, tab)
+    sim.cylinder_cov_options(d, nint=0, samplesz=8, pcavar=True, npca=1, npca0=0)
+    sim.cylinder_pca_options(d, tk_type="Hall", snr=1.0, hexp=1.0)
+    sim.begin_run()
+    sm_c, sm_s, _ = sim.cylinder_coefs(d)
+    cov, pca = sim.cylinder_covariance(d, covar=False, pcavar=True), sim.cylinder_pca(d)
+    assert pca is not None
+    raw_c, raw_s = pca["raw_cos"], pca["raw_sin"]
+    want = cyl_pca_hall(3, 6, cov["numbT"], cov["massT"], cov["covV"], cov["covM"], n, tk_type="Hall", snr=1.0,
+                        hexp=1.0, cosv=raw_c, sinv=raw_s)
+    assert np.abs(pca["ratio"] - want["ratio"]).max() <= 1e-12 * np.abs(want["ratio"]).max()
+    assert np.abs(sm_c - want["cos"]).max() <= 1e-12 * np.abs(raw_c).max()
+    assert np.abs(sm_s - want["sin"]).max() <= 1e-12 * np.abs(raw_c).max()
+    assert np.abs(sm_c - raw_c).max() > 1e-4 * np.abs(raw_c).max()        # smoothing did something
+    sim.do_steps(1)                         # multistep = 0: analysis refreshed, coefficients not smoothed
+    c1, _, _ = sim.cylinder_coefs(d)
+    pca1 = sim.cylinder_pca(d)
+    assert not np.array_equal(pca1["ratio"], pca["ratio"]) and np.array_equal(pca1["raw_cos"], raw_c)
+    assert np.abs(c1 - raw_c).max() > 1e-4 * np.abs(raw_c).max()
+    # the unsmoothed coefficients are what a run without smoothing installs (a new Simulation replaces
+    # the process-wide container of the first)
+    sim2 = Simulation(0.002, 0)
+    d2 = sim2.add_component("disk", pos, vel, mass)
+    sim2.set_cylinder(d2, tab)
+    sim2.begin_run()
+    c2, s2, _ = sim2.cylinder_coefs(d2)
+    assert np.array_equal(c2, raw_c) and np.array_equal(s2, raw_s)
+
+
 @pytest.mark.gpu
 def test_host_driver_cylinder_covariance_wiring():
     """nint gating of the cylinder's covar accumulation through do_step, against the oracle on the
