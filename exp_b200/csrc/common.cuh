@@ -174,6 +174,7 @@ struct expb200_component_s {
   bool never_reordered = true;
   int sorts_since_reorder = 0;
   const expb200::rec4 *psort = nullptr; // positions in sorted order: posm_sorted, or posm itself
+  bool psort_pending = false;           // posm_sorted is still to be written by the first deposit sweep
                                         // right after a re-ordering
   unsigned *level = nullptr;
   unsigned *prev_level = nullptr;      // level before the last adjust_multistep_level

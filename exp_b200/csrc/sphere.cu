@@ -185,12 +185,18 @@ __device__ __forceinline__ int deposit_row_of(int idx)
   return row;
 }
 
-template <int L, int M0, int M1, int MINB>
+// GATHER: the sorted position stream does not exist yet -- this sweep reads the records of the
+// store through the sort permutation (two batches ahead) and writes the stream (ps_out) for the
+// sweeps and the force pass that follow; the binning pass then moves keys and slots only
+// (expb200_sphere_steps).
+struct DepositGather { const uint32_t *perm = nullptr; const rec4 *store = nullptr; rec4 *out = nullptr; };
+
+template <int L, int M0, int M1, int MINB, bool GATHER = false>
 __global__ void __launch_bounds__(kDepositWarps * 32, MINB)
 sph_deposit_reg_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__restrict__ ps,
                        const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg,
                        int keybase0, int CH, double adb, int batched, double *__restrict__ PA,
-                       double *__restrict__ PB)
+                       double *__restrict__ PB, DepositGather G = DepositGather())
 {
   constexpr int NROW = (L + 1) * (L + 1);
   constexpr int NACC = sph_compact_count<L, M0, M1>();
@@ -228,8 +234,13 @@ sph_deposit_reg_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__r
   };
 
   rec4 nxt = rec4{1.0, 0.0, 0.0, 0.0};
-  uint32_t nkey = 0;
-  if (beg + lane < end) { nxt = ld_rec(&ps[beg + lane]); nkey = skeys[beg + lane]; }
+  uint32_t nkey = 0, slot1 = 0;
+  if (GATHER) {
+    if (beg + lane < end) { nxt = ld_rec(&G.store[G.perm[beg + lane]]); nkey = skeys[beg + lane]; }
+    if (beg + 32 + lane < end) slot1 = G.perm[beg + 32 + lane];
+  } else {
+    if (beg + lane < end) { nxt = ld_rec(&ps[beg + lane]); nkey = skeys[beg + lane]; }
+  }
 
   for (size_t k0 = beg; k0 < end; k0 += 32) {
     const bool valid = k0 + lane < end;
@@ -237,7 +248,11 @@ sph_deposit_reg_kernel(SphGeom g, const double *__restrict__ p0, const rec4 *__r
     int cell = valid ? (int)nkey - keybase : 0x7fffffff;
     {
       const size_t kn = k0 + 32 + lane;      // prefetch the next batch
-      if (kn < end) { nxt = ld_rec(&ps[kn]); nkey = skeys[kn]; }
+      if (GATHER) {
+        if (valid) st_rec(&G.out[k0 + lane], pm);
+        if (kn < end) { nxt = ld_rec(&G.store[slot1]); nkey = skeys[kn]; }
+        if (kn + 32 < end) slot1 = G.perm[kn + 32];
+      } else if (kn < end) { nxt = ld_rec(&ps[kn]); nkey = skeys[kn]; }
     }
     SphDep d;
     sph_deposit_setup(g, p0, pm, adb, valid ? cell : 0, d);
@@ -1395,10 +1410,11 @@ int launch_cov_deposit(int lmax, cudaStream_t st, dim3 grid, const SphGeom &g, c
 template <int L> struct Launch {
   static int deposit(cudaStream_t st, unsigned nchunks, const SphGeom &g, const double *p0,
                      const rec4 *ps, const uint32_t *skeys, const uint32_t *seg, int keybase,
-                     int CH, double adb, double *PA, double *PB, int nbatch)
+                     int CH, double adb, double *PA, double *PB, int nbatch, DepositGather G)
   {
     const dim3 nblocks(div_up(nchunks, kDepositWarps), nbatch > 0 ? nbatch : 1);
     const int batched = nbatch > 0;
+    bool gathered = false;
     if constexpr (L <= 4) {
       sph_deposit_reg_kernel<L, 0, L, 3><<<nblocks, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg,
                                                                                  keybase, CH, adb, batched, PA, PB);
@@ -1406,6 +1422,13 @@ template <int L> struct Launch {
       static const int variant = getenv("EXPB200_DEPOSIT_VARIANT") ? atoi(getenv("EXPB200_DEPOSIT_VARIANT")) : 1;
 #define DEP(M0, M1, MB) sph_deposit_reg_kernel<L, M0, M1, MB><<<nblocks, kDepositWarps * 32, 0, st>>>(g, p0, ps, skeys, seg, keybase, CH, adb, batched, PA, PB)
       if (variant == 0) { DEP(0, 2, 3); DEP(3, L, 3); }
+      else if (variant == 1 && G.perm && !batched) {
+        // first sweep materialises the sorted stream (G.out == ps), the second streams it
+        sph_deposit_reg_kernel<L, 0, 2, 2, true><<<nblocks, kDepositWarps * 32, 0, st>>>(
+            g, p0, ps, skeys, seg, keybase, CH, adb, batched, PA, PB, G);
+        gathered = true;
+        DEP(3, L, 3);
+      }
       else if (variant == 1) { DEP(0, 2, 2); DEP(3, L, 3); }
       else if (variant == 2) { DEP(0, 1, 3); DEP(2, 3, 3); DEP(4, L, 3); }
       else { DEP(0, 1, 4); DEP(2, 3, 4); DEP(4, L, 4); }
@@ -1423,6 +1446,7 @@ template <int L> struct Launch {
                                                                       CH, adb, batched, PA, PB);
     }
     CU_LAUNCH_CHECK();
+    if (G.perm && !gathered) { set_error("deposit: gather requested on a path without it"); return EXPB200_ESTATE; }
     return EXPB200_OK;
   }
   template <int TH, int MINB, int ROWS, int NST>
@@ -1525,9 +1549,17 @@ template <int L> struct Launch {
 
 int launch_deposit(int lmax, cudaStream_t st, unsigned nchunks, const SphGeom &g, const double *p0,
                    const rec4 *ps, const uint32_t *skeys, const uint32_t *seg, int keybase, int CH,
-                   double adb, double *PA, double *PB, int nbatch = 0)
+                   double adb, double *PA, double *PB, int nbatch = 0, DepositGather G = DepositGather())
 {
-  DISPATCH_L(lmax, deposit(st, nchunks, g, p0, ps, skeys, seg, keybase, CH, adb, PA, PB, nbatch))
+  DISPATCH_L(lmax, deposit(st, nchunks, g, p0, ps, skeys, seg, keybase, CH, adb, PA, PB, nbatch, G))
+}
+
+// true where launch_deposit's first sweep can build the sorted position stream itself
+bool deposit_can_gather(int lmax)
+{
+  static const int variant = getenv("EXPB200_DEPOSIT_VARIANT") ? atoi(getenv("EXPB200_DEPOSIT_VARIANT")) : 1;
+  static const bool off = getenv("EXPB200_NO_DEPOSIT_GATHER") != nullptr;
+  return !off && variant == 1 && lmax > 4 && lmax <= kRegDepositMaxL;
 }
 
 int launch_force(int lmax, cudaStream_t st, const SphGeom &g, const double2 *T, const rec4 *ps,
@@ -1609,19 +1641,26 @@ SphGeom geom_for(const expb200_sphere_s *s, const expb200_component_s *c)
 // With allow_reorder the particle store is physically re-ordered into this order when it has
 // never been (random order: every access through the permutation would be a random
 // 32-byte DRAM transaction) or every kReorderEvery sorts (particles drift across cells).
-int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool allow_reorder)
+int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool allow_reorder,
+               bool defer_stream = false)
 {
+  // defer_stream: leave the sorted position stream to the first deposit sweep (c->psort_pending),
+  // unless this sort is due to re-order the store, which takes the stream as the new store
+  const bool reorder_due = allow_reorder && (c->never_reordered ||
+      c->sorts_since_reorder + 1 >= (s->nlev > 1 ? kReorderEveryMulti : kReorderEvery));
+  if (reorder_due) defer_stream = false;
   int cur = 0;
   {
     ProfRegion pr(K_SORT, c->stream, radix_sort_launches(c->n, nkeys, true));
     SortPayload pl;
-    pl.src = c->posm;
-    pl.dst = c->posm_sorted;
+    pl.src = defer_stream ? nullptr : c->posm;
+    pl.dst = defer_stream ? nullptr : c->posm_sorted;
     int rc = radix_sort_pairs(c->stream, c->keys, c->perm, c->hist, c->rank, c->n, nkeys, &cur, c->seg, pl);
     if (rc) return rc;
   }
   c->cur = cur;
   c->psort = c->posm_sorted;
+  c->psort_pending = defer_stream;
   c->sorts_since_reorder++;
   if (allow_reorder && (c->never_reordered || c->sorts_since_reorder >= (s->nlev > 1 ? kReorderEveryMulti : kReorderEvery)))
     return component_reorder(c);
@@ -1767,9 +1806,12 @@ int accumulate_sorted(expb200_sphere_s *s, expb200_component_s *c, int mlevel, d
   if (c->n) {
     unsigned nchunks = div_up(c->n, CH);
     ProfRegion pr(K_DEPOSIT, c->stream);
+    DepositGather G;
+    if (c->psort_pending) { G.perm = c->perm[c->cur]; G.store = c->posm; G.out = c->posm_sorted; }
     rc = launch_deposit(s->cfg.lmax, c->stream, nchunks, g, s->p0, c->psort, c->keys[c->cur],
-                        c->seg, keybase, CH, adb, s->PA, s->PB);
+                        c->seg, keybase, CH, adb, s->PA, s->PB, 0, G);
     if (rc) return rc;
+    c->psort_pending = false;
   }
   { ProfRegion pr(K_COMBINE, c->stream);
     sph_combine_kernel<<<g.numr, 64, 0, c->stream>>>(g, c->seg, keybase, CH, 0, s->PA, s->PB, s->G); }
@@ -2178,7 +2220,7 @@ int expb200_sphere_steps(expb200_sphere s, expb200_component c, double dt, int n
       CU_LAUNCH_CHECK();
     }
     c->pos_ver++;
-    if ((rc = sort_keyed(s, c, nkeys, true))) return rc;
+    if ((rc = sort_keyed(s, c, nkeys, true, deposit_can_gather(s->cfg.lmax)))) return rc;
     mark_sorted(s, c);
     if ((rc = accumulate_sorted(s, c, 0, adb))) return rc;
     if (nccl_comm) {
