@@ -33,8 +33,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic HBM bytes per particle-step of the sphere step
-STEP_BYTES = {"sort": 100, "deposit": 72, "force": 168}
+# Algorithmic HBM bytes per particle-step of the sphere step: the binning pass moves
+# keys and slots (28 B), the first deposit sweep gathers the 32-byte position records through the
+# permutation and writes the sorted stream (72 B), the second streams it (36 B), the force pass 168 B
+STEP_BYTES = {"sort": 28, "deposit": 108, "force": 168}
 
 
 def _hbm_peak():
