@@ -813,7 +813,7 @@ int ensure_sorted(expb200_cylinder_s *s, expb200_component_s *c, int mlevel, dou
     }
     int rc;
     if (nsub) {
-      ProfRegion pr(K_SORT, c->stream, radix_sort_launches(nsub, nks, true) + 2);
+      ProfRegion pr(K_SORT, c->stream, radix_sort_launches(nsub, nks, false) + 2);
       rc = radix_sort_suffix(c->stream, c->keys, c->perm, c->cur, c->hist, c->rank, off, c->n, nks, seg_sub,
                              SortPayload(), (uint32_t)m * kpl);
     } else {

@@ -149,10 +149,16 @@ sort_scan2b_kernel(const uint32_t *__restrict__ dtot, uint32_t *__restrict__ dba
 // lane of a group is its leader and advances the digit's counter with one shared-memory
 // atomic whose old value is the group's base.  Output: rank[i] = sorted position of item i
 // (a coalesced write); the data movement is sort_apply_kernel's.
+// DIRECT: no payload rides on this pass, so the key and the slot go straight to their sorted
+// positions from here (4-byte scatters into runs of equal digits) and sort_apply_kernel, with its
+// write and re-read of the ranks and second read of the keys, is skipped.
+template <bool DIRECT>
 __global__ void __launch_bounds__(kSortThreads, 3)
 sort_rank_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ rank, size_t n,
                  int shift, uint32_t mask, const uint32_t *__restrict__ hist,
-                 const uint32_t *__restrict__ gtot, const uint32_t *__restrict__ dbase, unsigned gs)
+                 const uint32_t *__restrict__ gtot, const uint32_t *__restrict__ dbase, unsigned gs,
+                 const uint32_t *__restrict__ perm_in, uint32_t *__restrict__ keys_out,
+                 uint32_t *__restrict__ perm_out)
 {
   extern __shared__ __align__(16) uint32_t wcount_all[];             // [kSortWarps][R]
   const uint32_t R = mask + 1;
@@ -210,7 +216,15 @@ sort_rank_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ ra
     if (ok && (grp & lt) == 0) base = atomicAdd(&wcount[dig[it]], (uint32_t)__popc(grp));
     __syncwarp();                   // orders this iteration's atomics before the next one's
     base = __shfl_sync(0xffffffffu, base, __ffs(grp) - 1);
-    if (ok) rout[it * 32] = base + __popc(grp & lt);
+    if (ok) {
+      const uint32_t pos = base + __popc(grp & lt);
+      if (DIRECT) {
+        keys_out[pos] = kin[it * 32];
+        perm_out[pos] = perm_in ? perm_in[wbase + it * 32] : wbase + it * 32;
+      } else {
+        rout[it * 32] = pos;
+      }
+    }
   }
 }
 
@@ -357,10 +371,12 @@ size_t sort_hist_words(size_t n)
   return (size_t)kMaxRadix * ((size_t)div_up(n ? n : 1, kSortTile) + kScanGroups + 2);
 }
 
-int radix_sort_launches(size_t n, uint32_t nkeys, bool want_seg)
+int radix_sort_launches(size_t n, uint32_t nkeys, bool want_seg, bool payload)
 {
+  // per pass: histogram, three scan kernels, rank (which also moves keys and slots); the last pass of
+  // a sort with a payload ranks and applies separately
   Plan p = plan_for(n, nkeys);
-  return 6 * p.npass + ((want_seg && p.npass > 1) ? 1 : 0);
+  return 5 * p.npass + (payload ? 1 : 0) + ((want_seg && p.npass > 1) ? 1 : 0);
 }
 
 int radix_sort_pairs(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], uint32_t *hist,
@@ -378,7 +394,9 @@ int radix_sort_pairs(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], uint
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    CU_TRY(cudaFuncSetAttribute(sort_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU_TRY(cudaFuncSetAttribute(sort_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSortWarps * kMaxRadix * sizeof(uint32_t))));
+    CU_TRY(cudaFuncSetAttribute(sort_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kSortWarps * kMaxRadix * sizeof(uint32_t))));
     attr_done[dev & 63] = true;
   }
@@ -391,16 +409,17 @@ int radix_sort_pairs(cudaStream_t st, uint32_t *keys[2], uint32_t *perm[2], uint
     sort_scan2a_kernel<<<div_up(R, 256), 256, 0, st>>>(gtot, dtot, R);
     sort_scan2b_kernel<<<1, 1024, 0, st>>>(dtot, dbase, R, (seg && p.npass == 1) ? seg : nullptr, nkeys,
                                            (uint32_t)n);
-    sort_rank_kernel<<<p.nctas, kSortThreads, smem, st>>>(keys[cur], rank, n, shift, mask, hist, gtot,
-                                                          dbase, p.gs);
     const uint32_t *pin = q == 0 ? perm_init : perm[cur];
-    if (last && payload.src)
+    if (last && payload.src) {
+      sort_rank_kernel<false><<<p.nctas, kSortThreads, smem, st>>>(keys[cur], rank, n, shift, mask, hist, gtot,
+                                                                   dbase, p.gs, nullptr, nullptr, nullptr);
       sort_apply_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(keys[cur], pin, rank, keys[cur ^ 1],
                                                                 perm[cur ^ 1], (uint32_t)n, payload.src,
                                                                 payload.dst);
-    else
-      sort_apply_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(keys[cur], pin, rank, keys[cur ^ 1],
-                                                                 perm[cur ^ 1], (uint32_t)n, nullptr, nullptr);
+    } else {
+      sort_rank_kernel<true><<<p.nctas, kSortThreads, smem, st>>>(keys[cur], rank, n, shift, mask, hist, gtot,
+                                                                  dbase, p.gs, pin, keys[cur ^ 1], perm[cur ^ 1]);
+    }
     cur ^= 1;
   }
   CU_LAUNCH_CHECK();

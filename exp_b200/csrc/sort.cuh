@@ -32,7 +32,7 @@ int compact_differing(cudaStream_t st, const unsigned *a, const unsigned *b, siz
                       uint32_t *list, size_t *count_host);
 
 // Number of kernels radix_sort_pairs launches for these sizes (for the launch counters).
-int radix_sort_launches(size_t n, uint32_t nkeys, bool want_seg);
+int radix_sort_launches(size_t n, uint32_t nkeys, bool want_seg, bool payload = false);
 
 // seg[k] = base + first sorted position whose key is >= k, for k in [0, nkeys].
 int segment_offsets(cudaStream_t st, const uint32_t *sorted, size_t n, uint32_t *seg, uint32_t nkeys,

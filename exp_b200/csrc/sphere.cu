@@ -1651,7 +1651,7 @@ int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool
   if (reorder_due) defer_stream = false;
   int cur = 0;
   {
-    ProfRegion pr(K_SORT, c->stream, radix_sort_launches(c->n, nkeys, true));
+    ProfRegion pr(K_SORT, c->stream, radix_sort_launches(c->n, nkeys, true, !defer_stream));
     SortPayload pl;
     pl.src = defer_stream ? nullptr : c->posm;
     pl.dst = defer_stream ? nullptr : c->posm_sorted;
@@ -1720,7 +1720,7 @@ int ensure_sorted(expb200_sphere_s *s, expb200_component_s *c, int mlevel = 0)
                                                                        nsub, m, s->nlev - 1, c->keys[W] + off);
       }
       CU_LAUNCH_CHECK();
-      ProfRegion pr(K_SORT, c->stream, radix_sort_launches(nsub, nks, true) + 2);
+      ProfRegion pr(K_SORT, c->stream, radix_sort_launches(nsub, nks, false, true) + 2);
       SortPayload pl;
       pl.src = c->posm;
       pl.dst = c->posm_sorted;
@@ -2134,7 +2134,7 @@ int expb200_sphere_multistep_update(expb200_sphere s, expb200_component c, doubl
         sph_switch_key_list_kernel<<<grid_for(nsw, 256), 256, 0, st>>>(gm, c->posm, c->level, c->prev_level, list,
                                                                        nsw, side, s->nlev, kl[0]);
         CU_LAUNCH_CHECK();
-        ProfRegion pr(K_SORT, st, radix_sort_launches(nsw, nkeys, true));
+        ProfRegion pr(K_SORT, st, radix_sort_launches(nsw, nkeys, true, true));
         SortPayload pl;
         pl.src = c->posm;
         pl.dst = c->posm_sorted;
