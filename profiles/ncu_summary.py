@@ -61,7 +61,7 @@ def traffic(path, n, out_json, tag):
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
-    fam = {"force": "sph_force", "deposit": "sph_deposit_reg", "sort": "sort_apply"}
+    fam = {"force": "sph_force", "deposit": "sph_deposit_reg", "sort": "sort_rank"}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     acc = {}
     for r in rows[2:]:
