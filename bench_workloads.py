@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import time
 
 import numpy as np
@@ -314,17 +315,60 @@ def run_diskhalo(args, B):
             "roofline": {"bound": "fp64", "kernel": "whole master step (see kernel_ms_per_step)", "achieved": None,
                          "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
                          "kernel_ms_per_step": per},
-            "cpu_baseline": None}
+            "cpu_baseline": None if (R.world > 1 or args.no_cpu) else _cpu_diskhalo(args, B)}
     B.emit(line)
     R.close()
+
+
+def _cpu_diskhalo(args, B, n=100_000, steps=1):
+    """one master step of the same disk+halo set-up on `n` particles with the oracle-driven stepper
+    (tests/ref_stepper.py: the reference's do_step ordering over the oracle's C functions), one thread"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    from ref_stepper import RefSim
+    from exp_b200 import ics
+    nd = n // 10
+    nh = n - nd
+    tabS, tabC = B.make_table(), cyl_table()
+    ph, vh, mh = ics.nfw_halo(nh, seed=43)
+    ph *= 0.02
+    vh *= 7.0
+    pd, vd, md = ics.exponential_disk(nd, seed=44)
+    sim = RefSim(0.004, args.multistep, dynfracV=0.01, dynfracA=0.03, dynfracP=0.05)
+    rh = sim.add("sphere", tabS, ph, vh, mh, scale=0.02)
+    rd = sim.add("cylinder", tabC, pd, vd, md)
+    sim.add_interaction(rh, rd)
+    sim.add_interaction(rd, rh)
+    sim.initialize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step()
+    dt = time.perf_counter() - t0
+    lv = np.bincount(np.concatenate([sim.S[rh].level, sim.S[rd].level]), minlength=args.multistep + 1)
+    return {"value": n * steps / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{nd} disk + {nh} halo particles of the same distributions, {steps} master step(s) of "
+                      f"{1 << args.multistep} sub-steps in {dt:.1f} s, one thread: tests/ref_stepper.py (the reference's "
+                      f"do_step / adjust_multistep_level ordering in Python) over the oracle's C functions; level "
+                      f"populations {lv.tolist()}"}
 
 
 def ref_diskhalo(args, B):
     R = B.Ranks()
     if R.rank != 0:
         return
-    B.emit({"impl": "reference", "unavailable": "the oracle-driven disk+halo stepper (tests/ref_stepper.py) is a "
-            "Python test harness, not a timed baseline; see the sphere and cylinder reference arms"})
+    world = max(args.gpus, 1)
+    ntot, nd, nh = _diskhalo_sizes(args, world)
+    n = 100_000
+    cpu = _cpu_diskhalo(args, B, n=n, steps=1)
+    cfg = _diskhalo_config(args, world, ntot, nd, nh)
+    cfg["reference_sample_particles_per_step"] = n
+    cfg["extrapolated"] = True
+    B.emit({"impl": "reference",
+            "metric": "particle-steps/sec (master steps; coef+force+kick-drift, multistep) disk+halo",
+            "value": cpu["value"], "unit": B.UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": n / cpu["value"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": B.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0})
 
 
 # ---- pyEXP createFromArray sweep --------------------------------------------------------------

@@ -102,7 +102,8 @@ class RefForce:
         self.kind, self.multistep = kind, multistep
         if kind == "sphere":
             self.g = O.Grid(tab)
-            self.P = O.sph_params(rmin=tab.rmin, rmax=tab.rmax)
+            sc = kw.get("scale", 1.0)
+            self.P = O.sph_params(scale=sc, rmin=kw.get("rmin", tab.rmin * sc), rmax=kw.get("rmax", tab.rmax * sc))
             shape = (1, (tab.lmax + 1) ** 2, tab.nmax)
         else:
             self.g = O.CylGridPy(tab)
