@@ -1336,9 +1336,10 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
     if (s->cov_cap[slot] < bytes) {
       if (s->cov_buf[slot]) cudaFree(s->cov_buf[slot]);
       s->cov_buf[slot] = nullptr; s->cov_cap[slot] = 0;
-      cudaError_t e = cudaMalloc(&s->cov_buf[slot], bytes);
+      const size_t want = bytes + bytes / 8;        // head-room: sizes drift a little from call to call
+      cudaError_t e = cudaMalloc(&s->cov_buf[slot], want);
       if (e != cudaSuccess) return e;
-      s->cov_cap[slot] = bytes;
+      s->cov_cap[slot] = want;
     }
     *ptr = s->cov_buf[slot];
     return cudaSuccess;
@@ -1357,6 +1358,8 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
   int CH = (int)(chq < 256 ? 256 : chq > 4096 ? 4096 : chq);
   const unsigned nchunks = div_up(nused, CH);
   const size_t slots = (size_t)nchunks + sampT + 1;
+  // scratch capacity from the component size, so that it does not move with nused
+  const size_t slots_cap = (size_t)div_up(c->n, CH) + sampT + 1;
   // harmonics per CTA: one DMMA warp each, and one panel thread per (m, n) of the group
   int MG = kCovPanel / N;
   if (MG > kCovMG) MG = kCovMG;
@@ -1365,9 +1368,9 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
   const int items = MG * N;
   int nsplit = kCovPanel / items;
   if (nsplit > kCovSplit) nsplit = kCovSplit;
-  COV_TRY(cov_alloc((void **)&PC, slots * M1 * R2 * R2 * sizeof(double), 1));
-  COV_TRY(cov_alloc((void **)&PV, slots * kCovSplit * MN * 2 * sizeof(double), 2));
-  COV_TRY(cov_alloc((void **)&PM, slots * 2 * sizeof(double), 3));
+  COV_TRY(cov_alloc((void **)&PC, slots_cap * M1 * R2 * R2 * sizeof(double), 1));
+  COV_TRY(cov_alloc((void **)&PV, slots_cap * kCovSplit * MN * 2 * sizeof(double), 2));
+  COV_TRY(cov_alloc((void **)&PM, slots_cap * 2 * sizeof(double), 3));
   COV_TRY(cudaMemsetAsync(PV, 0, slots * kCovSplit * MN * 2 * sizeof(double), st));
   COV_TRY(cov_alloc((void **)&dMV, (size_t)sampT * MN * N * 2 * sizeof(double), 4));
   COV_TRY(cov_alloc((void **)&dVC, (size_t)sampT * MN * 2 * sizeof(double), 5));
@@ -1377,11 +1380,13 @@ static int cylinder_covariance_impl(expb200_cylinder s, expb200_component c, int
   // geometry records of the used particles, in sorted order (164 B per particle at mmax = 6)
   double *GW = nullptr, *GT = nullptr, *GS = nullptr, *GM = nullptr;
   int *GN = nullptr;
-  COV_TRY(cov_alloc((void **)&GW, (size_t)nused * 4 * sizeof(double), 8));
-  COV_TRY(cov_alloc((void **)&GT, (size_t)nused * M1 * 2 * sizeof(double), 9));
-  COV_TRY(cov_alloc((void **)&GS, (size_t)nused * sizeof(double), 10));
-  COV_TRY(cov_alloc((void **)&GM, (size_t)nused * sizeof(double), 11));
-  COV_TRY(cov_alloc((void **)&GN, (size_t)nused * sizeof(int), 12));
+  // sized for the whole component (nused <= n changes from call to call as particles cross the
+  // grid's edge: buffers sized by nused were re-allocated, 1.6 GB at a time, on most steps)
+  COV_TRY(cov_alloc((void **)&GW, (size_t)c->n * 4 * sizeof(double), 8));
+  COV_TRY(cov_alloc((void **)&GT, (size_t)c->n * M1 * 2 * sizeof(double), 9));
+  COV_TRY(cov_alloc((void **)&GS, (size_t)c->n * sizeof(double), 10));
+  COV_TRY(cov_alloc((void **)&GM, (size_t)c->n * sizeof(double), 11));
+  COV_TRY(cov_alloc((void **)&GN, (size_t)c->n * sizeof(int), 12));
   cyl_cov_geom_kernel<<<div_up(nused, 256), 256, 0, st>>>(g, c->posm, c->perm[c->cur], nused, adb, GW, GT, GS, GM, GN);
   COV_TRY(cudaGetLastError());
   constexpr int P = kCovTile;

@@ -2327,9 +2327,10 @@ static int sphere_covariance_impl(expb200_sphere s, expb200_component c, int mle
     if (s->cov_cap[slot] < bytes) {
       if (s->cov_buf[slot]) cudaFree(s->cov_buf[slot]);
       s->cov_buf[slot] = nullptr; s->cov_cap[slot] = 0;
-      cudaError_t e = cudaMalloc(&s->cov_buf[slot], bytes);
+      const size_t want = bytes + bytes / 8;        // head-room: bin populations drift from call to call
+      cudaError_t e = cudaMalloc(&s->cov_buf[slot], want);
       if (e != cudaSuccess) return e;
-      s->cov_cap[slot] = bytes;
+      s->cov_cap[slot] = want;
     }
     *ptr = static_cast<double *>(s->cov_buf[slot]);
     return cudaSuccess;
