@@ -1,8 +1,10 @@
 /*
  * cyl_oracle.cc -- CPU oracle for the cylinder force (Cylinder + EmpCylSL tables).
  *
- * TEST INFRASTRUCTURE ONLY (see exp_oracle.h).  PARITY UNPINNED: the reference has no
- * golden vectors for this path and cannot be built here.
+ * TEST INFRASTRUCTURE ONLY (see exp_oracle.h).  PARITY PINNED: tests/test_oracle_ref.py holds
+ * these functions bit for bit to the reference's own EmpCylSL::r_to_xi / z_to_y / get_pot /
+ * accumulate / accumulated_eval, cut from exputil/EmpCylSL.cc and compiled in place
+ * (oracle/ref_extract.py -> oracle/_ref/libexpref_path.so; the covar branch to 1e-14).
  *
  * Restates, in the reference's evaluation order:
  *   EmpCylSL::r_to_xi / z_to_y           exputil/EmpCylSL.cc:6446-6463, 7109-7117

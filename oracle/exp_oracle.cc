@@ -2,9 +2,10 @@
  * exp_oracle.cc -- CPU oracle for EXP's basis-function-expansion force loop
  * (sphereSL part, leapfrog, multistep bookkeeping).
  *
- * TEST INFRASTRUCTURE ONLY (see exp_oracle.h).  PARITY UNPINNED except for the
- * recursions, which tests/test_oracle_ref.py pins bit-for-bit against the
- * reference's own src/Basis.cc compiled into oracle/_ref/.
+ * TEST INFRASTRUCTURE ONLY (see exp_oracle.h).  PARITY PINNED: tests/test_oracle_ref.py holds
+ * the recursions, the SLGridSph maps and table interpolation, the coefficient and force
+ * threads, the leapfrog and the level assignment bit for bit to the reference's own member
+ * functions compiled in place (oracle/ref_extract.py -> oracle/_ref/libexpref_path.so).
  *
  * Written from the behaviour of the reference sources; every function names
  * the reference file:line it restates.  Arithmetic is kept in the reference's

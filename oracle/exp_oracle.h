@@ -20,9 +20,12 @@
  * accumulated_eval (the covar branch to 1e-14: Eigen expression order), incr_position/
  * incr_velocity threads, adjust_multistep_level_thread.  The reference's own N-body test case
  * (tests/Halo: SLGridSph.model, Lmax=2 nmax=10 numr=4000 multistep=4, 2T/VC check) runs from
- * tests/golden/halo_fixture.npz (tests/test_halo_reference_case.py).  Not pinned (restated
- * only): the Cylinder:: thread wrappers around EmpCylSL (orientation, erf blend), the
- * multistep difference tables, fix_positions, and the pyEXP twins (oracle/pyexp_oracle.py).
+ * tests/golden/halo_fixture.npz (tests/test_halo_reference_case.py).  The pyEXP twins
+ * (oracle/pyexp_oracle.py) are held to the reference's own BasisClasses::Spherical::accumulate /
+ * sph_eval / cyl_eval / crt_eval / computeAccel and BiorthBasis::legendre_R (expui/BiorthBasis.cc,
+ * same mechanism) to 1e-13.  Not pinned (restated only): the Cylinder:: thread wrappers around
+ * EmpCylSL (orientation, erf blend), the multistep difference tables, fix_positions, and the
+ * cylindrical pyEXP twin.
  *
  * All arrays are plain row-major C arrays.  Coefficient layout is the
  * reference's: row index = l*l + {0 (m=0), 2m-1 (cos), 2m (sin)}, nmax

@@ -2,7 +2,10 @@
 ``BasisClasses::Spherical::accumulate`` / ``load_coefs`` / ``sph_eval`` / ``cyl_eval`` /
 ``crt_eval`` / ``computeAccel`` (reference expui/BiorthBasis.cc:583-665, 480-516, 711-816,
 930-958, 818-926), in plain Python loops over the oracle's C table functions.  Small cases only.
-PARITY UNPINNED (pyEXP cannot be built here; see oracle/exp_oracle.h)."""
+PARITY PINNED: pyEXP itself cannot be built here, but the reference's own Spherical::accumulate /
+sph_eval / cyl_eval / crt_eval / computeAccel and BiorthBasis::legendre_R are cut from
+expui/BiorthBasis.cc and compiled in place (oracle/ref_extract.py, oracle/ref_path_wrap.cc), and
+tests/test_oracle_ref.py::test_pyexp_twin_against_reference holds this file to them (<= 1e-13)."""
 import ctypes as C
 import math
 

@@ -45,6 +45,17 @@ PIECES = {
     "cyl_get_pot":         ("exputil/EmpCylSL.cc", 5557, 5632, r"^void EmpCylSL::get_pot\(Eigen::MatrixXd& Vc, Eigen::MatrixXd& Vs,"),
     "cyl_r_to_xi":         ("exputil/EmpCylSL.cc", 6446, 6463, r"^double EmpCylSL::r_to_xi\(double r\)"),
     "cyl_z_to_y":          ("exputil/EmpCylSL.cc", 7109, 7117, r"^double EmpCylSL::z_to_y\(double z\)"),
+    # --- pyEXP twin (expui/BiorthBasis.cc): BasisClasses::Spherical accumulate / field evaluation.
+    # accumulate is cut around its pcavar block (lines 652-659: Eigen expression templates on complex
+    # vectors, the covariance of pyEXP's own subsampling, not on the path)
+    "biorth_factorial":    ("expui/BiorthBasis.cc", 321, 329, r"^    factorial.resize\(lmax\+1, lmax\+1\);"),
+    "biorth_accumulate_head": ("expui/BiorthBasis.cc", 583, 651, r"^  void Spherical::accumulate\(double x, double y, double z, double mass,"),
+    "biorth_accumulate_tail": ("expui/BiorthBasis.cc", 660, 665, r"^$"),
+    "biorth_sph_eval":     ("expui/BiorthBasis.cc", 711, 816, r"^  std::vector<double>"),
+    "biorth_compute_accel": ("expui/BiorthBasis.cc", 818, 926, r"^  void Spherical::computeAccel\(double x, double y, double z,"),
+    "biorth_cyl_eval":     ("expui/BiorthBasis.cc", 929, 942, r"^  std::vector<double>"),
+    "biorth_crt_eval":     ("expui/BiorthBasis.cc", 945, 958, r"^  std::vector<double>"),
+    "biorth_legendre":     ("expui/BiorthBasis.cc", 1034, 1122, r"^  void BiorthBasis::legendre_R\(int lmax, double x, Eigen::MatrixXd& p\)"),
     # --- leapfrog (src/incpos.cc, src/incvel.cc)
     "incpos_thread":       ("src/incpos.cc", 15, 70, r"^void \* incr_position_thread\(void \*ptr\)"),
     "incvel_thread":       ("src/incvel.cc", 15, 89, r"^void \* incr_velocity_thread\(void \*ptr\)"),

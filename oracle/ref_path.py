@@ -74,6 +74,14 @@ def lib():
         L.ref_sph_step.argtypes = [C.c_void_p, C.c_double, C.c_int]
         L.ref_sph_read.argtypes = [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.ref_cyl_create.restype = C.c_void_p
+        L.ref_pyexp_create.restype = C.c_void_p
+        L.ref_pyexp_create.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.ref_pyexp_destroy.argtypes = [C.c_void_p]
+        L.ref_pyexp_accumulate.restype = C.c_int
+        L.ref_pyexp_accumulate.argtypes = [C.c_void_p, C.c_size_t, c_dp, c_dp, c_dp]
+        L.ref_pyexp_set_coefs.argtypes = [C.c_void_p, c_dp]
+        L.ref_pyexp_eval.argtypes = [C.c_void_p, C.c_int, C.c_size_t, c_dp, c_dp]
+        L.ref_pyexp_accel.argtypes = [C.c_void_p, C.c_size_t, c_dp, c_dp]
         L.ref_cyl_create.argtypes = [C.c_int] * 6 + [C.c_double] * 7 + [c_ip] + [c_dp] * 6
         L.ref_cyl_destroy.argtypes = [C.c_void_p]
         L.ref_cyl_r_to_xi.restype = C.c_double
@@ -332,3 +340,46 @@ def adjust_levels(vel, acc, pot, potext, scale, level, dtreq, dtime, multistep, 
                                   lev.ctypes.data_as(c_up), dq.ctypes.data_as(c_fp), C.byref(P),
                                   C.byref(lo), C.byref(hi))
     return lev, dq, nsw, lo.value, hi.value
+
+
+class RefPyexp:
+    """The reference's BasisClasses::Spherical (pyEXP's sphereSL basis: expui/BiorthBasis.cc:583-958,
+    1034-1122) over the SLGridSph of a RefSphere: accumulate -> expcoef, sph/cyl/crt_eval -> the nine
+    field values, computeAccel."""
+
+    def __init__(self, sph: "RefSphere", scale=1.0, rmin=0.0, rmax=1.0e300, NO_L0=False, NO_L1=False,
+                 EVEN_L=False, EVEN_M=False, M0_only=False):
+        self.sph = sph                      # keeps the grid alive
+        self.lmax, self.nmax = sph.lmax, sph.nmax
+        bits = sum(1 << k for k, f in enumerate((NO_L0, NO_L1, EVEN_L, EVEN_M, M0_only)) if f)
+        self.h = lib().ref_pyexp_create(sph.h, float(scale), float(rmin), float(rmax), bits)
+
+    def __del__(self):
+        try:
+            lib().ref_pyexp_destroy(self.h)
+        except Exception:
+            pass
+
+    def accumulate(self, mass, pos):
+        mass, pos = _f64(mass), _f64(pos)
+        out = np.zeros(((self.lmax + 1) ** 2, self.nmax))
+        used = lib().ref_pyexp_accumulate(self.h, len(mass), _dp(mass), _dp(pos), _dp(out))
+        return out, used
+
+    def set_coefs(self, expcoef):
+        e = _f64(expcoef)
+        assert e.shape == ((self.lmax + 1) ** 2, self.nmax)
+        lib().ref_pyexp_set_coefs(self.h, _dp(e))
+
+    def eval(self, which, pts):
+        """which: 'sph' (r, costh, phi), 'cyl' (R, z, phi) or 'crt' (x, y, z); -> [n][9]"""
+        pts = _f64(pts).reshape(-1, 3)
+        out = np.zeros((len(pts), 9))
+        lib().ref_pyexp_eval(self.h, {"sph": 0, "cyl": 1, "crt": 2}[which], len(pts), _dp(pts), _dp(out))
+        return out
+
+    def accel(self, pos):
+        pos = _f64(pos).reshape(-1, 3)
+        out = np.zeros((len(pos), 3))
+        lib().ref_pyexp_accel(self.h, len(pos), _dp(pos), _dp(out))
+        return out

@@ -617,3 +617,116 @@ long ref_adjust_levels(long n, const double *vel, const double *acc, const doubl
 }
 
 } // extern "C"
+
+
+// =============================================================================================
+// pyEXP twin: BasisClasses::Spherical::accumulate / sph_eval / cyl_eval / crt_eval / computeAccel
+// and BiorthBasis::legendre_R, the reference's own bodies (expui/BiorthBasis.cc, cut by
+// ref_extract.py) over the SLGridSph of a ref_sph_create handle.  accumulate is compiled around its
+// pcavar block (pyEXP's own subsample covariance: not on the path), so pcavar stays false here.
+// =============================================================================================
+static inline int omp_get_thread_num() { return 0; }
+
+namespace BasisClasses {
+
+class BiorthBasis {
+public:
+  void legendre_R(int lmax, double x, Eigen::MatrixXd &p);
+  void legendre_R(int lmax, double x, Eigen::MatrixXd &p, Eigen::MatrixXd &dp);
+};
+
+class Spherical : public BiorthBasis {
+public:
+  SLGridSph *sl = nullptr;
+  int lmax = 0, nmax = 0, N1 = 0, N2 = 1 << 30, used = 0;
+  unsigned sampT = 1;
+  double scale = 1.0, rmin = 0.0, rmax = 1.0e300, totalMass = 0.0, G = 1.0;
+  bool NO_L0 = false, NO_L1 = false, EVEN_L = false, EVEN_M = false, M0_only = false, pcavar = false;
+  std::vector<Eigen::MatrixXd> potd, dpot, dend, legs, dlegs;
+  Eigen::MatrixXd factorial, expcoef;
+  Eigen::VectorXi sampleCounts;
+  Eigen::VectorXd sampleMasses;
+
+  void get_pot(Eigen::MatrixXd &tab, double r) { sl->get_pot(tab, r); }       // SphericalSL, BiorthBasis.H:522-531
+  void get_dens(Eigen::MatrixXd &tab, double r) { sl->get_dens(tab, r); }
+  void get_force(Eigen::MatrixXd &tab, double r) { sl->get_force(tab, r); }
+
+  void initialize()
+  {
+    potd.resize(1); dpot.resize(1); dend.resize(1); legs.resize(1); dlegs.resize(1);
+    potd[0].resize(lmax + 1, nmax); dpot[0].resize(lmax + 1, nmax); dend[0].resize(lmax + 1, nmax);
+    legs[0].resize(lmax + 1, lmax + 1); dlegs[0].resize(lmax + 1, lmax + 1);
+    expcoef.resize((lmax + 1) * (lmax + 1), nmax);
+    expcoef.setZero();
+#include "_ref/gen/biorth_factorial.inc"
+  }
+  void accumulate(double x, double y, double z, double mass, unsigned long indx);
+  std::vector<double> sph_eval(double r, double costh, double phi);
+  std::vector<double> cyl_eval(double R, double z, double phi);
+  std::vector<double> crt_eval(double x, double y, double z);
+  void computeAccel(double x, double y, double z, Eigen::Ref<Eigen::Vector3d> acc);
+};
+
+#include "_ref/gen/biorth_legendre.inc"
+#include "_ref/gen/biorth_accumulate_head.inc"
+#include "_ref/gen/biorth_accumulate_tail.inc"
+#include "_ref/gen/biorth_sph_eval.inc"
+#include "_ref/gen/biorth_compute_accel.inc"
+#include "_ref/gen/biorth_cyl_eval.inc"
+#include "_ref/gen/biorth_crt_eval.inc"
+
+} // namespace BasisClasses
+
+extern "C" {
+
+// flags: bit 0 NO_L0, 1 NO_L1, 2 EVEN_L, 3 EVEN_M, 4 M0_only
+void *ref_pyexp_create(void *sph_handle, double scale, double rmin, double rmax, int flags)
+{
+  SphHandle *h = static_cast<SphHandle *>(sph_handle);
+  auto *b = new BasisClasses::Spherical;
+  b->sl = &h->grid;
+  b->lmax = h->grid.lmax; b->nmax = h->grid.nmax;
+  b->scale = scale; b->rmin = rmin; b->rmax = rmax;
+  b->NO_L0 = flags & 1; b->NO_L1 = flags & 2; b->EVEN_L = flags & 4; b->EVEN_M = flags & 8; b->M0_only = flags & 16;
+  b->initialize();
+  return b;
+}
+void ref_pyexp_destroy(void *bb) { delete static_cast<BasisClasses::Spherical *>(bb); }
+
+// Spherical::accumulate over n particles (reset first): expcoef [(lmax+1)^2][nmax], returns used
+int ref_pyexp_accumulate(void *bb, size_t n, const double *mass, const double *pos, double *expcoef)
+{
+  auto *b = static_cast<BasisClasses::Spherical *>(bb);
+  b->expcoef.setZero();
+  b->used = 0; b->totalMass = 0.0;
+  for (size_t i = 0; i < n; i++) b->accumulate(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i], i);
+  copy_mat(b->expcoef, expcoef);
+  return b->used;
+}
+void ref_pyexp_set_coefs(void *bb, const double *expcoef)
+{
+  auto *b = static_cast<BasisClasses::Spherical *>(bb);
+  for (int i = 0; i < b->expcoef.rows(); i++)
+    for (int j = 0; j < b->expcoef.cols(); j++) b->expcoef(i, j) = expcoef[(size_t)i * b->expcoef.cols() + j];
+}
+// which: 0 sph_eval(r, costh, phi), 1 cyl_eval(R, z, phi), 2 crt_eval(x, y, z); out[9] per point
+void ref_pyexp_eval(void *bb, int which, size_t n, const double *pts, double *out)
+{
+  auto *b = static_cast<BasisClasses::Spherical *>(bb);
+  for (size_t i = 0; i < n; i++) {
+    const double a = pts[3 * i], c = pts[3 * i + 1], d = pts[3 * i + 2];
+    std::vector<double> v = which == 0 ? b->sph_eval(a, c, d) : which == 1 ? b->cyl_eval(a, c, d) : b->crt_eval(a, c, d);
+    for (int k = 0; k < 9; k++) out[9 * i + k] = v[k];
+  }
+}
+void ref_pyexp_accel(void *bb, size_t n, const double *pos, double *acc)
+{
+  auto *b = static_cast<BasisClasses::Spherical *>(bb);
+  for (size_t i = 0; i < n; i++) {
+    Eigen::Vector3d a;
+    b->computeAccel(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], a);
+    for (int k = 0; k < 3; k++) acc[3 * i + k] = a.d[k];
+  }
+}
+
+} // extern "C"

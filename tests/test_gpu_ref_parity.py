@@ -304,3 +304,41 @@ def test_cylinder_default_grid_vs_reference_code():
         p0, p, fr, fz, fp = ref.accumulated_eval(rc["cos"], rc["sin"], r, z, math.atan2(y, x))
         facc[k] = (fr * x / r - fp * y / (r * r), fr * y / r + fp * x / (r * r), fz)
     assert acc_rel_err(out["acc"][idx], facc).max() <= 1e-8
+
+
+def test_pyexp_sphere_against_reference_code():
+    """exp_b200.pyexp.SphericalSL (createFromArray, getFields, getAccel) against the reference's own
+    BasisClasses::Spherical code compiled in place (expui/BiorthBasis.cc:583-958)"""
+    from exp_b200 import pyexp
+    tab = get_table("hernquist", 4, 10)
+    n = 4000
+    pos, vel, mass = ics.hernquist_halo(n, seed=3)
+    pos = pos + np.array([0.01, -0.02, 0.005])
+    rs = R.RefSphere(tab)
+    rp = R.RefPyexp(rs, rmin=tab.rmin, rmax=tab.rmax)
+    want, used = rp.accumulate(mass, pos)
+    b = pyexp.SphericalSL(tab)
+    cf = b.createFromArray(mass, pos, time=0.0)
+    assert b.used == used
+    L = tab.lmax
+    k = 0
+    for l in range(L + 1):                      # (l, m) complex packing of load_coefs (:480-516)
+        for m in range(l + 1):
+            row = l * l + (0 if m == 0 else 2 * m - 1)
+            assert rel_rms(cf.coefs[k].real, want[row]) <= 1e-10
+            if m:
+                assert rel_rms(cf.coefs[k].imag, want[row + 1]) <= 1e-10
+            k += 1
+    rp.set_coefs(want)
+    rng = np.random.default_rng(1)
+    pts = rng.normal(size=(50, 3)) * np.array([1.0, 1.0, 0.6]) * rng.uniform(0.05, 5.0, size=(50, 1))
+    ref = rp.eval("crt", pts)
+    got = b.getFields(pts[:, 0], pts[:, 1], pts[:, 2])
+    acc = b.getAccel(pts)
+    racc = rp.accel(pts)
+    for j in range(len(pts)):
+        fn = np.linalg.norm(ref[j, 6:9])
+        assert np.abs(got[3:6, j] - ref[j, 3:6]).max() <= 1e-8 * max(abs(ref[j, 5]), abs(ref[j, 3]))
+        assert np.abs(got[6:9, j] - ref[j, 6:9]).max() <= 1e-8 * fn
+        assert np.abs(got[0:3, j] - ref[j, 0:3]).max() <= 1e-8 * max(abs(ref[j, 2]), abs(ref[j, 0]))
+        assert np.abs(acc[j] - racc[j]).max() <= 1e-8 * fn

@@ -354,3 +354,42 @@ def test_full_step_bit_exact():
     o = st.read()
     for k, v in (("pos", S.pos), ("vel", S.vel), ("acc", S.acc), ("pot", S.pot), ("coef", coef)):
         assert o[k].tobytes() == v.tobytes(), k
+
+
+# ---- pyEXP twin: BasisClasses::Spherical (expui/BiorthBasis.cc) ---------------------------------
+@pytest.mark.parametrize("flags,scale", [({}, 1.0), (dict(NO_L0=True), 1.0), (dict(NO_L1=True, EVEN_M=True), 0.5),
+                                         (dict(EVEN_L=True), 1.0), (dict(M0_only=True), 2.0)])
+def test_pyexp_twin_against_reference(flags, scale):
+    """oracle/pyexp_oracle.py (accumulate, sph/crt_eval) against the reference's own
+    Spherical::accumulate / sph_eval / cyl_eval / crt_eval / computeAccel and BiorthBasis::legendre_R
+    (expui/BiorthBasis.cc:583-651+660-665, 711-958, 1034-1122) compiled in place.  The restatement sums
+    with numpy dot products and forms the Y_lm prefactor as sqrt((2l+1)/4pi) exp(..)/2 instead of
+    sqrt((0.5l+0.25)/pi exp(..)): agreement is to rounding (1e-13), not bit for bit."""
+    from oracle import pyexp_oracle as PO
+    tab = get_table("hernquist", 4, 8)
+    n = 2500
+    pos, vel, mass = ics.hernquist_halo(n, seed=5)
+    pos = pos * scale + np.array([0.01, -0.02, 0.005])
+    rmin, rmax = tab.rmin * scale * 3.0, tab.rmax * scale * 0.5      # both cuts bite
+    rs = R.RefSphere(tab)
+    rp = R.RefPyexp(rs, scale=scale, rmin=rmin, rmax=rmax, **flags)
+    g = O.Grid(tab)
+    c_ref, used = rp.accumulate(mass, pos)
+    c_or, used_or = PO.accumulate(g, mass, pos, scale=scale, rmin=rmin, rmax=rmax)
+    assert used == used_or and 0 < used < n
+    assert np.abs(c_ref - c_or).max() <= 1e-13 * np.abs(c_ref).max()
+    rp.set_coefs(c_ref)
+    rng = np.random.default_rng(2)
+    pts = rng.normal(size=(60, 3)) * np.array([1.0, 1.0, 0.6]) * rng.uniform(0.05, 5.0, size=(60, 1)) * scale
+    f_ref = rp.eval("crt", pts)
+    f_or = np.array([PO.crt_eval(g, c_ref, *p, scale=scale, **flags) for p in pts])
+    for k in range(9):
+        assert np.abs(f_ref[:, k] - f_or[:, k]).max() <= 1e-12 * max(np.abs(f_ref[:, k]).max(), 1e-300), k
+    # sph_eval directly, and computeAccel against the force columns of crt_eval
+    r = np.linalg.norm(pts, axis=1)
+    sph = np.stack([r, pts[:, 2] / r, np.arctan2(pts[:, 1], pts[:, 0])], axis=1)
+    s_ref = rp.eval("sph", sph)
+    s_or = np.array([PO.sph_eval(g, c_ref, *q, scale=scale, **flags) for q in sph])
+    assert np.abs(s_ref - s_or).max() <= 1e-12 * np.abs(s_ref).max()
+    acc = rp.accel(pts)
+    assert np.abs(acc - f_ref[:, 6:9]).max() <= 1e-11 * np.abs(acc).max()
