@@ -3,7 +3,8 @@
  *
  * TEST INFRASTRUCTURE ONLY (see exp_oracle.h).  PARITY PINNED: tests/test_oracle_ref.py holds
  * these functions bit for bit to the reference's own EmpCylSL::r_to_xi / z_to_y / get_pot /
- * accumulate / accumulated_eval, cut from exputil/EmpCylSL.cc and compiled in place
+ * accumulate / accumulated_eval and Cylinder::determine_coefficients_thread /
+ * determine_acceleration_and_potential_thread, cut from exputil/EmpCylSL.cc and src/Cylinder.cc and compiled in place
  * (oracle/ref_extract.py -> oracle/_ref/libexpref_path.so; the covar branch to 1e-14).
  *
  * Restates, in the reference's evaluation order:

@@ -23,8 +23,9 @@
  * tests/golden/halo_fixture.npz (tests/test_halo_reference_case.py).  The pyEXP twins
  * (oracle/pyexp_oracle.py) are held to the reference's own BasisClasses::Spherical::accumulate /
  * sph_eval / cyl_eval / crt_eval / computeAccel and BiorthBasis::legendre_R (expui/BiorthBasis.cc,
- * same mechanism) to 1e-13.  Not pinned (restated only): the Cylinder:: thread wrappers around
- * EmpCylSL (orientation, erf blend), the multistep difference tables, fix_positions, and the
+ * same mechanism) to 1e-13, and the Cylinder:: thread functions around EmpCylSL (centre / rtrunc /
+ * rcylmax gates, orientation, erf blend to the monopole; src/Cylinder.cc:748-896, 1266-1446) bit
+ * for bit.  Not pinned (restated only): the multistep difference tables, fix_positions, and the
  * cylindrical pyEXP twin.
  *
  * All arrays are plain row-major C arrays.  Coefficient layout is the

@@ -45,6 +45,10 @@ PIECES = {
     "cyl_get_pot":         ("exputil/EmpCylSL.cc", 5557, 5632, r"^void EmpCylSL::get_pot\(Eigen::MatrixXd& Vc, Eigen::MatrixXd& Vs,"),
     "cyl_r_to_xi":         ("exputil/EmpCylSL.cc", 6446, 6463, r"^double EmpCylSL::r_to_xi\(double r\)"),
     "cyl_z_to_y":          ("exputil/EmpCylSL.cc", 7109, 7117, r"^double EmpCylSL::z_to_y\(double z\)"),
+    # --- Cylinder (src/Cylinder.cc): the thread functions around EmpCylSL (orientation, rcylmax gate,
+    # erf blend to the monopole)
+    "cylinder_coef_thread": ("src/Cylinder.cc", 748, 896, r"^void \* Cylinder::determine_coefficients_thread\(void \* arg\)"),
+    "cylinder_accel_thread": ("src/Cylinder.cc", 1266, 1446, r"^void \* Cylinder::determine_acceleration_and_potential_thread\(void \* arg\)"),
     # --- pyEXP twin (expui/BiorthBasis.cc): BasisClasses::Spherical accumulate / field evaluation.
     # accumulate is cut around its pcavar block (lines 652-659: Eigen expression templates on complex
     # vectors, the covariance of pyEXP's own subsampling, not on the path)

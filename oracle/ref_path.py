@@ -84,6 +84,10 @@ def lib():
         L.ref_pyexp_accel.argtypes = [C.c_void_p, C.c_size_t, c_dp, c_dp]
         L.ref_cyl_create.argtypes = [C.c_int] * 6 + [C.c_double] * 7 + [c_ip] + [c_dp] * 6
         L.ref_cyl_destroy.argtypes = [C.c_void_p]
+        L.ref_cylinder_coef_thread.argtypes = ([C.c_void_p, C.c_long, c_dp, c_dp, c_up, C.c_int, C.c_int, c_dp]
+                                               + [C.c_double] * 4 + [c_dp] * 4 + [c_ip, c_dp])
+        L.ref_cylinder_accel_thread.argtypes = ([C.c_void_p, C.c_long, c_dp, c_up, C.c_int, C.c_int, c_dp, C.c_double,
+                                                 c_dp, c_dp, c_dp, C.c_double, c_dp, c_dp, c_dp, c_dp])
         L.ref_cyl_r_to_xi.restype = C.c_double
         L.ref_cyl_r_to_xi.argtypes = [C.c_void_p, C.c_double]
         L.ref_cyl_z_to_y.restype = C.c_double
@@ -252,6 +256,44 @@ class RefCylinder:
 
     def r_to_xi(self, r): return lib().ref_cyl_r_to_xi(self.h, float(r))
     def z_to_y(self, z): return lib().ref_cyl_z_to_y(self.h, float(z))
+
+    def coef_thread(self, pos, mass, level=None, nlev=1, mlevel=0, center=None, rtrunc=1.0e20, rcylmax=20.0,
+                    acyl=0.01, adb=1.0, body=None, orig=None):
+        """Cylinder::determine_coefficients_thread (src/Cylinder.cc:748-896) for levlist[mlevel], one thread
+        -> cos, sin [(mmax+1)][norder], used, cylmass0"""
+        pos, mass = _f64(pos), _f64(mass)
+        lev = None if level is None else np.ascontiguousarray(level, dtype=np.uint32)
+        ctr = None if center is None else _f64(center)
+        b, o = (None, None) if body is None else (_f64(body), _f64(orig))
+        cs, sn = np.zeros((self.mmax + 1, self.norder)), np.zeros((self.mmax + 1, self.norder))
+        used, cm = C.c_int(0), C.c_double(0.0)
+        lib().ref_cylinder_coef_thread(self.h, len(pos), _dp(pos), _dp(mass),
+                                       None if lev is None else lev.ctypes.data_as(c_up), nlev, mlevel,
+                                       None if ctr is None else _dp(ctr), rtrunc, rcylmax, acyl, adb,
+                                       None if b is None else _dp(b), None if o is None else _dp(o),
+                                       _dp(cs), _dp(sn), C.byref(used), C.byref(cm))
+        return cs, sn, used.value, cm.value
+
+    def accel_thread(self, pos, cos, sin, cylmass, level=None, nlev=1, mlevel=0, center=None, rtrunc=1.0e20,
+                     owner_center=None, body=None, orig=None, acc=None, pot=None):
+        """Cylinder::determine_acceleration_and_potential_thread (src/Cylinder.cc:1266-1446) for the levels
+        >= mlevel, one thread; owner_center: the use_external case.  Returns acc [n][3], pot [n] (added to
+        the given ones)."""
+        pos = _f64(pos)
+        n = len(pos)
+        lev = None if level is None else np.ascontiguousarray(level, dtype=np.uint32)
+        ctr = None if center is None else _f64(center)
+        own = None if owner_center is None else _f64(owner_center)
+        b, o = (None, None) if body is None else (_f64(body), _f64(orig))
+        acc = np.zeros((n, 3)) if acc is None else _f64(acc).copy()
+        pot = np.zeros(n) if pot is None else _f64(pot).copy()
+        cs, sn = _f64(cos), _f64(sin)
+        lib().ref_cylinder_accel_thread(self.h, n, _dp(pos), None if lev is None else lev.ctypes.data_as(c_up),
+                                        nlev, mlevel, None if ctr is None else _dp(ctr), rtrunc,
+                                        None if own is None else _dp(own), _dp(cs), _dp(sn), float(cylmass),
+                                        None if b is None else _dp(b), None if o is None else _dp(o),
+                                        _dp(acc), _dp(pot))
+        return acc, pot
 
     def get_pot(self, r, z):
         Vc, Vs = np.zeros((self.mmax + 1, self.norder)), np.zeros((self.mmax + 1, self.norder))

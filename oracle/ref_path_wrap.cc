@@ -620,6 +620,129 @@ long ref_adjust_levels(long n, const double *vel, const double *acc, const doubl
 
 
 // =============================================================================================
+// Cylinder::determine_coefficients_thread / determine_acceleration_and_potential_thread
+// (src/Cylinder.cc:748-896, 1266-1446), the reference's own bodies over the EmpCylSL of a
+// ref_cyl_create handle and a flat Component: centre / rtrunc gate, body-frame rotation, the
+// rcylmax gate, the erf blend to the monopole and the rotation of the force back.
+// =============================================================================================
+class Cylinder : public Basis {
+public:
+  EmpCylSL *ortho = nullptr;
+  MixtureBasis *mix = nullptr;
+  bool eof = false, compute = false;
+  double rcylmax = 20.0, acyl = 1.0, cylmass = 0.0;
+  std::vector<Eigen::Vector3d> pos, frc;
+  std::vector<double> cylmass0;
+  std::vector<int> offgrid;
+  void *determine_coefficients_thread(void *arg);
+  void *determine_acceleration_and_potential_thread(void *arg);
+};
+
+#include "_ref/gen/cylinder_coef_thread.inc"
+#include "_ref/gen/cylinder_accel_thread.inc"
+
+namespace {
+void cyl_component(Component &c, Orient &o, long n, const double *pos, const double *mass, const double *acc,
+                   const double *pot, const unsigned *level, int nlev, const double *center, double rtrunc,
+                   const double *body, const double *orig)
+{
+  fill_component(c, n, pos, nullptr, acc, pot, nullptr, mass, nullptr, level, nullptr, center, rtrunc);
+  c.levlist.assign(nlev, std::vector<int>());
+  for (long i = 0; i < n; i++) c.levlist[level ? level[i] : 0].push_back((int)i);
+  for (long i = 0; i < n; i++) c.pmap[(unsigned long)i] = &c.store[i];
+  if (body) {
+    for (int k = 0; k < 9; k++) { o.body.m[k] = body[k]; o.orig.m[k] = orig[k]; }
+    c.EJ = Orient::AXIS;
+    c.orient = &o;
+  }
+}
+} // namespace
+
+extern "C" {
+
+/* coefficient thread for levlist[mlevel] of one component, one thread: cosN/sinN [(MMAX+1)][NORDER],
+ * *used, *cylmass0 as Cylinder::determine_coefficients sums them over threads (:1080-1086) */
+void ref_cylinder_coef_thread(void *hh, long n, const double *pos, const double *mass, const unsigned *level,
+                              int nlev, int mlevel, const double *center, double rtrunc, double rcylmax,
+                              double acyl, double adb, const double *body, const double *orig, double *cosN,
+                              double *sinN, int *used, double *cylmass0)
+{
+  EmpCylSL &e = static_cast<CylHandle *>(hh)->e;
+  const int M = e.MMAX, N = e.NORDER;
+  e.coefs_made.assign(nlev, false);
+  e.howmany1.assign(nlev, std::vector<unsigned>(1, 0));
+  e.vc.assign(1, Eigen::MatrixXd());
+  e.vs.assign(1, Eigen::MatrixXd());
+  e.cylmass1.assign(1, 0.0);
+  e.cosN.clear(); e.sinN.clear();
+  for (int L = 0; L < nlev; L++) {
+    e.cosN.push_back(std::make_shared<EmpCylSL::VectorD2>(1, std::vector<Eigen::VectorXd>(M + 1, Eigen::VectorXd(N))));
+    e.sinN.push_back(std::make_shared<EmpCylSL::VectorD2>(1, std::vector<Eigen::VectorXd>(M + 1, Eigen::VectorXd(N))));
+  }
+  e.covar = e.PCAVAR = e.PCAEOF = false;
+  Component c;
+  Orient o;
+  cyl_component(c, o, n, pos, mass, nullptr, nullptr, level, nlev, center, rtrunc, body, orig);
+  c.adiabatic_value = adb;
+  Cylinder cy;
+  cy.ortho = &e; cy.component = &c; cy.cC = &c; cy.mlevel = (unsigned)mlevel;
+  cy.rcylmax = rcylmax; cy.acyl = acyl;
+  cy.pos.resize(1); cy.frc.resize(1); cy.use.assign(1, 0); cy.cylmass0.assign(1, 0.0);
+  multistep = (unsigned)(nlev - 1);
+  nthrds = 1;
+  int id = 0;
+  cy.determine_coefficients_thread(&id);
+  for (int m = 0; m <= M; m++)
+    for (int k = 0; k < N; k++) {
+      cosN[(size_t)m * N + k] = e.cosN(mlevel)[0][m][k];
+      sinN[(size_t)m * N + k] = e.sinN(mlevel)[0][m][k];
+    }
+  *used = cy.use[0];
+  *cylmass0 = cy.cylmass0[0];
+}
+
+/* force thread: levels >= mlevel of the target component (pos/level/center/rtrunc) with the
+ * coefficients accum_cos/accum_sin and cylmass installed; owner_center != NULL is the use_external
+ * case (origin = the owning component's centre, orientation = the owner's).  acc[n][3], pot[n] are
+ * added to. */
+void ref_cylinder_accel_thread(void *hh, long n, const double *pos, const unsigned *level, int nlev, int mlevel,
+                               const double *center, double rtrunc, const double *owner_center,
+                               const double *accum_cos, const double *accum_sin, double cylmass,
+                               const double *body, const double *orig, double *acc, double *pot)
+{
+  EmpCylSL &e = static_cast<CylHandle *>(hh)->e;
+  for (int m = 0; m <= e.MMAX; m++)
+    for (int k = 0; k < e.NORDER; k++) {
+      e.accum_cos[m][k] = accum_cos[(size_t)m * e.NORDER + k];
+      e.accum_sin[m][k] = accum_sin[(size_t)m * e.NORDER + k];
+    }
+  Component target, owner;
+  Orient o, o2;
+  cyl_component(target, o2, n, pos, nullptr, acc, pot, level, nlev, center, rtrunc, nullptr, nullptr);
+  Cylinder cy;
+  cy.ortho = &e; cy.cC = &target; cy.mlevel = (unsigned)mlevel; cy.cylmass = cylmass;
+  if (owner_center) {
+    cyl_component(owner, o, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nlev, owner_center, 1.0e20, body, orig);
+    cy.component = &owner;
+    cy.use_external = 1;
+  } else {
+    if (body) { for (int k = 0; k < 9; k++) { o.body.m[k] = body[k]; o.orig.m[k] = orig[k]; } target.EJ = Orient::AXIS; target.orient = &o; }
+    cy.component = &target;
+  }
+  cy.pos.resize(1); cy.frc.resize(1); cy.offgrid.assign(1, 0);
+  multistep = (unsigned)(nlev - 1);
+  nthrds = 1;
+  int id = 0;
+  cy.determine_acceleration_and_potential_thread(&id);
+  for (long i = 0; i < n; i++) {
+    for (int k = 0; k < 3; k++) acc[3 * i + k] = target.store[i].acc[k];
+    pot[i] = target.store[i].pot;
+  }
+}
+
+} // extern "C"
+
+// =============================================================================================
 // pyEXP twin: BasisClasses::Spherical::accumulate / sph_eval / cyl_eval / crt_eval / computeAccel
 // and BiorthBasis::legendre_R, the reference's own bodies (expui/BiorthBasis.cc, cut by
 // ref_extract.py) over the SLGridSph of a ref_sph_create handle.  accumulate is compiled around its

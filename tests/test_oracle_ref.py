@@ -393,3 +393,55 @@ def test_pyexp_twin_against_reference(flags, scale):
     assert np.abs(s_ref - s_or).max() <= 1e-12 * np.abs(s_ref).max()
     acc = rp.accel(pts)
     assert np.abs(acc - f_ref[:, 6:9]).max() <= 1e-11 * np.abs(acc).max()
+
+
+# ---- Cylinder thread functions (src/Cylinder.cc) ------------------------------------------------
+def _rot(th=0.3, ph=0.2):
+    cz, sz, cx, sx = math.cos(th), math.sin(th), math.cos(ph), math.sin(ph)
+    A = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]]) @ np.array([[1.0, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    return np.ascontiguousarray(A), np.ascontiguousarray(A.T)
+
+
+@pytest.mark.parametrize("rotate", [False, True])
+def test_cylinder_threads_bit_exact(rotate):
+    """a16/a19: Cylinder::determine_coefficients_thread and determine_acceleration_and_potential_thread
+    (src/Cylinder.cc:748-896, 1266-1446) -- centre, rtrunc and rcylmax gates, adiabatic factor, body-frame
+    rotation, erf blend to the monopole, the force rotated back, levels >= mlevel -- against the oracle's
+    restatement, bit for bit"""
+    from test_emul_cyl import disk
+    tab, g, consts = _cyl()
+    ref = R.RefCylinder(tab, consts)
+    n = 6000
+    pos, vel, mass = disk(n)
+    rng = np.random.default_rng(12)
+    pos[: n // 6] *= rng.uniform(5.0, 40.0, size=(n // 6, 1))        # beyond rcylmax, into the blend and past the table
+    ctr = np.array([0.002, -0.001, 0.0005])
+    pos = pos + ctr
+    lev = rng.integers(0, 3, n).astype(np.uint32)
+    body, orig = _rot() if rotate else (None, None)
+    kw = dict(rcylmax=6.0, acyl=tab.ascale)
+    P = O.cyl_params(body=body, orig=orig, **kw)
+    S = O.ParticleSet(pos, vel, mass, center=ctr, rtrunc=0.2, level=lev)
+    for M in (0, 2):
+        cs, sn, used, cm = O.cyl_coefficients(g, P, S, lst=S.levlist(M), adb=0.7)
+        rc, rs, rused, rcm = ref.coef_thread(pos, mass, level=lev, nlev=3, mlevel=M, center=ctr, rtrunc=0.2,
+                                             adb=0.7, body=body, orig=orig, **kw)
+        assert used == rused and 0 < used < len(S.levlist(M))
+        assert cs.tobytes() == rc.tobytes() and sn[1:].tobytes() == rs[1:].tobytes()
+        assert cm == rcm
+    cs, sn, used, cm = O.cyl_coefficients(g, P, S)
+    act = np.nonzero(lev >= 1)[0].astype(np.int32)
+    S.acc[:] = 0.01
+    S.pot[:] = -0.5
+    O.cyl_accel(g, P, S, cs, sn, cm, lst=act)
+    racc, rpot = ref.accel_thread(pos, cs, sn, cm, level=lev, nlev=3, mlevel=1, center=ctr, rtrunc=0.2,
+                                  body=body, orig=orig, acc=np.full((n, 3), 0.01), pot=np.full(n, -0.5))
+    assert S.acc.tobytes() == racc.tobytes() and S.pot.tobytes() == rpot.tobytes()
+    assert np.all(racc[lev < 1] == 0.01)
+    # use_external: the origin and the orientation are the owning component's, the particles another's
+    own = ctr + np.array([0.01, 0.02, -0.005])
+    S2 = O.ParticleSet(pos, vel, mass, center=own, rtrunc=0.2, level=lev)
+    O.cyl_accel(g, P, S2, cs, sn, cm, lst=act)
+    racc2, rpot2 = ref.accel_thread(pos, cs, sn, cm, level=lev, nlev=3, mlevel=1, center=ctr, rtrunc=0.2,
+                                    owner_center=own, body=body, orig=orig)
+    assert S2.acc.tobytes() == racc2.tobytes() and S2.pot.tobytes() == rpot2.tobytes()
