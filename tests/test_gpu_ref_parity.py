@@ -342,3 +342,54 @@ def test_pyexp_sphere_against_reference_code():
         assert np.abs(got[6:9, j] - ref[j, 6:9]).max() <= 1e-8 * fn
         assert np.abs(got[0:3, j] - ref[j, 0:3]).max() <= 1e-8 * max(abs(ref[j, 2]), abs(ref[j, 0]))
         assert np.abs(acc[j] - racc[j]).max() <= 1e-8 * fn
+
+
+@pytest.mark.parametrize("rotate", [False, True])
+def test_cylinder_threads_vs_reference_code(rotate):
+    """the GPU cylinder path against the reference's own Cylinder thread functions
+    (src/Cylinder.cc:748-896, 1266-1446): centre, rtrunc and rcylmax gates, adiabatic factor, body-frame
+    rotation, the erf blend to the monopole, multistep levels"""
+    tab = cyltable.synthetic_cyl_table(mmax=4, norder=8, numx=64, numy=32)
+    g = O.CylGridPy(tab)
+    consts = (g.c.Rtable, g.c.XMIN, g.c.dX, g.c.YMIN, g.c.dY)
+    ref = R.RefCylinder(tab, consts)
+    n = 30000
+    pos, vel, mass = ics.exponential_disk(n, seed=45)
+    rng = np.random.default_rng(13)
+    pos[: n // 6] *= rng.uniform(5.0, 40.0, size=(n // 6, 1))       # blend region and beyond the table
+    ctr = np.array([0.002, -0.001, 0.0005])
+    pos = pos + ctr
+    lev = rng.integers(0, 3, n).astype(np.uint32)
+    body = orig = None
+    if rotate:
+        th, ph = 0.3, 0.2
+        A = (np.array([[math.cos(th), -math.sin(th), 0], [math.sin(th), math.cos(th), 0], [0, 0, 1.0]])
+             @ np.array([[1.0, 0, 0], [0, math.cos(ph), -math.sin(ph)], [0, math.sin(ph), math.cos(ph)]]))
+        body, orig = np.ascontiguousarray(A), np.ascontiguousarray(A.T)
+    kw = dict(rcylmax=6.0, acyl=tab.ascale)
+    c = Component(n)
+    c.upload(pos, vel, mass, level=lev)
+    c.set_center(ctr, rtrunc=0.2)
+    cyl = Cylinder(tab, multistep=2, **kw)
+    if rotate:
+        cyl.set_orientation(body, orig)
+    tot_c, tot_s, tot_m = 0.0, 0.0, 0.0
+    for M in range(3):
+        rc, rs, rused, rcm = ref.coef_thread(pos, mass, level=lev, nlev=3, mlevel=M, center=ctr, rtrunc=0.2,
+                                             adb=0.7, body=body, orig=orig, **kw)
+        cyl.set_multistep_level(M)
+        cs, sn = cyl.determine_coefficients(c, adb=0.7)
+        assert cyl.used == rused
+        assert rel_rms(cs, rc) <= 1e-10 and rel_rms(sn[1:], rs[1:]) <= 1e-10
+        tot_c, tot_s, tot_m = tot_c + rc, tot_s + rs, tot_m + rcm
+    cyl.set_coefficients(tot_c, tot_s, tot_m)
+    cyl.set_multistep_level(1)
+    c.zero_pot_acc()
+    cyl.get_acceleration_and_potential(c)
+    out = c.download()
+    racc, rpot = ref.accel_thread(pos, tot_c, tot_s, tot_m, level=lev, nlev=3, mlevel=1, center=ctr, rtrunc=0.2,
+                                  body=body, orig=orig)
+    act = lev >= 1
+    assert acc_rel_err(out["acc"][act], racc[act]).max() <= 1e-8
+    assert np.abs(out["pot"][act] - rpot[act]).max() <= 1e-8 * np.abs(rpot).max()
+    assert np.all(out["acc"][~act] == 0.0)
