@@ -49,6 +49,8 @@ PIECES = {
     # erf blend to the monopole)
     "cylinder_coef_thread": ("src/Cylinder.cc", 748, 896, r"^void \* Cylinder::determine_coefficients_thread\(void \* arg\)"),
     "cylinder_accel_thread": ("src/Cylinder.cc", 1266, 1446, r"^void \* Cylinder::determine_acceleration_and_potential_thread\(void \* arg\)"),
+    # --- centre-of-mass sums (src/Component.cc): thrd_pass_posn + fix_positions_thread
+    "fix_positions_thread": ("src/Component.cc", 3266, 3352, r"^struct thrd_pass_posn"),
     # --- pyEXP twin (expui/BiorthBasis.cc): BasisClasses::Spherical accumulate / field evaluation.
     # accumulate is cut around its pcavar block (lines 652-659: Eigen expression templates on complex
     # vectors, the covariance of pyEXP's own subsampling, not on the path)

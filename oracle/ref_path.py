@@ -84,6 +84,8 @@ def lib():
         L.ref_pyexp_accel.argtypes = [C.c_void_p, C.c_size_t, c_dp, c_dp]
         L.ref_cyl_create.argtypes = [C.c_int] * 6 + [C.c_double] * 7 + [c_ip] + [c_dp] * 6
         L.ref_cyl_destroy.argtypes = [C.c_void_p]
+        L.ref_fix_positions.argtypes = [C.c_long, c_dp, c_dp, c_dp, c_dp, c_up, C.c_int, C.c_int, C.c_int, c_dp,
+                                        C.c_double, c_dp]
         L.ref_cylinder_coef_thread.argtypes = ([C.c_void_p, C.c_long, c_dp, c_dp, c_up, C.c_int, C.c_int, c_dp]
                                                + [C.c_double] * 4 + [c_dp] * 4 + [c_ip, c_dp])
         L.ref_cylinder_accel_thread.argtypes = ([C.c_void_p, C.c_long, c_dp, c_up, C.c_int, C.c_int, c_dp, C.c_double,
@@ -425,3 +427,15 @@ class RefPyexp:
         out = np.zeros((len(pos), 3))
         lib().ref_pyexp_accel(self.h, len(pos), _dp(pos), _dp(out))
         return out
+
+
+def fix_positions(pos, vel, acc, mass, level, nlev, mlevel=0, dim=3, center=(0.0, 0.0, 0.0), rtrunc=1.0e20):
+    """fix_positions_thread (src/Component.cc:3280-3352), one thread -> [nlev][10] = mtot, com, cov, coa
+    per level (rows below mlevel zero)"""
+    pos, vel, acc, mass = _f64(pos), _f64(vel), _f64(acc), _f64(mass)
+    lev = np.ascontiguousarray(level, dtype=np.uint32)
+    ctr = _f64(center)
+    out = np.zeros((nlev, 10))
+    lib().ref_fix_positions(len(pos), _dp(pos), _dp(vel), _dp(acc), _dp(mass), lev.ctypes.data_as(c_up), nlev,
+                            mlevel, dim, _dp(ctr), float(rtrunc), _dp(out))
+    return out

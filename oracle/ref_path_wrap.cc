@@ -743,6 +743,40 @@ void ref_cylinder_accel_thread(void *hh, long n, const double *pos, const unsign
 } // extern "C"
 
 // =============================================================================================
+// fix_positions_thread (src/Component.cc:3266-3352): per-level sums of mass, mass*pos, mass*vel,
+// mass*acc over the non-frozen particles of the levels >= mlevel
+// =============================================================================================
+#include "_ref/gen/fix_positions_thread.inc"
+
+extern "C" {
+/* out[nlev][10] = {mtot, com[3], cov[3], coa[3]} per level (rows below mlevel stay zero) */
+void ref_fix_positions(long n, const double *pos, const double *vel, const double *acc, const double *mass,
+                       const unsigned *level, int nlev, int mlevel, int dim, const double *center, double rtrunc,
+                       double *out)
+{
+  Component c;
+  fill_component(c, n, pos, vel, acc, nullptr, nullptr, mass, nullptr, level, nullptr, center, rtrunc);
+  c.dim = dim;
+  c.levlist.assign(nlev, std::vector<int>());
+  for (long i = 0; i < n; i++) c.levlist[level ? level[i] : 0].push_back((int)i);
+  multistep = (unsigned)(nlev - 1);
+  nthrds = 1;
+  thrd_pass_posn d;
+  d.id = 0; d.c = &c; d.tidal = -1; d.consp = false; d.com_system = false; d.mlevel = (unsigned)mlevel;
+  d.com.assign(3 * nlev, 0.0); d.cov.assign(3 * nlev, 0.0); d.coa.assign(3 * nlev, 0.0); d.mtot.assign(nlev, 0.0);
+  fix_positions_thread(&d);
+  for (int mm = 0; mm < nlev; mm++) {
+    out[10 * mm] = d.mtot[mm];
+    for (int k = 0; k < 3; k++) {
+      out[10 * mm + 1 + k] = d.com[3 * mm + k];
+      out[10 * mm + 4 + k] = d.cov[3 * mm + k];
+      out[10 * mm + 7 + k] = d.coa[3 * mm + k];
+    }
+  }
+}
+} // extern "C"
+
+// =============================================================================================
 // pyEXP twin: BasisClasses::Spherical::accumulate / sph_eval / cyl_eval / crt_eval / computeAccel
 // and BiorthBasis::legendre_R, the reference's own bodies (expui/BiorthBasis.cc, cut by
 // ref_extract.py) over the SLGridSph of a ref_sph_create handle.  accumulate is compiled around its

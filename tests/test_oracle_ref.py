@@ -445,3 +445,21 @@ def test_cylinder_threads_bit_exact(rotate):
     racc2, rpot2 = ref.accel_thread(pos, cs, sn, cm, level=lev, nlev=3, mlevel=1, center=ctr, rtrunc=0.2,
                                     owner_center=own, body=body, orig=orig)
     assert S2.acc.tobytes() == racc2.tobytes() and S2.pot.tobytes() == rpot2.tobytes()
+
+
+@pytest.mark.parametrize("mlevel,dim", [(0, 3), (1, 3), (0, 2)])
+def test_fix_positions_bit_exact(mlevel, dim):
+    """f1: fix_positions_thread (src/Component.cc:3280-3352) -- per-level mass, m*pos, m*vel, m*acc of the
+    non-frozen particles of the levels >= mlevel -- against the oracle, bit for bit"""
+    n = 8000
+    pos, vel, mass = ics.hernquist_halo(n, seed=21)
+    rng = np.random.default_rng(4)
+    acc = rng.normal(size=(n, 3))
+    lev = rng.integers(0, 4, n).astype(np.uint32)
+    ctr = np.array([0.05, -0.02, 0.01])
+    S = O.ParticleSet(pos, vel, mass, center=ctr, rtrunc=2.0, level=lev)
+    S.acc[:] = acc
+    sums, _ = O.fix_positions(S, mlevel, 3, dim=dim)
+    ref = R.fix_positions(pos, vel, acc, mass, lev, 4, mlevel=mlevel, dim=dim, center=ctr, rtrunc=2.0)
+    assert sums.tobytes() == ref.tobytes()
+    assert np.all(ref[:mlevel] == 0.0) and ref[mlevel:, 0].sum() < mass[lev >= mlevel].sum()   # rtrunc bites
