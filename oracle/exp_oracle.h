@@ -25,8 +25,9 @@
  * sph_eval / cyl_eval / crt_eval / computeAccel and BiorthBasis::legendre_R (expui/BiorthBasis.cc,
  * same mechanism) to 1e-13, and the Cylinder:: thread functions around EmpCylSL (centre / rtrunc /
  * rcylmax gates, orientation, erf blend to the monopole; src/Cylinder.cc:748-896, 1266-1446) bit
- * for bit, as is fix_positions_thread (src/Component.cc:3280-3352).  Not pinned (restated only): the
- * multistep difference tables and the cylindrical pyEXP twin.
+ * for bit, as are fix_positions_thread (src/Component.cc:3280-3352) and SphericalBasis::multistep_update
+ * (src/SphericalBasis.cc:1156-1228).  Not pinned (restated only): the cylinder's multistep difference
+ * tables (CylEXP::multistep_update) and the cylindrical pyEXP twin.
  *
  * All arrays are plain row-major C arrays.  Coefficient layout is the
  * reference's: row index = l*l + {0 (m=0), 2m-1 (cos), 2m (sin)}, nmax

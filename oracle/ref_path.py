@@ -68,6 +68,9 @@ def lib():
         L.ref_sph_accel.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip, C.c_long,
                                     c_dp, c_dp, C.c_double, c_ip, C.c_long, c_dp, C.c_int, c_dp,
                                     c_dp, c_dp]
+        L.ref_sph_multistep_update.argtypes = ([C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip, C.c_long, c_dp,
+                                                c_dp, c_dp, C.c_double, C.c_double, C.c_int, C.c_long, c_ip, c_ip,
+                                                c_ip, c_dp])
         L.ref_sph_load.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip, C.c_long, c_dp, c_dp,
                                    c_dp, C.c_int]
         L.ref_sph_step.restype = C.c_long
@@ -147,6 +150,18 @@ class RefSphere:
             lib().ref_sph_destroy(self.h)
         except Exception:
             pass
+
+    def multistep_update(self, pos, mass, idx, frm, to, nlev, center=(0.0, 0.0, 0.0), rtrunc=1.0e20, adb=1.0):
+        """SphericalBasis::multistep_update (src/SphericalBasis.cc:1156-1228) for the switching particles
+        idx (old level frm, new level to) -> differ [nlev][(lmax+1)^2][nmax]"""
+        pos, mass, ctr = _f64(pos), _f64(mass), _f64(center)
+        idx, frm, to = (np.ascontiguousarray(a, dtype=np.int32) for a in (idx, frm, to))
+        out = np.zeros((nlev, (self.lmax + 1) ** 2, self.nmax))
+        lib().ref_sph_multistep_update(self.h, self.scale, self.rmin, self.rmax, self.flags, len(pos), _dp(pos),
+                                       _dp(mass), _dp(ctr), float(rtrunc), float(adb), nlev, len(idx),
+                                       idx.ctypes.data_as(c_ip), frm.ctypes.data_as(c_ip),
+                                       to.ctypes.data_as(c_ip), _dp(out))
+        return out
 
     def consts(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

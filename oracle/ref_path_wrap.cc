@@ -75,6 +75,8 @@ void SphericalBasis::setup(int L, int N, int nthr)
   (void)ldim;
 }
 
+#include "_ref/gen/sph_multistep_update.inc"
+
 #include "_ref/gen/cyl_r_to_xi.inc"
 #include "_ref/gen/cyl_z_to_y.inc"
 #include "_ref/gen/cyl_get_pot.inc"
@@ -740,6 +742,29 @@ void ref_cylinder_accel_thread(void *hh, long n, const double *pos, const unsign
   }
 }
 
+} // extern "C"
+
+// SphericalBasis::multistep_update (src/SphericalBasis.cc:1156-1228) for a list of switching
+// particles: differ[nlev][(Lmax+1)^2][nmax] accumulates -contribution at the old level and
+// +contribution at the new one
+extern "C" {
+void ref_sph_multistep_update(void *hh, double scale, double rmin, double rmax, const int *flags, long n,
+                              const double *pos, const double *mass, const double *center, double rtrunc,
+                              double adb, int nlev, long nsw, const int *idx, const int *from, const int *to,
+                              double *differ)
+{
+  SphHandle *h = static_cast<SphHandle *>(hh);
+  sph_config(h, scale, rmin, rmax, flags, 1);
+  Sphere &s = h->sph;
+  fill_component(h->comp, n, pos, nullptr, nullptr, nullptr, nullptr, mass, nullptr, nullptr, nullptr, center, rtrunc);
+  h->comp.adiabatic_value = adb;
+  const int nrow = (s.Lmax + 1) * (s.Lmax + 1), N = s.nmax;
+  s.differ1.assign(1, std::vector<Eigen::MatrixXd>(nlev, Eigen::MatrixXd(nrow, N)));
+  for (long k = 0; k < nsw; k++) s.multistep_update(from[k], to[k], &h->comp, idx[k], 0);
+  for (int L = 0; L < nlev; L++)
+    for (int r = 0; r < nrow; r++)
+      for (int c = 0; c < N; c++) differ[((size_t)L * nrow + r) * N + c] = s.differ1[0][L](r, c);
+}
 } // extern "C"
 
 // =============================================================================================

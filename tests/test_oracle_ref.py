@@ -463,3 +463,29 @@ def test_fix_positions_bit_exact(mlevel, dim):
     ref = R.fix_positions(pos, vel, acc, mass, lev, 4, mlevel=mlevel, dim=dim, center=ctr, rtrunc=2.0)
     assert sums.tobytes() == ref.tobytes()
     assert np.all(ref[:mlevel] == 0.0) and ref[mlevel:, 0].sum() < mass[lev >= mlevel].sum()   # rtrunc bites
+
+
+def test_sphere_multistep_update_bit_exact():
+    """a13: SphericalBasis::multistep_update (src/SphericalBasis.cc:1156-1228): the switching particle's
+    contribution leaves differ[old level] and enters differ[new level] (freeze and rmax gates, adiabatic
+    factor, scale) -- oracle against the reference's own code, bit for bit"""
+    tab = get_table("hernquist", 4, 8)
+    n = 3000
+    pos, vel, mass = ics.hernquist_halo(n, seed=23)
+    ctr = np.array([0.01, -0.02, 0.005])
+    pos = pos * 0.5 + ctr
+    rng = np.random.default_rng(6)
+    idx = rng.choice(n, 400, replace=False).astype(np.int32)
+    frm = rng.integers(0, 4, 400).astype(np.int32)
+    to = (frm + rng.integers(1, 4, 400)).astype(np.int32) % 4
+    rmax = tab.rmax * 0.5 * 0.3                     # the r < rmax gate bites
+    ref = R.RefSphere(tab, scale=0.5, rmin=tab.rmin * 0.5, rmax=rmax)
+    want = ref.multistep_update(pos, mass, idx, frm, to, 4, center=ctr, rtrunc=1.5, adb=0.8)
+    g = O.Grid(tab)
+    P = O.sph_params(scale=0.5, rmin=tab.rmin * 0.5, rmax=rmax)
+    S = O.ParticleSet(pos, vel, mass, center=ctr, rtrunc=1.5)
+    d = np.zeros((4, (tab.lmax + 1) ** 2, tab.nmax))
+    for i, a, b in zip(idx, frm, to):
+        O.sph_multistep_update(g, P, S, int(i), int(a), int(b), d, adb=0.8)
+    assert d.tobytes() == want.tobytes()
+    assert np.abs(want).max() > 0 and np.abs(want.sum(axis=0)).max() <= 1e-12 * np.abs(want).max()
