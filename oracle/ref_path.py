@@ -87,6 +87,8 @@ def lib():
         L.ref_pyexp_accel.argtypes = [C.c_void_p, C.c_size_t, c_dp, c_dp]
         L.ref_cyl_create.argtypes = [C.c_int] * 6 + [C.c_double] * 7 + [c_ip] + [c_dp] * 6
         L.ref_cyl_destroy.argtypes = [C.c_void_p]
+        L.ref_cylinder_multistep_update.argtypes = [C.c_void_p, C.c_long, c_dp, c_dp, c_dp, C.c_double, C.c_double,
+                                                    C.c_int, C.c_long, c_ip, c_ip, c_ip, c_dp, c_dp]
         L.ref_fix_positions.argtypes = [C.c_long, c_dp, c_dp, c_dp, c_dp, c_up, C.c_int, C.c_int, C.c_int, c_dp,
                                         C.c_double, c_dp]
         L.ref_cylinder_coef_thread.argtypes = ([C.c_void_p, C.c_long, c_dp, c_dp, c_up, C.c_int, C.c_int, c_dp]
@@ -290,6 +292,18 @@ class RefCylinder:
                                        None if b is None else _dp(b), None if o is None else _dp(o),
                                        _dp(cs), _dp(sn), C.byref(used), C.byref(cm))
         return cs, sn, used.value, cm.value
+
+    def multistep_update(self, pos, mass, idx, frm, to, nlev, center=(0.0, 0.0, 0.0), rtrunc=1.0e20, adb=1.0):
+        """Cylinder::multistep_update -> CylEXP::multistep_update (src/Cylinder.cc:1752-1773,
+        src/CylEXP.cc:159-188) for the switching particles -> differC, differS [nlev][mmax+1][norder]"""
+        pos, mass, ctr = _f64(pos), _f64(mass), _f64(center)
+        idx, frm, to = (np.ascontiguousarray(a, dtype=np.int32) for a in (idx, frm, to))
+        dC = np.zeros((nlev, self.mmax + 1, self.norder))
+        dS = np.zeros((nlev, self.mmax + 1, self.norder))
+        lib().ref_cylinder_multistep_update(self.h, len(pos), _dp(pos), _dp(mass), _dp(ctr), float(rtrunc),
+                                            float(adb), nlev, len(idx), idx.ctypes.data_as(c_ip),
+                                            frm.ctypes.data_as(c_ip), to.ctypes.data_as(c_ip), _dp(dC), _dp(dS))
+        return dC, dS
 
     def accel_thread(self, pos, cos, sin, cylmass, level=None, nlev=1, mlevel=0, center=None, rtrunc=1.0e20,
                      owner_center=None, body=None, orig=None, acc=None, pot=None):

@@ -389,7 +389,16 @@ void ref_sph_read(void *hh, double *pos, double *vel, double *acc, double *pot, 
 }
 
 /* ---- EmpCylSL ------------------------------------------------------------------------------ */
-struct CylHandle { EmpCylSL e; };
+/* CylEXP (src/CylEXP.H): EmpCylSL + the multistep level tables; only the level-switch update is
+ * compiled here (src/CylEXP.cc:159-188) */
+class CylEXP : public EmpCylSL {
+public:
+  std::vector<std::vector<Eigen::MatrixXd>> differC1, differS1;     /* [thread][level](MMAX+1, rank3) */
+  void multistep_update(int from, int to, double r, double z, double phi, double mass, int id);
+};
+#include "_ref/gen/cylexp_multistep_update.inc"
+
+struct CylHandle { CylEXP e; };
 
 void *ref_cyl_create(int MMAX, int NORDER, int NUMX, int NUMY, int CMAPR, int CMAPZ, double ASCALE,
                      double HSCALE, double Rtable, double XMIN, double dX, double YMIN, double dY,
@@ -629,7 +638,9 @@ long ref_adjust_levels(long n, const double *vel, const double *acc, const doubl
 // =============================================================================================
 class Cylinder : public Basis {
 public:
-  EmpCylSL *ortho = nullptr;
+  CylEXP *ortho = nullptr;
+  bool play_back = false, self_consistent = true;
+  void multistep_update(int from, int to, Component *c, int i, int id) override;
   MixtureBasis *mix = nullptr;
   bool eof = false, compute = false;
   double rcylmax = 20.0, acyl = 1.0, cylmass = 0.0;
@@ -640,6 +651,7 @@ public:
   void *determine_acceleration_and_potential_thread(void *arg);
 };
 
+#include "_ref/gen/cylinder_multistep_update.inc"
 #include "_ref/gen/cylinder_coef_thread.inc"
 #include "_ref/gen/cylinder_accel_thread.inc"
 
@@ -669,7 +681,7 @@ void ref_cylinder_coef_thread(void *hh, long n, const double *pos, const double 
                               double acyl, double adb, const double *body, const double *orig, double *cosN,
                               double *sinN, int *used, double *cylmass0)
 {
-  EmpCylSL &e = static_cast<CylHandle *>(hh)->e;
+  CylEXP &e = static_cast<CylHandle *>(hh)->e;
   const int M = e.MMAX, N = e.NORDER;
   e.coefs_made.assign(nlev, false);
   e.howmany1.assign(nlev, std::vector<unsigned>(1, 0));
@@ -703,6 +715,33 @@ void ref_cylinder_coef_thread(void *hh, long n, const double *pos, const double 
   *cylmass0 = cy.cylmass0[0];
 }
 
+/* Cylinder::multistep_update + CylEXP::multistep_update (src/Cylinder.cc:1752-1773, src/CylEXP.cc:159-188)
+ * for a list of switching particles: differC/differS [nlev][MMAX+1][NORDER] */
+void ref_cylinder_multistep_update(void *hh, long n, const double *pos, const double *mass, const double *center,
+                                   double rtrunc, double adb, int nlev, long nsw, const int *idx, const int *from,
+                                   const int *to, double *differC, double *differS)
+{
+  CylEXP &e = static_cast<CylHandle *>(hh)->e;
+  const int M = e.MMAX, N = e.NORDER;
+  e.vc.assign(1, Eigen::MatrixXd());
+  e.vs.assign(1, Eigen::MatrixXd());
+  e.differC1.assign(1, std::vector<Eigen::MatrixXd>(nlev, Eigen::MatrixXd(M + 1, N)));
+  e.differS1.assign(1, std::vector<Eigen::MatrixXd>(nlev, Eigen::MatrixXd(M + 1, N)));
+  Component c;
+  Orient o;
+  cyl_component(c, o, n, pos, mass, nullptr, nullptr, nullptr, 1, center, rtrunc, nullptr, nullptr);
+  c.adiabatic_value = adb;
+  Cylinder cy;
+  cy.ortho = &e; cy.component = &c; cy.cC = &c;
+  for (long k = 0; k < nsw; k++) cy.multistep_update(from[k], to[k], &c, idx[k], 0);
+  for (int L = 0; L < nlev; L++)
+    for (int m = 0; m <= M; m++)
+      for (int k = 0; k < N; k++) {
+        differC[((size_t)L * (M + 1) + m) * N + k] = e.differC1[0][L](m, k);
+        differS[((size_t)L * (M + 1) + m) * N + k] = e.differS1[0][L](m, k);
+      }
+}
+
 /* force thread: levels >= mlevel of the target component (pos/level/center/rtrunc) with the
  * coefficients accum_cos/accum_sin and cylmass installed; owner_center != NULL is the use_external
  * case (origin = the owning component's centre, orientation = the owner's).  acc[n][3], pot[n] are
@@ -712,7 +751,7 @@ void ref_cylinder_accel_thread(void *hh, long n, const double *pos, const unsign
                                const double *accum_cos, const double *accum_sin, double cylmass,
                                const double *body, const double *orig, double *acc, double *pot)
 {
-  EmpCylSL &e = static_cast<CylHandle *>(hh)->e;
+  CylEXP &e = static_cast<CylHandle *>(hh)->e;
   for (int m = 0; m <= e.MMAX; m++)
     for (int k = 0; k < e.NORDER; k++) {
       e.accum_cos[m][k] = accum_cos[(size_t)m * e.NORDER + k];

@@ -489,3 +489,29 @@ def test_sphere_multistep_update_bit_exact():
         O.sph_multistep_update(g, P, S, int(i), int(a), int(b), d, adb=0.8)
     assert d.tobytes() == want.tobytes()
     assert np.abs(want).max() > 0 and np.abs(want.sum(axis=0)).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_cylinder_multistep_update_bit_exact():
+    """a20: Cylinder::multistep_update -> CylEXP::multistep_update (src/Cylinder.cc:1752-1773,
+    src/CylEXP.cc:159-188): the switching particle's contribution moves from differ[old level] to
+    differ[new level] (freeze and table-radius gates, adiabatic factor) -- oracle against the reference's
+    own code, bit for bit"""
+    from test_emul_cyl import disk
+    tab, g, consts = _cyl()
+    ref = R.RefCylinder(tab, consts)
+    n = 4000
+    pos, vel, mass = disk(n)
+    rng = np.random.default_rng(14)
+    pos[: n // 8] *= rng.uniform(5.0, 60.0, size=(n // 8, 1))          # some beyond the table radius
+    ctr = np.array([0.002, -0.001, 0.0005])
+    pos = pos + ctr
+    idx = rng.choice(n, 500, replace=False).astype(np.int32)
+    frm = rng.integers(0, 3, 500).astype(np.int32)
+    to = (frm + rng.integers(1, 3, 500)).astype(np.int32) % 3
+    wC, wS = ref.multistep_update(pos, mass, idx, frm, to, 3, center=ctr, rtrunc=0.3, adb=0.9)
+    S = O.ParticleSet(pos, vel, mass, center=ctr, rtrunc=0.3)
+    dC, dS = np.zeros_like(wC), np.zeros_like(wS)
+    for i, a, b in zip(idx, frm, to):
+        O.cyl_multistep_update(g, S, int(i), int(a), int(b), dC, dS, adb=0.9)
+    assert dC.tobytes() == wC.tobytes() and dS.tobytes() == wS.tobytes()
+    assert np.abs(wC).max() > 0 and np.abs(wC.sum(axis=0)).max() <= 1e-12 * np.abs(wC).max()
