@@ -27,8 +27,9 @@
  * rcylmax gates, orientation, erf blend to the monopole; src/Cylinder.cc:748-896, 1266-1446) bit
  * for bit, as are fix_positions_thread (src/Component.cc:3280-3352) and SphericalBasis::multistep_update
  * (src/SphericalBasis.cc:1156-1228) and Cylinder::multistep_update / CylEXP::multistep_update
- * (src/Cylinder.cc:1752-1773, src/CylEXP.cc:159-188).  Not pinned (restated only): the level-table
- * interpolation (compute_multistep_coefficients) and the cylindrical pyEXP twin.
+ * (src/Cylinder.cc:1752-1773, src/CylEXP.cc:159-188) and the level-table interpolation
+ * SphericalBasis::compute_multistep_coefficients (:1231-1474).  Not pinned (restated only): the
+ * cylinder's copy of that interpolation (src/CylEXP.cc:192-282) and the cylindrical pyEXP twin.
  *
  * All arrays are plain row-major C arrays.  Coefficient layout is the
  * reference's: row index = l*l + {0 (m=0), 2m-1 (cos), 2m (sin)}, nmax

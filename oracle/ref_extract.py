@@ -38,6 +38,7 @@ PIECES = {
     "sph_factorial":       ("src/SphericalBasis.cc", 328, 335, r"^  factorial.resize\(Lmax\+1, Lmax\+1\);"),
     "sph_coef_thread":     ("src/SphericalBasis.cc", 429, 599, r"^void \* SphericalBasis::determine_coefficients_thread\(void \* arg\)"),
     "sph_accel_thread":    ("src/SphericalBasis.cc", 1476, 1660, r"^void \* SphericalBasis::determine_acceleration_and_potential_thread\(void \* arg\)"),
+    "sph_compute_multistep_coefficients": ("src/SphericalBasis.cc", 1231, 1474, r"^void SphericalBasis::compute_multistep_coefficients\(\)"),
     "sph_multistep_update": ("src/SphericalBasis.cc", 1156, 1228, r"^void SphericalBasis::multistep_update\(int from, int to, Component \*c, int i, int id\)"),
     "sph_get_pot_coefs_safe": ("src/SphericalBasis.cc", 1797, 1813, r"^void SphericalBasis::get_pot_coefs_safe\("),
     # --- EmpCylSL (exputil/EmpCylSL.cc)

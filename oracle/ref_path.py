@@ -71,6 +71,8 @@ def lib():
         L.ref_sph_multistep_update.argtypes = ([C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip, C.c_long, c_dp,
                                                 c_dp, c_dp, C.c_double, C.c_double, C.c_int, C.c_long, c_ip, c_ip,
                                                 c_ip, c_dp])
+        L.ref_sph_compute_multistep_coefficients.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip,
+                                                             c_dp, c_dp, c_dp]
         L.ref_sph_load.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip, C.c_long, c_dp, c_dp,
                                    c_dp, C.c_int]
         L.ref_sph_step.restype = C.c_long
@@ -163,6 +165,18 @@ class RefSphere:
                                        _dp(mass), _dp(ctr), float(rtrunc), float(adb), nlev, len(idx),
                                        idx.ctypes.data_as(c_ip), frm.ctypes.data_as(c_ip),
                                        to.ctypes.data_as(c_ip), _dp(out))
+        return out
+
+    def compute_multistep_coefficients(self, mdrft, mfirst, dL, dN, coefL, coefN):
+        """SphericalBasis::compute_multistep_coefficients (src/SphericalBasis.cc:1231-1474) with the tables
+        of initialize_multistep; coefL, coefN [nlev][(lmax+1)^2][nmax] -> the table in use"""
+        coefL, coefN = _f64(coefL), _f64(coefN)
+        nlev = coefL.shape[0]
+        mfirst, dL, dN = (np.ascontiguousarray(a, dtype=np.int32) for a in (mfirst, dL, dN))
+        out = np.zeros(coefL.shape[1:])
+        lib().ref_sph_compute_multistep_coefficients(self.h, nlev, dL.shape[1], int(mdrft),
+                                                     mfirst.ctypes.data_as(c_ip), dL.ctypes.data_as(c_ip),
+                                                     dN.ctypes.data_as(c_ip), _dp(coefL), _dp(coefN), _dp(out))
         return out
 
     def consts(self):

@@ -18,6 +18,8 @@ unsigned multistep = 0;
 int this_step = 1, mdrft = 0, mstep = 0, Mstep = 1, shiftlevl = 0;
 double dtime = 0.0, dynfracS = 1.0, dynfracD = 1.0e32, dynfracV = 0.01, dynfracA = 0.03, dynfracP = 0.05;
 std::vector<int> mfirst;
+std::vector<std::vector<int>> dstepL, dstepN;
+double tnow = 0.0;
 ComponentContainer *comp = nullptr;
 bool EmpCylSL::enforce_limits = false;          /* exputil/EmpCylSL.cc:56 */
 
@@ -76,6 +78,7 @@ void SphericalBasis::setup(int L, int N, int nthr)
 }
 
 #include "_ref/gen/sph_multistep_update.inc"
+#include "_ref/gen/sph_compute_multistep_coefficients.inc"
 
 #include "_ref/gen/cyl_r_to_xi.inc"
 #include "_ref/gen/cyl_z_to_y.inc"
@@ -781,6 +784,44 @@ void ref_cylinder_accel_thread(void *hh, long n, const double *pos, const unsign
   }
 }
 
+} // extern "C"
+
+// SphericalBasis::compute_multistep_coefficients (src/SphericalBasis.cc:1231-1474): the coefficient
+// table in use at drift sub-step mdrft_ = levels below mfirst[mdrft_] interpolated between their
+// last (L) and next (N) tables, the active levels' N tables added.  coefL, coefN [nlev][nrow][nmax];
+// mfirst_ [Mstep+1], dL, dN [nlev][Mstep] are initialize_multistep's tables.
+extern "C" {
+void ref_sph_compute_multistep_coefficients(void *hh, int nlev, int Mstep_, int mdrft_, const int *mfirst_,
+                                            const int *dL, const int *dN, const double *coefL,
+                                            const double *coefN, double *out)
+{
+  SphHandle *h = static_cast<SphHandle *>(hh);
+  const int flags[5] = {0, 0, 0, 0, 0};
+  sph_config(h, 1.0, 0.0, 1.0e300, flags, 1);
+  Sphere &s = h->sph;
+  const int nrow = (s.Lmax + 1) * (s.Lmax + 1), N = s.nmax;
+  multistep = (unsigned)(nlev - 1);
+  Mstep = Mstep_; mdrft = mdrft_; mstep = mdrft_ > 0 ? mdrft_ - 1 : 0;
+  mfirst.assign(mfirst_, mfirst_ + Mstep_ + 1);
+  dstepL.assign(nlev, std::vector<int>(Mstep_ + 1, 0));
+  dstepN.assign(nlev, std::vector<int>(Mstep_ + 1, 0));
+  for (int M = 0; M < nlev; M++)
+    for (int k = 0; k < Mstep_; k++) { dstepL[M][k] = dL[M * Mstep_ + k]; dstepN[M][k] = dN[M * Mstep_ + k]; }
+  s.expcoefN.assign(nlev, std::vector<SphericalBasis::VectorP>(nrow));
+  s.expcoefL.assign(nlev, std::vector<SphericalBasis::VectorP>(nrow));
+  for (int M = 0; M < nlev; M++)
+    for (int r = 0; r < nrow; r++) {
+      s.expcoefN[M][r] = std::make_shared<Eigen::VectorXd>(N);
+      s.expcoefL[M][r] = std::make_shared<Eigen::VectorXd>(N);
+      for (int c = 0; c < N; c++) {
+        (*s.expcoefN[M][r])[c] = coefN[((size_t)M * nrow + r) * N + c];
+        (*s.expcoefL[M][r])[c] = coefL[((size_t)M * nrow + r) * N + c];
+      }
+    }
+  s.compute_multistep_coefficients();
+  for (int r = 0; r < nrow; r++)
+    for (int c = 0; c < N; c++) out[(size_t)r * N + c] = (*s.expcoef[r])[c];
+}
 } // extern "C"
 
 // SphericalBasis::multistep_update (src/SphericalBasis.cc:1156-1228) for a list of switching

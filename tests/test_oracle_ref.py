@@ -515,3 +515,19 @@ def test_cylinder_multistep_update_bit_exact():
         O.cyl_multistep_update(g, S, int(i), int(a), int(b), dC, dS, adb=0.9)
     assert dC.tobytes() == wC.tobytes() and dS.tobytes() == wS.tobytes()
     assert np.abs(wC).max() > 0 and np.abs(wC.sum(axis=0)).max() <= 1e-12 * np.abs(wC).max()
+
+
+@pytest.mark.parametrize("multistep", [1, 3])
+def test_compute_multistep_coefficients_bit_exact(multistep):
+    """a12: SphericalBasis::compute_multistep_coefficients (src/SphericalBasis.cc:1231-1474) at every drift
+    sub-step of the hierarchy, with the reference's own code fed the oracle's initialize_multistep tables"""
+    tab = get_table("hernquist", 3, 6)
+    ref = R.RefSphere(tab)
+    _, mfirst, dL, dN = O.multistep_tables(multistep)
+    rng = np.random.default_rng(7)
+    shape = (multistep + 1, (tab.lmax + 1) ** 2, tab.nmax)
+    coefL, coefN = rng.normal(size=shape), rng.normal(size=shape)
+    for mdrft in range(0, (1 << multistep) + 1):
+        want = ref.compute_multistep_coefficients(mdrft, mfirst, dL, dN, coefL, coefN)
+        got = O.multistep_interp(multistep, mdrft, coefL, coefN)
+        assert got.reshape(want.shape).tobytes() == want.tobytes(), mdrft
