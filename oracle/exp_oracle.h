@@ -28,8 +28,9 @@
  * for bit, as are fix_positions_thread (src/Component.cc:3280-3352) and SphericalBasis::multistep_update
  * (src/SphericalBasis.cc:1156-1228) and Cylinder::multistep_update / CylEXP::multistep_update
  * (src/Cylinder.cc:1752-1773, src/CylEXP.cc:159-188) and the level-table interpolation
- * SphericalBasis::compute_multistep_coefficients (:1231-1474).  Not pinned (restated only): the
- * cylinder's copy of that interpolation (src/CylEXP.cc:192-282) and the cylindrical pyEXP twin.
+ * SphericalBasis::compute_multistep_coefficients (:1231-1474) with the cylinder's copy
+ * CylEXP::compute_multistep_coefficients (src/CylEXP.cc:192-282).  Not pinned (restated only): the
+ * cylindrical pyEXP twin (a thin wrapper over the pinned EmpCylSL::accumulate / accumulated_eval).
  *
  * All arrays are plain row-major C arrays.  Coefficient layout is the
  * reference's: row index = l*l + {0 (m=0), 2m-1 (cos), 2m (sin)}, nmax

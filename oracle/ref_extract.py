@@ -52,6 +52,7 @@ PIECES = {
     "cylinder_coef_thread": ("src/Cylinder.cc", 748, 896, r"^void \* Cylinder::determine_coefficients_thread\(void \* arg\)"),
     "cylinder_multistep_update": ("src/Cylinder.cc", 1752, 1773, r"^void Cylinder::multistep_update\(int from, int to, Component\* c, int i, int id\)"),
     "cylexp_multistep_update": ("src/CylEXP.cc", 159, 188, r"^void CylEXP::multistep_update\(int from, int to, double r, double z, double phi, double mass, int id\)"),
+    "cylexp_compute_multistep_coefficients": ("src/CylEXP.cc", 192, 282, r"^void CylEXP::compute_multistep_coefficients\(unsigned mlevel\)"),
     "cylinder_accel_thread": ("src/Cylinder.cc", 1266, 1446, r"^void \* Cylinder::determine_acceleration_and_potential_thread\(void \* arg\)"),
     # --- centre-of-mass sums (src/Component.cc): thrd_pass_posn + fix_positions_thread
     "fix_positions_thread": ("src/Component.cc", 3266, 3352, r"^struct thrd_pass_posn"),

@@ -91,6 +91,8 @@ def lib():
         L.ref_cyl_destroy.argtypes = [C.c_void_p]
         L.ref_cylinder_multistep_update.argtypes = [C.c_void_p, C.c_long, c_dp, c_dp, c_dp, C.c_double, C.c_double,
                                                     C.c_int, C.c_long, c_ip, c_ip, c_ip, c_dp, c_dp]
+        L.ref_cylexp_compute_multistep_coefficients.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip]
+                                                                + [c_dp] * 6)
         L.ref_fix_positions.argtypes = [C.c_long, c_dp, c_dp, c_dp, c_dp, c_up, C.c_int, C.c_int, C.c_int, c_dp,
                                         C.c_double, c_dp]
         L.ref_cylinder_coef_thread.argtypes = ([C.c_void_p, C.c_long, c_dp, c_dp, c_up, C.c_int, C.c_int, c_dp]
@@ -318,6 +320,18 @@ class RefCylinder:
                                             float(adb), nlev, len(idx), idx.ctypes.data_as(c_ip),
                                             frm.ctypes.data_as(c_ip), to.ctypes.data_as(c_ip), _dp(dC), _dp(dS))
         return dC, dS
+
+    def compute_multistep_coefficients(self, mdrft, mfirst, dL, dN, cosL, cosN, sinL, sinN):
+        """CylEXP::compute_multistep_coefficients (src/CylEXP.cc:192-282); tables [nlev][mmax+1][norder]"""
+        arrs = [_f64(a) for a in (cosL, cosN, sinL, sinN)]
+        nlev = arrs[0].shape[0]
+        mfirst, dL, dN = (np.ascontiguousarray(a, dtype=np.int32) for a in (mfirst, dL, dN))
+        ac, as_ = np.zeros(arrs[0].shape[1:]), np.zeros(arrs[0].shape[1:])
+        lib().ref_cylexp_compute_multistep_coefficients(self.h, nlev, dL.shape[1], int(mdrft),
+                                                        mfirst.ctypes.data_as(c_ip), dL.ctypes.data_as(c_ip),
+                                                        dN.ctypes.data_as(c_ip), *[_dp(a) for a in arrs],
+                                                        _dp(ac), _dp(as_))
+        return ac, as_
 
     def accel_thread(self, pos, cos, sin, cylmass, level=None, nlev=1, mlevel=0, center=None, rtrunc=1.0e20,
                      owner_center=None, body=None, orig=None, acc=None, pot=None):

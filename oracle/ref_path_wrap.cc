@@ -397,9 +397,12 @@ void ref_sph_read(void *hh, double *pos, double *vel, double *acc, double *pot, 
 class CylEXP : public EmpCylSL {
 public:
   std::vector<std::vector<Eigen::MatrixXd>> differC1, differS1;     /* [thread][level](MMAX+1, rank3) */
+  MstepArray cosL, sinL;
   void multistep_update(int from, int to, double r, double z, double phi, double mass, int id);
+  void compute_multistep_coefficients(unsigned mlevel);
 };
 #include "_ref/gen/cylexp_multistep_update.inc"
+#include "_ref/gen/cylexp_compute_multistep_coefficients.inc"
 
 struct CylHandle { CylEXP e; };
 
@@ -743,6 +746,40 @@ void ref_cylinder_multistep_update(void *hh, long n, const double *pos, const do
         differC[((size_t)L * (M + 1) + m) * N + k] = e.differC1[0][L](m, k);
         differS[((size_t)L * (M + 1) + m) * N + k] = e.differS1[0][L](m, k);
       }
+}
+
+/* CylEXP::compute_multistep_coefficients (src/CylEXP.cc:192-282) with the tables of
+ * initialize_multistep: cosL/cosN/sinL/sinN [nlev][MMAX+1][NORDER] -> accum_cos, accum_sin */
+void ref_cylexp_compute_multistep_coefficients(void *hh, int nlev, int Mstep_, int mdrft_, const int *mfirst_,
+                                               const int *dL, const int *dN, const double *cosL,
+                                               const double *cosN, const double *sinL, const double *sinN,
+                                               double *accum_cos, double *accum_sin)
+{
+  CylEXP &e = static_cast<CylHandle *>(hh)->e;
+  const int M1 = e.MMAX + 1, N = e.NORDER;
+  multistep = (unsigned)(nlev - 1);
+  Mstep = Mstep_; mdrft = mdrft_; mstep = mdrft_ > 0 ? mdrft_ - 1 : 0;
+  mfirst.assign(mfirst_, mfirst_ + Mstep_ + 1);
+  dstepL.assign(nlev, std::vector<int>(Mstep_ + 1, 0));
+  dstepN.assign(nlev, std::vector<int>(Mstep_ + 1, 0));
+  for (int M = 0; M < nlev; M++)
+    for (int k = 0; k < Mstep_; k++) { dstepL[M][k] = dL[M * Mstep_ + k]; dstepN[M][k] = dN[M * Mstep_ + k]; }
+  auto fill = [&](EmpCylSL::MstepArray &dst, const double *src) {
+    dst.clear();
+    for (int M = 0; M < nlev; M++) {
+      dst.push_back(std::make_shared<EmpCylSL::VectorD2>(1, std::vector<Eigen::VectorXd>(M1, Eigen::VectorXd(N))));
+      for (int m = 0; m < M1; m++)
+        for (int k = 0; k < N; k++) dst(M)[0][m][k] = src[((size_t)M * M1 + m) * N + k];
+    }
+  };
+  fill(e.cosL, cosL); fill(e.cosN, cosN); fill(e.sinL, sinL); fill(e.sinN, sinN);
+  for (int m = 0; m < M1; m++) { e.accum_cos[m].setZero(); e.accum_sin[m].setZero(); }
+  e.compute_multistep_coefficients(0);
+  for (int m = 0; m < M1; m++)
+    for (int k = 0; k < N; k++) {
+      accum_cos[(size_t)m * N + k] = e.accum_cos[m][k];
+      accum_sin[(size_t)m * N + k] = e.accum_sin[m][k];
+    }
 }
 
 /* force thread: levels >= mlevel of the target component (pos/level/center/rtrunc) with the

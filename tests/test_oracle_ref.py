@@ -531,3 +531,21 @@ def test_compute_multistep_coefficients_bit_exact(multistep):
         want = ref.compute_multistep_coefficients(mdrft, mfirst, dL, dN, coefL, coefN)
         got = O.multistep_interp(multistep, mdrft, coefL, coefN)
         assert got.reshape(want.shape).tobytes() == want.tobytes(), mdrft
+
+
+def test_cylinder_compute_multistep_coefficients_bit_exact():
+    """a20: CylEXP::compute_multistep_coefficients (src/CylEXP.cc:192-282) at every drift sub-step"""
+    tab, g, consts = _cyl()
+    ref = R.RefCylinder(tab, consts)
+    multistep = 2
+    _, mfirst, dL, dN = O.multistep_tables(multistep)
+    rng = np.random.default_rng(8)
+    shape = (multistep + 1, tab.mmax + 1, tab.norder)
+    cL, cN, sL, sN = (rng.normal(size=shape) for _ in range(4))
+    for a in (sL, sN):
+        a[:, 0] = 0.0                       # no sine terms at m = 0
+    for mdrft in range(0, (1 << multistep) + 1):
+        wc, ws = ref.compute_multistep_coefficients(mdrft, mfirst, dL, dN, cL, cN, sL, sN)
+        gc = O.multistep_interp(multistep, mdrft, cL, cN).reshape(wc.shape)
+        gs = O.multistep_interp(multistep, mdrft, sL, sN).reshape(ws.shape)
+        assert gc.tobytes() == wc.tobytes() and gs[1:].tobytes() == ws[1:].tobytes(), mdrft
