@@ -147,7 +147,11 @@ namespace expb200 {
 // the level partition of perm[cur] is then known exactly.
 int component_read_bounds(expb200_component_s *c, uint32_t kpl, int nlev, int from);
 int component_reorder(expb200_component_s *c);
-constexpr int kReorderEvery = 64;      // sorts between physical re-orderings
+constexpr int kReorderEvery = 24;      // sorts between physical re-orderings: the force pass scatters its
+                                       // results through the permutation and slows as the store's order
+                                       // ages (7.3 -> 8.9 ms per step over 40 steps at 1e8 bodies); a
+                                       // re-ordering costs 8.5 ms; 96-step averages: every 64 sorts
+                                       // 13.3 ms/step, 32: 12.2, 24: 12.0, 16: 11.9-12.0, 8: 12.4
 constexpr int kReorderEveryMulti = 16; // the same with multistep levels (tail sorts count): the level-filtered
                                        // passes (kick, drift, zero) stream best over a level-major store
 }

@@ -1641,13 +1641,22 @@ SphGeom geom_for(const expb200_sphere_s *s, const expb200_component_s *c)
 // With allow_reorder the particle store is physically re-ordered into this order when it has
 // never been (random order: every access through the permutation would be a random
 // 32-byte DRAM transaction) or every kReorderEvery sorts (particles drift across cells).
+// sorts between two physical re-orderings of the store (EXPB200_REORDER_EVERY overrides the
+// single-level default for experiments)
+int reorder_every(int nlev)
+{
+  static const int env = getenv("EXPB200_REORDER_EVERY") ? atoi(getenv("EXPB200_REORDER_EVERY")) : 0;
+  if (nlev > 1) return kReorderEveryMulti;
+  return env > 0 ? env : kReorderEvery;
+}
+
 int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool allow_reorder,
                bool defer_stream = false)
 {
   // defer_stream: leave the sorted position stream to the first deposit sweep (c->psort_pending),
   // unless this sort is due to re-order the store, which takes the stream as the new store
   const bool reorder_due = allow_reorder && (c->never_reordered ||
-      c->sorts_since_reorder + 1 >= (s->nlev > 1 ? kReorderEveryMulti : kReorderEvery));
+      c->sorts_since_reorder + 1 >= reorder_every(s->nlev));
   if (reorder_due) defer_stream = false;
   int cur = 0;
   {
@@ -1662,7 +1671,7 @@ int sort_keyed(expb200_sphere_s *s, expb200_component_s *c, uint32_t nkeys, bool
   c->psort = c->posm_sorted;
   c->psort_pending = defer_stream;
   c->sorts_since_reorder++;
-  if (allow_reorder && (c->never_reordered || c->sorts_since_reorder >= (s->nlev > 1 ? kReorderEveryMulti : kReorderEvery)))
+  if (allow_reorder && (c->never_reordered || c->sorts_since_reorder >= reorder_every(s->nlev)))
     return component_reorder(c);
   return EXPB200_OK;
 }
