@@ -273,7 +273,10 @@ def run_diskhalo(args, B):
     sim.add_interaction(h, d)
     sim.add_interaction(d, h)
     sim.begin_run()
-    clocks = B.ClockSampler(R.local) if R.rank == 0 else None
+    # nvidia-smi polled every 500 ms here: this workload is launch- and sync-bound on the host side
+    # (2000 kernels and ~130 stream synchronisations per master step) and the 50 ms polling of the
+    # other workloads slowed the timed region by up to 2x and made it erratic
+    clocks = B.ClockSampler(R.local, period_ms=500) if R.rank == 0 else None
     if clocks:
         clocks.start()
     sim.do_steps(max(1, args.warmup // 3))

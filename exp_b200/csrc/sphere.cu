@@ -1646,7 +1646,8 @@ SphGeom geom_for(const expb200_sphere_s *s, const expb200_component_s *c)
 int reorder_every(int nlev)
 {
   static const int env = getenv("EXPB200_REORDER_EVERY") ? atoi(getenv("EXPB200_REORDER_EVERY")) : 0;
-  if (nlev > 1) return kReorderEveryMulti;
+  static const int envm = getenv("EXPB200_REORDER_EVERY_MULTI") ? atoi(getenv("EXPB200_REORDER_EVERY_MULTI")) : 0;
+  if (nlev > 1) return envm > 0 ? envm : kReorderEveryMulti;
   return env > 0 ? env : kReorderEvery;
 }
 
